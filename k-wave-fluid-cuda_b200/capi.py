@@ -1,0 +1,263 @@
+"""ctypes binding of include/kwave_b200.h.  Mirrors the call order of KSpaceFirstOrderSolver
+(allocateMemory -> loadInputData -> compute, KSpaceSolver/KSpaceFirstOrderSolver.cpp:124-439)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_HEADER = os.path.join(os.path.dirname(_HERE), "include", "kwave_b200.h")
+
+
+class KwError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"kwave_b200 error {code}: {msg}")
+        self.code = code
+
+
+class KwConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("struct_size", C.c_uint32),
+        ("nx", C.c_uint64), ("ny", C.c_uint64), ("nz", C.c_uint64), ("nt", C.c_uint64),
+        ("dt", C.c_float), ("dx", C.c_float), ("dy", C.c_float), ("dz", C.c_float), ("c_ref", C.c_float),
+        ("alpha_power", C.c_float),
+        ("nonlinear_flag", C.c_int32), ("absorbing_flag", C.c_int32), ("nonuniform_grid_flag", C.c_int32),
+        ("p_source_flag", C.c_uint64), ("ux_source_flag", C.c_uint64), ("uy_source_flag", C.c_uint64),
+        ("uz_source_flag", C.c_uint64), ("transducer_source_flag", C.c_uint64),
+        ("p0_source_flag", C.c_int32),
+        ("p_source_mode", C.c_int32), ("p_source_many", C.c_int32), ("u_source_mode", C.c_int32), ("u_source_many", C.c_int32),
+        ("sensor_mask_type", C.c_int32),
+        ("sampling_start_index", C.c_uint64),
+        ("c_period", C.c_float), ("c_mos", C.c_uint32), ("c_harmonics", C.c_uint32),
+        ("c_no_overlap", C.c_int32), ("c_40bit", C.c_int32),
+        ("device", C.c_int32),
+        ("raw_rows_capacity", C.c_uint64),
+        ("rank", C.c_int32), ("nranks", C.c_int32),
+        ("nccl_unique_id", C.c_void_p),
+    ]  # fmt: skip
+
+
+def _parse_enum(name):
+    """Read an enum's identifiers from the header so the ids can never drift from the C side."""
+    src = open(_HEADER).read()
+    body = re.search(r"enum\s+" + name + r"\s*\{(.*?)\};", src, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    out, val = {}, 0
+    for tok in body.split(","):
+        tok = tok.strip()
+        if not tok:
+            continue
+        if "=" in tok:
+            k, v = tok.split("=")
+            val = int(v.strip(), 0)
+            tok = k.strip()
+        out[tok] = val
+        val += 1
+    return out
+
+
+ARRAY_IDS = _parse_enum("kw_array")
+STREAM_IDS = _parse_enum("kw_stream")
+KW_ABI_VERSION = 1
+
+# dataset name in the k-Wave input file (Utils/MatrixNames.h) -> array id
+INPUT_NAMES = {
+    "c0": "KW_C0", "rho0": "KW_RHO0", "rho0_sgx": "KW_RHO0_SGX", "rho0_sgy": "KW_RHO0_SGY", "rho0_sgz": "KW_RHO0_SGZ",
+    "BonA": "KW_BONA", "alpha_coeff": "KW_ALPHA_COEFF",
+    "ddx_k_shift_pos_r": "KW_DDX_K_SHIFT_POS_R", "ddy_k_shift_pos": "KW_DDY_K_SHIFT_POS", "ddz_k_shift_pos": "KW_DDZ_K_SHIFT_POS",
+    "ddx_k_shift_neg_r": "KW_DDX_K_SHIFT_NEG_R", "ddy_k_shift_neg": "KW_DDY_K_SHIFT_NEG", "ddz_k_shift_neg": "KW_DDZ_K_SHIFT_NEG",
+    "pml_x_sgx": "KW_PML_X_SGX", "pml_y_sgy": "KW_PML_Y_SGY", "pml_z_sgz": "KW_PML_Z_SGZ",
+    "pml_x": "KW_PML_X", "pml_y": "KW_PML_Y", "pml_z": "KW_PML_Z",
+    "sensor_mask_index": "KW_SENSOR_MASK_INDEX", "sensor_mask_corners": "KW_SENSOR_MASK_CORNERS",
+    "p0_source_input": "KW_P0_SOURCE_INPUT", "p_source_input": "KW_P_SOURCE_INPUT", "p_source_index": "KW_P_SOURCE_INDEX",
+    "u_source_index": "KW_U_SOURCE_INDEX", "ux_source_input": "KW_UX_SOURCE_INPUT", "uy_source_input": "KW_UY_SOURCE_INPUT",
+    "uz_source_input": "KW_UZ_SOURCE_INPUT", "transducer_source_input": "KW_TRANSDUCER_SOURCE_INPUT",
+    "delay_mask": "KW_DELAY_MASK",
+    "x_shift_neg_r": "KW_X_SHIFT_NEG_R", "y_shift_neg_r": "KW_Y_SHIFT_NEG_R", "z_shift_neg_r": "KW_Z_SHIFT_NEG_R",
+}  # fmt: skip
+
+_lib = None
+
+
+def library_path():
+    return os.path.join(_HERE, "libkwave_b200.so")
+
+
+def load_library():
+    """Load the CUDA library.  Fails loudly when it has not been built (``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise KwError(-2, f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    u64, vp, i32 = C.c_uint64, C.c_void_p, C.c_int
+    lib.kw_last_error.restype = C.c_char_p
+    sigs = {
+        "kw_abi_version": [],
+        "kw_cuda_code_version": [C.POINTER(C.c_int)],
+        "kw_ctx_create": [C.POINTER(KwConfig), C.POINTER(vp)],
+        "kw_ctx_destroy": [vp],
+        "kw_set_array": [vp, i32, vp, u64],
+        "kw_get_array": [vp, i32, vp, u64],
+        "kw_stream_enable": [vp, i32],
+        "kw_preprocess": [vp],
+        "kw_run": [vp, u64, C.POINTER(u64), i32],
+        "kw_time_index": [vp, C.POINTER(u64)],
+        "kw_synchronize": [vp],
+        "kw_stream_info": [vp, i32, C.POINTER(u64), C.POINTER(u64)],
+        "kw_stream_fetch": [vp, i32, vp, u64, C.POINTER(u64)],
+        "kw_finish": [vp],
+        "kw_set_source_row": [vp, i32, u64, vp, u64],
+        "kw_fft_r2c_3d": [u64, u64, u64, vp, vp],
+        "kw_fft_c2r_3d": [u64, u64, u64, vp, vp],
+        "kw_last_run_ms": [vp, C.POINTER(C.c_float)],
+        "kw_launch_count": [vp, C.POINTER(u64)],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise KwError(rc, load_library().kw_last_error().decode())
+
+
+def fft_r2c_3d(x):
+    """CufftComplexMatrix::computeR2CFftND on a host array of shape (nz, ny, nx)."""
+    lib = load_library()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    nz, ny, nx = x.shape
+    out = np.empty((nz, ny, nx // 2 + 1), dtype=np.complex64)
+    _check(lib.kw_fft_r2c_3d(nx, ny, nz, x.ctypes.data, out.ctypes.data))
+    return out
+
+
+def fft_c2r_3d(xk, nx):
+    lib = load_library()
+    xk = np.ascontiguousarray(xk, dtype=np.complex64)
+    nz, ny, nxr = xk.shape
+    assert nxr == nx // 2 + 1
+    out = np.empty((nz, ny, nx), dtype=np.float32)
+    _check(lib.kw_fft_c2r_3d(nx, ny, nz, xk.ctypes.data, out.ctypes.data))
+    return out
+
+
+class Simulation:
+    """One simulation == one kw_ctx.  ``cfg``/``arrays`` use the input-file names (see synth.make_case)."""
+
+    def __init__(self, cfg, arrays, streams=(), start_index=0, raw_rows_capacity=0, device=-1, compression=None):
+        self.lib = load_library()
+        self.cfg = dict(cfg)
+        kc = KwConfig()
+        kc.abi_version, kc.struct_size = KW_ABI_VERSION, C.sizeof(KwConfig)
+        kc.nx, kc.ny, kc.nz, kc.nt = cfg["Nx"], cfg["Ny"], cfg["Nz"], cfg["Nt"]
+        for k in ("dt", "dx", "dy", "dz", "c_ref"):
+            setattr(kc, k, float(cfg[k]))
+        kc.alpha_power = float(cfg.get("alpha_power", 0.0))
+        for k in ("nonlinear_flag", "absorbing_flag", "nonuniform_grid_flag", "p_source_flag", "ux_source_flag",
+                  "uy_source_flag", "uz_source_flag", "transducer_source_flag", "p0_source_flag", "p_source_mode",
+                  "p_source_many", "u_source_mode", "u_source_many", "sensor_mask_type"):  # fmt: skip
+            setattr(kc, k, int(cfg.get(k, 0)))
+        kc.sampling_start_index = start_index
+        kc.device = device
+        kc.raw_rows_capacity = raw_rows_capacity
+        kc.rank, kc.nranks, kc.nccl_unique_id = 0, 1, None
+        if compression:
+            kc.c_period, kc.c_mos, kc.c_harmonics = compression["period"], compression.get("mos", 1), compression.get("harmonics", 1)
+            kc.c_no_overlap, kc.c_40bit = int(compression.get("no_overlap", 0)), int(compression.get("c40", 0))
+        self.ctx = C.c_void_p()
+        _check(self.lib.kw_ctx_create(C.byref(kc), C.byref(self.ctx)))
+        self.n = cfg["Nx"] * cfg["Ny"] * cfg["Nz"]
+        self.shape = (cfg["Nz"], cfg["Ny"], cfg["Nx"])
+        for name, arr in arrays.items():
+            self.set_array(name, arr)
+        self.streams = []
+        for s in streams:
+            self.enable(s)
+        _check(self.lib.kw_preprocess(self.ctx))
+
+    # -- arrays ----------------------------------------------------------------------------------------------------
+    def set_array(self, name, arr):
+        aid = ARRAY_IDS[INPUT_NAMES.get(name, name)]
+        a = np.asarray(arr)
+        if a.dtype.kind in "ui":
+            a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1)
+            count = a.size
+        elif a.dtype.kind == "c":
+            a = np.ascontiguousarray(a, dtype=np.complex64).reshape(-1)
+            count = a.size
+        else:
+            a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+            count = a.size
+        _check(self.lib.kw_set_array(self.ctx, aid, a.ctypes.data, count))
+
+    def get_array(self, name, shape=None):
+        aid = ARRAY_IDS[INPUT_NAMES.get(name, name)]
+        shape = self.shape if shape is None else shape
+        out = np.empty(shape, dtype=np.float32)
+        _check(self.lib.kw_get_array(self.ctx, aid, out.ctypes.data, out.size))
+        return out
+
+    # -- streams ---------------------------------------------------------------------------------------------------
+    def enable(self, stream):
+        sid = STREAM_IDS[stream]
+        _check(self.lib.kw_stream_enable(self.ctx, sid))
+        self.streams.append(stream)
+
+    def fetch(self, stream):
+        sid = STREAM_IDS[stream]
+        row, rows = C.c_uint64(), C.c_uint64()
+        _check(self.lib.kw_stream_info(self.ctx, sid, C.byref(row), C.byref(rows)))
+        out = np.empty((rows.value, row.value), dtype=np.float32)
+        got = C.c_uint64()
+        _check(self.lib.kw_stream_fetch(self.ctx, sid, out.ctypes.data, out.size, C.byref(got)))
+        return out[: got.value]
+
+    # -- time loop -------------------------------------------------------------------------------------------------
+    def run(self, nsteps, sync=True):
+        done = C.c_uint64()
+        _check(self.lib.kw_run(self.ctx, nsteps, C.byref(done), int(sync)))
+        return done.value
+
+    def synchronize(self):
+        _check(self.lib.kw_synchronize(self.ctx))
+
+    def finish(self):
+        _check(self.lib.kw_finish(self.ctx))
+
+    def last_run_ms(self):
+        ms = C.c_float()
+        _check(self.lib.kw_last_run_ms(self.ctx, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_uint64()
+        _check(self.lib.kw_launch_count(self.ctx, C.byref(n)))
+        return n.value
+
+    @property
+    def t_index(self):
+        t = C.c_uint64()
+        _check(self.lib.kw_time_index(self.ctx, C.byref(t)))
+        return t.value
+
+    def close(self):
+        if self.ctx:
+            self.lib.kw_ctx_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

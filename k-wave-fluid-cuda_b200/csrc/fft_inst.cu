@@ -1,0 +1,82 @@
+// One translation unit per transform length: nvcc ... -DKW_N=<N> fft_inst.cu -o fft_inst_<N>.o
+#include "ops.h"
+
+#ifndef KW_N
+#error "compile with -DKW_N=<transform length>"
+#endif
+
+namespace kw {
+#define KW_CAT2(a, b) a##b
+#define KW_CAT(a, b) KW_CAT2(a, b)
+// a distinctly named namespace per length so that every translation unit gets distinct symbols
+namespace KW_CAT(inst_, KW_N) {
+
+constexpr int N = KW_N;
+
+template <class K> static int blocks_per_sm(K kernel, int threads, size_t smem) {
+  int b = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, threads, smem);
+  return b > 0 ? b : 1;
+}
+
+static int x_grid(int nrows, int per_sm) {
+  constexpr int RP = kXThreads / (N / 8);
+  const int groups = ((nrows >> 1) + RP - 1) / RP;
+  const int cap = sm_count() * per_sm;
+  return groups < cap ? groups : cap;
+}
+
+static void xfwd(const XFwdArgs& a, int nfields, cudaStream_t st) {
+  static const int per_sm = blocks_per_sm(k_xfwd<N>, kXThreads, 0);
+  k_xfwd<N><<<dim3(x_grid(a.nrows, per_sm), nfields), kXThreads, 0, st>>>(a);
+}
+template <int NF, class Epi> static void xinv(const XInvArgs<NF>& a, const Epi& e, int gy, cudaStream_t st) {
+  static const int per_sm = blocks_per_sm(k_xinv<N, NF, Epi>, kXThreads, 0);
+  k_xinv<N, NF, Epi><<<dim3(x_grid(a.nrows, per_sm), gy), kXThreads, 0, st>>>(a, e);
+}
+static void xinv_store(const XInvArgs<1>& a, const EpiStore& e, int nf, cudaStream_t st) { xinv<1>(a, e, nf, st); }
+static void xinv_add(const XInvArgs<1>& a, const EpiAdd& e, cudaStream_t st) { xinv<1>(a, e, 1, st); }
+static void xinv_velocity(const XInvArgs<1>& a, const EpiVelocity& e, int nf, cudaStream_t st) { xinv<1>(a, e, nf, st); }
+static void xinv_density(const XInvArgs<3>& a, const EpiDensity& e, cudaStream_t st) { xinv<3>(a, e, 1, st); }
+static void xinv_psum(const XInvArgs<2>& a, const EpiPressureSum& e, cudaStream_t st) { xinv<2>(a, e, 1, st); }
+
+// ID distinguishes kernels of identical function type (the statics below are per kernel)
+template <int ID, class K> static int col_grid(K kernel, int ntiles) {
+  using C = ColCfg<N>;
+  static bool once = false;
+  static int per_sm = 1;
+  if (!once) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    per_sm = blocks_per_sm(kernel, C::THREADS, C::SMEM);
+    once = true;
+  }
+  const int groups = (ntiles + C::TPC - 1) / C::TPC;
+  const int cap = sm_count() * per_sm;
+  return groups < cap ? groups : cap;
+}
+
+static void col(const ColArgs& a, int dir, int nfields, cudaStream_t st) {
+  using C = ColCfg<N>;
+  const dim3 block(C::W, C::TY, C::TPC);
+  if (dir < 0) {
+    const int g = col_grid<0>(k_col<N, -1>, a.ntiles);
+    k_col<N, -1><<<dim3(g, nfields), block, C::SMEM, st>>>(a);
+  } else {
+    const int g = col_grid<1>(k_col<N, +1>, a.ntiles);
+    k_col<N, +1><<<dim3(g, nfields), block, C::SMEM, st>>>(a);
+  }
+}
+static void zmid(const ZMidArgs& a, int nfields, cudaStream_t st) {
+  using C = ColCfg<N>;
+  const int g = col_grid<2>(k_zmid<N>, a.ntiles);
+  k_zmid<N><<<dim3(g, nfields), dim3(C::W, C::TY, C::TPC), C::SMEM, st>>>(a);
+}
+
+}  // namespace inst_<N>
+
+#define KW_OPS_NAME2(n) fft_ops_##n
+#define KW_OPS_NAME(n) KW_OPS_NAME2(n)
+extern const FftOps KW_OPS_NAME(KW_N) = {KW_N, KW_CAT(inst_, KW_N)::xfwd, KW_CAT(inst_, KW_N)::xinv_store, KW_CAT(inst_, KW_N)::xinv_add, KW_CAT(inst_, KW_N)::xinv_velocity,
+                                            KW_CAT(inst_, KW_N)::xinv_density, KW_CAT(inst_, KW_N)::xinv_psum, KW_CAT(inst_, KW_N)::col, KW_CAT(inst_, KW_N)::zmid};
+
+}  // namespace kw

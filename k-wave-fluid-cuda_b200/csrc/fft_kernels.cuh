@@ -1,0 +1,249 @@
+// The four kernel shapes every 3-D transform of the time step is built from (all FP32, sm_100a, no cuFFT):
+//
+//   k_xfwd   real [z][y][x]  -> half spectrum along x [z][y][NXP]       (two real rows per complex transform)
+//   k_col    in-place complex transform along y (or z) of [z][y][NXP]   (W neighbouring kx per worker)
+//   k_zmid   forward z transform -> k-space operator -> inverse z transform, one HBM round trip
+//   k_xinv   half spectrum -> real rows, with the real-space update fused as an epilogue functor
+//
+// NXP = (Nx/2+1) rounded up to 16 complex values so that column tiles are 128-byte segments.
+// Together they replace cufftExecR2C/C2R (MatrixClasses/CufftComplexMatrix.cpp:511,527) and the k-space kernels
+// cudaComputePressureGradient / cudaComputeVelocityGradient / cudaComputeAbsorbtionTerm / cudaComputeSourceGradient
+// (KSpaceSolver/SolverCudaKernels.cu:1139,1210,1812,740).
+#pragma once
+#include "fft_core.cuh"
+
+namespace kw {
+
+constexpr int kMaxFields = 3;
+constexpr int kXThreads = 256;
+
+// ---------------------------------------------------------------------------------------------------------------------
+struct XFwdArgs {
+  const float* in[kMaxFields];
+  float2* out[kMaxFields];
+  const float2* tab;  // forward twiddle table of length Nx
+  int nrows;          // Ny*Nz
+  int nxp;
+};
+
+template <int N> __global__ void __launch_bounds__(kXThreads) k_xfwd(XFwdArgs a) {
+  using P = Plan<N>;
+  constexpr int T = P::T;
+  constexpr int RP = kXThreads / T;  // row pairs per CTA iteration
+  __shared__ float2 sbuf[RP * N];
+  const int t = threadIdx.x % T, rp = threadIdx.x / T;
+  float2 twr[P::NTW > 0 ? P::NTW : 1];
+  const float2* tab = a.tab;
+  load_twiddles<N>(twr, t, [tab](int m) { return __ldg(tab + m); });
+  RegTw twp{twr};
+  RowExchange ex{sbuf, rp * N};
+  const float* __restrict__ in = a.in[blockIdx.y];
+  float2* __restrict__ out = a.out[blockIdx.y];
+  const int npairs = a.nrows >> 1;
+  for (int g = blockIdx.x; g * RP < npairs; g += gridDim.x) {
+    const int pair = g * RP + rp;
+    const bool valid = pair < npairs;
+    const size_t row0 = valid ? 2 * (size_t)pair : 0;
+    const float* ra = in + row0 * N;
+    float2 v[1][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[0][r] = make_float2(__ldg(ra + t + r * T), __ldg(ra + N + t + r * T));
+    fft_worker<N, -1, 1>(v, t, 0, twp, ex);
+    // mirror exchange: Z[N-k] lives in worker T-t
+#pragma unroll
+    for (int m = 0; m < 8; ++m) ex.put(0, t + m * T, v[0][m]);
+    ex.sync();
+    float2 zp[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) zp[m] = ex.get(0, (N - (t + m * T)) & (N - 1));
+    ex.sync();
+    if (valid) {
+      float2* oa = out + row0 * a.nxp;
+      float2* ob = oa + a.nxp;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const float2 z = v[0][m], q = zp[m];
+        oa[t + m * T] = make_float2(0.5f * (z.x + q.x), 0.5f * (z.y - q.y));
+        ob[t + m * T] = make_float2(0.5f * (z.y + q.y), -0.5f * (z.x - q.x));
+      }
+      if (t == 0) {  // Nyquist: Z[N/2] is its own mirror
+        oa[N / 2] = make_float2(v[0][4].x, 0.f);
+        ob[N / 2] = make_float2(v[0][4].y, 0.f);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NF> struct XInvArgs {
+  const float2* in[kMaxFields];  // NF == 1: field selected by blockIdx.y; NF > 1: the NF fields of one voxel
+  const float2* tab;
+  int nrows, nxp, ny;
+};
+
+// Epilogue contract:  epi.apply(field_select, res, t, T, row0, y, z)  where res[f][m] = (row a, row b) values at
+// x = t + m*T of field f, row0 = flattened (z*Ny + y) index of row a (row b = row0 + 1, same z).
+template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads) k_xinv(XInvArgs<NF> a, Epi epi) {
+  using P = Plan<N>;
+  constexpr int T = P::T;
+  constexpr int RP = kXThreads / T;
+  __shared__ float2 sbuf[RP * N];
+  const int t = threadIdx.x % T, rp = threadIdx.x / T;
+  float2 twr[P::NTW > 0 ? P::NTW : 1];
+  const float2* tab = a.tab;
+  load_twiddles<N>(twr, t, [tab](int m) { return __ldg(tab + m); });
+  RegTw twp{twr};
+  RowExchange ex{sbuf, rp * N};
+  const int npairs = a.nrows >> 1;
+  for (int g = blockIdx.x; g * RP < npairs; g += gridDim.x) {
+    const int pair = g * RP + rp;
+    const bool valid = pair < npairs;
+    const size_t row0 = valid ? 2 * (size_t)pair : 0;
+    float2 res[NF][8];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      const float2* __restrict__ in = (NF == 1) ? a.in[blockIdx.y] : a.in[f];
+      const float2* ia = in + row0 * a.nxp;
+      const float2* ib = ia + a.nxp;
+      float2 v[1][8];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int k = t + m * T;
+        float2 A = __ldg(ia + k), B = __ldg(ib + k);
+        if (m == 0 && t == 0) A.y = 0.f, B.y = 0.f;  // C2R ignores the imaginary part of DC
+        v[0][m] = make_float2(A.x - B.y, A.y + B.x);  // Z[k] = A + iB
+        if (!(m == 0 && t == 0)) ex.put(0, N - k, make_float2(A.x + B.y, B.x - A.y));  // Z[N-k] = conj(A) + i conj(B)
+      }
+      if (t == 0) {
+        const float2 A = __ldg(ia + N / 2), B = __ldg(ib + N / 2);
+        ex.put(0, N / 2, make_float2(A.x, B.x));  // imaginary parts of the Nyquist bin ignored
+      }
+      ex.sync();
+#pragma unroll
+      for (int m = 4; m < 8; ++m) v[0][m] = ex.get(0, t + m * T);
+      ex.sync();
+      fft_worker<N, +1, 1>(v, t, 0, twp, ex);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) res[f][m] = v[0][m];
+    }
+    if (valid) {
+      const int y = (int)(row0 % a.ny), z = (int)(row0 / a.ny);
+      epi.template apply<N>(res, t, row0, y, z);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// column passes
+template <int N> struct ColCfg {
+  static constexpr int W = 16;
+  static constexpr int T = N / 8;
+  static constexpr int B = (N >= 512) ? 2 : 1;                                // transforms' workers per thread
+  static constexpr int TY = T / B;                                             // blockDim.y
+  static constexpr int TPC = (W * TY >= 256) ? 1 : 256 / (W * TY);             // tiles per CTA
+  static constexpr int THREADS = W * TY * TPC;
+  static constexpr size_t SMEM = (size_t)TPC * N * W * sizeof(float2);
+};
+
+struct TabTw {  // twiddles fetched from the (L1/const cached) table; index is uniform per W lanes
+  const float2* tab;
+  __device__ __forceinline__ float2 get(int, int m) const { return __ldg(tab + m); }
+};
+
+struct ColArgs {
+  float2* data[kMaxFields];
+  const float2* tab;
+  size_t stride;        // elements between consecutive points of the transform axis
+  size_t outer_stride;  // elements between consecutive "outer" tiles
+  int ngroups;          // NXP / W
+  int ntiles;           // nouter * ngroups
+};
+
+template <int N, int DIR> __global__ void __launch_bounds__(ColCfg<N>::THREADS) k_col(ColArgs a) {
+  using C = ColCfg<N>;
+  constexpr int W = C::W, T = C::T, B = C::B;
+  extern __shared__ float2 smem[];
+  const int lane = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
+  ColExchange<W> ex{smem + (size_t)tz * N * W + lane};
+  TabTw twp{a.tab};
+  float2* __restrict__ data = a.data[blockIdx.y];
+  for (int g = blockIdx.x; g * C::TPC < a.ntiles; g += gridDim.x) {
+    const int tile = g * C::TPC + tz;
+    const bool valid = tile < a.ntiles;
+    const int tl = valid ? tile : 0;
+    const size_t base = (size_t)(tl / a.ngroups) * a.outer_stride + (size_t)(tl % a.ngroups) * W + lane;
+    float2 v[B][8];
+#pragma unroll
+    for (int b = 0; b < B; ++b)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[b][r] = data[base + (size_t)(ty + b * C::TY + r * T) * a.stride];
+    fft_worker<N, DIR, B>(v, ty, C::TY, twp, ex);
+    if (valid) {
+#pragma unroll
+      for (int b = 0; b < B; ++b)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) data[base + (size_t)(ty + b * C::TY + r * T) * a.stride] = v[b][r];
+    }
+  }
+}
+
+// fused z pass:  out = IFFT_z( (FFT_z(in) * (mul * scal)) (x) vec[coord(axis)] )
+struct ZField {
+  const float2* in;
+  float2* out;
+  const float* mul;   // real multiplier on the padded reduced grid [kz][ky][NXP], or nullptr
+  float scal;         // scalar folded into the multiplier (fftDivider where the reference folds it there)
+  const float2* vec;  // 1-D complex operator, or nullptr
+  int axis;           // 0: indexed by kx, 1: ky, 2: kz
+};
+struct ZMidArgs {
+  ZField f[kMaxFields];
+  const float2* tab;
+  int ny, nxp, ngroups, ntiles;  // ntiles = Ny * ngroups
+  size_t plane;                  // Ny * NXP
+};
+
+template <int N> __global__ void __launch_bounds__(ColCfg<N>::THREADS) k_zmid(ZMidArgs a) {
+  using C = ColCfg<N>;
+  constexpr int W = C::W, T = C::T, B = C::B;
+  extern __shared__ float2 smem[];
+  const int lane = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
+  ColExchange<W> ex{smem + (size_t)tz * N * W + lane};
+  TabTw twp{a.tab};
+  const ZField fld = a.f[blockIdx.y];
+  for (int g = blockIdx.x; g * C::TPC < a.ntiles; g += gridDim.x) {
+    const int tile = g * C::TPC + tz;
+    const bool valid = tile < a.ntiles;
+    const int tl = valid ? tile : 0;
+    const int y = tl / a.ngroups, kx = (tl % a.ngroups) * W + lane;
+    const size_t base = (size_t)y * a.nxp + kx;
+    float2 v[B][8];
+#pragma unroll
+    for (int b = 0; b < B; ++b)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[b][r] = __ldg(fld.in + base + (size_t)(ty + b * C::TY + r * T) * a.plane);
+    fft_worker<N, -1, B>(v, ty, C::TY, twp, ex);
+    float2 w01 = make_float2(1.f, 0.f);
+    if (fld.vec && fld.axis < 2) w01 = __ldg(fld.vec + (fld.axis == 0 ? kx : y));
+#pragma unroll
+    for (int b = 0; b < B; ++b)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int kz = ty + b * C::TY + r * T;
+        float m = fld.scal;
+        if (fld.mul) m = __ldg(fld.mul + base + (size_t)kz * a.plane) * fld.scal;
+        float2 e = cscale(v[b][r], m);
+        if (fld.vec) e = cmul(e, fld.axis == 2 ? __ldg(fld.vec + kz) : w01);
+        v[b][r] = e;
+      }
+    fft_worker<N, +1, B>(v, ty, C::TY, twp, ex);
+    if (valid) {
+#pragma unroll
+      for (int b = 0; b < B; ++b)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) fld.out[base + (size_t)(ty + b * C::TY + r * T) * a.plane] = v[b][r];
+    }
+  }
+}
+
+}  // namespace kw

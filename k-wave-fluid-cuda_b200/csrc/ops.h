@@ -1,0 +1,34 @@
+// Per-length launch table: every FFT-bearing kernel is instantiated once per transform length N in its own translation
+// unit (fft_inst.cu compiled with -DKW_N=<N>) so the build parallelises; the solver picks the tables of Nx, Ny, Nz.
+#pragma once
+#include <cuda_runtime.h>
+#include "fft_kernels.cuh"
+#include "solver_kernels.cuh"
+
+namespace kw {
+
+struct FftOps {
+  int n;
+  void (*xfwd)(const XFwdArgs&, int nfields, cudaStream_t);
+  void (*xinv_store)(const XInvArgs<1>&, const EpiStore&, int nfields, cudaStream_t);
+  void (*xinv_add)(const XInvArgs<1>&, const EpiAdd&, cudaStream_t);
+  void (*xinv_velocity)(const XInvArgs<1>&, const EpiVelocity&, int nfields, cudaStream_t);
+  void (*xinv_density)(const XInvArgs<3>&, const EpiDensity&, cudaStream_t);
+  void (*xinv_psum)(const XInvArgs<2>&, const EpiPressureSum&, cudaStream_t);
+  void (*col)(const ColArgs&, int dir, int nfields, cudaStream_t);
+  void (*zmid)(const ZMidArgs&, int nfields, cudaStream_t);
+};
+
+const FftOps* get_fft_ops(int n);  // nullptr when n is not a supported length
+int sm_count();
+
+#define KW_DECLARE_OPS(N) extern const FftOps fft_ops_##N;
+KW_DECLARE_OPS(16)
+KW_DECLARE_OPS(32)
+KW_DECLARE_OPS(64)
+KW_DECLARE_OPS(128)
+KW_DECLARE_OPS(256)
+KW_DECLARE_OPS(512)
+KW_DECLARE_OPS(1024)
+
+}  // namespace kw

@@ -1,0 +1,943 @@
+// Host side of the C ABI (include/kwave_b200.h): context, pre-processing, per-step sequencing, output streams.
+//
+// Mirrors, for the hot path only, KSpaceFirstOrderSolver::{preProcessing, computeMainLoop, storeSensorData,
+// postProcessing} (KSpaceSolver/KSpaceFirstOrderSolver.cpp:784-857, :864-943, :1060-1093, :950-973) and the parts of
+// MatrixContainer / OutputStreamContainer that decide which arrays and streams exist.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/kwave_b200.h"
+#include "ops.h"
+
+namespace kw {
+
+// ---------------------------------------------------------------------------------------------------------------------
+thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define KW_CUDA(call)                                                                                    \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(e_ == cudaErrorMemoryAllocation ? KW_ERR_ALLOC : KW_ERR_CUDA,                          \
+                  std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+#define KW_TRY(expr)          \
+  do {                        \
+    int r_ = (expr);          \
+    if (r_ != KW_OK) return r_; \
+  } while (0)
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+const FftOps* get_fft_ops(int n) {
+  switch (n) {
+    case 16: return &fft_ops_16;
+    case 32: return &fft_ops_32;
+    case 64: return &fft_ops_64;
+    case 128: return &fft_ops_128;
+    case 256: return &fft_ops_256;
+    case 512: return &fft_ops_512;
+    case 1024: return &fft_ops_1024;
+    default: return nullptr;
+  }
+}
+
+// forward twiddle table e^{-2 pi i m/N}, generated in double precision, one device copy per (device, N)
+static int twiddle_table(int n, const float2** out) {
+  static std::mutex mu;
+  static std::map<std::pair<int, int>, float2*> cache;
+  int dev = 0;
+  KW_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find({dev, n});
+  if (it == cache.end()) {
+    std::vector<float2> h(n);
+    for (int m = 0; m < n; ++m) {
+      const double a = -2.0 * M_PI * (double)m / (double)n;
+      h[m] = make_float2((float)cos(a), (float)sin(a));
+    }
+    float2* d = nullptr;
+    KW_CUDA(cudaMalloc(&d, n * sizeof(float2)));
+    KW_CUDA(cudaMemcpy(d, h.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
+    it = cache.emplace(std::make_pair(dev, n), d).first;
+  }
+  *out = it->second;
+  return KW_OK;
+}
+
+static inline int ew_grid(size_t n) {
+  const size_t b = (n + 255) / 256;
+  const size_t cap = (size_t)sm_count() * 8;
+  return (int)(b < cap ? (b ? b : 1) : cap);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+struct Stream {
+  bool enabled = false;
+  int op = kOpNone;
+  int src = 0;       // 0: p, 1..3: ux,uy,uz (staggered)
+  bool all = false;  // whole-domain aggregate
+  float* dbuf = nullptr;
+  size_t row = 0, cap_rows = 0, rows = 0;
+};
+
+struct Geometry {
+  int nx = 0, ny = 0, nz = 0, nxr = 0, nxp = 0;
+  size_t n = 0, nc = 0;  // real voxels, padded complex elements
+  const FftOps *ox = nullptr, *oy = nullptr, *oz = nullptr;
+  const float2 *tx = nullptr, *ty = nullptr, *tz = nullptr;
+  int init(uint64_t nx_, uint64_t ny_, uint64_t nz_) {
+    nx = (int)nx_, ny = (int)ny_, nz = (int)nz_;
+    ox = get_fft_ops(nx), oy = get_fft_ops(ny), oz = get_fft_ops(nz);
+    if (!ox || !oy || !oz)
+      return fail(KW_ERR_INVALID, "grid sizes must be powers of two in [16,1024] (hand-written FFT plan table); got " +
+                                      std::to_string(nx_) + "x" + std::to_string(ny_) + "x" + std::to_string(nz_));
+    nxr = nx / 2 + 1;
+    nxp = (nxr + 15) / 16 * 16;
+    n = (size_t)nx * ny * nz;
+    nc = (size_t)nxp * ny * nz;
+    KW_TRY(twiddle_table(nx, &tx));
+    KW_TRY(twiddle_table(ny, &ty));
+    KW_TRY(twiddle_table(nz, &tz));
+    return KW_OK;
+  }
+};
+
+}  // namespace kw
+
+using namespace kw;
+
+struct kw_ctx {
+  kw_config cfg{};
+  Geometry g;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool preprocessed = false, finished = false;
+  uint64_t t = 0;
+  uint64_t launches = 0;
+  float last_ms = 0.f;
+  // host copies of inputs needed by pre-processing
+  std::vector<float> h_in[KW_ARRAY_COUNT];
+  std::vector<uint64_t> h_idx[KW_ARRAY_COUNT];
+  // device arrays (nullptr when absent); float arrays indexed by kw_array
+  float* d[KW_ARRAY_COUNT] = {};
+  uint64_t* di[KW_ARRAY_COUNT] = {};
+  size_t count[KW_ARRAY_COUNT] = {};
+  float scalar[KW_ARRAY_COUNT] = {};
+  float2* S[4] = {};
+  float *tA = nullptr, *tB = nullptr, *tNL = nullptr, *tSrc = nullptr;
+  uint64_t* cub_offsets = nullptr;
+  size_t nsens = 0;  // sensor points (index mask) or total cuboid points
+  int ncuboids = 0;
+  Stream streams[KW_STREAM_COUNT];
+  std::vector<void*> owned;
+
+  Fld fld(int id) const { return Fld{count[id] > 1 ? d[id] : nullptr, scalar[id]}; }
+};
+
+namespace kw {
+
+static int dalloc(kw_ctx* c, void** p, size_t bytes, bool zero = true) {
+  KW_CUDA(cudaMalloc(p, bytes ? bytes : 4));
+  c->owned.push_back(*p);
+  if (zero) KW_CUDA(cudaMemsetAsync(*p, 0, bytes ? bytes : 4, c->st));
+  return KW_OK;
+}
+
+static bool is_index_array(int id) {
+  return id == KW_SENSOR_MASK_INDEX || id == KW_SENSOR_MASK_CORNERS || id == KW_P_SOURCE_INDEX || id == KW_U_SOURCE_INDEX ||
+         id == KW_DELAY_MASK;
+}
+static bool is_complex_vec(int id) {
+  return (id >= KW_DDX_K_SHIFT_POS_R && id <= KW_DDZ_K_SHIFT_NEG) || (id >= KW_X_SHIFT_NEG_R && id <= KW_Z_SHIFT_NEG_R);
+}
+static bool is_reduced_real(int id) {
+  return id == KW_KAPPA || id == KW_SOURCE_KAPPA || id == KW_ABSORB_NABLA1 || id == KW_ABSORB_NABLA2;
+}
+
+// upload a host float array into a (new or existing) device array
+static int upload_f(kw_ctx* c, int id, const float* h, size_t n) {
+  if (!c->d[id] || c->count[id] != n) KW_TRY(dalloc(c, (void**)&c->d[id], n * sizeof(float), false));
+  c->count[id] = n;
+  KW_CUDA(cudaMemcpyAsync(c->d[id], h, n * sizeof(float), cudaMemcpyHostToDevice, c->st));
+  KW_CUDA(cudaStreamSynchronize(c->st));
+  return KW_OK;
+}
+// reduced-grid real operator given in the reference layout [nz][ny][nxr] -> padded device array
+static int upload_reduced(kw_ctx* c, int id, const float* h) {
+  const Geometry& g = c->g;
+  const size_t rows = (size_t)g.ny * g.nz;
+  float* tmp = nullptr;
+  KW_CUDA(cudaMalloc(&tmp, rows * g.nxr * sizeof(float)));
+  KW_CUDA(cudaMemcpyAsync(tmp, h, rows * g.nxr * sizeof(float), cudaMemcpyHostToDevice, c->st));
+  if (!c->d[id]) KW_TRY(dalloc(c, (void**)&c->d[id], g.nc * sizeof(float), false));
+  c->count[id] = rows * g.nxr;
+  k_pad_real<<<ew_grid(g.nc), 256, 0, c->st>>>(c->d[id], tmp, g.nxr, g.nxp, rows);
+  c->launches++;
+  KW_CUDA(cudaStreamSynchronize(c->st));
+  KW_CUDA(cudaFree(tmp));
+  return KW_OK;
+}
+
+// ---- host pre-processing, FP32 as in the reference -----------------------------------------------------------------
+// KSpaceFirstOrderSolver.cpp:2404-2452 (kappa), :2460-2506 (source kappa), :2514-2577 (kappa + nablas)
+static void generate_k_operators(const kw_config& cf, const Geometry& g, std::vector<float>* kappa, std::vector<float>* n1,
+                                 std::vector<float>* n2, std::vector<float>* skappa) {
+  const float dx2 = 1.0f / (cf.dx * cf.dx), dy2 = 1.0f / (cf.dy * cf.dy), dz2 = 1.0f / (cf.dz * cf.dz);
+  const float cRefDtPi = cf.c_ref * cf.dt * static_cast<float>(M_PI);
+  const float cRefDt2 = cf.c_ref * cf.dt * 0.5f;
+  const float pi2 = static_cast<float>(M_PI) * 2.0f;
+  const float nxRec = 1.0f / static_cast<float>(g.nx), nyRec = 1.0f / static_cast<float>(g.ny),
+              nzRec = 1.0f / static_cast<float>(g.nz);
+  const float ap = cf.alpha_power;
+  const size_t tot = (size_t)g.nxr * g.ny * g.nz;
+  if (kappa) kappa->resize(tot);
+  if (n1) n1->resize(tot), n2->resize(tot);
+  if (skappa) skappa->resize(tot);
+#pragma omp parallel for schedule(static)
+  for (int z = 0; z < g.nz; z++) {
+    float zPart = 0.5f - fabsf(0.5f - (float)z * nzRec);
+    zPart = (zPart * zPart) * dz2;
+    for (int y = 0; y < g.ny; y++) {
+      float yPart = 0.5f - fabsf(0.5f - (float)y * nyRec);
+      yPart = (yPart * yPart) * dy2;
+      const float yzPart = zPart + yPart;
+      for (int x = 0; x < g.nxr; x++) {
+        float xPart = 0.5f - fabsf(0.5f - (float)x * nxRec);
+        xPart = (xPart * xPart) * dx2;
+        const size_t i = ((size_t)z * g.ny + y) * g.nxr + x;
+        const float root = sqrtf(xPart + yzPart);
+        if (n1) {  // absorbing: kappa from pi2 * root * cRefDt2 (cpp:2556-2561)
+          const float k = pi2 * root;
+          const float cRefK = cRefDt2 * k;
+          if (kappa) (*kappa)[i] = (cRefK == 0.0f) ? 1.0f : sinf(cRefK) / cRefK;
+          float a = powf(k, ap - 2.0f), b = powf(k, ap - 1.0f);
+          if (a == std::numeric_limits<float>::infinity()) a = 0.0f;
+          if (b == std::numeric_limits<float>::infinity()) b = 0.0f;
+          (*n1)[i] = a;
+          (*n2)[i] = b;
+        } else if (kappa) {  // lossless: kappa from cRefDtPi * root (cpp:2440-2446)
+          const float k = cRefDtPi * root;
+          (*kappa)[i] = (k == 0.0f) ? 1.0f : sinf(k) / k;
+        }
+        if (skappa) (*skappa)[i] = cosf(cRefDtPi * root);
+      }
+    }
+  }
+}
+
+}  // namespace kw
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+extern "C" {
+
+int kw_abi_version(void) { return KW_ABI_VERSION; }
+const char* kw_last_error(void) { return g_err.c_str(); }
+
+__global__ void k_code_version(int* v) {
+#ifdef __CUDA_ARCH__
+  *v = __CUDA_ARCH__ / 10;
+#endif
+}
+int kw_cuda_code_version(int* version) {
+  int* d = nullptr;
+  KW_CUDA(cudaMalloc(&d, sizeof(int)));
+  KW_CUDA(cudaMemset(d, 0, sizeof(int)));
+  k_code_version<<<1, 1>>>(d);
+  KW_CUDA(cudaGetLastError());
+  KW_CUDA(cudaMemcpy(version, d, sizeof(int), cudaMemcpyDeviceToHost));
+  KW_CUDA(cudaFree(d));
+  return KW_OK;
+}
+
+int kw_ctx_create(const kw_config* cfg, kw_ctx** out) {
+  if (!cfg || !out) return fail(KW_ERR_INVALID, "null argument");
+  if (cfg->abi_version != KW_ABI_VERSION || cfg->struct_size != sizeof(kw_config))
+    return fail(KW_ERR_INVALID, "kw_config ABI mismatch");
+  if (cfg->nonuniform_grid_flag) return fail(KW_ERR_INVALID, "nonuniform_grid_flag must be 0 (main.cpp:460)");
+  if (cfg->nz <= 1) return fail(KW_ERR_INVALID, "2-D simulations (Nz == 1) are not supported by this build");
+  if (cfg->absorbing_flag && cfg->alpha_power == 1.0f)
+    return fail(KW_ERR_INVALID, "alpha_power == 1 is not supported (Parameters.cpp:421-424)");
+  if (cfg->nranks > 1) return fail(KW_ERR_INVALID, "sharded runs are not available in this build");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(KW_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  if (cfg->device >= 0) KW_CUDA(cudaSetDevice(cfg->device));
+  kw_ctx* c = new kw_ctx();
+  c->cfg = *cfg;
+  int r = c->g.init(cfg->nx, cfg->ny, cfg->nz);
+  if (r != KW_OK) {
+    delete c;
+    return r;
+  }
+  KW_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  KW_CUDA(cudaEventCreate(&c->ev0));
+  KW_CUDA(cudaEventCreate(&c->ev1));
+  *out = c;
+  return KW_OK;
+}
+
+int kw_ctx_destroy(kw_ctx* c) {
+  if (!c) return KW_OK;
+  cudaStreamSynchronize(c->st);
+  for (void* p : c->owned) cudaFree(p);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->st) cudaStreamDestroy(c->st);
+  delete c;
+  return KW_OK;
+}
+
+int kw_set_array(kw_ctx* c, int id, const void* host, uint64_t count) {
+  if (!c || !host || id < 0 || id >= KW_ARRAY_COUNT || count == 0) return fail(KW_ERR_INVALID, "kw_set_array: bad argument");
+  const Geometry& g = c->g;
+  if (is_index_array(id)) {
+    const uint64_t* h = static_cast<const uint64_t*>(host);
+    c->h_idx[id].assign(h, h + count);
+    return KW_OK;  // shifted to 0-based and uploaded by kw_preprocess
+  }
+  if (is_complex_vec(id)) {  // count complex values; x vectors are padded to nxp
+    const bool xvec = (id == KW_DDX_K_SHIFT_POS_R || id == KW_DDX_K_SHIFT_NEG_R || id == KW_X_SHIFT_NEG_R);
+    const size_t want = xvec ? g.nxr
+                             : (id == KW_DDY_K_SHIFT_POS || id == KW_DDY_K_SHIFT_NEG) ? g.ny
+                             : (id == KW_DDZ_K_SHIFT_POS || id == KW_DDZ_K_SHIFT_NEG) ? g.nz
+                             : (id == KW_Y_SHIFT_NEG_R) ? g.ny / 2 + 1 : g.nz / 2 + 1;
+    if (count != want) return fail(KW_ERR_INVALID, "kw_set_array: wrong length for complex vector " + std::to_string(id));
+    const size_t padded = xvec ? g.nxp : want;
+    std::vector<float> tmp(2 * padded, 0.f);
+    memcpy(tmp.data(), host, 2 * count * sizeof(float));
+    KW_TRY(upload_f(c, id, tmp.data(), 2 * padded));
+    return KW_OK;
+  }
+  const float* h = static_cast<const float*>(host);
+  if (is_reduced_real(id)) {
+    if (count != (size_t)g.nxr * g.ny * g.nz) return fail(KW_ERR_INVALID, "kw_set_array: wrong size for reduced-grid operator");
+    return upload_reduced(c, id, h);
+  }
+  switch (id) {
+    case KW_C0: case KW_ALPHA_COEFF: case KW_RHO0_SGX: case KW_RHO0_SGY: case KW_RHO0_SGZ:
+      // transformed by kw_preprocess on the host, as the reference does
+      if (count != 1 && count != g.n) return fail(KW_ERR_INVALID, "kw_set_array: medium array must have 1 or Nx*Ny*Nz elements");
+      c->h_in[id].assign(h, h + count);
+      return KW_OK;
+    case KW_RHO0: case KW_BONA: case KW_ABSORB_TAU: case KW_ABSORB_ETA:
+      if (count != 1 && count != g.n) return fail(KW_ERR_INVALID, "kw_set_array: medium array must have 1 or Nx*Ny*Nz elements");
+      if (count == 1) { c->scalar[id] = h[0]; c->count[id] = 1; return KW_OK; }
+      return upload_f(c, id, h, count);
+    case KW_P: case KW_RHOX: case KW_RHOY: case KW_RHOZ: case KW_UX_SGX: case KW_UY_SGY: case KW_UZ_SGZ: case KW_P0_SOURCE_INPUT:
+      if (count != g.n) return fail(KW_ERR_INVALID, "kw_set_array: field must have Nx*Ny*Nz elements");
+      return upload_f(c, id, h, count);
+    case KW_PML_X_SGX: case KW_PML_X: if (count != (size_t)g.nx) return fail(KW_ERR_INVALID, "pml x length"); return upload_f(c, id, h, count);
+    case KW_PML_Y_SGY: case KW_PML_Y: if (count != (size_t)g.ny) return fail(KW_ERR_INVALID, "pml y length"); return upload_f(c, id, h, count);
+    case KW_PML_Z_SGZ: case KW_PML_Z: if (count != (size_t)g.nz) return fail(KW_ERR_INVALID, "pml z length"); return upload_f(c, id, h, count);
+    case KW_P_SOURCE_INPUT: case KW_TRANSDUCER_SOURCE_INPUT: case KW_UX_SOURCE_INPUT: case KW_UY_SOURCE_INPUT: case KW_UZ_SOURCE_INPUT:
+      return upload_f(c, id, h, count);
+    default:
+      return fail(KW_ERR_INVALID, "kw_set_array: array id " + std::to_string(id) + " is not an input");
+  }
+}
+
+int kw_set_source_row(kw_ctx* c, int id, uint64_t t, const float* row, uint64_t count) {
+  if (!c || !row) return fail(KW_ERR_INVALID, "null argument");
+  if (id != KW_P_SOURCE_INPUT && id != KW_UX_SOURCE_INPUT && id != KW_UY_SOURCE_INPUT && id != KW_UZ_SOURCE_INPUT)
+    return fail(KW_ERR_INVALID, "kw_set_source_row: not a source input");
+  if (!c->d[id] || (t + 1) * count > c->count[id]) return fail(KW_ERR_INVALID, "kw_set_source_row: row outside the signal");
+  KW_CUDA(cudaMemcpyAsync(c->d[id] + t * count, row, count * sizeof(float), cudaMemcpyHostToDevice, c->st));
+  return KW_OK;
+}
+
+static const struct { int op; int src; bool all; bool supported; } kStreamTable[KW_STREAM_COUNT] = {
+    /* P_RAW */ {kOpNone, 0, false, true}, /* P_C */ {0, 0, false, false}, /* P_RMS */ {kOpRms, 0, false, true},
+    /* P_MAX */ {kOpMax, 0, false, true}, /* P_MIN */ {kOpMin, 0, false, true}, /* P_MAX_ALL */ {kOpMax, 0, true, true},
+    /* P_MIN_ALL */ {kOpMin, 0, true, true},
+    /* U*_RAW */ {kOpNone, 1, false, true}, {kOpNone, 2, false, true}, {kOpNone, 3, false, true},
+    /* U*_C */ {0, 1, false, false}, {0, 2, false, false}, {0, 3, false, false},
+    /* U*_NS_RAW */ {0, 4, false, false}, {0, 5, false, false}, {0, 6, false, false},
+    /* U*_NS_C */ {0, 4, false, false}, {0, 5, false, false}, {0, 6, false, false},
+    /* U*_RMS */ {kOpRms, 1, false, true}, {kOpRms, 2, false, true}, {kOpRms, 3, false, true},
+    /* U*_MAX */ {kOpMax, 1, false, true}, {kOpMax, 2, false, true}, {kOpMax, 3, false, true},
+    /* U*_MIN */ {kOpMin, 1, false, true}, {kOpMin, 2, false, true}, {kOpMin, 3, false, true},
+    /* U*_MAX_ALL */ {kOpMax, 1, true, true}, {kOpMax, 2, true, true}, {kOpMax, 3, true, true},
+    /* U*_MIN_ALL */ {kOpMin, 1, true, true}, {kOpMin, 2, true, true}, {kOpMin, 3, true, true},
+    /* I*_AVG */ {0, 0, false, false}, {0, 0, false, false}, {0, 0, false, false},
+    /* I*_AVG_C */ {0, 0, false, false}, {0, 0, false, false}, {0, 0, false, false},
+    /* Q_TERM */ {0, 0, false, false}, /* Q_TERM_C */ {0, 0, false, false}};
+
+int kw_stream_enable(kw_ctx* c, int sid) {
+  if (!c || sid < 0 || sid >= KW_STREAM_COUNT) return fail(KW_ERR_INVALID, "kw_stream_enable: bad stream id");
+  if (c->preprocessed) return fail(KW_ERR_STATE, "kw_stream_enable must precede kw_preprocess");
+  if (!kStreamTable[sid].supported) return fail(KW_ERR_INVALID, "stream " + std::to_string(sid) + " is not available in this build");
+  Stream& s = c->streams[sid];
+  s.enabled = true;
+  s.op = kStreamTable[sid].op;
+  s.src = kStreamTable[sid].src;
+  s.all = kStreamTable[sid].all;
+  return KW_OK;
+}
+
+int kw_preprocess(kw_ctx* c) {
+  if (!c) return fail(KW_ERR_INVALID, "null context");
+  if (c->preprocessed) return fail(KW_ERR_STATE, "kw_preprocess called twice");
+  const kw_config& cf = c->cfg;
+  const Geometry& g = c->g;
+  // --- 1. index arrays: 1-based -> 0-based (cpp:787-813; IndexMatrix.cpp:161-169)
+  for (int id : {KW_SENSOR_MASK_INDEX, KW_SENSOR_MASK_CORNERS, KW_P_SOURCE_INDEX, KW_U_SOURCE_INDEX, KW_DELAY_MASK}) {
+    auto& h = c->h_idx[id];
+    if (h.empty()) continue;
+    for (auto& v : h) {
+      if (v == 0) return fail(KW_ERR_INVALID, "index arrays are 1-based in the input file; found 0");
+      v -= 1;
+    }
+    if (id != KW_DELAY_MASK && id != KW_SENSOR_MASK_CORNERS)
+      for (auto v : h)
+        if (v >= g.n) return fail(KW_ERR_INVALID, "index outside the grid in array " + std::to_string(id));
+    KW_TRY(dalloc(c, (void**)&c->di[id], h.size() * sizeof(uint64_t), false));
+    KW_CUDA(cudaMemcpyAsync(c->di[id], h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->st));
+    c->count[id] = h.size();
+  }
+  // --- 2. dt / rho0_sg (cpp:825-830)
+  for (int k = 0; k < 3; ++k) {
+    const int id = KW_RHO0_SGX + k;
+    auto& h = c->h_in[id];
+    if (h.empty()) return fail(KW_ERR_INVALID, "rho0_sg* missing");
+    for (auto& v : h) v = cf.dt / v;
+    if (h.size() == 1) c->scalar[id] = h[0], c->count[id] = 1;
+    else KW_TRY(upload_f(c, id, h.data(), h.size()));
+  }
+  // --- 3. k-space operators (cpp:835-843) unless supplied through kw_set_array
+  auto& c0 = c->h_in[KW_C0];
+  if (c0.empty()) return fail(KW_ERR_INVALID, "c0 missing");
+  {
+    std::vector<float> kappa, n1, n2, sk;
+    const bool need_kappa = !c->d[KW_KAPPA];
+    const bool need_nabla = cf.absorbing_flag && !c->d[KW_ABSORB_NABLA1];
+    const bool need_sk = ((cf.p_source_flag && cf.p_source_mode == KW_SRC_ADDITIVE) ||
+                          ((cf.ux_source_flag || cf.uy_source_flag || cf.uz_source_flag) && cf.u_source_mode == KW_SRC_ADDITIVE)) &&
+                         !c->d[KW_SOURCE_KAPPA];
+    if (need_kappa || need_nabla || need_sk)
+      generate_k_operators(cf, g, need_kappa ? &kappa : nullptr, cf.absorbing_flag ? &n1 : nullptr,
+                           cf.absorbing_flag ? &n2 : nullptr, need_sk ? &sk : nullptr);
+    if (need_kappa) KW_TRY(upload_reduced(c, KW_KAPPA, kappa.data()));
+    if (need_nabla) {
+      KW_TRY(upload_reduced(c, KW_ABSORB_NABLA1, n1.data()));
+      KW_TRY(upload_reduced(c, KW_ABSORB_NABLA2, n2.data()));
+    }
+    if (need_sk) KW_TRY(upload_reduced(c, KW_SOURCE_KAPPA, sk.data()));
+  }
+  if (cf.absorbing_flag && c->count[KW_ABSORB_TAU] == 0) {  // tau, eta (cpp:2584-2643); c0 still unsquared here
+    auto& al = c->h_in[KW_ALPHA_COEFF];
+    if (al.empty()) return fail(KW_ERR_INVALID, "alpha_coeff missing");
+    const float ap = cf.alpha_power;
+    const float tanPi2 = tanf(static_cast<float>(M_PI_2) * ap);
+    const float neper = (100.0f * powf(1.0e-6f / (2.0f * static_cast<float>(M_PI)), ap)) / (20.0f * static_cast<float>(M_LOG10E));
+    const size_t m = std::max(al.size(), c0.size());
+    std::vector<float> tau(m), eta(m);
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)m; ++i) {
+      const float a2 = 2.0f * neper * (al.size() == 1 ? al[0] : al[i]);
+      const float cc = c0.size() == 1 ? c0[0] : c0[i];
+      tau[i] = (-a2) * powf(cc, ap - 1.0f);
+      eta[i] = a2 * powf(cc, ap) * tanPi2;
+    }
+    if (m == 1) {
+      c->scalar[KW_ABSORB_TAU] = tau[0], c->scalar[KW_ABSORB_ETA] = eta[0];
+      c->count[KW_ABSORB_TAU] = c->count[KW_ABSORB_ETA] = 1;
+    } else {
+      KW_TRY(upload_f(c, KW_ABSORB_TAU, tau.data(), m));
+      KW_TRY(upload_f(c, KW_ABSORB_ETA, eta.data(), m));
+    }
+  }
+  // --- 5. c2 = c0^2 (cpp:2690-2703)
+  for (auto& v : c0) v = v * v;
+  if (c0.size() == 1) c->scalar[KW_C0] = c0[0], c->count[KW_C0] = 1;
+  else KW_TRY(upload_f(c, KW_C0, c0.data(), c0.size()));
+  for (auto& v : c->h_in) std::vector<float>().swap(v);
+  // --- validation of what the loop needs
+  if (c->count[KW_RHO0] == 0) return fail(KW_ERR_INVALID, "rho0 missing");
+  if (cf.nonlinear_flag && c->count[KW_BONA] == 0) return fail(KW_ERR_INVALID, "BonA missing (nonlinear_flag = 1)");
+  for (int id : {KW_DDX_K_SHIFT_POS_R, KW_DDY_K_SHIFT_POS, KW_DDZ_K_SHIFT_POS, KW_DDX_K_SHIFT_NEG_R, KW_DDY_K_SHIFT_NEG,
+                 KW_DDZ_K_SHIFT_NEG, KW_PML_X_SGX, KW_PML_Y_SGY, KW_PML_Z_SGZ, KW_PML_X, KW_PML_Y, KW_PML_Z})
+    if (!c->d[id]) return fail(KW_ERR_INVALID, "k-space shift vector or PML vector missing (array id " + std::to_string(id) + ")");
+  if (cf.p_source_flag && (!c->di[KW_P_SOURCE_INDEX] || !c->d[KW_P_SOURCE_INPUT])) return fail(KW_ERR_INVALID, "p source arrays missing");
+  if ((cf.ux_source_flag || cf.uy_source_flag || cf.uz_source_flag || cf.transducer_source_flag) && !c->di[KW_U_SOURCE_INDEX])
+    return fail(KW_ERR_INVALID, "u_source_index missing");
+  if (cf.ux_source_flag && !c->d[KW_UX_SOURCE_INPUT]) return fail(KW_ERR_INVALID, "ux_source_input missing");
+  if (cf.uy_source_flag && !c->d[KW_UY_SOURCE_INPUT]) return fail(KW_ERR_INVALID, "uy_source_input missing");
+  if (cf.uz_source_flag && !c->d[KW_UZ_SOURCE_INPUT]) return fail(KW_ERR_INVALID, "uz_source_input missing");
+  if (cf.transducer_source_flag && (!c->d[KW_TRANSDUCER_SOURCE_INPUT] || !c->di[KW_DELAY_MASK]))
+    return fail(KW_ERR_INVALID, "transducer source arrays missing");
+  if (cf.p0_source_flag && !c->d[KW_P0_SOURCE_INPUT]) return fail(KW_ERR_INVALID, "p0_source_input missing");
+  if (cf.p_source_flag && cf.p_source_many && c->count[KW_P_SOURCE_INPUT] < cf.p_source_flag * c->count[KW_P_SOURCE_INDEX])
+    return fail(KW_ERR_INVALID, "p_source_input shorter than p_source_flag * Nsrc");
+  // --- state and temporaries (state starts at zero, BaseFloatMatrix.cpp:144-145)
+  for (int id : {KW_P, KW_RHOX, KW_RHOY, KW_RHOZ, KW_UX_SGX, KW_UY_SGY, KW_UZ_SGZ})
+    if (!c->d[id]) {
+      KW_TRY(dalloc(c, (void**)&c->d[id], g.n * sizeof(float)));
+      c->count[id] = g.n;
+    }
+  for (int k = 0; k < 4; ++k) KW_TRY(dalloc(c, (void**)&c->S[k], g.nc * sizeof(float2)));
+  if (cf.absorbing_flag) {
+    KW_TRY(dalloc(c, (void**)&c->tA, g.n * sizeof(float)));
+    KW_TRY(dalloc(c, (void**)&c->tB, g.n * sizeof(float)));
+    if (cf.nonlinear_flag) KW_TRY(dalloc(c, (void**)&c->tNL, g.n * sizeof(float)));
+  }
+  if (c->d[KW_SOURCE_KAPPA]) KW_TRY(dalloc(c, (void**)&c->tSrc, g.n * sizeof(float)));
+  // --- sensors and streams
+  bool any_sensor_stream = false;
+  for (int s = 0; s < KW_STREAM_COUNT; ++s) any_sensor_stream |= c->streams[s].enabled && !c->streams[s].all;
+  if (any_sensor_stream) {
+    if (cf.sensor_mask_type == 0) {
+      if (!c->di[KW_SENSOR_MASK_INDEX]) return fail(KW_ERR_INVALID, "sensor_mask_index missing");
+      c->nsens = c->count[KW_SENSOR_MASK_INDEX];
+    } else {
+      auto& h = c->h_idx[KW_SENSOR_MASK_CORNERS];
+      if (h.empty() || h.size() % 6) return fail(KW_ERR_INVALID, "sensor_mask_corners missing or not a multiple of 6");
+      c->ncuboids = (int)(h.size() / 6);
+      std::vector<uint64_t> off(c->ncuboids + 1, 0);
+      for (int k = 0; k < c->ncuboids; ++k) {
+        const uint64_t* q = &h[6 * k];
+        if (q[3] < q[0] || q[4] < q[1] || q[5] < q[2] || q[3] >= (uint64_t)g.nx || q[4] >= (uint64_t)g.ny || q[5] >= (uint64_t)g.nz)
+          return fail(KW_ERR_INVALID, "sensor_mask_corners: cuboid outside the grid");
+        off[k + 1] = off[k] + (q[3] - q[0] + 1) * (q[4] - q[1] + 1) * (q[5] - q[2] + 1);
+      }
+      c->nsens = off.back();
+      KW_TRY(dalloc(c, (void**)&c->cub_offsets, off.size() * sizeof(uint64_t), false));
+      KW_CUDA(cudaMemcpyAsync(c->cub_offsets, off.data(), off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->st));
+      KW_CUDA(cudaStreamSynchronize(c->st));
+    }
+  }
+  const uint64_t nsamp = cf.nt > cf.sampling_start_index ? cf.nt - cf.sampling_start_index : 0;
+  for (int sid = 0; sid < KW_STREAM_COUNT; ++sid) {
+    Stream& s = c->streams[sid];
+    if (!s.enabled) continue;
+    s.row = s.all ? g.n : c->nsens;
+    if (s.op == kOpNone) {
+      uint64_t cap = cf.raw_rows_capacity;
+      if (cap == 0) cap = std::max<uint64_t>(1, std::min<uint64_t>(nsamp ? nsamp : 1, (256ull << 20) / (s.row * sizeof(float) + 1)));
+      s.cap_rows = cap;
+      KW_TRY(dalloc(c, (void**)&s.dbuf, s.cap_rows * s.row * sizeof(float)));
+    } else {
+      s.cap_rows = 1;
+      KW_TRY(dalloc(c, (void**)&s.dbuf, s.row * sizeof(float)));
+      const float init = s.op == kOpMax ? -FLT_MAX : s.op == kOpMin ? FLT_MAX : 0.f;  // BaseOutputStream.cpp:338-366
+      k_fill<<<ew_grid(s.row), 256, 0, c->st>>>(s.dbuf, init, s.row);
+      c->launches++;
+    }
+  }
+  KW_CUDA(cudaStreamSynchronize(c->st));
+  KW_CUDA(cudaGetLastError());
+  c->preprocessed = true;
+  return KW_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// the time step
+// =====================================================================================================================
+namespace kw {
+
+struct StepCtx {
+  kw_ctx* c;
+  const Geometry& g;
+  cudaStream_t st;
+};
+
+// forward x and y passes of `nf` real fields into spectral buffers
+static void forward_xy(kw_ctx* c, const float* const* in, float2* const* out, int nf) {
+  const Geometry& g = c->g;
+  XFwdArgs xa{};
+  ColArgs ca{};
+  for (int f = 0; f < nf; ++f) xa.in[f] = in[f], xa.out[f] = out[f], ca.data[f] = out[f];
+  xa.tab = g.tx, xa.nrows = g.ny * g.nz, xa.nxp = g.nxp;
+  g.ox->xfwd(xa, nf, c->st);
+  ca.tab = g.ty, ca.stride = g.nxp, ca.outer_stride = (size_t)g.ny * g.nxp, ca.ngroups = g.nxp / 16, ca.ntiles = g.nz * ca.ngroups;
+  g.oy->col(ca, -1, nf, c->st);
+  c->launches += 2;
+}
+static void inverse_y(kw_ctx* c, float2* const* data, int nf) {
+  const Geometry& g = c->g;
+  ColArgs ca{};
+  for (int f = 0; f < nf; ++f) ca.data[f] = data[f];
+  ca.tab = g.ty, ca.stride = g.nxp, ca.outer_stride = (size_t)g.ny * g.nxp, ca.ngroups = g.nxp / 16, ca.ntiles = g.nz * ca.ngroups;
+  g.oy->col(ca, +1, nf, c->st);
+  c->launches += 1;
+}
+static void zmid_launch(kw_ctx* c, ZMidArgs& za, int nf) {
+  const Geometry& g = c->g;
+  za.tab = g.tz, za.ny = g.ny, za.nxp = g.nxp, za.ngroups = g.nxp / 16, za.ntiles = g.ny * za.ngroups, za.plane = (size_t)g.ny * g.nxp;
+  g.oz->zmid(za, nf, c->st);
+  c->launches += 1;
+}
+template <int NF> static XInvArgs<NF> xinv_args(kw_ctx* c, float2* const* in, int nfields = NF) {
+  XInvArgs<NF> a{};
+  for (int f = 0; f < nfields; ++f) a.in[f] = in[f];
+  a.tab = c->g.tx, a.nrows = c->g.ny * c->g.nz, a.nxp = c->g.nxp, a.ny = c->g.ny;
+  return a;
+}
+
+// F[p]*kappa*ddk_pos -> inverse y; result left in S0..S2 ready for the x inverse  (cpp:2087-2101)
+static void pressure_gradient_spectra(kw_ctx* c) {
+  const float* in[1] = {c->d[KW_P]};
+  float2* out[1] = {c->S[3]};
+  forward_xy(c, in, out, 1);
+  ZMidArgs za{};
+  const int vec[3] = {KW_DDX_K_SHIFT_POS_R, KW_DDY_K_SHIFT_POS, KW_DDZ_K_SHIFT_POS};
+  for (int f = 0; f < 3; ++f)
+    za.f[f] = ZField{c->S[3], c->S[f], c->d[KW_KAPPA], 1.0f, reinterpret_cast<const float2*>(c->d[vec[f]]), f};
+  zmid_launch(c, za, 3);
+  inverse_y(c, c->S, 3);
+}
+
+// additive source: scaled = IFFT(FFT(scatter) * (source_kappa * fd)), added to the targets  (cpp:2339-2352)
+static void add_scaled_source(kw_ctx* c, const float* signal, const uint64_t* index, size_t nsrc, int many, float* const* targets, int ntargets) {
+  const Geometry& g = c->g;
+  cudaMemsetAsync(c->tSrc, 0, g.n * sizeof(float), c->st);
+  k_insert_source<<<ew_grid(nsrc), 256, 0, c->st>>>(c->tSrc, signal, index, nsrc, c->t, many);
+  const float* in[1] = {c->tSrc};
+  float2* out[1] = {c->S[3]};
+  forward_xy(c, in, out, 1);
+  ZMidArgs za{};
+  za.f[0] = ZField{c->S[3], c->S[3], c->d[KW_SOURCE_KAPPA], 1.0f / (float)g.n, nullptr, 0};
+  zmid_launch(c, za, 1);
+  inverse_y(c, out, 1);
+  EpiAdd e{};
+  for (int k = 0; k < ntargets; ++k) e.out[k] = targets[k];
+  e.ntargets = ntargets;
+  g.ox->xinv_add(xinv_args<1>(c, out), e, c->st);
+  c->launches += 2;
+}
+
+static TermsArgs terms_args(kw_ctx* c) {
+  TermsArgs ta{};
+  ta.rho[0] = c->d[KW_RHOX], ta.rho[1] = c->d[KW_RHOY], ta.rho[2] = c->d[KW_RHOZ];
+  ta.rho0 = c->fld(KW_RHO0), ta.bona = c->fld(KW_BONA), ta.c2 = c->fld(KW_C0);
+  ta.nonlinear = c->cfg.nonlinear_flag, ta.absorbing = c->cfg.absorbing_flag;
+  ta.outB = c->tB, ta.outNL = c->tNL, ta.p = c->d[KW_P];
+  return ta;
+}
+
+template <int OP> static void sample_one(kw_ctx* c, Stream& s, const float* src, float* dst) {
+  const Geometry& g = c->g;
+  if (s.all) {
+    k_sample_all<OP><<<ew_grid(g.n), 256, 0, c->st>>>(dst, src, g.n);
+  } else if (c->cfg.sensor_mask_type == 0) {
+    k_sample_index<OP><<<ew_grid(c->nsens), 256, 0, c->st>>>(dst, src, c->di[KW_SENSOR_MASK_INDEX], c->nsens);
+  } else {
+    CuboidArgs ca{c->di[KW_SENSOR_MASK_CORNERS], c->cub_offsets, c->ncuboids, g.nx, g.ny};
+    k_sample_cuboid<OP><<<ew_grid(c->nsens), 256, 0, c->st>>>(dst, src, ca, c->nsens);
+  }
+  c->launches++;
+}
+
+// OutputStreamContainer::sampleStreams (Containers/OutputStreamContainer.cpp:364-373): enum order
+static void sample_streams(kw_ctx* c) {
+  for (int sid = 0; sid < KW_STREAM_COUNT; ++sid) {
+    Stream& s = c->streams[sid];
+    if (!s.enabled) continue;
+    const float* src = s.src == 0 ? c->d[KW_P] : c->d[KW_UX_SGX + (s.src - 1)];
+    switch (s.op) {
+      case kOpNone: sample_one<kOpNone>(c, s, src, s.dbuf + s.rows * s.row); s.rows++; break;
+      case kOpRms: sample_one<kOpRms>(c, s, src, s.dbuf); break;
+      case kOpMax: sample_one<kOpMax>(c, s, src, s.dbuf); break;
+      default: sample_one<kOpMin>(c, s, src, s.dbuf); break;
+    }
+  }
+}
+
+static int step(kw_ctx* c) {
+  const kw_config& cf = c->cfg;
+  const Geometry& g = c->g;
+  const uint64_t t = c->t;
+  const float fd = 1.0f / (float)g.n;  // fftDivider, CudaParameters.cpp:259
+  float* u[3] = {c->d[KW_UX_SGX], c->d[KW_UY_SGY], c->d[KW_UZ_SGZ]};
+  float* rho[3] = {c->d[KW_RHOX], c->d[KW_RHOY], c->d[KW_RHOZ]};
+
+  // ---- computeVelocity (cpp:2087-2119)
+  pressure_gradient_spectra(c);
+  {
+    EpiVelocity e{};
+    for (int k = 0; k < 3; ++k) e.u[k] = u[k], e.dtrho[k] = c->fld(KW_RHO0_SGX + k), e.pml_sg[k] = c->d[KW_PML_X_SGX + k];
+    e.fd = fd, e.init = 0;
+    g.ox->xinv_velocity(xinv_args<1>(c, c->S, 3), e, 3, c->st);
+    c->launches++;
+  }
+  // ---- addVelocitySource (cpp:2252-2303), transducer (cpp:894-897)
+  const uint64_t uflag[3] = {cf.ux_source_flag, cf.uy_source_flag, cf.uz_source_flag};
+  for (int k = 0; k < 3; ++k) {
+    if (uflag[k] <= t) continue;
+    const size_t nsrc = c->count[KW_U_SOURCE_INDEX];
+    if (cf.u_source_mode != KW_SRC_ADDITIVE) {
+      SourceArgs sa{};
+      sa.target[0] = u[k], sa.ntargets = 1, sa.signal = c->d[KW_UX_SOURCE_INPUT + k], sa.index = c->di[KW_U_SOURCE_INDEX];
+      sa.nsrc = nsrc, sa.t = t, sa.many = cf.u_source_many, sa.mode = cf.u_source_mode;
+      k_add_source<<<ew_grid(nsrc), 256, 0, c->st>>>(sa);
+      c->launches++;
+    } else {
+      float* tg[1] = {u[k]};
+      add_scaled_source(c, c->d[KW_UX_SOURCE_INPUT + k], c->di[KW_U_SOURCE_INDEX], nsrc, cf.u_source_many, tg, 1);
+    }
+  }
+  if (cf.transducer_source_flag > t) {
+    const size_t nsrc = c->count[KW_U_SOURCE_INDEX];
+    k_add_transducer<<<ew_grid(nsrc), 256, 0, c->st>>>(u[0], c->di[KW_U_SOURCE_INDEX], c->d[KW_TRANSDUCER_SOURCE_INPUT],
+                                                        c->di[KW_DELAY_MASK], nsrc, t);
+    c->launches++;
+  }
+  // ---- computeVelocityGradient (cpp:2126-2150) + computeDensity (cpp:2157/2169) [+ pressure terms / lossless p]
+  {
+    forward_xy(c, u, c->S, 3);
+    ZMidArgs za{};
+    const int vec[3] = {KW_DDX_K_SHIFT_NEG_R, KW_DDY_K_SHIFT_NEG, KW_DDZ_K_SHIFT_NEG};
+    for (int f = 0; f < 3; ++f)
+      za.f[f] = ZField{c->S[f], c->S[f], c->d[KW_KAPPA], fd, reinterpret_cast<const float2*>(c->d[vec[f]]), f};
+    zmid_launch(c, za, 3);
+    inverse_y(c, c->S, 3);
+    const bool p_src = cf.p_source_flag > t;
+    EpiDensity e{};
+    for (int k = 0; k < 3; ++k) e.rho[k] = rho[k], e.pml[k] = c->d[KW_PML_X + k];
+    e.rho0 = c->fld(KW_RHO0), e.bona = c->fld(KW_BONA), e.c2 = c->fld(KW_C0);
+    e.dt = cf.dt, e.nonlinear = cf.nonlinear_flag, e.absorbing = cf.absorbing_flag;
+    e.defer_terms = p_src && cf.p_source_mode == KW_SRC_ADDITIVE;
+    e.outA = c->tA, e.outB = c->tB, e.outNL = c->tNL, e.p = c->d[KW_P];
+    g.ox->xinv_density(xinv_args<3>(c, c->S), e, c->st);
+    c->launches++;
+    // ---- addPressureSource (cpp:2310-2334)
+    if (p_src) {
+      const size_t nsrc = c->count[KW_P_SOURCE_INDEX];
+      TermsArgs ta = terms_args(c);
+      if (cf.p_source_mode != KW_SRC_ADDITIVE) {
+        SourceArgs sa{};
+        for (int k = 0; k < 3; ++k) sa.target[k] = rho[k];
+        sa.ntargets = 3, sa.signal = c->d[KW_P_SOURCE_INPUT], sa.index = c->di[KW_P_SOURCE_INDEX];
+        sa.nsrc = nsrc, sa.t = t, sa.many = cf.p_source_many, sa.mode = cf.p_source_mode;
+        k_add_source<<<ew_grid(nsrc), 256, 0, c->st>>>(sa);
+        // the fused epilogue computed the sum-of-density terms before the source landed: redo them at the source voxels
+        ta.index = c->di[KW_P_SOURCE_INDEX], ta.n = nsrc;
+        k_pressure_terms<<<ew_grid(nsrc), 256, 0, c->st>>>(ta);
+      } else {
+        add_scaled_source(c, c->d[KW_P_SOURCE_INPUT], c->di[KW_P_SOURCE_INDEX], nsrc, cf.p_source_many, rho, 3);
+        ta.index = nullptr, ta.n = g.n;
+        k_pressure_terms<<<ew_grid(g.n), 256, 0, c->st>>>(ta);
+      }
+      c->launches += 2;
+    }
+  }
+  // ---- computePressure, absorbing branch (cpp:2180-2246)
+  if (cf.absorbing_flag) {
+    const float* in[2] = {c->tA, c->tB};
+    forward_xy(c, in, c->S, 2);
+    ZMidArgs za{};
+    za.f[0] = ZField{c->S[0], c->S[0], c->d[KW_ABSORB_NABLA1], 1.0f, nullptr, 0};
+    za.f[1] = ZField{c->S[1], c->S[1], c->d[KW_ABSORB_NABLA2], 1.0f, nullptr, 0};
+    zmid_launch(c, za, 2);
+    inverse_y(c, c->S, 2);
+    EpiPressureSum e{};
+    e.p = c->d[KW_P], e.base = cf.nonlinear_flag ? c->tNL : c->tB;
+    e.c2 = c->fld(KW_C0), e.tau = c->fld(KW_ABSORB_TAU), e.eta = c->fld(KW_ABSORB_ETA), e.fd = fd;
+    g.ox->xinv_psum(xinv_args<2>(c, c->S), e, c->st);
+    c->launches++;
+  }
+  // ---- addInitialPressureSource (cpp:2359-2396)
+  if (t == 0 && cf.p0_source_flag == 1) {
+    k_initial_pressure<<<ew_grid(g.n), 256, 0, c->st>>>(c->d[KW_P], rho[0], rho[1], rho[2], c->d[KW_P0_SOURCE_INPUT], c->fld(KW_C0), g.n);
+    pressure_gradient_spectra(c);
+    EpiVelocity e{};
+    for (int k = 0; k < 3; ++k) e.u[k] = u[k], e.dtrho[k] = c->fld(KW_RHO0_SGX + k), e.pml_sg[k] = c->d[KW_PML_X_SGX + k];
+    e.fd = fd, e.init = 1;
+    g.ox->xinv_velocity(xinv_args<1>(c, c->S, 3), e, 3, c->st);
+    c->launches += 2;
+  }
+  // ---- storeSensorData (cpp:1060-1093)
+  if (t >= cf.sampling_start_index) sample_streams(c);
+  c->t++;
+  return KW_OK;
+}
+
+}  // namespace kw
+
+extern "C" {
+
+int kw_run(kw_ctx* c, uint64_t nsteps, uint64_t* steps_done, int sync) {
+  if (steps_done) *steps_done = 0;
+  if (!c) return fail(KW_ERR_INVALID, "null context");
+  if (!c->preprocessed) return fail(KW_ERR_STATE, "kw_run before kw_preprocess");
+  uint64_t done = 0;
+  int rc = KW_OK;
+  KW_CUDA(cudaEventRecord(c->ev0, c->st));
+  for (; done < nsteps && c->t < c->cfg.nt; ++done) {
+    bool full = false;
+    if (c->t >= c->cfg.sampling_start_index)
+      for (auto& s : c->streams) full |= s.enabled && s.op == kOpNone && s.rows >= s.cap_rows;
+    if (full) {
+      rc = fail(KW_ERR_STREAM_FULL, "a raw stream buffer is full: fetch it with kw_stream_fetch");
+      break;
+    }
+    KW_TRY(step(c));
+  }
+  KW_CUDA(cudaEventRecord(c->ev1, c->st));
+  KW_CUDA(cudaGetLastError());
+  if (steps_done) *steps_done = done;
+  if (sync) {
+    KW_CUDA(cudaStreamSynchronize(c->st));
+    KW_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  }
+  return rc;
+}
+
+int kw_time_index(kw_ctx* c, uint64_t* t) {
+  if (!c || !t) return fail(KW_ERR_INVALID, "null argument");
+  *t = c->t;
+  return KW_OK;
+}
+int kw_synchronize(kw_ctx* c) {
+  if (!c) return fail(KW_ERR_INVALID, "null context");
+  KW_CUDA(cudaStreamSynchronize(c->st));
+  cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+  KW_CUDA(cudaGetLastError());
+  return KW_OK;
+}
+int kw_last_run_ms(kw_ctx* c, float* ms) {
+  if (!c || !ms) return fail(KW_ERR_INVALID, "null argument");
+  *ms = c->last_ms;
+  return KW_OK;
+}
+int kw_launch_count(kw_ctx* c, uint64_t* n) {
+  if (!c || !n) return fail(KW_ERR_INVALID, "null argument");
+  *n = c->launches;
+  return KW_OK;
+}
+
+int kw_get_array(kw_ctx* c, int id, void* host, uint64_t count) {
+  if (!c || !host || id < 0 || id >= KW_ARRAY_COUNT) return fail(KW_ERR_INVALID, "kw_get_array: bad argument");
+  const Geometry& g = c->g;
+  KW_CUDA(cudaStreamSynchronize(c->st));
+  if (is_reduced_real(id)) {
+    if (!c->d[id]) return fail(KW_ERR_INVALID, "array not present");
+    const size_t rows = (size_t)g.ny * g.nz;
+    if (count < rows * g.nxr) return fail(KW_ERR_INVALID, "kw_get_array: buffer too small");
+    KW_CUDA(cudaMemcpy2D(host, g.nxr * sizeof(float), c->d[id], g.nxp * sizeof(float), g.nxr * sizeof(float), rows, cudaMemcpyDeviceToHost));
+    return KW_OK;
+  }
+  if (c->count[id] == 1 && !c->d[id]) {
+    static_cast<float*>(host)[0] = c->scalar[id];
+    return KW_OK;
+  }
+  if (!c->d[id] || is_index_array(id)) return fail(KW_ERR_INVALID, "array not present on the device");
+  size_t n = c->count[id];
+  if (is_complex_vec(id)) n = std::min<size_t>(n, 2 * count);
+  else if (count < n) return fail(KW_ERR_INVALID, "kw_get_array: buffer too small");
+  KW_CUDA(cudaMemcpy(host, c->d[id], n * sizeof(float), cudaMemcpyDeviceToHost));
+  return KW_OK;
+}
+
+int kw_stream_info(kw_ctx* c, int sid, uint64_t* row_floats, uint64_t* rows) {
+  if (!c || sid < 0 || sid >= KW_STREAM_COUNT || !c->streams[sid].enabled) return fail(KW_ERR_INVALID, "stream not enabled");
+  if (row_floats) *row_floats = c->streams[sid].row;
+  if (rows) *rows = c->streams[sid].op == kOpNone ? c->streams[sid].rows : 1;
+  return KW_OK;
+}
+
+int kw_stream_fetch(kw_ctx* c, int sid, float* host, uint64_t cap, uint64_t* rows_fetched) {
+  if (rows_fetched) *rows_fetched = 0;
+  if (!c || !host || sid < 0 || sid >= KW_STREAM_COUNT || !c->streams[sid].enabled) return fail(KW_ERR_INVALID, "stream not enabled");
+  Stream& s = c->streams[sid];
+  const uint64_t rows = s.op == kOpNone ? s.rows : 1;
+  if (cap < rows * s.row) return fail(KW_ERR_INVALID, "kw_stream_fetch: host buffer too small");
+  if (rows) {
+    KW_CUDA(cudaMemcpyAsync(host, s.dbuf, rows * s.row * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    KW_CUDA(cudaStreamSynchronize(c->st));
+  }
+  if (s.op == kOpNone) s.rows = 0;
+  if (rows_fetched) *rows_fetched = rows;
+  return KW_OK;
+}
+
+int kw_finish(kw_ctx* c) {
+  if (!c) return fail(KW_ERR_INVALID, "null context");
+  if (c->finished) return KW_OK;
+  const uint64_t nsamp = c->cfg.nt - c->cfg.sampling_start_index;
+  for (auto& s : c->streams)
+    if (s.enabled && s.op == kOpRms) {  // BaseOutputStream.cpp:172-178
+      k_post_rms<<<ew_grid(s.row), 256, 0, c->st>>>(s.dbuf, 1.0f / (float)nsamp, s.row);
+      c->launches++;
+    }
+  KW_CUDA(cudaStreamSynchronize(c->st));
+  KW_CUDA(cudaGetLastError());
+  c->finished = true;
+  return KW_OK;
+}
+
+// ---- stand-alone 3-D transforms on host buffers (cuFFT layout) ----------------------------------------------------
+static int fft3d_host(uint64_t nx, uint64_t ny, uint64_t nz, const float* in, float* out, bool forward) {
+  if (!in || !out) return fail(KW_ERR_INVALID, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(KW_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  Geometry g;
+  KW_TRY(g.init(nx, ny, nz));
+  const size_t rows = (size_t)g.ny * g.nz;
+  float* dreal = nullptr;
+  float2 *dspec = nullptr, *dnat = nullptr;
+  KW_CUDA(cudaMalloc(&dreal, g.n * sizeof(float)));
+  KW_CUDA(cudaMalloc(&dspec, g.nc * sizeof(float2)));
+  KW_CUDA(cudaMalloc(&dnat, rows * g.nxr * sizeof(float2)));
+  KW_CUDA(cudaMemset(dspec, 0, g.nc * sizeof(float2)));
+  ColArgs cy{}, cz{};
+  cy.data[0] = cz.data[0] = dspec;
+  cy.tab = g.ty, cy.stride = g.nxp, cy.outer_stride = (size_t)g.ny * g.nxp, cy.ngroups = g.nxp / 16, cy.ntiles = g.nz * cy.ngroups;
+  cz.tab = g.tz, cz.stride = (size_t)g.ny * g.nxp, cz.outer_stride = g.nxp, cz.ngroups = g.nxp / 16, cz.ntiles = g.ny * cz.ngroups;
+  if (forward) {
+    KW_CUDA(cudaMemcpy(dreal, in, g.n * sizeof(float), cudaMemcpyHostToDevice));
+    XFwdArgs xa{};
+    xa.in[0] = dreal, xa.out[0] = dspec, xa.tab = g.tx, xa.nrows = (int)rows, xa.nxp = g.nxp;
+    g.ox->xfwd(xa, 1, 0);
+    g.oy->col(cy, -1, 1, 0);
+    g.oz->col(cz, -1, 1, 0);
+    k_pad_complex<<<ew_grid(g.nc), 256>>>(dnat, dspec, g.nxr, g.nxp, rows, 0);
+    KW_CUDA(cudaGetLastError());
+    KW_CUDA(cudaMemcpy(out, dnat, rows * g.nxr * sizeof(float2), cudaMemcpyDeviceToHost));
+  } else {
+    KW_CUDA(cudaMemcpy(dnat, in, rows * g.nxr * sizeof(float2), cudaMemcpyHostToDevice));
+    k_pad_complex<<<ew_grid(g.nc), 256>>>(dspec, dnat, g.nxr, g.nxp, rows, 1);
+    g.oz->col(cz, +1, 1, 0);
+    g.oy->col(cy, +1, 1, 0);
+    XInvArgs<1> xa{};
+    xa.in[0] = dspec, xa.tab = g.tx, xa.nrows = (int)rows, xa.nxp = g.nxp, xa.ny = g.ny;
+    EpiStore e{};
+    e.out[0] = dreal, e.scale = 1.0f;
+    g.ox->xinv_store(xa, e, 1, 0);
+    KW_CUDA(cudaGetLastError());
+    KW_CUDA(cudaMemcpy(out, dreal, g.n * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  KW_CUDA(cudaDeviceSynchronize());
+  cudaFree(dreal), cudaFree(dspec), cudaFree(dnat);
+  return KW_OK;
+}
+int kw_fft_r2c_3d(uint64_t nx, uint64_t ny, uint64_t nz, const float* host_real, float* host_complex) {
+  return fft3d_host(nx, ny, nz, host_real, host_complex, true);
+}
+int kw_fft_c2r_3d(uint64_t nx, uint64_t ny, uint64_t nz, const float* host_complex, float* host_real) {
+  return fft3d_host(nx, ny, nz, host_complex, host_real, false);
+}
+
+}  // extern "C"

@@ -1,0 +1,303 @@
+// Real-space updates of the time step, written as epilogues of the last inverse FFT pass (k_xinv) so that no
+// full-grid element-wise pass remains, plus the O(Nsrc)/O(Nsens) scatter, gather and fix-up kernels.
+//
+// Replaces (KSpaceSolver/SolverCudaKernels.cu): cudaComputeVelocity* :184/:278, cudaComputeDensity{Nonlinear,Linear}
+// :1358/:1470, cudaComputePressureTerms* :1577/:1724, cudaSumPressureTerms* :1865/:1966, cudaSumPressure*Lossless
+// :2067/:2224, cudaAdd*Source :463/:504/:570/:679/:765/:795, cudaAddInitialPressureSource :864,
+// cudaComputeInitialVelocity :949; and (OutputStreams/OutputStreamsCudaKernels.cu) cudaSampleIndex :83,
+// cudaSampleCuboid :202, cudaSampleAll :297, cudaPostProcessingRms :359.
+#pragma once
+#include <cfloat>
+#include <cstdint>
+#include "fft_core.cuh"
+
+namespace kw {
+
+// a medium property that is either a full-grid array or a scalar (homogeneous variants of the reference kernels)
+struct Fld {
+  const float* p;
+  float s;
+  __device__ __forceinline__ float at(size_t i) const { return p ? __ldg(p + i) : s; }
+};
+
+// ---- epilogues of k_xinv -----------------------------------------------------------------------------------------
+// res[f][m] = (value in row a, value in row b) at x = t + m*T; row b = row a + 1 (same z, y+1).
+
+struct EpiStore {  // plain C2R:  out = scale * ifft
+  float* out[3];
+  float scale;
+  template <int N> __device__ __forceinline__ void apply(float2 (&res)[1][8], int t, size_t row0, int, int) const {
+    constexpr int T = N / 8;
+    float* o = out[blockIdx.y] + row0 * N;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      o[t + m * T] = res[0][m].x * scale;
+      o[N + t + m * T] = res[0][m].y * scale;
+    }
+  }
+};
+
+struct EpiAdd {  // additive (k-space corrected) source: target_j += ifft   (SolverCudaKernels.cu:765-807)
+  float* out[3];
+  int ntargets;
+  template <int N> __device__ __forceinline__ void apply(float2 (&res)[1][8], int t, size_t row0, int, int) const {
+    constexpr int T = N / 8;
+    for (int j = 0; j < ntargets; ++j) {
+      float* o = out[j] + row0 * N;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        o[t + m * T] += res[0][m].x;
+        o[N + t + m * T] += res[0][m].y;
+      }
+    }
+  }
+};
+
+// u_i = (u_i*pml_i - (fd*g_i)*dtrho_i)*pml_i      (SolverCudaKernels.cu:199-212; homogeneous :287-305)
+// init: u_i = g_i * (dtrho_i * (fd*0.5))            (SolverCudaKernels.cu:971-980)
+struct EpiVelocity {
+  float* u[3];
+  Fld dtrho[3];
+  const float* pml_sg[3];
+  float fd;
+  int init;
+  template <int N> __device__ __forceinline__ void apply(float2 (&res)[1][8], int t, size_t row0, int y, int z) const {
+    constexpr int T = N / 8;
+    const int f = blockIdx.y;
+    float* ua = u[f] + row0 * N;
+    const Fld d = dtrho[f];
+    if (init) {
+      const float div = fd * 0.5f;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int x = t + m * T;
+        const size_t i = row0 * N + x;
+        ua[x] = res[0][m].x * (d.at(i) * div);
+        ua[N + x] = res[0][m].y * (d.at(i + N) * div);
+      }
+      return;
+    }
+    const float py_a = (f == 1) ? __ldg(pml_sg[1] + y) : (f == 2) ? __ldg(pml_sg[2] + z) : 0.f;
+    const float py_b = (f == 1) ? __ldg(pml_sg[1] + y + 1) : py_a;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int x = t + m * T;
+      const size_t i = row0 * N + x;
+      const float pa = (f == 0) ? __ldg(pml_sg[0] + x) : py_a;
+      const float pb = (f == 0) ? pa : py_b;
+      ua[x] = (ua[x] * pa - (fd * res[0][m].x) * d.at(i)) * pa;
+      ua[N + x] = (ua[N + x] * pb - (fd * res[0][m].y) * d.at(i + N)) * pb;
+    }
+  }
+};
+
+// density update (+ pressure terms or lossless pressure), three gradients at the same voxel.
+//  nonlinear: s = (2(rx+ry+rz) + rho0)*dt ; r_i = pml_i*((pml_i*r_i) - s*du_i)        (SolverCudaKernels.cu:1377-1390)
+//  linear:    r_i = pml_i*(pml_i*r_i - (dt*rho0)*du_i)                                 (:1486-1494)
+//  absorbing: A = rho0*(dux+duy+duz) ; B = sum r ; NL = (BonA*B*B)/(2 rho0) + B        (:1588-1601, :1733-1741)
+//  lossless:  p = c2*(B + BonA*(B*B)/(2 rho0))  |  p = c2*B                            (:2079-2082, :2229-2235)
+struct EpiDensity {
+  float* rho[3];
+  Fld rho0, bona, c2;
+  const float* pml[3];
+  float dt;
+  int nonlinear, absorbing;
+  int defer_terms;  // a pressure source follows: B / NL / p are (re)computed by k_pressure_terms afterwards
+  float* outA;
+  float* outB;
+  float* outNL;
+  float* p;
+  __device__ __forceinline__ void voxel(size_t i, float px, float py, float pz, float dux, float duy, float duz) const {
+    float rx = rho[0][i], ry = rho[1][i], rz = rho[2][i];
+    const float r0 = rho0.at(i);
+    if (nonlinear) {
+      const float s = (2.0f * (rx + ry + rz) + r0) * dt;
+      rx = px * ((px * rx) - s * dux);
+      ry = py * ((py * ry) - s * duy);
+      rz = pz * ((pz * rz) - s * duz);
+    } else {
+      const float d = dt * r0;
+      rx = px * (px * rx - d * dux);
+      ry = py * (py * ry - d * duy);
+      rz = pz * (pz * rz - d * duz);
+    }
+    rho[0][i] = rx;
+    rho[1][i] = ry;
+    rho[2][i] = rz;
+    if (absorbing) outA[i] = r0 * (dux + duy + duz);
+    if (defer_terms) return;
+    const float sum = rx + ry + rz;
+    if (absorbing) {
+      outB[i] = sum;
+      if (nonlinear) outNL[i] = ((bona.at(i) * sum * sum) / (2.0f * r0)) + sum;
+    } else {
+      p[i] = nonlinear ? c2.at(i) * (sum + (bona.at(i) * (sum * sum) / (2.0f * r0))) : c2.at(i) * sum;
+    }
+  }
+  template <int N> __device__ __forceinline__ void apply(float2 (&res)[3][8], int t, size_t row0, int y, int z) const {
+    constexpr int T = N / 8;
+    const float pya = __ldg(pml[1] + y), pyb = __ldg(pml[1] + y + 1), pz = __ldg(pml[2] + z);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int x = t + m * T;
+      const size_t i = row0 * N + x;
+      const float px = __ldg(pml[0] + x);
+      voxel(i, px, pya, pz, res[0][m].x, res[1][m].x, res[2][m].x);
+      voxel(i + N, px, pyb, pz, res[0][m].y, res[1][m].y, res[2][m].y);
+    }
+  }
+};
+
+// p = c2*(NL + fd*((ta*tau) - (tb*eta)))   nonlinear  (SolverCudaKernels.cu:1872-1878)
+// p = c2*(B  + fd*(ta*tau - tb*eta))       linear     (:1973-1979)
+struct EpiPressureSum {
+  float* p;
+  const float* base;  // NL (nonlinear) or B (linear)
+  Fld c2, tau, eta;
+  float fd;
+  template <int N> __device__ __forceinline__ void apply(float2 (&res)[2][8], int t, size_t row0, int, int) const {
+    constexpr int T = N / 8;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const size_t i = row0 * N + t + m * T;
+      p[i] = c2.at(i) * (__ldg(base + i) + fd * ((res[0][m].x * tau.at(i)) - (res[1][m].x * eta.at(i))));
+      p[i + N] = c2.at(i + N) * (__ldg(base + i + N) + fd * ((res[0][m].y * tau.at(i + N)) - (res[1][m].y * eta.at(i + N))));
+    }
+  }
+};
+
+// ---- pressure terms from the densities (used after a pressure source touched rho, and on the unfused path) --------
+struct TermsArgs {
+  const float* rho[3];
+  Fld rho0, bona, c2;
+  int nonlinear, absorbing;
+  float* outB;
+  float* outNL;
+  float* p;
+  const uint64_t* index;  // nullptr: whole grid; else only these voxels (source points)
+  size_t n;
+};
+__device__ __forceinline__ void pressure_terms_voxel(const TermsArgs& a, size_t i) {
+  const float sum = a.rho[0][i] + a.rho[1][i] + a.rho[2][i];
+  const float r0 = a.rho0.at(i);
+  if (a.absorbing) {
+    a.outB[i] = sum;
+    if (a.nonlinear) a.outNL[i] = ((a.bona.at(i) * sum * sum) / (2.0f * r0)) + sum;
+  } else {
+    a.p[i] = a.nonlinear ? a.c2.at(i) * (sum + (a.bona.at(i) * (sum * sum) / (2.0f * r0))) : a.c2.at(i) * sum;
+  }
+}
+static __global__ void k_pressure_terms(TermsArgs a) {
+  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < a.n; j += (size_t)gridDim.x * blockDim.x)
+    pressure_terms_voxel(a, a.index ? (size_t)a.index[j] : j);
+}
+
+// ---- sources -----------------------------------------------------------------------------------------------------
+// mode 0: '=' (Dirichlet), 1: '+=' (additive, no correction); many: signal[t*Nsrc + j] else signal[t]
+// (SolverCudaKernels.cu:504-527, :570-629).  ntargets = 1 (velocity component) or 3 (rhox, rhoy, rhoz).
+struct SourceArgs {
+  float* target[3];
+  int ntargets;
+  const float* signal;
+  const uint64_t* index;
+  size_t nsrc;
+  size_t t;
+  int many, mode;
+};
+static __global__ void k_add_source(SourceArgs a) {
+  const size_t base = a.many ? a.t * a.nsrc : a.t;
+  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < a.nsrc; j += (size_t)gridDim.x * blockDim.x) {
+    const float s = a.many ? a.signal[base + j] : a.signal[base];
+    const size_t i = a.index[j];
+    for (int k = 0; k < a.ntargets; ++k) {
+      if (a.mode == 0) a.target[k][i] = s;
+      else a.target[k][i] += s;
+    }
+  }
+}
+// ux[idx[j]] += signal[delay[j] + t]   (SolverCudaKernels.cu:463-471)
+static __global__ void k_add_transducer(float* ux, const uint64_t* index, const float* signal, const uint64_t* delay, size_t nsrc, size_t t) {
+  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < nsrc; j += (size_t)gridDim.x * blockDim.x)
+    ux[index[j]] += signal[delay[j] + t];
+}
+// scaled[idx[j]] = s_j   into a zeroed grid (SolverCudaKernels.cu:679-697)
+static __global__ void k_insert_source(float* grid, const float* signal, const uint64_t* index, size_t nsrc, size_t t, int many) {
+  const size_t base = many ? t * nsrc : t;
+  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < nsrc; j += (size_t)gridDim.x * blockDim.x)
+    grid[index[j]] = many ? signal[base + j] : signal[base];
+}
+// p = p0 ; rho_i = p0 / (3*c2)   (SolverCudaKernels.cu:870-883)
+static __global__ void k_initial_pressure(float* p, float* rx, float* ry, float* rz, const float* p0, Fld c2, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float tmp = p[i] = p0[i];
+    tmp = tmp / (3.0f * c2.at(i));
+    rx[i] = tmp;
+    ry[i] = tmp;
+    rz[i] = tmp;
+  }
+}
+
+// ---- sampling ----------------------------------------------------------------------------------------------------
+enum SampleOp { kOpNone = 0, kOpRms = 1, kOpMax = 2, kOpMin = 3 };  // BaseOutputStream::ReduceOperator
+template <int OP> __device__ __forceinline__ void reduce_into(float* buf, size_t i, float x) {
+  if (OP == kOpNone) buf[i] = x;
+  else if (OP == kOpRms) buf[i] += x * x;
+  else if (OP == kOpMax) buf[i] = fmaxf(buf[i], x);
+  else buf[i] = fminf(buf[i], x);
+}
+template <int OP> static __global__ void k_sample_index(float* buf, const float* __restrict__ src, const uint64_t* __restrict__ mask, size_t n) {
+  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x)
+    reduce_into<OP>(buf, j, __ldg(src + mask[j]));
+}
+// all cuboids in one launch: corners are 0-based (x0,y0,z0,x1,y1,z1) per cuboid, offsets = running start of each
+// cuboid in the concatenated buffer, x fastest inside a cuboid (OutputStreamsCudaKernels.cu:164-230).
+struct CuboidArgs {
+  const uint64_t* corners;
+  const uint64_t* offsets;  // ncuboids + 1
+  int ncuboids;
+  int nx, ny;
+};
+template <int OP> static __global__ void k_sample_cuboid(float* buf, const float* __restrict__ src, CuboidArgs a, size_t total) {
+  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < total; j += (size_t)gridDim.x * blockDim.x) {
+    int c = 0;
+    while (c + 1 < a.ncuboids && j >= a.offsets[c + 1]) ++c;
+    const uint64_t* k = a.corners + 6 * c;
+    const size_t l = j - a.offsets[c];
+    const size_t cx = k[3] - k[0] + 1, cy = k[4] - k[1] + 1;
+    const size_t x = l % cx, y = (l / cx) % cy, z = l / (cx * cy);
+    const size_t i = ((z + k[2]) * a.ny + (y + k[1])) * a.nx + (x + k[0]);
+    reduce_into<OP>(buf, j, __ldg(src + i));
+  }
+}
+template <int OP> static __global__ void k_sample_all(float* buf, const float* __restrict__ src, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    reduce_into<OP>(buf, i, __ldg(src + i));
+}
+static __global__ void k_fill(float* buf, float v, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = v;
+}
+// sqrt(buf * 1/(Nt - s))   (OutputStreamsCudaKernels.cu:359-363)
+static __global__ void k_post_rms(float* buf, float scaling, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    buf[i] = sqrtf(buf[i] * scaling);
+}
+
+// ---- layout helpers ------------------------------------------------------------------------------------------------
+// reduced-grid real operator [nz][ny][nxr] (reference layout) -> padded [nz][ny][nxp]
+static __global__ void k_pad_real(float* dst, const float* src, int nxr, int nxp, size_t rows) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < rows * nxp; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / nxp;
+    const int x = (int)(i % nxp);
+    dst[i] = x < nxr ? src[r * nxr + x] : 0.f;
+  }
+}
+static __global__ void k_pad_complex(float2* dst, const float2* src, int nxr, int nxp, size_t rows, int to_padded) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < rows * nxp; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / nxp;
+    const int x = (int)(i % nxp);
+    if (to_padded) dst[i] = x < nxr ? src[r * nxr + x] : make_float2(0.f, 0.f);
+    else if (x < nxr) dst[r * nxr + x] = src[i];
+  }
+}
+
+}  // namespace kw
