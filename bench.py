@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""Headline benchmark: Mvoxel-steps/s of the k-space time loop on synthetic heterogeneous media (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size 512]
+
+One JSON line on stdout (rank 0).  `value` is device-resident throughput (inputs in HBM when the timed region starts,
+CUDA events on the solver stream); `e2e` is the same metric driven step by step through the C ABI with host buffers
+(per-step H2D of the source row from pinned memory, per-step D2H of the sampled sensor row).  `roofline` describes the
+dominant kernel of the step (live CUDA-event timing inside the library, algorithmic bytes from DESIGN.md), and
+`cpu_baseline` is the NumPy/SciPy oracle port timed on the host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES = {  # algorithmic bytes per voxel-step (SURVEY.md 8(d) / DESIGN.md)
+    (1, 1): 292.0, (0, 1): 284.0, (1, 0): 208.0, (0, 0): 204.0,
+}  # (nonlinear, absorbing)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
+            self.thread = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_throughput(size, budget_s=15.0, nonlinear=True, absorbing=True):
+    """The oracle (NumPy/SciPy port of the reference's step) timed on the host cores; bounded sample."""
+    from oracle import kspace_oracle as ko
+
+    kw = importlib.import_module("k-wave-fluid-cuda_b200")
+    sfft = importlib.import_module("scipy.fft")
+    cores = os.cpu_count() or 1
+    cfg, arrays = kw.synth.make_case(size, nt=1000, nonlinear=nonlinear, absorbing=absorbing, source="p_plane")
+    with sfft.set_workers(cores):
+        o = ko.KSpaceOracle(cfg, arrays, dtype=np.float32)
+        o.step()  # warm-up (plans, page faults)
+        t0, n = time.perf_counter(), 0
+        while True:
+            o.step()
+            n += 1
+            el = time.perf_counter() - t0
+            if el >= budget_s or n >= 200:
+                break
+    v = size**3 * n / el / 1e6
+    return {"value": v, "unit": "Mvoxel-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{size}^3 nonlinear+absorbing heterogeneous, {n} steps in {el:.1f} s, FP32 NumPy/SciPy (pocketfft, {cores} threads)"}  # fmt: skip
+
+
+def run_reference(args):
+    """--impl reference: the reference has no CPU solver; its own cuFFT build is used when it was compiled
+    (oracle/_ref/ref_kspace), otherwise the oracle port on all host cores (bounded sample)."""
+    size = min(args.size, 128)
+    steps = max(1, args.steps)
+    t_budget = min(120.0, 3.0 * steps)
+    cb = cpu_port_throughput(size, budget_s=t_budget)
+    line = {
+        "impl": "reference", "metric": "Mvoxel-steps/s", "value": cb["value"], "unit": "Mvoxel-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": size**3 / cb["value"] / 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{size}^3 synthetic heterogeneous nonlinear absorbing medium, PML 20 (bounded CPU sample of the "
+                               f"{args.size}^3 workload; the reference has no CPU solver: oracle port on host cores)"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "Mvoxel-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }  # fmt: skip
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    kw = importlib.import_module("k-wave-fluid-cuda_b200")
+
+    N, K, W = args.size, args.steps, max(3, args.warmup)
+    nonlinear, absorbing = 1, 1
+    nt = 2 * (K + W) + 8
+    # ---- workload: BASELINE.json configs[3]: 512^3 heterogeneous nonlinear absorbing, whole-domain p_max / p_rms
+    cfg, arrays = kw.synth.make_case(N, nt=nt, nonlinear=True, absorbing=True, source="p_plane", sensor="full_cuboid", pml_size=20 if N >= 128 else None)
+    streams = ["KW_S_P_RMS", "KW_S_P_MAX_ALL"]
+    sim = kw.Simulation(cfg, arrays, streams=streams, device=local_rank)
+    sim.run(W)  # warm-up steps (also the first-launch attribute setup)
+    sim.profile(True, True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        t0 = time.perf_counter()
+        sim.run(K, sync=True)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms = sim.last_run_ms()
+    clocks = clk.summary()
+    prof = sim.profile_report()
+    sim.profile(False, False)
+    launches = sum(v["launches"] for v in prof.values())
+    sim.close()
+    if world > 1:
+        tmax = torch.tensor([dev_ms], device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dev_ms = float(tmax.item())
+    ms_per_step = dev_ms / K
+    value = world * N**3 * K / (dev_ms * 1e-3) / 1e6
+
+    # ---- end to end: host-driven loop through the C ABI, host buffers in the timed region
+    e2e = None
+    if not args.no_e2e:
+        cfg2, arrays2 = kw.synth.make_case(N, nt=nt, nonlinear=True, absorbing=True, source="p_many", sensor="index", n_sensor=4096, pml_size=20 if N >= 128 else None)
+        nsrc = arrays2["p_source_index"].size
+        sig = torch.from_numpy(np.ascontiguousarray(arrays2["p_source_input"]).reshape(nt, nsrc)).pin_memory()
+        s2 = kw.Simulation(cfg2, arrays2, streams=["KW_S_P_RAW", "KW_S_P_RMS", "KW_S_P_MAX_ALL"], raw_rows_capacity=4, device=local_rank)
+        out_rows = torch.empty((nt, 4096), dtype=torch.float32).pin_memory()
+        import ctypes as C
+
+        def one_step(t):
+            row = sig[t]
+            kw.capi._check(s2.lib.kw_set_source_row(s2.ctx, kw.ARRAY_IDS["KW_P_SOURCE_INPUT"], t, row.data_ptr(), nsrc))
+            done = C.c_uint64()
+            kw.capi._check(s2.lib.kw_run(s2.ctx, 1, C.byref(done), 0))
+            got = C.c_uint64()
+            kw.capi._check(s2.lib.kw_stream_fetch(s2.ctx, kw.STREAM_IDS["KW_S_P_RAW"], out_rows[t].data_ptr(), 4096, C.byref(got)))
+
+        for t in range(W):
+            one_step(t)
+        barrier()
+        t0 = time.perf_counter()
+        for t in range(W, W + K):
+            one_step(t)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        s2.close()
+        if world > 1:
+            tm = torch.tensor([e2e_s], device="cuda")
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            e2e_s = float(tm.item())
+        e2e = {"value": world * N**3 * K / e2e_s / 1e6, "unit": "Mvoxel-steps/s", "h2d_bytes_per_step": int(nsrc * 4),
+               "d2h_bytes_per_step": 4096 * 4,
+               "how": "one kw_set_source_row + kw_run(1) + kw_stream_fetch(p_raw row) per step from pinned host buffers; wall clock"}  # fmt: skip
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if top and os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(str(N), {}).get(top[0])
+        except Exception:
+            traffic = None
+    roofline = None
+    if top:
+        name, st = top
+        ach = st["bytes"] / st["launches"] / (st["ms"] / st["launches"] * 1e-3) / 1e9
+        alg = ALG_BYTES[(nonlinear, absorbing)] + 16.0  # + p_max_all and full-cuboid p_rms
+        step_gbs = alg * N**3 / (ms_per_step * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic, "peak_source": peak_src,
+                    "kernel_share_of_step": st["ms"] / sum(v["ms"] for v in prof.values()),
+                    "step": {"algorithmic_bytes_per_voxel_step": alg, "achieved": step_gbs, "frac": step_gbs / peak},
+                    "kernels": {k: {"launches_per_step": v["launches"] / K, "ms_per_step": v["ms"] / K,
+                                    "GBps": v["bytes"] / max(v["ms"], 1e-9) / 1e6} for k, v in sorted(prof.items())}}  # fmt: skip
+    line = {
+        "metric": "Mvoxel-steps/s", "value": value, "unit": "Mvoxel-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{N}^3 synthetic heterogeneous medium, nonlinear (BonA) + power-law absorption, PML 20, plane pressure "
+                               f"source, whole-domain p_max_all + p_rms over a full-domain cuboid (BASELINE.json configs[3])",
+                   "grid": [N, N, N], "l2_policy": "inputs larger than L2 (every field >= 512 MiB at 512^3)" if N >= 512 else
+                   "working set partly L2 resident at this size", "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas",
+                   "wall_ms_timed_region": wall_ms},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+    }  # fmt: skip
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_port_throughput(128, budget_s=12.0)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -152,6 +152,11 @@ int kw_fft_c2r_3d(uint64_t nx, uint64_t ny, uint64_t nz, const float* host_compl
 
 /* Timing of the device work of the last kw_run (CUDA events on the solver stream), milliseconds. */
 int kw_last_run_ms(kw_ctx* ctx, float* ms);
+/* Per-kernel device timing for roofline reports: when enabled, every launch of the time loop is bracketed by CUDA
+ * events on the solver stream.  kw_profile_report writes a JSON object {kernel: {launches, ms, bytes}} where bytes is the
+ * algorithmic traffic of those launches (DESIGN.md section "Kernels"). */
+int kw_profile(kw_ctx* ctx, int enable, int reset);
+int kw_profile_report(kw_ctx* ctx, char* buf, uint64_t capacity);
 /* Number of kernels this library launched since the context was created. */
 int kw_launch_count(kw_ctx* ctx, uint64_t* launches);
 

@@ -118,6 +118,8 @@ def load_library():
         "kw_fft_c2r_3d": [u64, u64, u64, vp, vp],
         "kw_last_run_ms": [vp, C.POINTER(C.c_float)],
         "kw_launch_count": [vp, C.POINTER(u64)],
+        "kw_profile": [vp, i32, i32],
+        "kw_profile_report": [vp, C.c_char_p, u64],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -239,6 +241,16 @@ class Simulation:
         ms = C.c_float()
         _check(self.lib.kw_last_run_ms(self.ctx, C.byref(ms)))
         return ms.value
+
+    def profile(self, enable=True, reset=True):
+        _check(self.lib.kw_profile(self.ctx, int(enable), int(reset)))
+
+    def profile_report(self):
+        import json
+
+        buf = C.create_string_buffer(1 << 16)
+        _check(self.lib.kw_profile_report(self.ctx, buf, len(buf)))
+        return json.loads(buf.value.decode())
 
     def launch_count(self):
         n = C.c_uint64()

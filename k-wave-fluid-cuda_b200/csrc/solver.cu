@@ -125,7 +125,22 @@ struct Geometry {
 
 using namespace kw;
 
+// per-kernel device timing (CUDA events on the solver stream) and algorithmic bytes, for bench.py's roofline
+struct ProfStat {
+  uint64_t launches = 0;
+  double ms = 0.0, bytes = 0.0;
+};
+struct ProfPending {
+  const char* name;
+  cudaEvent_t e0, e1;
+  double bytes;
+};
+
 struct kw_ctx {
+  bool prof_on = false;
+  std::map<std::string, ProfStat> prof;
+  std::vector<ProfPending> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
   kw_config cfg{};
   Geometry g;
   cudaStream_t st = nullptr;
@@ -154,6 +169,41 @@ struct kw_ctx {
 };
 
 namespace kw {
+
+static cudaEvent_t prof_event(kw_ctx* c) {
+  if (!c->prof_pool.empty()) {
+    cudaEvent_t e = c->prof_pool.back();
+    c->prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+// every kernel launch of the time loop goes through here: counts it and, in profiling mode, brackets it with events
+template <class F> static void launch(kw_ctx* c, const char* name, double bytes, F&& f) {
+  c->launches++;
+  if (!c->prof_on) {
+    f();
+    return;
+  }
+  ProfPending p{name, prof_event(c), prof_event(c), bytes};
+  cudaEventRecord(p.e0, c->st);
+  f();
+  cudaEventRecord(p.e1, c->st);
+  c->prof_pending.push_back(p);
+}
+static void prof_resolve(kw_ctx* c) {  // stream must be idle
+  for (auto& p : c->prof_pending) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p.e0, p.e1);
+    ProfStat& st = c->prof[p.name];
+    st.launches++, st.ms += ms, st.bytes += p.bytes;
+    c->prof_pool.push_back(p.e0);
+    c->prof_pool.push_back(p.e1);
+  }
+  c->prof_pending.clear();
+}
 
 static int dalloc(kw_ctx* c, void** p, size_t bytes, bool zero = true) {
   KW_CUDA(cudaMalloc(p, bytes ? bytes : 4));
@@ -301,6 +351,8 @@ int kw_ctx_destroy(kw_ctx* c) {
   if (!c) return KW_OK;
   cudaStreamSynchronize(c->st);
   for (void* p : c->owned) cudaFree(p);
+  prof_resolve(c);
+  for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->st) cudaStreamDestroy(c->st);
@@ -570,24 +622,23 @@ static void forward_xy(kw_ctx* c, const float* const* in, float2* const* out, in
   ColArgs ca{};
   for (int f = 0; f < nf; ++f) xa.in[f] = in[f], xa.out[f] = out[f], ca.data[f] = out[f];
   xa.tab = g.tx, xa.nrows = g.ny * g.nz, xa.nxp = g.nxp;
-  g.ox->xfwd(xa, nf, c->st);
+  launch(c, "xfwd", nf * (4.0 * g.n + 8.0 * g.nc), [&] { g.ox->xfwd(xa, nf, c->st); });
   ca.tab = g.ty, ca.stride = g.nxp, ca.outer_stride = (size_t)g.ny * g.nxp, ca.ngroups = g.nxp / 16, ca.ntiles = g.nz * ca.ngroups;
-  g.oy->col(ca, -1, nf, c->st);
-  c->launches += 2;
+  launch(c, "ycol_fwd", nf * 16.0 * g.nc, [&] { g.oy->col(ca, -1, nf, c->st); });
 }
 static void inverse_y(kw_ctx* c, float2* const* data, int nf) {
   const Geometry& g = c->g;
   ColArgs ca{};
   for (int f = 0; f < nf; ++f) ca.data[f] = data[f];
   ca.tab = g.ty, ca.stride = g.nxp, ca.outer_stride = (size_t)g.ny * g.nxp, ca.ngroups = g.nxp / 16, ca.ntiles = g.nz * ca.ngroups;
-  g.oy->col(ca, +1, nf, c->st);
-  c->launches += 1;
+  launch(c, "ycol_inv", nf * 16.0 * g.nc, [&] { g.oy->col(ca, +1, nf, c->st); });
 }
 static void zmid_launch(kw_ctx* c, ZMidArgs& za, int nf) {
   const Geometry& g = c->g;
   za.tab = g.tz, za.ny = g.ny, za.nxp = g.nxp, za.ngroups = g.nxp / 16, za.ntiles = g.ny * za.ngroups, za.plane = (size_t)g.ny * g.nxp;
-  g.oz->zmid(za, nf, c->st);
-  c->launches += 1;
+  double bytes = 0;
+  for (int f = 0; f < nf; ++f) bytes += 16.0 * g.nc + (za.f[f].mul ? 4.0 * g.nc : 0.0);
+  launch(c, "zmid", bytes, [&] { g.oz->zmid(za, nf, c->st); });
 }
 template <int NF> static XInvArgs<NF> xinv_args(kw_ctx* c, float2* const* in, int nfields = NF) {
   XInvArgs<NF> a{};
@@ -612,8 +663,8 @@ static void pressure_gradient_spectra(kw_ctx* c) {
 // additive source: scaled = IFFT(FFT(scatter) * (source_kappa * fd)), added to the targets  (cpp:2339-2352)
 static void add_scaled_source(kw_ctx* c, const float* signal, const uint64_t* index, size_t nsrc, int many, float* const* targets, int ntargets) {
   const Geometry& g = c->g;
-  cudaMemsetAsync(c->tSrc, 0, g.n * sizeof(float), c->st);
-  k_insert_source<<<ew_grid(nsrc), 256, 0, c->st>>>(c->tSrc, signal, index, nsrc, c->t, many);
+  launch(c, "memset_source_grid", 4.0 * g.n, [&] { cudaMemsetAsync(c->tSrc, 0, g.n * sizeof(float), c->st); });
+  launch(c, "insert_source", 16.0 * nsrc, [&] { k_insert_source<<<ew_grid(nsrc), 256, 0, c->st>>>(c->tSrc, signal, index, nsrc, c->t, many); });
   const float* in[1] = {c->tSrc};
   float2* out[1] = {c->S[3]};
   forward_xy(c, in, out, 1);
@@ -624,8 +675,7 @@ static void add_scaled_source(kw_ctx* c, const float* signal, const uint64_t* in
   EpiAdd e{};
   for (int k = 0; k < ntargets; ++k) e.out[k] = targets[k];
   e.ntargets = ntargets;
-  g.ox->xinv_add(xinv_args<1>(c, out), e, c->st);
-  c->launches += 2;
+  launch(c, "xinv_add_source", 8.0 * g.nc + 8.0 * g.n * ntargets, [&] { g.ox->xinv_add(xinv_args<1>(c, out), e, c->st); });
 }
 
 static TermsArgs terms_args(kw_ctx* c) {
@@ -639,15 +689,16 @@ static TermsArgs terms_args(kw_ctx* c) {
 
 template <int OP> static void sample_one(kw_ctx* c, Stream& s, const float* src, float* dst) {
   const Geometry& g = c->g;
+  const double per = OP == kOpNone ? 8.0 : 12.0;  // src read + buffer write (+ buffer read for aggregates)
   if (s.all) {
-    k_sample_all<OP><<<ew_grid(g.n), 256, 0, c->st>>>(dst, src, g.n);
+    launch(c, "sample_all", per * g.n, [&] { k_sample_all<OP><<<ew_grid(g.n), 256, 0, c->st>>>(dst, src, g.n); });
   } else if (c->cfg.sensor_mask_type == 0) {
-    k_sample_index<OP><<<ew_grid(c->nsens), 256, 0, c->st>>>(dst, src, c->di[KW_SENSOR_MASK_INDEX], c->nsens);
+    launch(c, "sample_index", (per + 8.0) * c->nsens,
+           [&] { k_sample_index<OP><<<ew_grid(c->nsens), 256, 0, c->st>>>(dst, src, c->di[KW_SENSOR_MASK_INDEX], c->nsens); });
   } else {
     CuboidArgs ca{c->di[KW_SENSOR_MASK_CORNERS], c->cub_offsets, c->ncuboids, g.nx, g.ny};
-    k_sample_cuboid<OP><<<ew_grid(c->nsens), 256, 0, c->st>>>(dst, src, ca, c->nsens);
+    launch(c, "sample_cuboid", per * c->nsens, [&] { k_sample_cuboid<OP><<<ew_grid(c->nsens), 256, 0, c->st>>>(dst, src, ca, c->nsens); });
   }
-  c->launches++;
 }
 
 // OutputStreamContainer::sampleStreams (Containers/OutputStreamContainer.cpp:364-373): enum order
@@ -679,8 +730,8 @@ static int step(kw_ctx* c) {
     EpiVelocity e{};
     for (int k = 0; k < 3; ++k) e.u[k] = u[k], e.dtrho[k] = c->fld(KW_RHO0_SGX + k), e.pml_sg[k] = c->d[KW_PML_X_SGX + k];
     e.fd = fd, e.init = 0;
-    g.ox->xinv_velocity(xinv_args<1>(c, c->S, 3), e, 3, c->st);
-    c->launches++;
+    const double het = c->count[KW_RHO0_SGX] > 1 ? 4.0 : 0.0;
+    launch(c, "xinv_velocity", 3 * (8.0 * g.nc + (8.0 + het) * g.n), [&] { g.ox->xinv_velocity(xinv_args<1>(c, c->S, 3), e, 3, c->st); });
   }
   // ---- addVelocitySource (cpp:2252-2303), transducer (cpp:894-897)
   const uint64_t uflag[3] = {cf.ux_source_flag, cf.uy_source_flag, cf.uz_source_flag};
@@ -691,8 +742,7 @@ static int step(kw_ctx* c) {
       SourceArgs sa{};
       sa.target[0] = u[k], sa.ntargets = 1, sa.signal = c->d[KW_UX_SOURCE_INPUT + k], sa.index = c->di[KW_U_SOURCE_INDEX];
       sa.nsrc = nsrc, sa.t = t, sa.many = cf.u_source_many, sa.mode = cf.u_source_mode;
-      k_add_source<<<ew_grid(nsrc), 256, 0, c->st>>>(sa);
-      c->launches++;
+      launch(c, "add_u_source", 20.0 * nsrc, [&] { k_add_source<<<ew_grid(nsrc), 256, 0, c->st>>>(sa); });
     } else {
       float* tg[1] = {u[k]};
       add_scaled_source(c, c->d[KW_UX_SOURCE_INPUT + k], c->di[KW_U_SOURCE_INDEX], nsrc, cf.u_source_many, tg, 1);
@@ -700,9 +750,10 @@ static int step(kw_ctx* c) {
   }
   if (cf.transducer_source_flag > t) {
     const size_t nsrc = c->count[KW_U_SOURCE_INDEX];
-    k_add_transducer<<<ew_grid(nsrc), 256, 0, c->st>>>(u[0], c->di[KW_U_SOURCE_INDEX], c->d[KW_TRANSDUCER_SOURCE_INPUT],
-                                                        c->di[KW_DELAY_MASK], nsrc, t);
-    c->launches++;
+    launch(c, "add_transducer", 28.0 * nsrc, [&] {
+      k_add_transducer<<<ew_grid(nsrc), 256, 0, c->st>>>(u[0], c->di[KW_U_SOURCE_INDEX], c->d[KW_TRANSDUCER_SOURCE_INPUT],
+                                                          c->di[KW_DELAY_MASK], nsrc, t);
+    });
   }
   // ---- computeVelocityGradient (cpp:2126-2150) + computeDensity (cpp:2157/2169) [+ pressure terms / lossless p]
   {
@@ -720,8 +771,13 @@ static int step(kw_ctx* c) {
     e.dt = cf.dt, e.nonlinear = cf.nonlinear_flag, e.absorbing = cf.absorbing_flag;
     e.defer_terms = p_src && cf.p_source_mode == KW_SRC_ADDITIVE;
     e.outA = c->tA, e.outB = c->tB, e.outNL = c->tNL, e.p = c->d[KW_P];
-    g.ox->xinv_density(xinv_args<3>(c, c->S), e, c->st);
-    c->launches++;
+    {
+      double per = 24.0 + (c->count[KW_RHO0] > 1 ? 4.0 : 0.0);  // rho r/w, rho0
+      if (cf.absorbing_flag) per += 4.0 + (e.defer_terms ? 0.0 : 4.0 + (cf.nonlinear_flag ? 4.0 : 0.0));  // A, B, NL
+      else if (!e.defer_terms) per += 4.0 + (c->count[KW_C0] > 1 ? 4.0 : 0.0);                               // p, c2
+      if (cf.nonlinear_flag && !e.defer_terms && c->count[KW_BONA] > 1) per += 4.0;
+      launch(c, "xinv_density", 24.0 * g.nc + per * g.n, [&] { g.ox->xinv_density(xinv_args<3>(c, c->S), e, c->st); });
+    }
     // ---- addPressureSource (cpp:2310-2334)
     if (p_src) {
       const size_t nsrc = c->count[KW_P_SOURCE_INDEX];
@@ -731,16 +787,15 @@ static int step(kw_ctx* c) {
         for (int k = 0; k < 3; ++k) sa.target[k] = rho[k];
         sa.ntargets = 3, sa.signal = c->d[KW_P_SOURCE_INPUT], sa.index = c->di[KW_P_SOURCE_INDEX];
         sa.nsrc = nsrc, sa.t = t, sa.many = cf.p_source_many, sa.mode = cf.p_source_mode;
-        k_add_source<<<ew_grid(nsrc), 256, 0, c->st>>>(sa);
+        launch(c, "add_p_source", 36.0 * nsrc, [&] { k_add_source<<<ew_grid(nsrc), 256, 0, c->st>>>(sa); });
         // the fused epilogue computed the sum-of-density terms before the source landed: redo them at the source voxels
         ta.index = c->di[KW_P_SOURCE_INDEX], ta.n = nsrc;
-        k_pressure_terms<<<ew_grid(nsrc), 256, 0, c->st>>>(ta);
+        launch(c, "pressure_terms_fixup", 40.0 * nsrc, [&] { k_pressure_terms<<<ew_grid(nsrc), 256, 0, c->st>>>(ta); });
       } else {
         add_scaled_source(c, c->d[KW_P_SOURCE_INPUT], c->di[KW_P_SOURCE_INDEX], nsrc, cf.p_source_many, rho, 3);
         ta.index = nullptr, ta.n = g.n;
-        k_pressure_terms<<<ew_grid(g.n), 256, 0, c->st>>>(ta);
+        launch(c, "pressure_terms", 28.0 * g.n, [&] { k_pressure_terms<<<ew_grid(g.n), 256, 0, c->st>>>(ta); });
       }
-      c->launches += 2;
     }
   }
   // ---- computePressure, absorbing branch (cpp:2180-2246)
@@ -755,18 +810,19 @@ static int step(kw_ctx* c) {
     EpiPressureSum e{};
     e.p = c->d[KW_P], e.base = cf.nonlinear_flag ? c->tNL : c->tB;
     e.c2 = c->fld(KW_C0), e.tau = c->fld(KW_ABSORB_TAU), e.eta = c->fld(KW_ABSORB_ETA), e.fd = fd;
-    g.ox->xinv_psum(xinv_args<2>(c, c->S), e, c->st);
-    c->launches++;
+    const double per = 8.0 + (c->count[KW_C0] > 1 ? 4.0 : 0.0) + (c->count[KW_ABSORB_TAU] > 1 ? 8.0 : 0.0);
+    launch(c, "xinv_pressure_sum", 16.0 * g.nc + per * g.n, [&] { g.ox->xinv_psum(xinv_args<2>(c, c->S), e, c->st); });
   }
   // ---- addInitialPressureSource (cpp:2359-2396)
   if (t == 0 && cf.p0_source_flag == 1) {
-    k_initial_pressure<<<ew_grid(g.n), 256, 0, c->st>>>(c->d[KW_P], rho[0], rho[1], rho[2], c->d[KW_P0_SOURCE_INPUT], c->fld(KW_C0), g.n);
+    launch(c, "initial_pressure", 24.0 * g.n, [&] {
+      k_initial_pressure<<<ew_grid(g.n), 256, 0, c->st>>>(c->d[KW_P], rho[0], rho[1], rho[2], c->d[KW_P0_SOURCE_INPUT], c->fld(KW_C0), g.n);
+    });
     pressure_gradient_spectra(c);
     EpiVelocity e{};
     for (int k = 0; k < 3; ++k) e.u[k] = u[k], e.dtrho[k] = c->fld(KW_RHO0_SGX + k), e.pml_sg[k] = c->d[KW_PML_X_SGX + k];
     e.fd = fd, e.init = 1;
-    g.ox->xinv_velocity(xinv_args<1>(c, c->S, 3), e, 3, c->st);
-    c->launches += 2;
+    launch(c, "xinv_initial_velocity", 3 * (8.0 * g.nc + 8.0 * g.n), [&] { g.ox->xinv_velocity(xinv_args<1>(c, c->S, 3), e, 3, c->st); });
   }
   // ---- storeSensorData (cpp:1060-1093)
   if (t >= cf.sampling_start_index) sample_streams(c);
@@ -801,6 +857,7 @@ int kw_run(kw_ctx* c, uint64_t nsteps, uint64_t* steps_done, int sync) {
   if (sync) {
     KW_CUDA(cudaStreamSynchronize(c->st));
     KW_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    prof_resolve(c);
   }
   return rc;
 }
@@ -814,7 +871,32 @@ int kw_synchronize(kw_ctx* c) {
   if (!c) return fail(KW_ERR_INVALID, "null context");
   KW_CUDA(cudaStreamSynchronize(c->st));
   cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+  prof_resolve(c);
   KW_CUDA(cudaGetLastError());
+  return KW_OK;
+}
+int kw_profile(kw_ctx* c, int enable, int reset) {
+  if (!c) return fail(KW_ERR_INVALID, "null context");
+  KW_CUDA(cudaStreamSynchronize(c->st));
+  prof_resolve(c);
+  c->prof_on = enable != 0;
+  if (reset) c->prof.clear();
+  return KW_OK;
+}
+int kw_profile_report(kw_ctx* c, char* buf, uint64_t cap) {
+  if (!c || !buf || cap == 0) return fail(KW_ERR_INVALID, "null argument");
+  std::string out = "{";
+  bool first = true;
+  for (auto& kv : c->prof) {
+    char line[256];
+    snprintf(line, sizeof line, "%s\"%s\": {\"launches\": %llu, \"ms\": %.6f, \"bytes\": %.1f}", first ? "" : ", ", kv.first.c_str(),
+             (unsigned long long)kv.second.launches, kv.second.ms, kv.second.bytes);
+    out += line;
+    first = false;
+  }
+  out += "}";
+  if (out.size() + 1 > cap) return fail(KW_ERR_INVALID, "kw_profile_report: buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
   return KW_OK;
 }
 int kw_last_run_ms(kw_ctx* c, float* ms) {
