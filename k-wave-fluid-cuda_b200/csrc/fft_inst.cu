@@ -1,4 +1,6 @@
 // One translation unit per transform length: nvcc ... -DKW_N=<N> fft_inst.cu -o fft_inst_<N>.o
+#include <cmath>
+
 #include "ops.h"
 
 #ifndef KW_N
@@ -19,20 +21,20 @@ template <class K> static int blocks_per_sm(K kernel, int threads, size_t smem) 
   return b > 0 ? b : 1;
 }
 
-static int x_grid(int nrows, int per_sm) {
+static int x_grid(int npairs, int per_sm) {
   constexpr int RP = kXThreads / (N / 8);
-  const int groups = ((nrows >> 1) + RP - 1) / RP;
+  const int groups = (npairs + RP - 1) / RP;
   const int cap = sm_count() * per_sm;
   return groups < cap ? groups : cap;
 }
 
 static void xfwd(const XFwdArgs& a, int nfields, cudaStream_t st) {
   static const int per_sm = blocks_per_sm(k_xfwd<N>, kXThreads, 0);
-  k_xfwd<N><<<dim3(x_grid(a.nrows, per_sm), nfields), kXThreads, 0, st>>>(a);
+  k_xfwd<N><<<dim3(x_grid(a.pair_end - a.pair_begin, per_sm), nfields), kXThreads, 0, st>>>(a);
 }
 template <int NF, class Epi> static void xinv(const XInvArgs<NF>& a, const Epi& e, int gy, cudaStream_t st) {
   static const int per_sm = blocks_per_sm(k_xinv<N, NF, Epi>, kXThreads, 0);
-  k_xinv<N, NF, Epi><<<dim3(x_grid(a.nrows, per_sm), gy), kXThreads, 0, st>>>(a, e);
+  k_xinv<N, NF, Epi><<<dim3(x_grid(a.pair_end - a.pair_begin, per_sm), gy), kXThreads, 0, st>>>(a, e);
 }
 static void xinv_store(const XInvArgs<1>& a, const EpiStore& e, int nf, cudaStream_t st) { xinv<1>(a, e, nf, st); }
 static void xinv_add(const XInvArgs<1>& a, const EpiAdd& e, cudaStream_t st) { xinv<1>(a, e, 1, st); }
@@ -41,13 +43,28 @@ static void xinv_density(const XInvArgs<3>& a, const EpiDensity& e, cudaStream_t
 static void xinv_psum(const XInvArgs<2>& a, const EpiPressureSum& e, cudaStream_t st) { xinv<2>(a, e, 1, st); }
 
 // ID distinguishes kernels of identical function type (the statics below are per kernel)
-template <int ID, class K> static int col_grid(K kernel, int ntiles) {
+static void upload_twiddles() {  // forward table e^{-2 pi i m/N} in double precision -> constant memory, once per device
+  static bool done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || done[dev]) return;
+  float2 h[N];
+  for (int m = 0; m < N; ++m) {
+    const double a = -2.0 * 3.14159265358979323846 * (double)m / (double)N;
+    h[m] = make_float2((float)cos(a), (float)sin(a));
+  }
+  cudaMemcpyToSymbol(c_tw, h, sizeof(h));
+  done[dev] = true;
+}
+
+template <int ID, class K> static int col_grid(K kernel, int ntiles, size_t smem) {
   using C = ColCfg<N>;
   static bool once = false;
   static int per_sm = 1;
+  upload_twiddles();
   if (!once) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    per_sm = blocks_per_sm(kernel, C::THREADS, C::SMEM);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    per_sm = blocks_per_sm(kernel, C::THREADS, smem);
     once = true;
   }
   const int groups = (ntiles + C::TPC - 1) / C::TPC;
@@ -57,26 +74,26 @@ template <int ID, class K> static int col_grid(K kernel, int ntiles) {
 
 static void col(const ColArgs& a, int dir, int nfields, cudaStream_t st) {
   using C = ColCfg<N>;
-  const dim3 block(C::W, C::TY, C::TPC);
+  const dim3 block(C::W, C::T, C::TPC);
   if (dir < 0) {
-    const int g = col_grid<0>(k_col<N, -1>, a.ntiles);
-    k_col<N, -1><<<dim3(g, nfields), block, C::SMEM, st>>>(a);
+    const int g = col_grid<0>(k_col<N, -1>, a.tile_end - a.tile_begin, C::SMEM_COL);
+    k_col<N, -1><<<dim3(g, nfields), block, C::SMEM_COL, st>>>(a);
   } else {
-    const int g = col_grid<1>(k_col<N, +1>, a.ntiles);
-    k_col<N, +1><<<dim3(g, nfields), block, C::SMEM, st>>>(a);
+    const int g = col_grid<1>(k_col<N, +1>, a.tile_end - a.tile_begin, C::SMEM_COL);
+    k_col<N, +1><<<dim3(g, nfields), block, C::SMEM_COL, st>>>(a);
   }
 }
 static void zmid(const ZMidArgs& a, int nfields, cudaStream_t st) {
   using C = ColCfg<N>;
-  const int g = col_grid<2>(k_zmid<N>, a.ntiles);
-  k_zmid<N><<<dim3(g, nfields), dim3(C::W, C::TY, C::TPC), C::SMEM, st>>>(a);
+  const int g = col_grid<2>(k_zmid<N>, a.ntiles, C::SMEM_ZMID);
+  k_zmid<N><<<dim3(g, nfields), dim3(C::W, C::T, C::TPC), C::SMEM_ZMID, st>>>(a);
 }
 
 }  // namespace inst_<N>
 
 #define KW_OPS_NAME2(n) fft_ops_##n
 #define KW_OPS_NAME(n) KW_OPS_NAME2(n)
-extern const FftOps KW_OPS_NAME(KW_N) = {KW_N, KW_CAT(inst_, KW_N)::xfwd, KW_CAT(inst_, KW_N)::xinv_store, KW_CAT(inst_, KW_N)::xinv_add, KW_CAT(inst_, KW_N)::xinv_velocity,
+extern const FftOps KW_OPS_NAME(KW_N) = {KW_N, ColCfg<KW_N>::W, KW_CAT(inst_, KW_N)::xfwd, KW_CAT(inst_, KW_N)::xinv_store, KW_CAT(inst_, KW_N)::xinv_add, KW_CAT(inst_, KW_N)::xinv_velocity,
                                             KW_CAT(inst_, KW_N)::xinv_density, KW_CAT(inst_, KW_N)::xinv_psum, KW_CAT(inst_, KW_N)::col, KW_CAT(inst_, KW_N)::zmid};
 
 }  // namespace kw

@@ -22,7 +22,7 @@ struct XFwdArgs {
   const float* in[kMaxFields];
   float2* out[kMaxFields];
   const float2* tab;  // forward twiddle table of length Nx
-  int nrows;          // Ny*Nz
+  int pair_begin, pair_end;  // range of row pairs (row = z*Ny + y) this launch transforms
   int nxp;
 };
 
@@ -39,11 +39,11 @@ template <int N> __global__ void __launch_bounds__(kXThreads) k_xfwd(XFwdArgs a)
   RowExchange ex{sbuf, rp * N};
   const float* __restrict__ in = a.in[blockIdx.y];
   float2* __restrict__ out = a.out[blockIdx.y];
-  const int npairs = a.nrows >> 1;
+  const int npairs = a.pair_end - a.pair_begin;
   for (int g = blockIdx.x; g * RP < npairs; g += gridDim.x) {
-    const int pair = g * RP + rp;
-    const bool valid = pair < npairs;
-    const size_t row0 = valid ? 2 * (size_t)pair : 0;
+    const int pair = a.pair_begin + g * RP + rp;
+    const bool valid = pair < a.pair_end;
+    const size_t row0 = 2 * (size_t)(valid ? pair : a.pair_begin);
     const float* ra = in + row0 * N;
     float2 v[1][8];
 #pragma unroll
@@ -78,7 +78,7 @@ template <int N> __global__ void __launch_bounds__(kXThreads) k_xfwd(XFwdArgs a)
 template <int NF> struct XInvArgs {
   const float2* in[kMaxFields];  // NF == 1: field selected by blockIdx.y; NF > 1: the NF fields of one voxel
   const float2* tab;
-  int nrows, nxp, ny;
+  int pair_begin, pair_end, nxp, ny;
 };
 
 // Epilogue contract:  epi.apply(field_select, res, t, T, row0, y, z)  where res[f][m] = (row a, row b) values at
@@ -94,11 +94,11 @@ template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads)
   load_twiddles<N>(twr, t, [tab](int m) { return __ldg(tab + m); });
   RegTw twp{twr};
   RowExchange ex{sbuf, rp * N};
-  const int npairs = a.nrows >> 1;
+  const int npairs = a.pair_end - a.pair_begin;
   for (int g = blockIdx.x; g * RP < npairs; g += gridDim.x) {
-    const int pair = g * RP + rp;
-    const bool valid = pair < npairs;
-    const size_t row0 = valid ? 2 * (size_t)pair : 0;
+    const int pair = a.pair_begin + g * RP + rp;
+    const bool valid = pair < a.pair_end;
+    const size_t row0 = 2 * (size_t)(valid ? pair : a.pair_begin);
     float2 res[NF][8];
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
@@ -134,58 +134,98 @@ template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// column passes
+// column passes (y and z axes)
+//
+// A tile is W neighbouring kx (W*8 bytes contiguous: 128-byte segments for W = 16) times all N points of the transform
+// axis.  One worker = W lanes; a thread owns 8 points of one kx.  Tiles are double buffered in shared memory: while
+// tile i is transformed, the points of tile i+1 arrive through cp.async (LDGSTS), each thread fetching exactly the
+// 8 points it will consume in the first radix-8 stage, so the global-load latency is off the critical path and no
+// registers are spent on staging.  The landing buffer of a tile is also its exchange buffer.
 template <int N> struct ColCfg {
-  static constexpr int W = 16;
+  static constexpr int W = (N >= 1024) ? 8 : 16;
   static constexpr int T = N / 8;
-  static constexpr int B = (N >= 512) ? 2 : 1;                                // transforms' workers per thread
-  static constexpr int TY = T / B;                                             // blockDim.y
-  static constexpr int TPC = (W * TY >= 256) ? 1 : 256 / (W * TY);             // tiles per CTA
-  static constexpr int THREADS = W * TY * TPC;
-  static constexpr size_t SMEM = (size_t)TPC * N * W * sizeof(float2);
+  static constexpr int TPC = (W * T >= 256) ? 1 : 256 / (W * T);  // tiles per CTA (small N)
+  static constexpr int THREADS = W * T * TPC;
+  static constexpr size_t TILE = (size_t)N * W * sizeof(float2);
+  static constexpr size_t SMEM_COL = 2 * TPC * TILE;
+  static constexpr size_t SMEM_ZMID = 2 * TPC * TILE + TPC * (size_t)N * W * sizeof(float);
 };
 
-struct TabTw {  // twiddles fetched from the (L1/const cached) table; index is uniform per W lanes
-  const float2* tab;
-  __device__ __forceinline__ float2 get(int, int m) const { return __ldg(tab + m); }
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory"); }
+
+// twiddles of the transform length of this translation unit, in constant memory (index is uniform per worker)
+#ifdef KW_N
+__constant__ float2 c_tw[KW_N];
+struct ConstTw {
+  __device__ __forceinline__ float2 get(int, int m) const { return c_tw[m]; }
 };
+#endif
 
 struct ColArgs {
   float2* data[kMaxFields];
-  const float2* tab;
   size_t stride;        // elements between consecutive points of the transform axis
   size_t outer_stride;  // elements between consecutive "outer" tiles
   int ngroups;          // NXP / W
-  int ntiles;           // nouter * ngroups
+  int tile_begin, tile_end;  // range of tiles (tile = outer * ngroups + group) this launch transforms
 };
 
-template <int N, int DIR> __global__ void __launch_bounds__(ColCfg<N>::THREADS) k_col(ColArgs a) {
+#ifdef KW_N
+template <int N, int DIR> __global__ void __launch_bounds__(ColCfg<N>::THREADS, 1) k_col(ColArgs a) {
   using C = ColCfg<N>;
-  constexpr int W = C::W, T = C::T, B = C::B;
+  constexpr int W = C::W, T = C::T;
   extern __shared__ float2 smem[];
-  const int lane = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
-  ColExchange<W> ex{smem + (size_t)tz * N * W + lane};
-  TabTw twp{a.tab};
+  const int lane = threadIdx.x, t = threadIdx.y, tz = threadIdx.z;
+  float2* const buf0 = smem + (size_t)tz * 2 * N * W + lane;  // two landing/exchange buffers per tile slot
+  ConstTw twp;
   float2* __restrict__ data = a.data[blockIdx.y];
-  for (int g = blockIdx.x; g * C::TPC < a.ntiles; g += gridDim.x) {
-    const int tile = g * C::TPC + tz;
-    const bool valid = tile < a.ntiles;
-    const int tl = valid ? tile : 0;
-    const size_t base = (size_t)(tl / a.ngroups) * a.outer_stride + (size_t)(tl % a.ngroups) * W + lane;
-    float2 v[B][8];
+  const int ntiles = a.tile_end - a.tile_begin;
+  const int niter = (ntiles + C::TPC - 1) / C::TPC;
+  auto tile_base = [&](int it, bool& valid) -> size_t {
+    const int tile = a.tile_begin + it * C::TPC + tz;
+    valid = tile < a.tile_end;
+    const int tl = valid ? tile : a.tile_begin;
+    return (size_t)(tl / a.ngroups) * a.outer_stride + (size_t)(tl % a.ngroups) * W + lane;
+  };
+  auto prefetch = [&](int it, int b) {
+    bool valid;
+    const size_t base = tile_base(it, valid);
+    float2* dst = buf0 + (size_t)b * N * W;
 #pragma unroll
-    for (int b = 0; b < B; ++b)
+    for (int r = 0; r < 8; ++r) cp_async8(dst + (t + r * T) * W, data + base + (size_t)(t + r * T) * a.stride);
+    cp_async_commit();
+  };
+  int it = blockIdx.x, b = 0;
+  if (it < niter) prefetch(it, 0);
+  for (; it < niter; it += gridDim.x, b ^= 1) {
+    const int nxt = it + gridDim.x;
+    if (nxt < niter) {
+      prefetch(nxt, b ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    ColExchange<W> ex{buf0 + (size_t)b * N * W};
+    float2 v[1][8];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) v[b][r] = data[base + (size_t)(ty + b * C::TY + r * T) * a.stride];
-    fft_worker<N, DIR, B>(v, ty, C::TY, twp, ex);
+    for (int r = 0; r < 8; ++r) v[0][r] = ex.get(0, t + r * T);
+    ex.sync();  // everyone holds its own points: the landing buffer becomes the exchange buffer
+    fft_worker<N, DIR, 1>(v, t, 0, twp, ex);
+    bool valid;
+    const size_t base = tile_base(it, valid);
     if (valid) {
 #pragma unroll
-      for (int b = 0; b < B; ++b)
-#pragma unroll
-        for (int r = 0; r < 8; ++r) data[base + (size_t)(ty + b * C::TY + r * T) * a.stride] = v[b][r];
+      for (int r = 0; r < 8; ++r) data[base + (size_t)(t + r * T) * a.stride] = v[0][r];
     }
   }
 }
+#endif
 
 // fused z pass:  out = IFFT_z( (FFT_z(in) * (mul * scal)) (x) vec[coord(axis)] )
 struct ZField {
@@ -198,52 +238,82 @@ struct ZField {
 };
 struct ZMidArgs {
   ZField f[kMaxFields];
-  const float2* tab;
   int ny, nxp, ngroups, ntiles;  // ntiles = Ny * ngroups
   size_t plane;                  // Ny * NXP
 };
 
-template <int N> __global__ void __launch_bounds__(ColCfg<N>::THREADS) k_zmid(ZMidArgs a) {
+#ifdef KW_N
+template <int N> __global__ void __launch_bounds__(ColCfg<N>::THREADS, 1) k_zmid(ZMidArgs a) {
   using C = ColCfg<N>;
-  constexpr int W = C::W, T = C::T, B = C::B;
+  constexpr int W = C::W, T = C::T;
   extern __shared__ float2 smem[];
-  const int lane = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
-  ColExchange<W> ex{smem + (size_t)tz * N * W + lane};
-  TabTw twp{a.tab};
+  const int lane = threadIdx.x, t = threadIdx.y, tz = threadIdx.z;
+  float2* const buf0 = smem + (size_t)tz * 2 * N * W + lane;
+  float* const mulbuf = reinterpret_cast<float*>(smem + (size_t)C::TPC * 2 * N * W) + (size_t)tz * N * W + lane;
+  ConstTw twp;
   const ZField fld = a.f[blockIdx.y];
-  for (int g = blockIdx.x; g * C::TPC < a.ntiles; g += gridDim.x) {
-    const int tile = g * C::TPC + tz;
-    const bool valid = tile < a.ntiles;
+  const int niter = (a.ntiles + C::TPC - 1) / C::TPC;
+  auto tile_base = [&](int it, bool& valid, int& y, int& kx) -> size_t {
+    const int tile = it * C::TPC + tz;
+    valid = tile < a.ntiles;
     const int tl = valid ? tile : 0;
-    const int y = tl / a.ngroups, kx = (tl % a.ngroups) * W + lane;
-    const size_t base = (size_t)y * a.nxp + kx;
-    float2 v[B][8];
+    y = tl / a.ngroups, kx = (tl % a.ngroups) * W + lane;
+    return (size_t)y * a.nxp + kx;
+  };
+  auto prefetch = [&](int it, int b) {
+    bool valid;
+    int y, kx;
+    const size_t base = tile_base(it, valid, y, kx);
+    float2* dst = buf0 + (size_t)b * N * W;
 #pragma unroll
-    for (int b = 0; b < B; ++b)
+    for (int r = 0; r < 8; ++r) cp_async8(dst + (t + r * T) * W, fld.in + base + (size_t)(t + r * T) * a.plane);
+    cp_async_commit();
+  };
+  int it = blockIdx.x, b = 0;
+  if (it < niter) prefetch(it, 0);
+  for (; it < niter; it += gridDim.x, b ^= 1) {
+    bool valid;
+    int y, kx;
+    const size_t base = tile_base(it, valid, y, kx);
+    // multiplier of this tile: lands while the forward transform runs (single buffer, consumed after it)
+    if (fld.mul) {
 #pragma unroll
-      for (int r = 0; r < 8; ++r) v[b][r] = __ldg(fld.in + base + (size_t)(ty + b * C::TY + r * T) * a.plane);
-    fft_worker<N, -1, B>(v, ty, C::TY, twp, ex);
+      for (int r = 0; r < 8; ++r) cp_async4(mulbuf + (t + r * T) * W, fld.mul + base + (size_t)(t + r * T) * a.plane);
+    }
+    cp_async_commit();
+    const int nxt = it + gridDim.x;
+    if (nxt < niter) {
+      prefetch(nxt, b ^ 1);
+      cp_async_wait<2>();  // tile `it` has landed; its multiplier and the next tile may still be in flight
+    } else {
+      cp_async_wait<1>();
+    }
+    ColExchange<W> ex{buf0 + (size_t)b * N * W};
+    float2 v[1][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[0][r] = ex.get(0, t + r * T);
+    ex.sync();
+    fft_worker<N, -1, 1>(v, t, 0, twp, ex);
+    if (nxt < niter) cp_async_wait<1>();
+    else cp_async_wait<0>();
     float2 w01 = make_float2(1.f, 0.f);
     if (fld.vec && fld.axis < 2) w01 = __ldg(fld.vec + (fld.axis == 0 ? kx : y));
 #pragma unroll
-    for (int b = 0; b < B; ++b)
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int kz = ty + b * C::TY + r * T;
-        float m = fld.scal;
-        if (fld.mul) m = __ldg(fld.mul + base + (size_t)kz * a.plane) * fld.scal;
-        float2 e = cscale(v[b][r], m);
-        if (fld.vec) e = cmul(e, fld.axis == 2 ? __ldg(fld.vec + kz) : w01);
-        v[b][r] = e;
-      }
-    fft_worker<N, +1, B>(v, ty, C::TY, twp, ex);
+    for (int r = 0; r < 8; ++r) {
+      const int kz = t + r * T;
+      float m = fld.scal;
+      if (fld.mul) m = mulbuf[kz * W] * fld.scal;
+      float2 e = cscale(v[0][r], m);
+      if (fld.vec) e = cmul(e, fld.axis == 2 ? __ldg(fld.vec + kz) : w01);
+      v[0][r] = e;
+    }
+    fft_worker<N, +1, 1>(v, t, 0, twp, ex);
     if (valid) {
 #pragma unroll
-      for (int b = 0; b < B; ++b)
-#pragma unroll
-        for (int r = 0; r < 8; ++r) fld.out[base + (size_t)(ty + b * C::TY + r * T) * a.plane] = v[b][r];
+      for (int r = 0; r < 8; ++r) fld.out[base + (size_t)(t + r * T) * a.plane] = v[0][r];
     }
   }
 }
+#endif
 
 }  // namespace kw

@@ -9,6 +9,7 @@ namespace kw {
 
 struct FftOps {
   int n;
+  int col_w;  // kx values per column tile of this length (ColCfg<N>::W)
   void (*xfwd)(const XFwdArgs&, int nfields, cudaStream_t);
   void (*xinv_store)(const XInvArgs<1>&, const EpiStore&, int nfields, cudaStream_t);
   void (*xinv_add)(const XInvArgs<1>&, const EpiAdd&, cudaStream_t);

@@ -5,6 +5,7 @@
 // MatrixContainer / OutputStreamContainer that decide which arrays and streams exist.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -615,39 +616,68 @@ struct StepCtx {
   cudaStream_t st;
 };
 
+// z-chunking: the x pass and the y pass of a transform are launched chunk by chunk over groups of z planes so that
+// the intermediate half-spectrum of a chunk is still in the 126 MB L2 when the next pass reads it (the two passes are
+// independent per z plane).  chunk_planes == nz means one launch per pass.
+static int chunk_planes(const kw_ctx* c, int nf) {
+  static const long long env = getenv("KW_ZCHUNK_MB") ? atoll(getenv("KW_ZCHUNK_MB")) : 0;
+  const Geometry& g = c->g;
+  if (env <= 0) return g.nz;
+  const double plane_mb = (double)g.ny * g.nxp * 8.0 * nf / (1 << 20);
+  int cz = (int)((double)env / plane_mb);
+  if (cz >= g.nz) return g.nz;
+  if (cz < 4) cz = 4;
+  while (g.nz % cz) --cz;  // nz is a power of two: ends at a divisor
+  return cz;
+}
+
 // forward x and y passes of `nf` real fields into spectral buffers
 static void forward_xy(kw_ctx* c, const float* const* in, float2* const* out, int nf) {
   const Geometry& g = c->g;
   XFwdArgs xa{};
   ColArgs ca{};
   for (int f = 0; f < nf; ++f) xa.in[f] = in[f], xa.out[f] = out[f], ca.data[f] = out[f];
-  xa.tab = g.tx, xa.nrows = g.ny * g.nz, xa.nxp = g.nxp;
-  launch(c, "xfwd", nf * (4.0 * g.n + 8.0 * g.nc), [&] { g.ox->xfwd(xa, nf, c->st); });
-  ca.tab = g.ty, ca.stride = g.nxp, ca.outer_stride = (size_t)g.ny * g.nxp, ca.ngroups = g.nxp / 16, ca.ntiles = g.nz * ca.ngroups;
-  launch(c, "ycol_fwd", nf * 16.0 * g.nc, [&] { g.oy->col(ca, -1, nf, c->st); });
+  xa.tab = g.tx, xa.nxp = g.nxp;
+  ca.stride = g.nxp, ca.outer_stride = (size_t)g.ny * g.nxp, ca.ngroups = g.nxp / g.oy->col_w;
+  const int cz = chunk_planes(c, nf);
+  const double frac = (double)cz / g.nz;
+  for (int z0 = 0; z0 < g.nz; z0 += cz) {
+    xa.pair_begin = z0 * g.ny / 2, xa.pair_end = (z0 + cz) * g.ny / 2;
+    ca.tile_begin = z0 * ca.ngroups, ca.tile_end = (z0 + cz) * ca.ngroups;
+    launch(c, "xfwd", frac * nf * (4.0 * g.n + 8.0 * g.nc), [&] { g.ox->xfwd(xa, nf, c->st); });
+    launch(c, "ycol_fwd", frac * nf * 16.0 * g.nc, [&] { g.oy->col(ca, -1, nf, c->st); });
+  }
 }
-static void inverse_y(kw_ctx* c, float2* const* data, int nf) {
+// inverse y pass then the x inverse (with its fused epilogue) chunk by chunk; xinv(pair_begin, pair_end) launches it
+template <class F> static void inverse_yx(kw_ctx* c, float2* const* data, int nf, const char* name, double xinv_bytes, F&& xinv) {
   const Geometry& g = c->g;
   ColArgs ca{};
   for (int f = 0; f < nf; ++f) ca.data[f] = data[f];
-  ca.tab = g.ty, ca.stride = g.nxp, ca.outer_stride = (size_t)g.ny * g.nxp, ca.ngroups = g.nxp / 16, ca.ntiles = g.nz * ca.ngroups;
-  launch(c, "ycol_inv", nf * 16.0 * g.nc, [&] { g.oy->col(ca, +1, nf, c->st); });
+  ca.stride = g.nxp, ca.outer_stride = (size_t)g.ny * g.nxp, ca.ngroups = g.nxp / g.oy->col_w;
+  const int cz = chunk_planes(c, nf);
+  const double frac = (double)cz / g.nz;
+  for (int z0 = 0; z0 < g.nz; z0 += cz) {
+    ca.tile_begin = z0 * ca.ngroups, ca.tile_end = (z0 + cz) * ca.ngroups;
+    launch(c, "ycol_inv", frac * nf * 16.0 * g.nc, [&] { g.oy->col(ca, +1, nf, c->st); });
+    const int pb = z0 * g.ny / 2, pe = (z0 + cz) * g.ny / 2;
+    launch(c, name, frac * xinv_bytes, [&] { xinv(pb, pe); });
+  }
 }
 static void zmid_launch(kw_ctx* c, ZMidArgs& za, int nf) {
   const Geometry& g = c->g;
-  za.tab = g.tz, za.ny = g.ny, za.nxp = g.nxp, za.ngroups = g.nxp / 16, za.ntiles = g.ny * za.ngroups, za.plane = (size_t)g.ny * g.nxp;
+  za.ny = g.ny, za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->col_w, za.ntiles = g.ny * za.ngroups, za.plane = (size_t)g.ny * g.nxp;
   double bytes = 0;
   for (int f = 0; f < nf; ++f) bytes += 16.0 * g.nc + (za.f[f].mul ? 4.0 * g.nc : 0.0);
   launch(c, "zmid", bytes, [&] { g.oz->zmid(za, nf, c->st); });
 }
-template <int NF> static XInvArgs<NF> xinv_args(kw_ctx* c, float2* const* in, int nfields = NF) {
+template <int NF> static XInvArgs<NF> xinv_args(kw_ctx* c, float2* const* in, int pb, int pe, int nfields = NF) {
   XInvArgs<NF> a{};
   for (int f = 0; f < nfields; ++f) a.in[f] = in[f];
-  a.tab = c->g.tx, a.nrows = c->g.ny * c->g.nz, a.nxp = c->g.nxp, a.ny = c->g.ny;
+  a.tab = c->g.tx, a.pair_begin = pb, a.pair_end = pe, a.nxp = c->g.nxp, a.ny = c->g.ny;
   return a;
 }
 
-// F[p]*kappa*ddk_pos -> inverse y; result left in S0..S2 ready for the x inverse  (cpp:2087-2101)
+// F[p]*kappa*ddk_pos after the fused z pass; S0..S2 are ready for the inverse y and x passes  (cpp:2087-2101)
 static void pressure_gradient_spectra(kw_ctx* c) {
   const float* in[1] = {c->d[KW_P]};
   float2* out[1] = {c->S[3]};
@@ -657,7 +687,6 @@ static void pressure_gradient_spectra(kw_ctx* c) {
   for (int f = 0; f < 3; ++f)
     za.f[f] = ZField{c->S[3], c->S[f], c->d[KW_KAPPA], 1.0f, reinterpret_cast<const float2*>(c->d[vec[f]]), f};
   zmid_launch(c, za, 3);
-  inverse_y(c, c->S, 3);
 }
 
 // additive source: scaled = IFFT(FFT(scatter) * (source_kappa * fd)), added to the targets  (cpp:2339-2352)
@@ -671,11 +700,11 @@ static void add_scaled_source(kw_ctx* c, const float* signal, const uint64_t* in
   ZMidArgs za{};
   za.f[0] = ZField{c->S[3], c->S[3], c->d[KW_SOURCE_KAPPA], 1.0f / (float)g.n, nullptr, 0};
   zmid_launch(c, za, 1);
-  inverse_y(c, out, 1);
   EpiAdd e{};
   for (int k = 0; k < ntargets; ++k) e.out[k] = targets[k];
   e.ntargets = ntargets;
-  launch(c, "xinv_add_source", 8.0 * g.nc + 8.0 * g.n * ntargets, [&] { g.ox->xinv_add(xinv_args<1>(c, out), e, c->st); });
+  inverse_yx(c, out, 1, "xinv_add_source", 8.0 * g.nc + 8.0 * g.n * ntargets,
+             [&](int pb, int pe) { g.ox->xinv_add(xinv_args<1>(c, out, pb, pe), e, c->st); });
 }
 
 static TermsArgs terms_args(kw_ctx* c) {
@@ -731,7 +760,8 @@ static int step(kw_ctx* c) {
     for (int k = 0; k < 3; ++k) e.u[k] = u[k], e.dtrho[k] = c->fld(KW_RHO0_SGX + k), e.pml_sg[k] = c->d[KW_PML_X_SGX + k];
     e.fd = fd, e.init = 0;
     const double het = c->count[KW_RHO0_SGX] > 1 ? 4.0 : 0.0;
-    launch(c, "xinv_velocity", 3 * (8.0 * g.nc + (8.0 + het) * g.n), [&] { g.ox->xinv_velocity(xinv_args<1>(c, c->S, 3), e, 3, c->st); });
+    inverse_yx(c, c->S, 3, "xinv_velocity", 3 * (8.0 * g.nc + (8.0 + het) * g.n),
+               [&](int pb, int pe) { g.ox->xinv_velocity(xinv_args<1>(c, c->S, pb, pe, 3), e, 3, c->st); });
   }
   // ---- addVelocitySource (cpp:2252-2303), transducer (cpp:894-897)
   const uint64_t uflag[3] = {cf.ux_source_flag, cf.uy_source_flag, cf.uz_source_flag};
@@ -763,7 +793,6 @@ static int step(kw_ctx* c) {
     for (int f = 0; f < 3; ++f)
       za.f[f] = ZField{c->S[f], c->S[f], c->d[KW_KAPPA], fd, reinterpret_cast<const float2*>(c->d[vec[f]]), f};
     zmid_launch(c, za, 3);
-    inverse_y(c, c->S, 3);
     const bool p_src = cf.p_source_flag > t;
     EpiDensity e{};
     for (int k = 0; k < 3; ++k) e.rho[k] = rho[k], e.pml[k] = c->d[KW_PML_X + k];
@@ -776,7 +805,8 @@ static int step(kw_ctx* c) {
       if (cf.absorbing_flag) per += 4.0 + (e.defer_terms ? 0.0 : 4.0 + (cf.nonlinear_flag ? 4.0 : 0.0));  // A, B, NL
       else if (!e.defer_terms) per += 4.0 + (c->count[KW_C0] > 1 ? 4.0 : 0.0);                               // p, c2
       if (cf.nonlinear_flag && !e.defer_terms && c->count[KW_BONA] > 1) per += 4.0;
-      launch(c, "xinv_density", 24.0 * g.nc + per * g.n, [&] { g.ox->xinv_density(xinv_args<3>(c, c->S), e, c->st); });
+      inverse_yx(c, c->S, 3, "xinv_density", 24.0 * g.nc + per * g.n,
+                 [&](int pb, int pe) { g.ox->xinv_density(xinv_args<3>(c, c->S, pb, pe), e, c->st); });
     }
     // ---- addPressureSource (cpp:2310-2334)
     if (p_src) {
@@ -806,12 +836,12 @@ static int step(kw_ctx* c) {
     za.f[0] = ZField{c->S[0], c->S[0], c->d[KW_ABSORB_NABLA1], 1.0f, nullptr, 0};
     za.f[1] = ZField{c->S[1], c->S[1], c->d[KW_ABSORB_NABLA2], 1.0f, nullptr, 0};
     zmid_launch(c, za, 2);
-    inverse_y(c, c->S, 2);
     EpiPressureSum e{};
     e.p = c->d[KW_P], e.base = cf.nonlinear_flag ? c->tNL : c->tB;
     e.c2 = c->fld(KW_C0), e.tau = c->fld(KW_ABSORB_TAU), e.eta = c->fld(KW_ABSORB_ETA), e.fd = fd;
     const double per = 8.0 + (c->count[KW_C0] > 1 ? 4.0 : 0.0) + (c->count[KW_ABSORB_TAU] > 1 ? 8.0 : 0.0);
-    launch(c, "xinv_pressure_sum", 16.0 * g.nc + per * g.n, [&] { g.ox->xinv_psum(xinv_args<2>(c, c->S), e, c->st); });
+    inverse_yx(c, c->S, 2, "xinv_pressure_sum", 16.0 * g.nc + per * g.n,
+               [&](int pb, int pe) { g.ox->xinv_psum(xinv_args<2>(c, c->S, pb, pe), e, c->st); });
   }
   // ---- addInitialPressureSource (cpp:2359-2396)
   if (t == 0 && cf.p0_source_flag == 1) {
@@ -822,7 +852,8 @@ static int step(kw_ctx* c) {
     EpiVelocity e{};
     for (int k = 0; k < 3; ++k) e.u[k] = u[k], e.dtrho[k] = c->fld(KW_RHO0_SGX + k), e.pml_sg[k] = c->d[KW_PML_X_SGX + k];
     e.fd = fd, e.init = 1;
-    launch(c, "xinv_initial_velocity", 3 * (8.0 * g.nc + 8.0 * g.n), [&] { g.ox->xinv_velocity(xinv_args<1>(c, c->S, 3), e, 3, c->st); });
+    inverse_yx(c, c->S, 3, "xinv_initial_velocity", 3 * (8.0 * g.nc + 8.0 * g.n),
+               [&](int pb, int pe) { g.ox->xinv_velocity(xinv_args<1>(c, c->S, pb, pe, 3), e, 3, c->st); });
   }
   // ---- storeSensorData (cpp:1060-1093)
   if (t >= cf.sampling_start_index) sample_streams(c);
@@ -986,12 +1017,12 @@ static int fft3d_host(uint64_t nx, uint64_t ny, uint64_t nz, const float* in, fl
   KW_CUDA(cudaMemset(dspec, 0, g.nc * sizeof(float2)));
   ColArgs cy{}, cz{};
   cy.data[0] = cz.data[0] = dspec;
-  cy.tab = g.ty, cy.stride = g.nxp, cy.outer_stride = (size_t)g.ny * g.nxp, cy.ngroups = g.nxp / 16, cy.ntiles = g.nz * cy.ngroups;
-  cz.tab = g.tz, cz.stride = (size_t)g.ny * g.nxp, cz.outer_stride = g.nxp, cz.ngroups = g.nxp / 16, cz.ntiles = g.ny * cz.ngroups;
+  cy.stride = g.nxp, cy.outer_stride = (size_t)g.ny * g.nxp, cy.ngroups = g.nxp / g.oy->col_w, cy.tile_begin = 0, cy.tile_end = g.nz * cy.ngroups;
+  cz.stride = (size_t)g.ny * g.nxp, cz.outer_stride = g.nxp, cz.ngroups = g.nxp / g.oz->col_w, cz.tile_begin = 0, cz.tile_end = g.ny * cz.ngroups;
   if (forward) {
     KW_CUDA(cudaMemcpy(dreal, in, g.n * sizeof(float), cudaMemcpyHostToDevice));
     XFwdArgs xa{};
-    xa.in[0] = dreal, xa.out[0] = dspec, xa.tab = g.tx, xa.nrows = (int)rows, xa.nxp = g.nxp;
+    xa.in[0] = dreal, xa.out[0] = dspec, xa.tab = g.tx, xa.pair_begin = 0, xa.pair_end = (int)(rows / 2), xa.nxp = g.nxp;
     g.ox->xfwd(xa, 1, 0);
     g.oy->col(cy, -1, 1, 0);
     g.oz->col(cz, -1, 1, 0);
@@ -1004,7 +1035,7 @@ static int fft3d_host(uint64_t nx, uint64_t ny, uint64_t nz, const float* in, fl
     g.oz->col(cz, +1, 1, 0);
     g.oy->col(cy, +1, 1, 0);
     XInvArgs<1> xa{};
-    xa.in[0] = dspec, xa.tab = g.tx, xa.nrows = (int)rows, xa.nxp = g.nxp, xa.ny = g.ny;
+    xa.in[0] = dspec, xa.tab = g.tx, xa.pair_begin = 0, xa.pair_end = (int)(rows / 2), xa.nxp = g.nxp, xa.ny = g.ny;
     EpiStore e{};
     e.out[0] = dreal, e.scale = 1.0f;
     g.ox->xinv_store(xa, e, 1, 0);
