@@ -83,7 +83,8 @@ _lib = None
 
 
 def library_path():
-    return os.path.join(_HERE, "libkwave_b200.so")
+    # KWAVE_B200_LIB selects an alternative build of the same library (kernel-variant experiments)
+    return os.environ.get("KWAVE_B200_LIB") or os.path.join(_HERE, "libkwave_b200.so")
 
 
 def load_library():

@@ -192,23 +192,34 @@ __device__ __forceinline__ void fft_worker(float2 (&v)[B][8], int t0, int ts, co
 // Row transforms (x axis): consecutive lanes are consecutive workers of one transform.  Flat float2 buffer of all
 // transforms of the CTA with an XOR swizzle that makes the three Stockham access patterns (contiguous, stride 8,
 // 8-contiguous/stride 64) conflict free per half warp (verified by tools/check_swizzle.py).
-struct RowExchange {
+// T workers (threads) cooperate on one transform and synchronise among themselves only: a named barrier per transform
+// when it spans whole warps, __syncwarp when several transforms share a warp -- the transforms of a CTA drift apart so
+// that the load, butterfly and store phases of different rows overlap.
+template <int T> struct RowExchange {
   float2* buf;  // CTA buffer
   int base;     // transform index * N
+  int bar;      // named barrier id of this transform (1..15)
   __device__ __forceinline__ static int swz(int g) { return g ^ ((g >> 3) & 7) ^ (((g >> 6) & 1) << 3); }
   __device__ __forceinline__ void put(int, int i, float2 x) { buf[swz(base + i)] = x; }
   __device__ __forceinline__ float2 get(int, int i) const { return buf[swz(base + i)]; }
-  __device__ __forceinline__ void sync() { __syncthreads(); }
+  __device__ __forceinline__ void sync() {
+    if (T >= 32) asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(T) : "memory");
+    else __syncwarp();
+  }
 };
 
 // Column transforms (y / z axes): W consecutive lanes hold W neighbouring kx of the same worker, so element i of
 // lane l lives at buf[i*W + l]: every access is W contiguous float2 -- conflict free without any swizzle.
 // All B transforms of a thread share one N*W tile (they are workers of the same transforms).
-template <int W> struct ColExchange {
+template <int W, int NTHREADS = 0> struct ColExchange {
   float2* buf;  // tile buffer + lane
+  int bar;      // named barrier of this tile slot (1..15); slots of a CTA synchronise independently
   __device__ __forceinline__ void put(int, int i, float2 x) { buf[i * W] = x; }
   __device__ __forceinline__ float2 get(int, int i) const { return buf[i * W]; }
-  __device__ __forceinline__ void sync() { __syncthreads(); }
+  __device__ __forceinline__ void sync() {
+    if (NTHREADS == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(NTHREADS) : "memory");
+  }
 };
 
 }  // namespace kw

@@ -26,7 +26,7 @@ struct XFwdArgs {
   int nxp;
 };
 
-template <int N> __global__ void __launch_bounds__(kXThreads) k_xfwd(XFwdArgs a) {
+template <int N> __global__ void __launch_bounds__(kXThreads, 3) k_xfwd(XFwdArgs a) {
   using P = Plan<N>;
   constexpr int T = P::T;
   constexpr int RP = kXThreads / T;  // row pairs per CTA iteration
@@ -36,7 +36,7 @@ template <int N> __global__ void __launch_bounds__(kXThreads) k_xfwd(XFwdArgs a)
   const float2* tab = a.tab;
   load_twiddles<N>(twr, t, [tab](int m) { return __ldg(tab + m); });
   RegTw twp{twr};
-  RowExchange ex{sbuf, rp * N};
+  RowExchange<T> ex{sbuf, rp * N, 1 + rp};
   const float* __restrict__ in = a.in[blockIdx.y];
   float2* __restrict__ out = a.out[blockIdx.y];
   const int npairs = a.pair_end - a.pair_begin;
@@ -83,7 +83,7 @@ template <int NF> struct XInvArgs {
 
 // Epilogue contract:  epi.apply(field_select, res, t, T, row0, y, z)  where res[f][m] = (row a, row b) values at
 // x = t + m*T of field f, row0 = flattened (z*Ny + y) index of row a (row b = row0 + 1, same z).
-template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads) k_xinv(XInvArgs<NF> a, Epi epi) {
+template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads, Epi::kMinBlocks) k_xinv(XInvArgs<NF> a, Epi epi) {
   using P = Plan<N>;
   constexpr int T = P::T;
   constexpr int RP = kXThreads / T;
@@ -93,7 +93,7 @@ template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads)
   const float2* tab = a.tab;
   load_twiddles<N>(twr, t, [tab](int m) { return __ldg(tab + m); });
   RegTw twp{twr};
-  RowExchange ex{sbuf, rp * N};
+  RowExchange<T> ex{sbuf, rp * N, 1 + rp};
   const int npairs = a.pair_end - a.pair_begin;
   for (int g = blockIdx.x; g * RP < npairs; g += gridDim.x) {
     const int pair = a.pair_begin + g * RP + rp;
@@ -141,10 +141,18 @@ template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads)
 // tile i is transformed, the points of tile i+1 arrive through cp.async (LDGSTS), each thread fetching exactly the
 // 8 points it will consume in the first radix-8 stage, so the global-load latency is off the critical path and no
 // registers are spent on staging.  The landing buffer of a tile is also its exchange buffer.
+#ifndef KW_COLW_512
+#define KW_COLW_512 16
+#endif
+#ifndef KW_COL_MAXTHREADS
+#define KW_COL_MAXTHREADS 1024
+#endif
 template <int N> struct ColCfg {
-  static constexpr int W = (N >= 1024) ? 8 : 16;
+  static constexpr int W = (N >= 1024) ? 8 : (N == 512) ? KW_COLW_512 : 16;
   static constexpr int T = N / 8;
-  static constexpr int TPC = (W * T >= 256) ? 1 : 256 / (W * T);  // tiles per CTA (small N)
+  // tile slots per CTA: each slot is an independent group of W*T threads with its own named barrier, so that the
+  // exchange phases of one slot overlap the butterfly phases of the other
+  static constexpr int TPC = (W * T >= KW_COL_MAXTHREADS) ? 1 : (W * T >= 256 ? KW_COL_MAXTHREADS / (W * T) : 256 / (W * T));
   static constexpr int THREADS = W * T * TPC;
   static constexpr size_t TILE = (size_t)N * W * sizeof(float2);
   static constexpr size_t SMEM_COL = 2 * TPC * TILE;
@@ -211,7 +219,7 @@ template <int N, int DIR> __global__ void __launch_bounds__(ColCfg<N>::THREADS, 
     } else {
       cp_async_wait<0>();
     }
-    ColExchange<W> ex{buf0 + (size_t)b * N * W};
+    ColExchange<W, (C::TPC > 1 && W * T >= 32) ? W * T : 0> ex{buf0 + (size_t)b * N * W, 1 + tz};
     float2 v[1][8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) v[0][r] = ex.get(0, t + r * T);
@@ -288,7 +296,7 @@ template <int N> __global__ void __launch_bounds__(ColCfg<N>::THREADS, 1) k_zmid
     } else {
       cp_async_wait<1>();
     }
-    ColExchange<W> ex{buf0 + (size_t)b * N * W};
+    ColExchange<W, (C::TPC > 1 && W * T >= 32) ? W * T : 0> ex{buf0 + (size_t)b * N * W, 1 + tz};
     float2 v[1][8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) v[0][r] = ex.get(0, t + r * T);

@@ -98,6 +98,7 @@ struct Stream {
   bool all = false;  // whole-domain aggregate
   float* dbuf = nullptr;
   size_t row = 0, cap_rows = 0, rows = 0;
+  bool fused_this_step = false;  // accumulated by the kernel that produced the field
 };
 
 struct Geometry {
@@ -730,11 +731,43 @@ template <int OP> static void sample_one(kw_ctx* c, Stream& s, const float* src,
   }
 }
 
+// Aggregates of p that the pressure-producing epilogue can accumulate itself.  Returns false when nothing is fused.
+static bool fused_p_sample(kw_ctx* c, FusedSample* fs, double* extra_bytes) {
+  memset(fs, 0, sizeof(*fs));
+  const kw_config& cf = c->cfg;
+  if (c->t < cf.sampling_start_index) return false;
+  if (c->t == 0 && cf.p0_source_flag == 1) return false;  // p is overwritten by the initial pressure afterwards
+  bool any = false;
+  *extra_bytes = 0;
+  auto take = [&](int sid, float** slot, double bytes) {
+    Stream& s = c->streams[sid];
+    if (!s.enabled) return;
+    *slot = s.dbuf, s.fused_this_step = true, any = true, *extra_bytes += bytes;
+  };
+  take(KW_S_P_MAX_ALL, &fs->max_all, 8.0 * c->g.n);
+  take(KW_S_P_MIN_ALL, &fs->min_all, 8.0 * c->g.n);
+  if (cf.sensor_mask_type == 1 && c->ncuboids == 1) {
+    take(KW_S_P_RMS, &fs->rms, 8.0 * c->nsens);
+    take(KW_S_P_MAX, &fs->mx, 8.0 * c->nsens);
+    take(KW_S_P_MIN, &fs->mn, 8.0 * c->nsens);
+    if (fs->rms || fs->mx || fs->mn) {
+      const auto& h = c->h_idx[KW_SENSOR_MASK_CORNERS];
+      fs->x0 = (int)h[0], fs->y0 = (int)h[1], fs->z0 = (int)h[2], fs->x1 = (int)h[3], fs->y1 = (int)h[4], fs->z1 = (int)h[5];
+      fs->cub = (c->nsens == c->g.n) ? 1 : 2;
+    }
+  }
+  return any;
+}
+
 // OutputStreamContainer::sampleStreams (Containers/OutputStreamContainer.cpp:364-373): enum order
 static void sample_streams(kw_ctx* c) {
   for (int sid = 0; sid < KW_STREAM_COUNT; ++sid) {
     Stream& s = c->streams[sid];
     if (!s.enabled) continue;
+    if (s.fused_this_step) {
+      s.fused_this_step = false;
+      continue;
+    }
     const float* src = s.src == 0 ? c->d[KW_P] : c->d[KW_UX_SGX + (s.src - 1)];
     switch (s.op) {
       case kOpNone: sample_one<kOpNone>(c, s, src, s.dbuf + s.rows * s.row); s.rows++; break;
@@ -800,12 +833,14 @@ static int step(kw_ctx* c) {
     e.dt = cf.dt, e.nonlinear = cf.nonlinear_flag, e.absorbing = cf.absorbing_flag;
     e.defer_terms = p_src && cf.p_source_mode == KW_SRC_ADDITIVE;
     e.outA = c->tA, e.outB = c->tB, e.outNL = c->tNL, e.p = c->d[KW_P];
+    double fused_bytes = 0;
+    if (!cf.absorbing_flag && !p_src) e.sample = fused_p_sample(c, &e.fs, &fused_bytes);
     {
       double per = 24.0 + (c->count[KW_RHO0] > 1 ? 4.0 : 0.0);  // rho r/w, rho0
       if (cf.absorbing_flag) per += 4.0 + (e.defer_terms ? 0.0 : 4.0 + (cf.nonlinear_flag ? 4.0 : 0.0));  // A, B, NL
       else if (!e.defer_terms) per += 4.0 + (c->count[KW_C0] > 1 ? 4.0 : 0.0);                               // p, c2
       if (cf.nonlinear_flag && !e.defer_terms && c->count[KW_BONA] > 1) per += 4.0;
-      inverse_yx(c, c->S, 3, "xinv_density", 24.0 * g.nc + per * g.n,
+      inverse_yx(c, c->S, 3, "xinv_density", 24.0 * g.nc + per * g.n + fused_bytes,
                  [&](int pb, int pe) { g.ox->xinv_density(xinv_args<3>(c, c->S, pb, pe), e, c->st); });
     }
     // ---- addPressureSource (cpp:2310-2334)
@@ -840,7 +875,9 @@ static int step(kw_ctx* c) {
     e.p = c->d[KW_P], e.base = cf.nonlinear_flag ? c->tNL : c->tB;
     e.c2 = c->fld(KW_C0), e.tau = c->fld(KW_ABSORB_TAU), e.eta = c->fld(KW_ABSORB_ETA), e.fd = fd;
     const double per = 8.0 + (c->count[KW_C0] > 1 ? 4.0 : 0.0) + (c->count[KW_ABSORB_TAU] > 1 ? 8.0 : 0.0);
-    inverse_yx(c, c->S, 2, "xinv_pressure_sum", 16.0 * g.nc + per * g.n,
+    double fused_bytes = 0;
+    e.sample = fused_p_sample(c, &e.fs, &fused_bytes);
+    inverse_yx(c, c->S, 2, "xinv_pressure_sum", 16.0 * g.nc + per * g.n + fused_bytes,
                [&](int pb, int pe) { g.ox->xinv_psum(xinv_args<2>(c, c->S, pb, pe), e, c->st); });
   }
   // ---- addInitialPressureSource (cpp:2359-2396)

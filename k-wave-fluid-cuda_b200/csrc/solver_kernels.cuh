@@ -20,10 +20,36 @@ struct Fld {
   __device__ __forceinline__ float at(size_t i) const { return p ? __ldg(p + i) : s; }
 };
 
+// Whole-domain and cuboid aggregates of a field, accumulated by the kernel that produces the field (in-step sampling:
+// the reference runs cudaSampleAll / cudaSampleCuboid as separate full passes, OutputStreamsCudaKernels.cu:202-316).
+struct FusedSample {
+  float* max_all;
+  float* min_all;
+  float* rms;  // aggregates over ONE sensor cuboid (x fastest inside the cuboid); more cuboids use the stand-alone kernel
+  float* mx;
+  float* mn;
+  int cub;  // 0: no cuboid aggregate, 1: cuboid == whole domain (buffer index == voxel index), 2: general cuboid
+  int x0, x1, y0, y1, z0, z1;
+  __device__ __forceinline__ void operator()(size_t i, int x, int y, int z, float p) const {
+    if (max_all) max_all[i] = fmaxf(max_all[i], p);
+    if (min_all) min_all[i] = fminf(min_all[i], p);
+    if (cub == 0) return;
+    size_t j = i;
+    if (cub == 2) {
+      if (x < x0 || x > x1 || y < y0 || y > y1 || z < z0 || z > z1) return;
+      j = ((size_t)(z - z0) * (y1 - y0 + 1) + (y - y0)) * (x1 - x0 + 1) + (x - x0);
+    }
+    if (rms) rms[j] += p * p;
+    if (mx) mx[j] = fmaxf(mx[j], p);
+    if (mn) mn[j] = fminf(mn[j], p);
+  }
+};
+
 // ---- epilogues of k_xinv -----------------------------------------------------------------------------------------
 // res[f][m] = (value in row a, value in row b) at x = t + m*T; row b = row a + 1 (same z, y+1).
 
-struct EpiStore {  // plain C2R:  out = scale * ifft
+struct EpiStore {
+  static constexpr int kMinBlocks = 3;  // CTAs per SM the register budget is sized for  // plain C2R:  out = scale * ifft
   float* out[3];
   float scale;
   template <int N> __device__ __forceinline__ void apply(float2 (&res)[1][8], int t, size_t row0, int, int) const {
@@ -37,7 +63,8 @@ struct EpiStore {  // plain C2R:  out = scale * ifft
   }
 };
 
-struct EpiAdd {  // additive (k-space corrected) source: target_j += ifft   (SolverCudaKernels.cu:765-807)
+struct EpiAdd {
+  static constexpr int kMinBlocks = 3;  // CTAs per SM the register budget is sized for  // additive (k-space corrected) source: target_j += ifft   (SolverCudaKernels.cu:765-807)
   float* out[3];
   int ntargets;
   template <int N> __device__ __forceinline__ void apply(float2 (&res)[1][8], int t, size_t row0, int, int) const {
@@ -56,6 +83,7 @@ struct EpiAdd {  // additive (k-space corrected) source: target_j += ifft   (Sol
 // u_i = (u_i*pml_i - (fd*g_i)*dtrho_i)*pml_i      (SolverCudaKernels.cu:199-212; homogeneous :287-305)
 // init: u_i = g_i * (dtrho_i * (fd*0.5))            (SolverCudaKernels.cu:971-980)
 struct EpiVelocity {
+  static constexpr int kMinBlocks = 3;  // CTAs per SM the register budget is sized for
   float* u[3];
   Fld dtrho[3];
   const float* pml_sg[3];
@@ -97,6 +125,7 @@ struct EpiVelocity {
 //  absorbing: A = rho0*(dux+duy+duz) ; B = sum r ; NL = (BonA*B*B)/(2 rho0) + B        (:1588-1601, :1733-1741)
 //  lossless:  p = c2*(B + BonA*(B*B)/(2 rho0))  |  p = c2*B                            (:2079-2082, :2229-2235)
 struct EpiDensity {
+  static constexpr int kMinBlocks = 2;  // CTAs per SM the register budget is sized for
   float* rho[3];
   Fld rho0, bona, c2;
   const float* pml[3];
@@ -107,43 +136,61 @@ struct EpiDensity {
   float* outB;
   float* outNL;
   float* p;
-  __device__ __forceinline__ void voxel(size_t i, float px, float py, float pz, float dux, float duy, float duz) const {
-    float rx = rho[0][i], ry = rho[1][i], rz = rho[2][i];
-    const float r0 = rho0.at(i);
-    if (nonlinear) {
-      const float s = (2.0f * (rx + ry + rz) + r0) * dt;
-      rx = px * ((px * rx) - s * dux);
-      ry = py * ((py * ry) - s * duy);
-      rz = pz * ((pz * rz) - s * duz);
-    } else {
-      const float d = dt * r0;
-      rx = px * (px * rx - d * dux);
-      ry = py * (py * ry - d * duy);
-      rz = pz * (pz * rz - d * duz);
-    }
-    rho[0][i] = rx;
-    rho[1][i] = ry;
-    rho[2][i] = rz;
-    if (absorbing) outA[i] = r0 * (dux + duy + duz);
-    if (defer_terms) return;
-    const float sum = rx + ry + rz;
-    if (absorbing) {
-      outB[i] = sum;
-      if (nonlinear) outNL[i] = ((bona.at(i) * sum * sum) / (2.0f * r0)) + sum;
-    } else {
-      p[i] = nonlinear ? c2.at(i) * (sum + (bona.at(i) * (sum * sum) / (2.0f * r0))) : c2.at(i) * sum;
-    }
-  }
+  FusedSample fs;  // sampling of p when this epilogue produces the final pressure of the step (lossless)
+  int sample;
   template <int N> __device__ __forceinline__ void apply(float2 (&res)[3][8], int t, size_t row0, int y, int z) const {
     constexpr int T = N / 8;
+    // restrict-qualified locals: the arrays never alias, which lets the loads of all voxels be issued ahead of the stores
+    float* __restrict__ rxp = rho[0];
+    float* __restrict__ ryp = rho[1];
+    float* __restrict__ rzp = rho[2];
+    float* __restrict__ oA = outA;
+    float* __restrict__ oB = outB;
+    float* __restrict__ oNL = outNL;
+    float* __restrict__ pp = p;
     const float pya = __ldg(pml[1] + y), pyb = __ldg(pml[1] + y + 1), pz = __ldg(pml[2] + z);
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      const int x = t + m * T;
-      const size_t i = row0 * N + x;
-      const float px = __ldg(pml[0] + x);
-      voxel(i, px, pya, pz, res[0][m].x, res[1][m].x, res[2][m].x);
-      voxel(i + N, px, pyb, pz, res[0][m].y, res[1][m].y, res[2][m].y);
+    for (int h = 0; h < 2; ++h) {  // two batches of 4 x-positions x 2 rows: loads first, then arithmetic, then stores
+      float rx[8], ry[8], rz[8], r0[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const size_t i = row0 * N + (q & 1) * N + t + (h * 4 + (q >> 1)) * T;
+        rx[q] = rxp[i], ry[q] = ryp[i], rz[q] = rzp[i], r0[q] = rho0.at(i);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int m = h * 4 + (q >> 1), x = t + m * T;
+        const size_t i = row0 * N + (q & 1) * N + x;
+        const float px = __ldg(pml[0] + x), py = (q & 1) ? pyb : pya;
+        const float dux = (q & 1) ? res[0][m].y : res[0][m].x;
+        const float duy = (q & 1) ? res[1][m].y : res[1][m].x;
+        const float duz = (q & 1) ? res[2][m].y : res[2][m].x;
+        float ax = rx[q], ay = ry[q], az = rz[q];
+        if (nonlinear) {
+          const float s = (2.0f * (ax + ay + az) + r0[q]) * dt;
+          ax = px * ((px * ax) - s * dux);
+          ay = py * ((py * ay) - s * duy);
+          az = pz * ((pz * az) - s * duz);
+        } else {
+          const float d = dt * r0[q];
+          ax = px * (px * ax - d * dux);
+          ay = py * (py * ay - d * duy);
+          az = pz * (pz * az - d * duz);
+        }
+        rxp[i] = ax, ryp[i] = ay, rzp[i] = az;
+        if (absorbing) oA[i] = r0[q] * (dux + duy + duz);
+        if (!defer_terms) {
+          const float sum = ax + ay + az;
+          if (absorbing) {
+            oB[i] = sum;
+            if (nonlinear) oNL[i] = ((bona.at(i) * sum * sum) / (2.0f * r0[q])) + sum;
+          } else {
+            const float pv = nonlinear ? c2.at(i) * (sum + (bona.at(i) * (sum * sum) / (2.0f * r0[q]))) : c2.at(i) * sum;
+            pp[i] = pv;
+            if (sample) fs(i, x, y + (q & 1), z, pv);
+          }
+        }
+      }
     }
   }
 };
@@ -151,18 +198,69 @@ struct EpiDensity {
 // p = c2*(NL + fd*((ta*tau) - (tb*eta)))   nonlinear  (SolverCudaKernels.cu:1872-1878)
 // p = c2*(B  + fd*(ta*tau - tb*eta))       linear     (:1973-1979)
 struct EpiPressureSum {
+  static constexpr int kMinBlocks = 2;  // CTAs per SM the register budget is sized for
   float* p;
   const float* base;  // NL (nonlinear) or B (linear)
   Fld c2, tau, eta;
   float fd;
-  template <int N> __device__ __forceinline__ void apply(float2 (&res)[2][8], int t, size_t row0, int, int) const {
+  FusedSample fs;
+  int sample;
+  template <int N> __device__ __forceinline__ void apply(float2 (&res)[2][8], int t, size_t row0, int y, int z) const {
     constexpr int T = N / 8;
+    float* __restrict__ pp = p;
+    float pv[16];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      const size_t i = row0 * N + t + m * T;
-      p[i] = c2.at(i) * (__ldg(base + i) + fd * ((res[0][m].x * tau.at(i)) - (res[1][m].x * eta.at(i))));
-      p[i + N] = c2.at(i + N) * (__ldg(base + i + N) + fd * ((res[0][m].y * tau.at(i + N)) - (res[1][m].y * eta.at(i + N))));
+    for (int q = 0; q < 16; ++q) {
+      const int m = q >> 1;
+      const size_t i = row0 * N + (q & 1) * N + t + m * T;
+      const float ta = (q & 1) ? res[0][m].y : res[0][m].x, tb = (q & 1) ? res[1][m].y : res[1][m].x;
+      pv[q] = c2.at(i) * (__ldg(base + i) + fd * ((ta * tau.at(i)) - (tb * eta.at(i))));
     }
+    if (sample) {
+      float* __restrict__ mxa = fs.max_all;
+      float* __restrict__ mna = fs.min_all;
+      float* __restrict__ rms = fs.rms;
+      float* __restrict__ cmx = fs.mx;
+      float* __restrict__ cmn = fs.mn;
+      if (fs.cub != 2) {  // whole-domain buffers: index == voxel index; batches of loads, then stores
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          float a0[4], a1[4], a2[4], a3[4], a4[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int q = h * 4 + k;
+            const size_t i = row0 * N + (q & 1) * N + t + (q >> 1) * T;
+            if (mxa) a0[k] = mxa[i];
+            if (mna) a1[k] = mna[i];
+            if (fs.cub == 1) {
+              if (rms) a2[k] = rms[i];
+              if (cmx) a3[k] = cmx[i];
+              if (cmn) a4[k] = cmn[i];
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int q = h * 4 + k;
+            const size_t i = row0 * N + (q & 1) * N + t + (q >> 1) * T;
+            if (mxa) mxa[i] = fmaxf(a0[k], pv[q]);
+            if (mna) mna[i] = fminf(a1[k], pv[q]);
+            if (fs.cub == 1) {
+              if (rms) rms[i] = a2[k] + pv[q] * pv[q];
+              if (cmx) cmx[i] = fmaxf(a3[k], pv[q]);
+              if (cmn) cmn[i] = fminf(a4[k], pv[q]);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int x = t + (q >> 1) * T;
+          fs(row0 * N + (q & 1) * N + x, x, y + (q & 1), z, pv[q]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) pp[row0 * N + (q & 1) * N + t + (q >> 1) * T] = pv[q];
   }
 };
 
