@@ -74,19 +74,19 @@ template <int ID, class K> static int col_grid(K kernel, int ntiles, size_t smem
 
 static void col(const ColArgs& a, int dir, int nfields, cudaStream_t st) {
   using C = ColCfg<N>;
-  const dim3 block(C::W, C::T, C::TPC);
+  const dim3 block(C::W, C::WK, C::TPC);
   if (dir < 0) {
-    const int g = col_grid<0>(k_col<N, -1>, a.tile_end - a.tile_begin, C::SMEM_COL);
-    k_col<N, -1><<<dim3(g, nfields), block, C::SMEM_COL, st>>>(a);
+    const int g = col_grid<0>(k_col<N, -1>, a.tile_end - a.tile_begin, C::SMEM);
+    k_col<N, -1><<<dim3(g, nfields), block, C::SMEM, st>>>(a);
   } else {
-    const int g = col_grid<1>(k_col<N, +1>, a.tile_end - a.tile_begin, C::SMEM_COL);
-    k_col<N, +1><<<dim3(g, nfields), block, C::SMEM_COL, st>>>(a);
+    const int g = col_grid<1>(k_col<N, +1>, a.tile_end - a.tile_begin, C::SMEM);
+    k_col<N, +1><<<dim3(g, nfields), block, C::SMEM, st>>>(a);
   }
 }
 static void zmid(const ZMidArgs& a, int nfields, cudaStream_t st) {
   using C = ColCfg<N>;
   const int g = col_grid<2>(k_zmid<N>, a.ntiles, C::SMEM_ZMID);
-  k_zmid<N><<<dim3(g, nfields), dim3(C::W, C::T, C::TPC), C::SMEM_ZMID, st>>>(a);
+  k_zmid<N><<<dim3(g, nfields), dim3(C::W, C::WK, C::TPC), C::SMEM_ZMID, st>>>(a);
 }
 
 }  // namespace inst_<N>

@@ -11,6 +11,7 @@
 // (KSpaceSolver/SolverCudaKernels.cu:1139,1210,1812,740).
 #pragma once
 #include "fft_core.cuh"
+#include "fft_core2.cuh"
 
 namespace kw {
 
@@ -136,43 +137,46 @@ template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads,
 // ---------------------------------------------------------------------------------------------------------------------
 // column passes (y and z axes)
 //
-// A tile is W neighbouring kx (W*8 bytes contiguous: 128-byte segments for W = 16) times all N points of the transform
-// axis.  One worker = W lanes; a thread owns 8 points of one kx.  Tiles are double buffered in shared memory: while
-// tile i is transformed, the points of tile i+1 arrive through cp.async (LDGSTS), each thread fetching exactly the
-// 8 points it will consume in the first radix-8 stage, so the global-load latency is off the critical path and no
-// registers are spent on staging.  The landing buffer of a tile is also its exchange buffer.
-#ifndef KW_COLW_512
-#define KW_COLW_512 16
-#endif
-#ifndef KW_COL_MAXTHREADS
-#define KW_COL_MAXTHREADS 1024
-#endif
+// A tile is W = 16 neighbouring kx (128-byte segments) times all N points of the transform axis.  One worker = 16 lanes;
+// a thread owns E = 8..32 points of one kx in registers and the transform is two register-resident butterflies
+// (radix 8/16/32, compile-time twiddles) around ONE shared-memory exchange (fft_core2.cuh).  Points go from global
+// memory straight into registers and back; shared memory only carries the exchange.
 template <int N> struct ColCfg {
-  static constexpr int W = (N >= 1024) ? 8 : (N == 512) ? KW_COLW_512 : 16;
-  static constexpr int T = N / 8;
-  // tile slots per CTA: each slot is an independent group of W*T threads with its own named barrier, so that the
-  // exchange phases of one slot overlap the butterfly phases of the other
-  static constexpr int TPC = (W * T >= KW_COL_MAXTHREADS) ? 1 : (W * T >= 256 ? KW_COL_MAXTHREADS / (W * T) : 256 / (W * T));
-  static constexpr int THREADS = W * T * TPC;
-  static constexpr size_t TILE = (size_t)N * W * sizeof(float2);
-  static constexpr size_t SMEM_COL = 2 * TPC * TILE;
-  static constexpr size_t SMEM_ZMID = 2 * TPC * TILE + TPC * (size_t)N * W * sizeof(float);
+  using P = Plan2<N>;
+  static constexpr int W = 16;
+  static constexpr int WK = P::WK;                                         // workers (threads per kx) of a tile
+  static constexpr int SLOT = W * WK;                                      // threads of a tile slot
+  static constexpr int TPC = (SLOT >= 256) ? 1 : 256 / SLOT;               // tile slots per CTA
+  static constexpr int THREADS = SLOT * TPC;
+  static constexpr int MINB = (THREADS * 128 <= 32768) ? 2 : 1;            // CTAs per SM at <= 128 registers
+  static constexpr size_t SMEM = (P::R2 > 1) ? (size_t)TPC * N * W * sizeof(float2) : 0;
+  static constexpr size_t SMEM_ZMID = SMEM + (size_t)TPC * N * W * sizeof(float);  // + landing area of the real multiplier
+  // barrier flavour of a slot: whole CTA, named barrier (slot spans whole warps), or none (single-stage plans)
+  static constexpr int BAR_THREADS = (P::R2 == 1) ? -1 : (TPC == 1 ? 0 : SLOT);
 };
 
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory"); }
 
+template <int W, int NTHREADS> struct ColExchange2 {
+  float2* buf;  // tile buffer + lane
+  int bar;      // named barrier id of this slot
+  __device__ __forceinline__ void put(int i, float2 x) { buf[i * W] = x; }
+  __device__ __forceinline__ float2 get(int i) const { return buf[i * W]; }
+  __device__ __forceinline__ void sync() {
+    if (NTHREADS == 0) __syncthreads();
+    else if (NTHREADS > 0) asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(NTHREADS > 0 ? NTHREADS : 32) : "memory");
+  }
+};
+
 // twiddles of the transform length of this translation unit, in constant memory (index is uniform per worker)
 #ifdef KW_N
 __constant__ float2 c_tw[KW_N];
-struct ConstTw {
-  __device__ __forceinline__ float2 get(int, int m) const { return c_tw[m]; }
+struct ConstTab {
+  __device__ __forceinline__ float2 operator()(int m) const { return c_tw[m]; }
 };
 #endif
 
@@ -185,51 +189,29 @@ struct ColArgs {
 };
 
 #ifdef KW_N
-template <int N, int DIR> __global__ void __launch_bounds__(ColCfg<N>::THREADS, 1) k_col(ColArgs a) {
+template <int N, int DIR> __global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MINB) k_col(ColArgs a) {
   using C = ColCfg<N>;
-  constexpr int W = C::W, T = C::T;
+  using P = Plan2<N>;
+  constexpr int W = C::W, WK = C::WK, E = P::E;
   extern __shared__ float2 smem[];
-  const int lane = threadIdx.x, t = threadIdx.y, tz = threadIdx.z;
-  float2* const buf0 = smem + (size_t)tz * 2 * N * W + lane;  // two landing/exchange buffers per tile slot
-  ConstTw twp;
+  const int lane = threadIdx.x, w = threadIdx.y, tz = threadIdx.z;
+  ColExchange2<W, C::BAR_THREADS> ex{smem + (size_t)tz * N * W + lane, 1 + tz};
   float2* __restrict__ data = a.data[blockIdx.y];
   const int ntiles = a.tile_end - a.tile_begin;
   const int niter = (ntiles + C::TPC - 1) / C::TPC;
-  auto tile_base = [&](int it, bool& valid) -> size_t {
+  for (int it = blockIdx.x; it < niter; it += gridDim.x) {
     const int tile = a.tile_begin + it * C::TPC + tz;
-    valid = tile < a.tile_end;
+    const bool valid = tile < a.tile_end;
     const int tl = valid ? tile : a.tile_begin;
-    return (size_t)(tl / a.ngroups) * a.outer_stride + (size_t)(tl % a.ngroups) * W + lane;
-  };
-  auto prefetch = [&](int it, int b) {
-    bool valid;
-    const size_t base = tile_base(it, valid);
-    float2* dst = buf0 + (size_t)b * N * W;
+    float2* p = data + (size_t)(tl / a.ngroups) * a.outer_stride + (size_t)(tl % a.ngroups) * W + lane + (size_t)w * a.stride;
+    const size_t estride = (size_t)WK * a.stride;
+    float2 v[E];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) cp_async8(dst + (t + r * T) * W, data + base + (size_t)(t + r * T) * a.stride);
-    cp_async_commit();
-  };
-  int it = blockIdx.x, b = 0;
-  if (it < niter) prefetch(it, 0);
-  for (; it < niter; it += gridDim.x, b ^= 1) {
-    const int nxt = it + gridDim.x;
-    if (nxt < niter) {
-      prefetch(nxt, b ^ 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    ColExchange<W, (C::TPC > 1 && W * T >= 32) ? W * T : 0> ex{buf0 + (size_t)b * N * W, 1 + tz};
-    float2 v[1][8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) v[0][r] = ex.get(0, t + r * T);
-    ex.sync();  // everyone holds its own points: the landing buffer becomes the exchange buffer
-    fft_worker<N, DIR, 1>(v, t, 0, twp, ex);
-    bool valid;
-    const size_t base = tile_base(it, valid);
+    for (int e = 0; e < E; ++e) v[e] = p[e * estride];
+    fft2_worker<N, DIR>(v, w, ex, ConstTab());
     if (valid) {
 #pragma unroll
-      for (int r = 0; r < 8; ++r) data[base + (size_t)(t + r * T) * a.stride] = v[0][r];
+      for (int e = 0; e < E; ++e) p[e * estride] = v[e];
     }
   }
 }
@@ -251,74 +233,54 @@ struct ZMidArgs {
 };
 
 #ifdef KW_N
-template <int N> __global__ void __launch_bounds__(ColCfg<N>::THREADS, 1) k_zmid(ZMidArgs a) {
+template <int N> __global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MINB) k_zmid(ZMidArgs a) {
   using C = ColCfg<N>;
-  constexpr int W = C::W, T = C::T;
+  using P = Plan2<N>;
+  constexpr int W = C::W, WK = C::WK, E = P::E;
   extern __shared__ float2 smem[];
-  const int lane = threadIdx.x, t = threadIdx.y, tz = threadIdx.z;
-  float2* const buf0 = smem + (size_t)tz * 2 * N * W + lane;
-  float* const mulbuf = reinterpret_cast<float*>(smem + (size_t)C::TPC * 2 * N * W) + (size_t)tz * N * W + lane;
-  ConstTw twp;
+  const int lane = threadIdx.x, w = threadIdx.y, tz = threadIdx.z;
+  ColExchange2<W, C::BAR_THREADS> ex{smem + (size_t)tz * N * W + lane, 1 + tz};
+  float* const mulbuf = reinterpret_cast<float*>(smem + C::SMEM / sizeof(float2)) + (size_t)tz * N * W + w * W + lane;
   const ZField fld = a.f[blockIdx.y];
   const int niter = (a.ntiles + C::TPC - 1) / C::TPC;
-  auto tile_base = [&](int it, bool& valid, int& y, int& kx) -> size_t {
+  const size_t estride = (size_t)WK * a.plane;
+  for (int it = blockIdx.x; it < niter; it += gridDim.x) {
     const int tile = it * C::TPC + tz;
-    valid = tile < a.ntiles;
+    const bool valid = tile < a.ntiles;
     const int tl = valid ? tile : 0;
-    y = tl / a.ngroups, kx = (tl % a.ngroups) * W + lane;
-    return (size_t)y * a.nxp + kx;
-  };
-  auto prefetch = [&](int it, int b) {
-    bool valid;
-    int y, kx;
-    const size_t base = tile_base(it, valid, y, kx);
-    float2* dst = buf0 + (size_t)b * N * W;
+    const int y = tl / a.ngroups, kx = (tl % a.ngroups) * W + lane;
+    const size_t base = (size_t)y * a.nxp + kx + (size_t)w * a.plane;  // point e of this worker: base + e*estride
+    float2 v[E];
+    {
+      const float2* __restrict__ p = fld.in + base;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) cp_async8(dst + (t + r * T) * W, fld.in + base + (size_t)(t + r * T) * a.plane);
-    cp_async_commit();
-  };
-  int it = blockIdx.x, b = 0;
-  if (it < niter) prefetch(it, 0);
-  for (; it < niter; it += gridDim.x, b ^= 1) {
-    bool valid;
-    int y, kx;
-    const size_t base = tile_base(it, valid, y, kx);
-    // multiplier of this tile: lands while the forward transform runs (single buffer, consumed after it)
-    if (fld.mul) {
+      for (int e = 0; e < E; ++e) v[e] = __ldg(p + e * estride);
+    }
+    // the real multiplier of this tile lands in shared memory (cp.async, thread-private slots) while the forward
+    // transform runs: no registers, no exposed latency
+    const float* __restrict__ mp = fld.mul ? fld.mul + base : nullptr;
+    if (mp) {
 #pragma unroll
-      for (int r = 0; r < 8; ++r) cp_async4(mulbuf + (t + r * T) * W, fld.mul + base + (size_t)(t + r * T) * a.plane);
+      for (int e = 0; e < E; ++e) cp_async4(mulbuf + e * (WK * W), mp + e * estride);
     }
     cp_async_commit();
-    const int nxt = it + gridDim.x;
-    if (nxt < niter) {
-      prefetch(nxt, b ^ 1);
-      cp_async_wait<2>();  // tile `it` has landed; its multiplier and the next tile may still be in flight
-    } else {
-      cp_async_wait<1>();
-    }
-    ColExchange<W, (C::TPC > 1 && W * T >= 32) ? W * T : 0> ex{buf0 + (size_t)b * N * W, 1 + tz};
-    float2 v[1][8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) v[0][r] = ex.get(0, t + r * T);
-    ex.sync();
-    fft_worker<N, -1, 1>(v, t, 0, twp, ex);
-    if (nxt < niter) cp_async_wait<1>();
-    else cp_async_wait<0>();
+    fft2_worker<N, -1>(v, w, ex, ConstTab());
+    cp_async_wait<0>();
     float2 w01 = make_float2(1.f, 0.f);
     if (fld.vec && fld.axis < 2) w01 = __ldg(fld.vec + (fld.axis == 0 ? kx : y));
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int kz = t + r * T;
-      float m = fld.scal;
-      if (fld.mul) m = mulbuf[kz * W] * fld.scal;
-      float2 e = cscale(v[0][r], m);
-      if (fld.vec) e = cmul(e, fld.axis == 2 ? __ldg(fld.vec + kz) : w01);
-      v[0][r] = e;
+    for (int e = 0; e < E; ++e) {
+      const int kz = w + WK * e;
+      const float m = mp ? mulbuf[e * (WK * W)] * fld.scal : fld.scal;
+      float2 x = cscale(v[e], m);
+      if (fld.vec) x = cmul(x, fld.axis == 2 ? __ldg(fld.vec + kz) : w01);
+      v[e] = x;
     }
-    fft_worker<N, +1, 1>(v, t, 0, twp, ex);
+    fft2_worker<N, +1>(v, w, ex, ConstTab());
     if (valid) {
+      float2* __restrict__ p = fld.out + base;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) fld.out[base + (size_t)(t + r * T) * a.plane] = v[0][r];
+      for (int e = 0; e < E; ++e) p[e * estride] = v[e];
     }
   }
 }
