@@ -3,6 +3,8 @@
 // (N = 16, 32).  Compared with the radix-8 Stockham chain of fft_core.cuh this halves the shared-memory instruction
 // count and the barriers per transform, which is what bounds the column passes on sm_100a (ncu: mio_throttle).
 #pragma once
+#include <utility>
+
 #include "fft_core.cuh"
 
 namespace kw {
@@ -15,6 +17,13 @@ KW_HD constexpr cf2 w32(int m) {
   constexpr cf2 t[32] = {{1.0f, 0.0f}, {0.9807852804032304f, -0.19509032201612825f}, {0.9238795325112867f, -0.3826834323650898f}, {0.8314696123025452f, -0.5555702330196022f}, {0.7071067811865476f, -0.7071067811865475f}, {0.5555702330196023f, -0.8314696123025452f}, {0.38268343236508984f, -0.9238795325112867f}, {0.19509032201612833f, -0.9807852804032304f}, {0.0f, -1.0f}, {-0.1950903220161282f, -0.9807852804032304f}, {-0.3826834323650897f, -0.9238795325112867f}, {-0.555570233019602f, -0.8314696123025455f}, {-0.7071067811865475f, -0.7071067811865476f}, {-0.8314696123025453f, -0.5555702330196022f}, {-0.9238795325112867f, -0.3826834323650899f}, {-0.9807852804032304f, -0.1950903220161286f}, {-1.0f, 0.0f}, {-0.9807852804032304f, 0.19509032201612836f}, {-0.9238795325112868f, 0.38268343236508967f}, {-0.8314696123025455f, 0.555570233019602f}, {-0.7071067811865477f, 0.7071067811865475f}, {-0.5555702330196022f, 0.8314696123025452f}, {-0.38268343236509034f, 0.9238795325112865f}, {-0.19509032201612866f, 0.9807852804032303f}, {0.0f, 1.0f}, {0.1950903220161283f, 0.9807852804032304f}, {0.38268343236509f, 0.9238795325112866f}, {0.5555702330196018f, 0.8314696123025455f}, {0.7071067811865474f, 0.7071067811865477f}, {0.8314696123025452f, 0.5555702330196022f}, {0.9238795325112865f, 0.3826834323650904f}, {0.9807852804032303f, 0.19509032201612872f}};
   return t[m & 31];
 }
+
+// compile-time loop: f(std::integral_constant<int, i>) for i in [0, N) -- the index is a constant expression for the
+// front end, so twiddles picked with it become immediates (a plain unrolled loop leaves the table in local memory)
+template <int... Is, class F> KW_HD void static_for_impl(std::integer_sequence<int, Is...>, F&& f) {
+  (f(std::integral_constant<int, Is>{}), ...);
+}
+template <int N, class F> KW_HD void static_for(F&& f) { static_for_impl(std::make_integer_sequence<int, N>{}, f); }
 
 template <int DIR> KW_HD float2 cmulc(float2 a, cf2 w) {  // a * w (forward) or a * conj(w) (inverse), w compile-time
   return DIR < 0 ? make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x)
@@ -70,10 +79,15 @@ template <int R, int DIR, int STR, int OFF, int LEN> KW_HD void dftR(float2 (&v)
     // 4 (n2) x 4 (n1):  slot n2 + 4 k1 <- DFT4 over n1 of x[4 n1 + n2]
 #pragma unroll
     for (int n2 = 0; n2 < 4; ++n2) dft4r<DIR>(KW_V(n2), KW_V(n2 + 4), KW_V(n2 + 8), KW_V(n2 + 12));
-#pragma unroll
-    for (int k1 = 1; k1 < 4; ++k1)
-#pragma unroll
-      for (int n2 = 1; n2 < 4; ++n2) KW_V(n2 + 4 * k1) = cmulc<DIR>(KW_V(n2 + 4 * k1), w32(2 * n2 * k1));
+    static_for<4>([&](auto K1) {
+      static_for<4>([&](auto N2) {
+        constexpr int k1 = decltype(K1)::value, n2 = decltype(N2)::value;
+        if constexpr (k1 > 0 && n2 > 0) {
+          constexpr cf2 tw = w32(2 * n2 * k1);
+          KW_V(n2 + 4 * k1) = cmulc<DIR>(KW_V(n2 + 4 * k1), tw);
+        }
+      });
+    });
     // slot k2 + 4 k1 <- X[k1 + 4 k2]
 #pragma unroll
     for (int k1 = 0; k1 < 4; ++k1) dft4r<DIR>(KW_V(4 * k1), KW_V(4 * k1 + 1), KW_V(4 * k1 + 2), KW_V(4 * k1 + 3));
@@ -89,10 +103,15 @@ template <int R, int DIR, int STR, int OFF, int LEN> KW_HD void dftR(float2 (&v)
 #pragma unroll
     for (int n2 = 0; n2 < 4; ++n2)
       dft8r<DIR>(KW_V(n2), KW_V(n2 + 4), KW_V(n2 + 8), KW_V(n2 + 12), KW_V(n2 + 16), KW_V(n2 + 20), KW_V(n2 + 24), KW_V(n2 + 28));
-#pragma unroll
-    for (int k1 = 1; k1 < 8; ++k1)
-#pragma unroll
-      for (int n2 = 1; n2 < 4; ++n2) KW_V(n2 + 4 * k1) = cmulc<DIR>(KW_V(n2 + 4 * k1), w32(n2 * k1));
+    static_for<8>([&](auto K1) {
+      static_for<4>([&](auto N2) {
+        constexpr int k1 = decltype(K1)::value, n2 = decltype(N2)::value;
+        if constexpr (k1 > 0 && n2 > 0) {
+          constexpr cf2 tw = w32(n2 * k1);
+          KW_V(n2 + 4 * k1) = cmulc<DIR>(KW_V(n2 + 4 * k1), tw);
+        }
+      });
+    });
     // slot k2 + 4 k1 <- X[k1 + 8 k2]
 #pragma unroll
     for (int k1 = 0; k1 < 8; ++k1) dft4r<DIR>(KW_V(4 * k1), KW_V(4 * k1 + 1), KW_V(4 * k1 + 2), KW_V(4 * k1 + 3));
@@ -122,7 +141,8 @@ template <int N> struct Plan2 {
 struct NoHook {
   __device__ __forceinline__ void operator()() const {}
 };
-// `hook` runs after the exchange reads of stage 2 have been issued (a good place to start unrelated global loads).
+// `hook` runs once every worker has read its stage-2 inputs back, i.e. when the exchange buffer is free again: the
+// kernels use it to start the asynchronous copy of the NEXT tile into that same buffer.
 template <int N, int DIR, class EX, class TAB, class HOOK = NoHook>
 __device__ __forceinline__ void fft2_worker(float2 (&v)[Plan2<N>::E], int w, EX& ex, TAB tab, HOOK hook = HOOK()) {
   using P = Plan2<N>;
@@ -146,6 +166,7 @@ __device__ __forceinline__ void fft2_worker(float2 (&v)[Plan2<N>::E], int w, EX&
     for (int q = 0; q < B2; ++q)
 #pragma unroll
       for (int r = 0; r < R2; ++r) v[q + B2 * r] = ex.get(w + q * WK + r * R1);
+    ex.sync();  // everyone holds its stage-2 inputs: the exchange buffer is free
     hook();
 #pragma unroll
     for (int q = 0; q < B2; ++q) {
@@ -159,7 +180,6 @@ __device__ __forceinline__ void fft2_worker(float2 (&v)[Plan2<N>::E], int w, EX&
       dftR<R2, DIR, B2, 1, E>(v);
       static_assert(B2 <= 2, "at most two butterflies per worker");
     }
-    ex.sync();  // the exchange buffer may be reused
   } else {
     hook();
   }

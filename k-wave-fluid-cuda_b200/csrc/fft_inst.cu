@@ -83,10 +83,19 @@ static void col(const ColArgs& a, int dir, int nfields, cudaStream_t st) {
     k_col<N, +1><<<dim3(g, nfields), block, C::SMEM, st>>>(a);
   }
 }
-static void zmid(const ZMidArgs& a, int nfields, cudaStream_t st) {
+template <int AXIS> static void zmid_axis(const ZMidArgs& a, cudaStream_t st) {
   using C = ColCfg<N>;
-  const int g = col_grid<2>(k_zmid<N>, a.ntiles, C::SMEM_ZMID);
-  k_zmid<N><<<dim3(g, nfields), dim3(C::W, C::WK, C::TPC), C::SMEM_ZMID, st>>>(a);
+  const int g = col_grid<10 + AXIS>(k_zmid<N, AXIS>, a.ntiles, C::SMEM_ZMID);
+  k_zmid<N, AXIS><<<g, dim3(C::W, C::WK, C::TPC), C::SMEM_ZMID, st>>>(a);
+}
+static void zmid(const ZMidArgs& a, cudaStream_t st) {
+  switch (a.axis) {
+    case 0: zmid_axis<0>(a, st); break;
+    case 1: zmid_axis<1>(a, st); break;
+    case 2: zmid_axis<2>(a, st); break;
+    case 3: zmid_axis<3>(a, st); break;
+    default: zmid_axis<-1>(a, st); break;
+  }
 }
 
 }  // namespace inst_<N>

@@ -150,11 +150,15 @@ template <int N> struct ColCfg {
   static constexpr int THREADS = SLOT * TPC;
   static constexpr int MINB = (THREADS * 128 <= 32768) ? 2 : 1;            // CTAs per SM at <= 128 registers
   static constexpr size_t SMEM = (P::R2 > 1) ? (size_t)TPC * N * W * sizeof(float2) : 0;
-  static constexpr size_t SMEM_ZMID = SMEM + (size_t)TPC * N * W * sizeof(float);  // + landing area of the real multiplier
+  // + landing area of the real multiplier + the z-indexed 1-D operator
+  static constexpr size_t SMEM_ZMID = SMEM + (size_t)TPC * N * W * sizeof(float) + (size_t)N * sizeof(float2);
   // barrier flavour of a slot: whole CTA, named barrier (slot spans whole warps), or none (single-stage plans)
   static constexpr int BAR_THREADS = (P::R2 == 1) ? -1 : (TPC == 1 ? 0 : SLOT);
 };
 
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
@@ -199,16 +203,44 @@ template <int N, int DIR> __global__ void __launch_bounds__(ColCfg<N>::THREADS, 
   float2* __restrict__ data = a.data[blockIdx.y];
   const int ntiles = a.tile_end - a.tile_begin;
   const int niter = (ntiles + C::TPC - 1) / C::TPC;
-  for (int it = blockIdx.x; it < niter; it += gridDim.x) {
+  const size_t estride = (size_t)WK * a.stride;
+  auto tile_ptr = [&](int it, bool& valid) -> float2* {
     const int tile = a.tile_begin + it * C::TPC + tz;
-    const bool valid = tile < a.tile_end;
+    valid = tile < a.tile_end;
     const int tl = valid ? tile : a.tile_begin;
-    float2* p = data + (size_t)(tl / a.ngroups) * a.outer_stride + (size_t)(tl % a.ngroups) * W + lane + (size_t)w * a.stride;
-    const size_t estride = (size_t)WK * a.stride;
-    float2 v[E];
+    return data + (size_t)(tl / a.ngroups) * a.outer_stride + (size_t)(tl % a.ngroups) * W + lane + (size_t)w * a.stride;
+  };
+  // The points of the next tile are copied asynchronously (LDGSTS) into the exchange buffer as soon as the current
+  // transform has read its last exchange back, each thread fetching exactly the points it will own: the global-load
+  // latency hides behind the second butterfly and the stores.  Single-stage plans (N <= 32) load straight to registers.
+  auto prefetch = [&](int it) {
+    if constexpr (P::R2 > 1) {
+      bool valid;
+      const float2* p = tile_ptr(it, valid);
 #pragma unroll
-    for (int e = 0; e < E; ++e) v[e] = p[e * estride];
-    fft2_worker<N, DIR>(v, w, ex, ConstTab());
+      for (int e = 0; e < E; ++e) cp_async8(ex.buf + (w + WK * e) * W, p + e * estride);
+      cp_async_commit();
+    }
+  };
+  int it = blockIdx.x;
+  if (it < niter) prefetch(it);
+  for (; it < niter; it += gridDim.x) {
+    bool valid;
+    float2* p = tile_ptr(it, valid);
+    float2 v[E];
+    if constexpr (P::R2 > 1) {
+      cp_async_wait<0>();
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[e] = ex.get(w + WK * e);
+      ex.sync();  // landing slots of other workers must be consumed before stage-1 outputs overwrite them
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[e] = p[e * estride];
+    }
+    const int nxt = it + gridDim.x;
+    fft2_worker<N, DIR>(v, w, ex, ConstTab(), [&] {
+      if (nxt < niter) prefetch(nxt);
+    });
     if (valid) {
 #pragma unroll
       for (int e = 0; e < E; ++e) p[e * estride] = v[e];
@@ -217,23 +249,39 @@ template <int N, int DIR> __global__ void __launch_bounds__(ColCfg<N>::THREADS, 
 }
 #endif
 
-// fused z pass:  out = IFFT_z( (FFT_z(in) * (mul * scal)) (x) vec[coord(axis)] )
+// fused z pass:  out = IFFT_z( (FFT_z(in) * (mul * scal)) (x) vec[coord(AXIS)] ), one field per launch.
+// AXIS (compile time): -1 no 1-D operator, 0: vec indexed by kx, 1: by ky, 2: by kz (staged in shared memory),
+// 3: gradient -- e = FFT_z(in)*mul*scal is kept in registers and three products e (x) vec_{x,y,z} are inverse-transformed
+// and stored (cudaComputePressureGradient fused between the z transforms, SolverCudaKernels.cu:1139-1157).
 struct ZField {
   const float2* in;
   float2* out;
   const float* mul;   // real multiplier on the padded reduced grid [kz][ky][NXP], or nullptr
   float scal;         // scalar folded into the multiplier (fftDivider where the reference folds it there)
-  const float2* vec;  // 1-D complex operator, or nullptr
-  int axis;           // 0: indexed by kx, 1: ky, 2: kz
+  const float2* vec;  // 1-D complex operator (AXIS >= 0)
+  // AXIS == 3 (gradient): one forward transform feeds three inverse transforms, out/out_y/out_z with the x/y/z operators
+  float2* out_y;
+  float2* out_z;
+  const float2* vec_y;
+  const float2* vec_z;
 };
 struct ZMidArgs {
-  ZField f[kMaxFields];
-  int ny, nxp, ngroups, ntiles;  // ntiles = Ny * ngroups
-  size_t plane;                  // Ny * NXP
+  ZField f;
+  int axis;
+  int nxp, ngroups, ntiles;  // ntiles = Ny * ngroups
+  unsigned plane;            // Ny * NXP
 };
 
 #ifdef KW_N
-template <int N> __global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MINB) k_zmid(ZMidArgs a) {
+#ifndef KW_ZMID_MINB
+// E = 32 points per thread need ~150 registers to stay spill free (ncu/ptxas: 128 registers spill 300+ bytes and run
+// 25-55% slower than one CTA per SM at 254 registers)
+#define KW_ZMID_MINB ((Plan2<N>::E >= 32 || AXIS == 3) ? 1 : ColCfg<N>::MINB)
+#endif
+#ifndef KW_ZMID_MULMODE
+#define KW_ZMID_MULMODE 0  // 0: multiplier lands in shared memory through cp.async; 1: plain loads at the point of use
+#endif
+template <int N, int AXIS> __global__ void __launch_bounds__(ColCfg<N>::THREADS, KW_ZMID_MINB) k_zmid(ZMidArgs a) {
   using C = ColCfg<N>;
   using P = Plan2<N>;
   constexpr int W = C::W, WK = C::WK, E = P::E;
@@ -241,46 +289,100 @@ template <int N> __global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>
   const int lane = threadIdx.x, w = threadIdx.y, tz = threadIdx.z;
   ColExchange2<W, C::BAR_THREADS> ex{smem + (size_t)tz * N * W + lane, 1 + tz};
   float* const mulbuf = reinterpret_cast<float*>(smem + C::SMEM / sizeof(float2)) + (size_t)tz * N * W + w * W + lane;
-  const ZField fld = a.f[blockIdx.y];
+  float2* const svec = smem + (C::SMEM + (size_t)C::TPC * N * W * sizeof(float)) / sizeof(float2);  // N entries (AXIS == 2)
+  const float2* __restrict__ in = a.f.in;
+  const float* __restrict__ mul = a.f.mul;
   const int niter = (a.ntiles + C::TPC - 1) / C::TPC;
-  const size_t estride = (size_t)WK * a.plane;
-  for (int it = blockIdx.x; it < niter; it += gridDim.x) {
+  const unsigned estride = (unsigned)WK * a.plane;
+  if (AXIS == 2 || AXIS == 3) {
+    const float2* zv = AXIS == 2 ? a.f.vec : a.f.vec_z;
+    for (int i = threadIdx.x + W * (threadIdx.y + WK * threadIdx.z); i < N; i += C::THREADS) svec[i] = __ldg(zv + i);
+    __syncthreads();
+  }
+  auto tile_base = [&](int it, bool& valid, int& y, int& kx) -> unsigned {
     const int tile = it * C::TPC + tz;
-    const bool valid = tile < a.ntiles;
+    valid = tile < a.ntiles;
     const int tl = valid ? tile : 0;
-    const int y = tl / a.ngroups, kx = (tl % a.ngroups) * W + lane;
-    const size_t base = (size_t)y * a.nxp + kx + (size_t)w * a.plane;  // point e of this worker: base + e*estride
-    float2 v[E];
-    {
-      const float2* __restrict__ p = fld.in + base;
+    y = tl / a.ngroups, kx = (tl % a.ngroups) * W + lane;
+    return (unsigned)y * a.nxp + kx + (unsigned)w * a.plane;  // point e of this worker: base + e*estride
+  };
+  auto prefetch = [&](int it) {  // see k_col
+    if constexpr (P::R2 > 1) {
+      bool valid;
+      int y, kx;
+      const float2* p = in + tile_base(it, valid, y, kx);
 #pragma unroll
-      for (int e = 0; e < E; ++e) v[e] = __ldg(p + e * estride);
+      for (int e = 0; e < E; ++e) cp_async8(ex.buf + (w + WK * e) * W, p + e * estride);
+      cp_async_commit();
     }
+  };
+  int it = blockIdx.x;
+  if (it < niter) prefetch(it);
+  for (; it < niter; it += gridDim.x) {
+    bool valid;
+    int y, kx;
+    const unsigned base = tile_base(it, valid, y, kx);
     // the real multiplier of this tile lands in shared memory (cp.async, thread-private slots) while the forward
-    // transform runs: no registers, no exposed latency
-    const float* __restrict__ mp = fld.mul ? fld.mul + base : nullptr;
-    if (mp) {
+    // transform runs: no registers, no exposed latency.  Issued before the points are taken into registers.
+    if (mul && KW_ZMID_MULMODE == 0) {
 #pragma unroll
-      for (int e = 0; e < E; ++e) cp_async4(mulbuf + e * (WK * W), mp + e * estride);
+      for (int e = 0; e < E; ++e) cp_async4(mulbuf + e * (WK * W), mul + base + e * estride);
     }
     cp_async_commit();
+    float2 v[E];
+    if constexpr (P::R2 > 1) {
+      cp_async_wait<1>();  // the tile (older group) has landed; the multiplier may still be in flight
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[e] = ex.get(w + WK * e);
+      ex.sync();
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[e] = __ldg(in + base + e * estride);
+    }
     fft2_worker<N, -1>(v, w, ex, ConstTab());
     cp_async_wait<0>();
-    float2 w01 = make_float2(1.f, 0.f);
-    if (fld.vec && fld.axis < 2) w01 = __ldg(fld.vec + (fld.axis == 0 ? kx : y));
+    asm volatile("" ::: "memory");  // keep the phases apart: interleaving them only lengthens live ranges
+    const float scal = a.f.scal;
+    const int nxt = it + gridDim.x;
+    if constexpr (AXIS == 3) {
+      float2 ev[E];
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const int kz = w + WK * e;
-      const float m = mp ? mulbuf[e * (WK * W)] * fld.scal : fld.scal;
-      float2 x = cscale(v[e], m);
-      if (fld.vec) x = cmul(x, fld.axis == 2 ? __ldg(fld.vec + kz) : w01);
-      v[e] = x;
-    }
-    fft2_worker<N, +1>(v, w, ex, ConstTab());
-    if (valid) {
-      float2* __restrict__ p = fld.out + base;
+      for (int e = 0; e < E; ++e) ev[e] = cscale(v[e], mul ? mulbuf[e * (WK * W)] * scal : scal);
+      const float2 wx = __ldg(a.f.vec + kx), wy = __ldg(a.f.vec_y + y);
 #pragma unroll
-      for (int e = 0; e < E; ++e) p[e * estride] = v[e];
+      for (int f = 0; f < 3; ++f) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = cmul(ev[e], f == 0 ? wx : f == 1 ? wy : svec[w + WK * e]);
+        if (f < 2) fft2_worker<N, +1>(v, w, ex, ConstTab());
+        else fft2_worker<N, +1>(v, w, ex, ConstTab(), [&] {
+          if (nxt < niter) prefetch(nxt);
+        });
+        if (valid) {
+          float2* __restrict__ p = (f == 0 ? a.f.out : f == 1 ? a.f.out_y : a.f.out_z) + base;
+#pragma unroll
+          for (int e = 0; e < E; ++e) p[e * estride] = v[e];
+        }
+      }
+    } else {
+      float2 w01 = make_float2(1.f, 0.f);
+      if (AXIS == 0) w01 = __ldg(a.f.vec + kx);
+      if (AXIS == 1) w01 = __ldg(a.f.vec + y);
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float m = mul ? (KW_ZMID_MULMODE == 0 ? mulbuf[e * (WK * W)] : __ldg(mul + base + e * estride)) * scal : scal;
+        float2 x = cscale(v[e], m);
+        if (AXIS == 0 || AXIS == 1) x = cmul(x, w01);
+        if (AXIS == 2) x = cmul(x, svec[w + WK * e]);
+        v[e] = x;
+      }
+      fft2_worker<N, +1>(v, w, ex, ConstTab(), [&] {
+        if (nxt < niter) prefetch(nxt);
+      });
+      if (valid) {
+        float2* __restrict__ p = a.f.out + base;
+#pragma unroll
+        for (int e = 0; e < E; ++e) p[e * estride] = v[e];
+      }
     }
   }
 }

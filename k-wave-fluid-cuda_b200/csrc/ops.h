@@ -17,7 +17,7 @@ struct FftOps {
   void (*xinv_density)(const XInvArgs<3>&, const EpiDensity&, cudaStream_t);
   void (*xinv_psum)(const XInvArgs<2>&, const EpiPressureSum&, cudaStream_t);
   void (*col)(const ColArgs&, int dir, int nfields, cudaStream_t);
-  void (*zmid)(const ZMidArgs&, int nfields, cudaStream_t);
+  void (*zmid)(const ZMidArgs&, cudaStream_t);  // one field per launch
 };
 
 const FftOps* get_fft_ops(int n);  // nullptr when n is not a supported length

@@ -664,12 +664,13 @@ template <class F> static void inverse_yx(kw_ctx* c, float2* const* data, int nf
     launch(c, name, frac * xinv_bytes, [&] { xinv(pb, pe); });
   }
 }
-static void zmid_launch(kw_ctx* c, ZMidArgs& za, int nf) {
+// one fused z pass per field (axis < 0: no 1-D operator)
+static void zmid_launch(kw_ctx* c, const ZField& f, int axis) {
   const Geometry& g = c->g;
-  za.ny = g.ny, za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->col_w, za.ntiles = g.ny * za.ngroups, za.plane = (size_t)g.ny * g.nxp;
-  double bytes = 0;
-  for (int f = 0; f < nf; ++f) bytes += 16.0 * g.nc + (za.f[f].mul ? 4.0 * g.nc : 0.0);
-  launch(c, "zmid", bytes, [&] { g.oz->zmid(za, nf, c->st); });
+  ZMidArgs za{};
+  za.f = f, za.axis = axis;
+  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->col_w, za.ntiles = g.ny * za.ngroups, za.plane = (unsigned)((size_t)g.ny * g.nxp);
+  launch(c, axis == 3 ? "zmid_grad" : "zmid", (axis == 3 ? 32.0 : 16.0) * g.nc + (f.mul ? 4.0 * g.nc : 0.0), [&] { g.oz->zmid(za, c->st); });
 }
 template <int NF> static XInvArgs<NF> xinv_args(kw_ctx* c, float2* const* in, int pb, int pe, int nfields = NF) {
   XInvArgs<NF> a{};
@@ -683,11 +684,10 @@ static void pressure_gradient_spectra(kw_ctx* c) {
   const float* in[1] = {c->d[KW_P]};
   float2* out[1] = {c->S[3]};
   forward_xy(c, in, out, 1);
-  ZMidArgs za{};
-  const int vec[3] = {KW_DDX_K_SHIFT_POS_R, KW_DDY_K_SHIFT_POS, KW_DDZ_K_SHIFT_POS};
-  for (int f = 0; f < 3; ++f)
-    za.f[f] = ZField{c->S[3], c->S[f], c->d[KW_KAPPA], 1.0f, reinterpret_cast<const float2*>(c->d[vec[f]]), f};
-  zmid_launch(c, za, 3);
+  ZField zf{c->S[3], c->S[0], c->d[KW_KAPPA], 1.0f, reinterpret_cast<const float2*>(c->d[KW_DDX_K_SHIFT_POS_R]),
+            c->S[1], c->S[2], reinterpret_cast<const float2*>(c->d[KW_DDY_K_SHIFT_POS]),
+            reinterpret_cast<const float2*>(c->d[KW_DDZ_K_SHIFT_POS])};
+  zmid_launch(c, zf, 3);
 }
 
 // additive source: scaled = IFFT(FFT(scatter) * (source_kappa * fd)), added to the targets  (cpp:2339-2352)
@@ -698,9 +698,7 @@ static void add_scaled_source(kw_ctx* c, const float* signal, const uint64_t* in
   const float* in[1] = {c->tSrc};
   float2* out[1] = {c->S[3]};
   forward_xy(c, in, out, 1);
-  ZMidArgs za{};
-  za.f[0] = ZField{c->S[3], c->S[3], c->d[KW_SOURCE_KAPPA], 1.0f / (float)g.n, nullptr, 0};
-  zmid_launch(c, za, 1);
+  zmid_launch(c, ZField{c->S[3], c->S[3], c->d[KW_SOURCE_KAPPA], 1.0f / (float)g.n, nullptr}, -1);
   EpiAdd e{};
   for (int k = 0; k < ntargets; ++k) e.out[k] = targets[k];
   e.ntargets = ntargets;
@@ -821,11 +819,9 @@ static int step(kw_ctx* c) {
   // ---- computeVelocityGradient (cpp:2126-2150) + computeDensity (cpp:2157/2169) [+ pressure terms / lossless p]
   {
     forward_xy(c, u, c->S, 3);
-    ZMidArgs za{};
     const int vec[3] = {KW_DDX_K_SHIFT_NEG_R, KW_DDY_K_SHIFT_NEG, KW_DDZ_K_SHIFT_NEG};
     for (int f = 0; f < 3; ++f)
-      za.f[f] = ZField{c->S[f], c->S[f], c->d[KW_KAPPA], fd, reinterpret_cast<const float2*>(c->d[vec[f]]), f};
-    zmid_launch(c, za, 3);
+      zmid_launch(c, ZField{c->S[f], c->S[f], c->d[KW_KAPPA], fd, reinterpret_cast<const float2*>(c->d[vec[f]])}, f);
     const bool p_src = cf.p_source_flag > t;
     EpiDensity e{};
     for (int k = 0; k < 3; ++k) e.rho[k] = rho[k], e.pml[k] = c->d[KW_PML_X + k];
@@ -867,10 +863,8 @@ static int step(kw_ctx* c) {
   if (cf.absorbing_flag) {
     const float* in[2] = {c->tA, c->tB};
     forward_xy(c, in, c->S, 2);
-    ZMidArgs za{};
-    za.f[0] = ZField{c->S[0], c->S[0], c->d[KW_ABSORB_NABLA1], 1.0f, nullptr, 0};
-    za.f[1] = ZField{c->S[1], c->S[1], c->d[KW_ABSORB_NABLA2], 1.0f, nullptr, 0};
-    zmid_launch(c, za, 2);
+    zmid_launch(c, ZField{c->S[0], c->S[0], c->d[KW_ABSORB_NABLA1], 1.0f, nullptr}, -1);
+    zmid_launch(c, ZField{c->S[1], c->S[1], c->d[KW_ABSORB_NABLA2], 1.0f, nullptr}, -1);
     EpiPressureSum e{};
     e.p = c->d[KW_P], e.base = cf.nonlinear_flag ? c->tNL : c->tB;
     e.c2 = c->fld(KW_C0), e.tau = c->fld(KW_ABSORB_TAU), e.eta = c->fld(KW_ABSORB_ETA), e.fd = fd;
@@ -1083,6 +1077,42 @@ static int fft3d_host(uint64_t nx, uint64_t ny, uint64_t nz, const float* in, fl
   cudaFree(dreal), cudaFree(dspec), cudaFree(dnat);
   return KW_OK;
 }
+// micro-benchmark of one column pass (axis 1: y, 2: z; fused != 0: the z pass with its forward+multiply+inverse body)
+int kw_bench_col(uint64_t nx, uint64_t ny, uint64_t nz, int axis, int fused, int iters, float* ms_per_pass) {
+  Geometry g;
+  KW_TRY(g.init(nx, ny, nz));
+  float2* d = nullptr;
+  float* mul = nullptr;
+  KW_CUDA(cudaMalloc(&d, g.nc * sizeof(float2)));
+  KW_CUDA(cudaMalloc(&mul, g.nc * sizeof(float)));
+  KW_CUDA(cudaMemset(d, 0, g.nc * sizeof(float2)));
+  KW_CUDA(cudaMemset(mul, 0, g.nc * sizeof(float)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0), cudaEventCreate(&e1);
+  ColArgs ca{};
+  ca.data[0] = d;
+  const FftOps* op = axis == 1 ? g.oy : g.oz;
+  if (axis == 1) ca.stride = g.nxp, ca.outer_stride = (size_t)g.ny * g.nxp, ca.ngroups = g.nxp / op->col_w, ca.tile_end = g.nz * ca.ngroups;
+  else ca.stride = (size_t)g.ny * g.nxp, ca.outer_stride = g.nxp, ca.ngroups = g.nxp / op->col_w, ca.tile_end = g.ny * ca.ngroups;
+  ZMidArgs za{};
+  za.f = ZField{d, d, mul, 1.0f, nullptr}, za.axis = -1;
+  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->col_w, za.ntiles = g.ny * za.ngroups, za.plane = (unsigned)((size_t)g.ny * g.nxp);
+  for (int i = 0; i < iters + 2; ++i) {
+    if (i == 2) cudaEventRecord(e0);
+    if (fused) g.oz->zmid(za, 0);
+    else op->col(ca, -1, 1, 0);
+  }
+  cudaEventRecord(e1);
+  KW_CUDA(cudaDeviceSynchronize());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  *ms_per_pass = ms / iters;
+  cudaFree(d), cudaFree(mul);
+  cudaEventDestroy(e0), cudaEventDestroy(e1);
+  KW_CUDA(cudaGetLastError());
+  return KW_OK;
+}
+
 int kw_fft_r2c_3d(uint64_t nx, uint64_t ny, uint64_t nz, const float* host_real, float* host_complex) {
   return fft3d_host(nx, ny, nz, host_real, host_complex, true);
 }

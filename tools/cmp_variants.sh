@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-for v in "" _w8; do
+for v in ""; do
   KWAVE_B200_LIB=$PWD/k-wave-fluid-cuda_b200/libkwave_b200$v.so python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/b$v.log 2>&1
   python - <<PY
 import json
