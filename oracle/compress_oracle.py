@@ -1,0 +1,173 @@
+"""CPU restatement of the reference's on-the-fly harmonic compression (TEST INFRASTRUCTURE ONLY; see kspace_oracle.py).
+
+Follows Compression/CompressHelper.cpp (:48-65 init, :672-778 basis generation, :224-389 40-bit codec) and the host-side
+accumulation of OutputStreams/IndexOutputStream.cpp (:373-470 flushRaw, :299-342 postSample) and
+BaseOutputStream.cpp (:117-133 postSample2).  Pinned against the reference's own CompressHelper.cpp compiled on the CPU
+(oracle/_ref/compress_ref -> tests/golden/compress_ref.json): bases to 1 ulp of libm cosf/sinf, codec bit-exact.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+F32 = np.float32
+K_MAX_EXP_P, K_MAX_EXP_U = 138, 114  # CompressHelper.h:91-92
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def triangular(osize):
+    """CompressHelper.cpp:700-710."""
+    x = np.arange(2 * osize + 1, dtype=F32)
+    w = np.where(x < osize, x / F32(osize), F32(2.0) - x / F32(osize))
+    return w.astype(F32)
+
+
+def generate_bases(period, mos, harmonics, normalize=True, shift=False):
+    """bE, bE_1 as complex64 arrays of shape (harmonics, bSize).  CompressHelper.cpp:48-65, :672-778."""
+    period = F32(period)
+    osize = int(period * F32(mos))
+    bsize = 2 * osize + 1
+    b = triangular(osize)
+    x = np.arange(bsize, dtype=F32)
+    be = np.zeros((harmonics, bsize), np.complex64)
+    be1 = np.zeros((harmonics, bsize), np.complex64)
+    for ih in range(harmonics):
+        h = F32(ih + 1)
+        # e = exp(-i * (2 pi / (period / h)) * x) [* exp(+i pi / (period / h)) when shifted], all in FP32 (:733-746)
+        w = F32(2.0) * F32(np.pi) / (period / h)
+        ang = (w * x).astype(F32)
+        e = (np.cos(ang, dtype=F32) - 1j * np.sin(ang, dtype=F32)).astype(np.complex64)
+        if shift:
+            s = F32(np.pi) / (period / h)
+            e = (e * np.complex64(np.cos(s, dtype=F32) + 1j * np.sin(s, dtype=F32))).astype(np.complex64)
+        idx = (np.arange(bsize) + osize) % (bsize - 1)
+        be[ih] = (b * e).astype(np.complex64)
+        be1[ih] = (b[idx] * e[idx]).astype(np.complex64)
+        if normalize:
+            sc = F32(2.0) / F32(osize)
+            be[ih] = (be[ih] * sc).astype(np.complex64)
+            be1[ih] = (be1[ih] * sc).astype(np.complex64)
+    return osize, bsize, be, be1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def _bits(f):
+    return int(np.array(f, dtype=F32).view(np.uint32))
+
+
+def _float(u):
+    return np.array(u & 0xFFFFFFFF, dtype=np.uint32).view(F32)[()]
+
+
+def encode40(re, im, e):
+    """convertFloatCTo40b (CompressHelper.cpp:292-389) -> 5 bytes."""
+    mr, mi = _bits(re), _bits(im)
+    sr, si = mr >> 31, mi >> 31
+    ers = ((mr & 0x7F800000) >> 23) - e
+    eis = ((mi & 0x7F800000) >> 23) - e
+    es = ers
+    mr &= 0x007FFFFF
+    mi &= 0x007FFFFF
+    rsr = rsi = 6
+    if ers > eis:
+        rsi += ers - eis
+        es = ers
+    elif eis > ers:
+        rsr += eis - ers
+        es = eis
+    if es < 0:
+        rsr += -es
+        rsi += -es
+        es = 0
+    # the reference keeps the shifts in uint8_t: wrap like it does before clamping
+    rsr &= 0xFF
+    rsi &= 0xFF
+    rsr, rsi = min(rsr, 23), min(rsi, 23)
+    mr >>= rsr
+    mi >>= rsi
+    if mr > 0 and mr != (0x7FFFFF >> rsr):
+        mr += 1
+    if mi > 0 and mi != (0x7FFFFF >> rsi):
+        mi += 1
+    mr |= 1 << (23 - rsr)
+    mr >>= 1
+    mi |= 1 << (23 - rsi)
+    mi >>= 1
+    if es > 0xF:
+        mr = mi = 0xFFFF
+        es = 0xF
+    b0 = ((sr << 7) | (si << 6) | ((mr & 0x10000) >> 11) | ((mi & 0x10000) >> 12) | (es & 0xF)) & 0xFF
+    return bytes([b0, mr & 0xFF, (mr >> 8) & 0xFF, mi & 0xFF, (mi >> 8) & 0xFF])
+
+
+def decode40(b, e):
+    """convert40bToFloatC (CompressHelper.cpp:224-290) -> (re, im) float32."""
+    b0 = b[0]
+    mr = ((b0 & 0x20) << 11) | (b[1] | (b[2] << 8))
+    mi = ((b0 & 0x10) << 12) | (b[3] | (b[4] << 8))
+    sr, si, es = b0 >> 7, (b0 & 0x40) >> 6, b0 & 0xF
+    mr <<= 6
+    mi <<= 6
+    er = ei = es + e
+
+    def norm(m, ex):
+        if m != 0:
+            index = m.bit_length() - 1
+            m = (m << (23 - index)) & 0xFFFFFFFF
+            ex -= 22 - index
+        else:
+            ex = 0
+        return m, ex
+
+    mr, er = norm(mr, er)
+    mi, ei = norm(mi, ei)
+    ccr = ((sr << 31) | ((er << 23) & 0xFFFFFFFF) | (mr & 0x007FFFFF)) & 0xFFFFFFFF
+    cci = ((si << 31) | ((ei << 23) & 0xFFFFFFFF) | (mi & 0x007FFFFF)) & 0xFFFFFFFF
+    return _float(ccr), _float(cci)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class CompressedStream:
+    """Host-side state machine of one `*_c` stream (IndexOutputStream::flushRaw, IndexOutputStream.cpp:373-470).
+    feed(x) takes the Nsens raw samples of one sampled step and returns the frame that the reference would write to the
+    file at that step (complex64 array of shape (Nsens, harmonics)), or None."""
+
+    def __init__(self, nsens, period, mos=1, harmonics=1, shifted=False, no_overlap=False, nsteps_total=None, dtype=np.complex64):
+        self.osize, self.bsize, self.be, self.be1 = generate_bases(period, mos, harmonics, True, shifted)
+        self.h = harmonics
+        self.no_overlap = no_overlap
+        self.buf1 = np.zeros((nsens, harmonics), dtype)
+        self.buf2 = self.buf1 if no_overlap else np.zeros((nsens, harmonics), dtype)  # BaseOutputStream.cpp:246-257
+        self.sampled = 0
+        self.compressed = 0
+        self.nsteps_total = nsteps_total
+        self.dtype = dtype
+
+    def feed(self, x):
+        step_local = self.sampled % (self.bsize - 1)
+        saving = (step_local + 1) % self.osize == 0
+        odd = (self.compressed + 1) % 2 == 0
+        mirror = self.compressed == 0 and saving and not self.no_overlap
+        x = np.asarray(x).astype(self.buf1.real.dtype)[:, None]
+        # NOTE with no_overlap buf1 is buf2: both updates land in the same accumulator, as in the reference
+        self.buf1 += self.be[:, step_local].astype(self.dtype)[None, :] * x
+        self.buf2 += self.be1[:, step_local].astype(self.dtype)[None, :] * x
+        if mirror:
+            self.buf2 += self.buf1
+        out = None
+        last = (
+            self.nsteps_total is not None
+            and (self.nsteps_total - self.sampled == 1)
+            and self.nsteps_total <= self.osize
+        )
+        if saving or last:
+            cur = self.buf1 if odd else self.buf2
+            out = cur.copy()
+            self.compressed += 1
+            cur[...] = 0  # postSample2 (BaseOutputStream.cpp:117-133)
+        self.sampled += 1
+        return out
+
+
+def intensity_frame(pc, uc):
+    """IndexOutputStream::postSample (:299-342): sum over harmonics of Re(P * conj(U)) / 2 for one saved frame."""
+    return (pc * np.conj(uc)).real.sum(axis=1) / 2.0

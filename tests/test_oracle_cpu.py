@@ -1,0 +1,204 @@
+"""CPU-side checks (run with -m "not gpu"): the oracle against the reference's own golden vectors, host logic,
+and the C ABI surface of the CUDA library (symbols only; no compute without a GPU)."""
+import ctypes
+import json
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+import fixtures
+from oracle import compress_oracle as co
+from oracle import kspace_oracle as ko
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def f32(u):
+    return np.array(u, dtype=np.uint32).view(np.float32)
+
+
+# ---- compression: pinned against the reference's CompressHelper.cpp (oracle/_ref/compress_ref) ---------------------
+@pytest.fixture(scope="module")
+def compress_gold():
+    return json.load(open(os.path.join(GOLD, "compress_ref.json")))
+
+
+def test_compression_bases_match_reference(compress_gold):
+    for g in compress_gold["bases"]:
+        period = float(f32(g["period_bits"]))
+        for shifted, sfx in ((False, ""), (True, "_shifted")):
+            osize, bsize, be, be1 = co.generate_bases(period, g["mos"], g["harmonics"], True, shifted)
+            assert (osize, bsize) == (g["oSize"], g["bSize"])
+            for got, key in ((be, "bE" + sfx), (be1, "bE_1" + sfx)):
+                ref = np.array(g[key], dtype=np.uint32).view(np.float32).reshape(-1, 2)
+                ref = (ref[:, 0] + 1j * ref[:, 1]).reshape(got.shape)
+                # libm cosf/sinf vs NumPy's: 1-2 ulp on values of magnitude <= 2/oSize
+                assert np.abs(got - ref).max() <= 4e-7 * (2.0 / osize) + 1e-12, key
+
+
+def test_40bit_codec_bit_exact(compress_gold):
+    for c in compress_gold["codec"]:
+        re_, im_ = f32(c["re"]), f32(c["im"])
+        enc = co.encode40(re_, im_, c["e"])
+        assert list(enc) == c["bytes"], (c, list(enc))
+        dre, dim = co.decode40(bytes(c["bytes"]), c["e"])
+        assert int(np.array(dre).view(np.uint32)) == c["dre"] and int(np.array(dim).view(np.uint32)) == c["dim"], c
+
+
+def test_known_answers_from_survey():
+    """values obtained from the reference's CompressHelper in the survey session."""
+    osize, bsize, be, be1 = co.generate_bases(50.0, 1, 2, True, False)
+    assert (osize, bsize) == (50, 101)
+    assert abs(be[0, 1] - (0.000793691725 - 0.000100266589j)) < 1e-10
+    assert abs(be1[0, 1] - (0.0388908945 - 0.00491307164j)) < 1e-8
+    assert abs(be[1, 3] - (0.00174952438 - 0.00164291321j)) < 1e-9
+    enc = co.encode40(np.float32(12345.678), np.float32(-0.5), 138)
+    assert enc.hex() == "62cd810400"
+    assert co.decode40(enc, 138) == (np.float32(12345.625), np.float32(-0.5))
+
+
+def test_compressed_stream_state_machine():
+    """Frames come out every oSize sampled steps, alternating accumulators; a pure tone at the basis frequency is
+    recovered as amplitude * e^{i phase} (normalised bases)."""
+    period, nsens, nt = 20.0, 3, 200
+    s = co.CompressedStream(nsens, period, mos=1, harmonics=2, dtype=np.complex128)
+    amp = np.array([1.0, 2.5, -0.75])
+    frames = []
+    for t in range(nt):
+        out = s.feed(amp * np.cos(2 * np.pi * t / period))
+        if out is not None:
+            frames.append((t, out))
+    assert [t for t, _ in frames] == list(range(19, nt, 20))
+    for t, f in frames[2:]:
+        np.testing.assert_allclose(np.abs(f[:, 0]), np.abs(amp), rtol=2e-2)
+        assert np.abs(f[:, 1]).max() < 5e-2 * np.abs(amp).max()
+
+
+# ---- solver oracle --------------------------------------------------------------------------------------------------
+def test_oracle_fp32_vs_fp64_noise_floor(synth):
+    """The FP32 evaluation of the same restatement stays within 2e-6 of FP64 over 60 steps: the floor against which the
+    1e-5 parity bar is read."""
+    cfg, arrays = synth.make_case(32, nt=60, source="p_plane")
+    a = ko.run(cfg, arrays, dtype=np.float64, record=("p_raw",))["p"]
+    b = ko.run(cfg, arrays, dtype=np.float32, record=("p_raw",))["p"]
+    assert np.isfinite(a).all()
+    assert np.linalg.norm(a - b) / np.linalg.norm(a) < 2e-6
+
+
+def test_oracle_k_operators(synth):
+    cfg, _ = synth.make_case(16, nt=1)
+    kappa, n1, n2 = ko.generate_kappa_and_nablas(cfg)
+    assert kappa.shape == (16, 16, 9) and kappa[0, 0, 0] == 1.0 and n1[0, 0, 0] == 0.0 and n2[0, 0, 0] == 0.0
+    k2 = ko.generate_kappa(cfg)
+    assert np.abs(k2 - kappa).max() < 1e-6  # two code paths of the reference (cpp:2440 vs :2556) agree to rounding
+    sk = ko.generate_source_kappa(cfg)
+    assert sk[0, 0, 0] == 1.0 and (np.abs(sk) <= 1).all()
+
+
+def test_cuboid_ordering():
+    """x fastest inside a cuboid, cuboids concatenated (OutputStreamsCudaKernels.cu:164-188)."""
+    o = ko.KSpaceOracle.__new__(ko.KSpaceOracle)
+    o.nx, o.ny, o.nz = 8, 4, 4
+    o.sensor_corners = np.array([[1, 0, 0, 2, 1, 0], [7, 3, 3, 7, 3, 3]])
+    idx = o.cuboid_indices()
+    assert idx[0].tolist() == [1, 2, 9, 10] and idx[1].tolist() == [(3 * 4 + 3) * 8 + 7]
+
+
+@pytest.mark.parametrize("name", fixtures.fixture_names())
+def test_oracle_matches_reference_run(name, synth):
+    """PIN: outputs of the reference's own solver (its unmodified sources + cuFFT, run on a B200 by
+    oracle/make_ref_goldens.py) against the FP64 oracle on the same synthetic input.  Bar: rel-L2 <= 1e-5."""
+    shape, kwargs, nt, flags, data = fixtures.load_fixture(name)
+    if "--p_c" in flags:
+        pytest.skip("compressed streams are checked in test_compression_matches_reference_run")
+    cfg, arrays = synth.make_case(*shape, nt=nt, **kwargs)
+    out = ko.run(cfg, arrays, nt=nt, dtype=np.float64,
+                 record=("p_raw", "p_max", "p_rms", "u_raw", "p_final", "p_max_all", "p_min_all", "u_max"))
+    checked = 0
+    for key, (got, ref) in fixtures.time_series_views(out["p"], data, nt).items():
+        err = fixtures.rel_l2(got, ref)
+        print(f"{name}: {key}: rel-L2 {err:.3e}, max-abs {np.abs(got - ref).max():.3e} (scale {np.abs(ref).max():.3e})")
+        assert err <= 1e-5, (name, key, err)
+        checked += 1
+    for key in ("p_max", "p_rms", "p_final", "p_max_all", "p_min_all", "ux", "ux_max"):
+        if key in data and key in out:
+            err = fixtures.rel_l2(out[key], data[key])
+            assert err <= 1e-5, (name, key, err)
+            checked += 1
+    assert checked
+
+
+def test_compression_matches_reference_run(synth):
+    """PIN of the compression state machine: p_c frames and Ix_avg_c written by the reference (host OpenMP loop,
+    IndexOutputStream.cpp:373-470, :299-342) vs CompressedStream fed with the oracle's sampled series."""
+    shape, kwargs, nt, flags, data = fixtures.load_fixture("compressed_p_and_intensity")
+    cfg, arrays = synth.make_case(*shape, nt=nt, **kwargs)
+    out = ko.run(cfg, arrays, nt=nt, dtype=np.float64, record=("p_raw", "u_non_staggered_raw"))
+    period, harm = 20.0, 2
+    nsens = out["p"].shape[1]
+    # the raw non-staggered velocity first (pins computeShiftedVelocity, cpp:2714-2735)
+    for a in "xyz":
+        ref = data[f"u{a}_non_staggered"].reshape(nt, nsens)
+        if a == "x":
+            assert fixtures.rel_l2(out[f"u{a}_non_staggered"], ref) <= 1e-5
+    sp = co.CompressedStream(nsens, period, 1, harm, shifted=False, nsteps_total=nt, dtype=np.complex128)
+    su = co.CompressedStream(nsens, period, 1, harm, shifted=True, nsteps_total=nt, dtype=np.complex128)
+    pf, uf, inten = [], [], np.zeros(nsens)
+    for t in range(nt):
+        a, b = sp.feed(out["p"][t]), su.feed(out["ux_non_staggered"][t])
+        if a is not None:
+            pf.append(a), uf.append(b)
+            inten += co.intensity_frame(a, b)
+    ref_pc = data["p_c"].reshape(-1, nsens, harm, 2)
+    ref_pc = ref_pc[..., 0] + 1j * ref_pc[..., 1]
+    assert ref_pc.shape[0] == len(pf)
+    assert fixtures.rel_l2(np.abs(np.stack(pf)), np.abs(ref_pc)) <= 1e-5
+    err = np.linalg.norm(np.stack(pf) - ref_pc) / np.linalg.norm(ref_pc)
+    assert err <= 1e-5, err
+    ref_uc = data["ux_non_staggered_c"].reshape(-1, nsens, harm, 2)
+    ref_uc = ref_uc[..., 0] + 1j * ref_uc[..., 1]
+    assert np.linalg.norm(np.stack(uf) - ref_uc) / np.linalg.norm(ref_uc) <= 1e-5
+    ix = inten / len(pf)  # postProcess: divided by the number of frames (IndexOutputStream.cpp:477-520)
+    assert fixtures.rel_l2(ix, data["Ix_avg_c"].reshape(-1)) <= 1e-5
+
+
+# ---- C ABI surface --------------------------------------------------------------------------------------------------
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "kwave_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(kw_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(kw):
+    lib = ctypes.CDLL(kw.library_path())
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/kwave_b200.h but not exported"
+    assert kw.load_library().kw_abi_version() == 1
+
+
+def test_enum_ids_follow_the_reference_order(kw):
+    assert kw.STREAM_IDS["KW_S_P_RAW"] == 0 and kw.STREAM_IDS["KW_S_P_MAX_ALL"] == 5
+    assert kw.STREAM_IDS["KW_S_UX_RAW"] == 7 and kw.STREAM_IDS["KW_S_Q_TERM_C"] == kw.STREAM_IDS["KW_STREAM_COUNT"] - 1
+    assert kw.ARRAY_IDS["KW_KAPPA"] == 0 and kw.ARRAY_IDS["KW_P"] == 3
+
+
+def test_no_cpu_fallback(kw):
+    """Without a CUDA device every compute entry point fails loudly (KW_ERR_CUDA), it never computes on the host."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(kw.KwError) as e:
+        kw.fft_r2c_3d(np.zeros((16, 16, 16), np.float32))
+    assert e.value.code == -2
+    cfg, arrays = kw.synth.make_case(16, nt=2)
+    with pytest.raises(kw.KwError) as e:
+        kw.Simulation(cfg, arrays)
+    assert e.value.code == -2
