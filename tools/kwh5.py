@@ -81,6 +81,22 @@ def read_file(path):
     return out
 
 
+def read_root_attrs(path):
+    """Attributes of the root group only (first record), without touching the datasets."""
+    with open(path, "rb") as f:
+        assert f.read(8) == MAGIC, "not a KWH5 file"
+        f.read(8)
+        assert _rstr(f) == "/"
+        f.read(1)
+        (na,) = struct.unpack("<I", f.read(4))
+        attrs = {}
+        for _ in range(na):
+            k = _rstr(f)
+            (t,) = struct.unpack("<B", f.read(1))
+            attrs[k] = _rstr(f) if t == 0 else struct.unpack("<q", f.read(8))[0] if t == 1 else struct.unpack("<f", f.read(4))[0]
+        return attrs
+
+
 # ---- k-Wave input file ------------------------------------------------------------------------------------------------
 _U64_SCALARS = ("Nx Ny Nz Nt pml_x_size pml_y_size pml_z_size sensor_mask_type p_source_flag p0_source_flag transducer_source_flag "
                 "ux_source_flag uy_source_flag uz_source_flag nonuniform_grid_flag absorbing_flag nonlinear_flag u_source_many "
