@@ -27,6 +27,39 @@ struct XFwdArgs {
   int nxp;
 };
 
+// One row pair (rows row0, row0+1) of one field: real -> half spectrum.  T = N/8 threads cooperate through `ex`.
+template <int N, class EX> __device__ __forceinline__ void xfwd_rows(const float* __restrict__ in, float2* __restrict__ out, int nxp,
+                                                                     size_t row0, bool valid, int t, const RegTw& twp, EX& ex) {
+  constexpr int T = N / 8;
+  const float* ra = in + row0 * N;
+  float2 v[1][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) v[0][r] = make_float2(__ldg(ra + t + r * T), __ldg(ra + N + t + r * T));
+  fft_worker<N, -1, 1>(v, t, 0, twp, ex);
+  // mirror exchange: Z[N-k] lives in worker T-t
+#pragma unroll
+  for (int m = 0; m < 8; ++m) ex.put(0, t + m * T, v[0][m]);
+  ex.sync();
+  float2 zp[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) zp[m] = ex.get(0, (N - (t + m * T)) & (N - 1));
+  ex.sync();
+  if (valid) {
+    float2* oa = out + row0 * nxp;
+    float2* ob = oa + nxp;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const float2 z = v[0][m], q = zp[m];
+      oa[t + m * T] = make_float2(0.5f * (z.x + q.x), 0.5f * (z.y - q.y));
+      ob[t + m * T] = make_float2(0.5f * (z.y + q.y), -0.5f * (z.x - q.x));
+    }
+    if (t == 0) {  // Nyquist: Z[N/2] is its own mirror
+      oa[N / 2] = make_float2(v[0][4].x, 0.f);
+      ob[N / 2] = make_float2(v[0][4].y, 0.f);
+    }
+  }
+}
+
 template <int N> __global__ void __launch_bounds__(kXThreads, 3) k_xfwd(XFwdArgs a) {
   using P = Plan<N>;
   constexpr int T = P::T;
@@ -44,34 +77,7 @@ template <int N> __global__ void __launch_bounds__(kXThreads, 3) k_xfwd(XFwdArgs
   for (int g = blockIdx.x; g * RP < npairs; g += gridDim.x) {
     const int pair = a.pair_begin + g * RP + rp;
     const bool valid = pair < a.pair_end;
-    const size_t row0 = 2 * (size_t)(valid ? pair : a.pair_begin);
-    const float* ra = in + row0 * N;
-    float2 v[1][8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) v[0][r] = make_float2(__ldg(ra + t + r * T), __ldg(ra + N + t + r * T));
-    fft_worker<N, -1, 1>(v, t, 0, twp, ex);
-    // mirror exchange: Z[N-k] lives in worker T-t
-#pragma unroll
-    for (int m = 0; m < 8; ++m) ex.put(0, t + m * T, v[0][m]);
-    ex.sync();
-    float2 zp[4];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) zp[m] = ex.get(0, (N - (t + m * T)) & (N - 1));
-    ex.sync();
-    if (valid) {
-      float2* oa = out + row0 * a.nxp;
-      float2* ob = oa + a.nxp;
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const float2 z = v[0][m], q = zp[m];
-        oa[t + m * T] = make_float2(0.5f * (z.x + q.x), 0.5f * (z.y - q.y));
-        ob[t + m * T] = make_float2(0.5f * (z.y + q.y), -0.5f * (z.x - q.x));
-      }
-      if (t == 0) {  // Nyquist: Z[N/2] is its own mirror
-        oa[N / 2] = make_float2(v[0][4].x, 0.f);
-        ob[N / 2] = make_float2(v[0][4].y, 0.f);
-      }
-    }
+    xfwd_rows<N>(in, out, a.nxp, 2 * (size_t)(valid ? pair : a.pair_begin), valid, t, twp, ex);
   }
 }
 
@@ -82,8 +88,45 @@ template <int NF> struct XInvArgs {
   int pair_begin, pair_end, nxp, ny;
 };
 
-// Epilogue contract:  epi.apply(field_select, res, t, T, row0, y, z)  where res[f][m] = (row a, row b) values at
-// x = t + m*T of field f, row0 = flattened (z*Ny + y) index of row a (row b = row0 + 1, same z).
+// One row pair of NF fields: half spectra -> real rows, then the epilogue on the registers.
+// Epilogue contract:  epi.apply<N>(res, field, t, row0, y, z)  where res[f][m] = (row a, row b) values at x = t + m*T of
+// field f, row0 = flattened (z*Ny + y) index of row a (row b = row0 + 1, same z).
+template <int N, int NF, class Epi, class EX>
+__device__ __forceinline__ void xinv_rows(const XInvArgs<NF>& a, const Epi& epi, int field, size_t row0, bool valid, int t, const RegTw& twp, EX& ex) {
+  constexpr int T = N / 8;
+  float2 res[NF][8];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) {
+    const float2* __restrict__ in = (NF == 1) ? a.in[field] : a.in[f];
+    const float2* ia = in + row0 * a.nxp;
+    const float2* ib = ia + a.nxp;
+    float2 v[1][8];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int k = t + m * T;
+      float2 A = __ldg(ia + k), B = __ldg(ib + k);
+      if (m == 0 && t == 0) A.y = 0.f, B.y = 0.f;  // C2R ignores the imaginary part of DC
+      v[0][m] = make_float2(A.x - B.y, A.y + B.x);  // Z[k] = A + iB
+      if (!(m == 0 && t == 0)) ex.put(0, N - k, make_float2(A.x + B.y, B.x - A.y));  // Z[N-k] = conj(A) + i conj(B)
+    }
+    if (t == 0) {
+      const float2 A = __ldg(ia + N / 2), B = __ldg(ib + N / 2);
+      ex.put(0, N / 2, make_float2(A.x, B.x));  // imaginary parts of the Nyquist bin ignored
+    }
+    ex.sync();
+#pragma unroll
+    for (int m = 4; m < 8; ++m) v[0][m] = ex.get(0, t + m * T);
+    ex.sync();
+    fft_worker<N, +1, 1>(v, t, 0, twp, ex);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) res[f][m] = v[0][m];
+  }
+  if (valid) {
+    const int y = (int)(row0 % a.ny), z = (int)(row0 / a.ny);
+    epi.template apply<N>(res, field, t, row0, y, z);
+  }
+}
+
 template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads, Epi::kMinBlocks) k_xinv(XInvArgs<NF> a, Epi epi) {
   using P = Plan<N>;
   constexpr int T = P::T;
@@ -99,38 +142,7 @@ template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads,
   for (int g = blockIdx.x; g * RP < npairs; g += gridDim.x) {
     const int pair = a.pair_begin + g * RP + rp;
     const bool valid = pair < a.pair_end;
-    const size_t row0 = 2 * (size_t)(valid ? pair : a.pair_begin);
-    float2 res[NF][8];
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      const float2* __restrict__ in = (NF == 1) ? a.in[blockIdx.y] : a.in[f];
-      const float2* ia = in + row0 * a.nxp;
-      const float2* ib = ia + a.nxp;
-      float2 v[1][8];
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int k = t + m * T;
-        float2 A = __ldg(ia + k), B = __ldg(ib + k);
-        if (m == 0 && t == 0) A.y = 0.f, B.y = 0.f;  // C2R ignores the imaginary part of DC
-        v[0][m] = make_float2(A.x - B.y, A.y + B.x);  // Z[k] = A + iB
-        if (!(m == 0 && t == 0)) ex.put(0, N - k, make_float2(A.x + B.y, B.x - A.y));  // Z[N-k] = conj(A) + i conj(B)
-      }
-      if (t == 0) {
-        const float2 A = __ldg(ia + N / 2), B = __ldg(ib + N / 2);
-        ex.put(0, N / 2, make_float2(A.x, B.x));  // imaginary parts of the Nyquist bin ignored
-      }
-      ex.sync();
-#pragma unroll
-      for (int m = 4; m < 8; ++m) v[0][m] = ex.get(0, t + m * T);
-      ex.sync();
-      fft_worker<N, +1, 1>(v, t, 0, twp, ex);
-#pragma unroll
-      for (int m = 0; m < 8; ++m) res[f][m] = v[0][m];
-    }
-    if (valid) {
-      const int y = (int)(row0 % a.ny), z = (int)(row0 / a.ny);
-      epi.template apply<N>(res, t, row0, y, z);
-    }
+    xinv_rows<N, NF>(a, epi, blockIdx.y, 2 * (size_t)(valid ? pair : a.pair_begin), valid, t, twp, ex);
   }
 }
 

@@ -52,9 +52,9 @@ struct EpiStore {
   static constexpr int kMinBlocks = 3;  // CTAs per SM the register budget is sized for  // plain C2R:  out = scale * ifft
   float* out[3];
   float scale;
-  template <int N> __device__ __forceinline__ void apply(float2 (&res)[1][8], int t, size_t row0, int, int) const {
+  template <int N> __device__ __forceinline__ void apply(float2 (&res)[1][8], int field, int t, size_t row0, int, int) const {
     constexpr int T = N / 8;
-    float* o = out[blockIdx.y] + row0 * N;
+    float* o = out[field] + row0 * N;
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
       o[t + m * T] = res[0][m].x * scale;
@@ -67,7 +67,7 @@ struct EpiAdd {
   static constexpr int kMinBlocks = 3;  // CTAs per SM the register budget is sized for  // additive (k-space corrected) source: target_j += ifft   (SolverCudaKernels.cu:765-807)
   float* out[3];
   int ntargets;
-  template <int N> __device__ __forceinline__ void apply(float2 (&res)[1][8], int t, size_t row0, int, int) const {
+  template <int N> __device__ __forceinline__ void apply(float2 (&res)[1][8], int, int t, size_t row0, int, int) const {
     constexpr int T = N / 8;
     for (int j = 0; j < ntargets; ++j) {
       float* o = out[j] + row0 * N;
@@ -89,9 +89,9 @@ struct EpiVelocity {
   const float* pml_sg[3];
   float fd;
   int init;
-  template <int N> __device__ __forceinline__ void apply(float2 (&res)[1][8], int t, size_t row0, int y, int z) const {
+  template <int N> __device__ __forceinline__ void apply(float2 (&res)[1][8], int field, int t, size_t row0, int y, int z) const {
     constexpr int T = N / 8;
-    const int f = blockIdx.y;
+    const int f = field;
     float* ua = u[f] + row0 * N;
     const Fld d = dtrho[f];
     if (init) {
@@ -138,7 +138,7 @@ struct EpiDensity {
   float* p;
   FusedSample fs;  // sampling of p when this epilogue produces the final pressure of the step (lossless)
   int sample;
-  template <int N> __device__ __forceinline__ void apply(float2 (&res)[3][8], int t, size_t row0, int y, int z) const {
+  template <int N> __device__ __forceinline__ void apply(float2 (&res)[3][8], int, int t, size_t row0, int y, int z) const {
     constexpr int T = N / 8;
     // restrict-qualified locals: the arrays never alias, which lets the loads of all voxels be issued ahead of the stores
     float* __restrict__ rxp = rho[0];
@@ -205,7 +205,7 @@ struct EpiPressureSum {
   float fd;
   FusedSample fs;
   int sample;
-  template <int N> __device__ __forceinline__ void apply(float2 (&res)[2][8], int t, size_t row0, int y, int z) const {
+  template <int N> __device__ __forceinline__ void apply(float2 (&res)[2][8], int, int t, size_t row0, int y, int z) const {
     constexpr int T = N / 8;
     float* __restrict__ pp = p;
     float pv[16];
