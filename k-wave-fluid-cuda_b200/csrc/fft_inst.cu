@@ -88,6 +88,66 @@ template <int AXIS> static void zmid_axis(const ZMidArgs& a, cudaStream_t st) {
   const int g = col_grid<10 + AXIS>(k_zmid<N, AXIS>, a.ntiles, C::SMEM_ZMID);
   k_zmid<N, AXIS><<<g, dim3(C::W, C::WK, C::TPC), C::SMEM_ZMID, st>>>(a);
 }
+// ---- plane-fused x/y passes (fft_xy.cuh) ----------------------------------------------------------------------------
+// Fills the scheduling part of the arguments: items per plane, lag and ring depth from the grid that will run.
+template <int ID, class K> static int xy_setup(K kernel, PipeState& ps, PipeArgs* q, int planes, int i1, int i2, size_t slot_elems) {
+  using X = XYCfg<N>;
+  static bool once = false;
+  static int per_sm = 1;
+  upload_twiddles();
+  if (!once) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X::SMEM);
+    per_sm = blocks_per_sm(kernel, X::THREADS, X::SMEM);
+    once = true;
+  }
+  const int total = planes * (i1 + i2);
+  int grid = sm_count() * per_sm;
+  if (grid > total) grid = total;
+  const int per = i1 + i2;
+  int lag = (5 * grid + 2 * per - 1) / (2 * per) + 1;  // ~2.5 waves of CTAs between the two passes of a plane
+  int ring = lag + (grid + per - 1) / per + 2;
+  const int cap = (int)(ps.ring_elems / slot_elems);
+  if (ring > cap) ring = cap, lag = ring > 4 ? ring - 3 : ring - 1;
+  if (lag > planes) lag = planes;
+  if (ring <= lag) ring = lag + 1;  // only when planes is tiny; cap >= 2 is guaranteed by the allocation
+  q->ctr = ps.ctr[ps.cur], q->ctr_other = ps.ctr[ps.cur ^ 1], q->nctr = ps.nctr;
+  q->P = planes, q->I1 = i1, q->I2 = i2, q->L = lag, q->R = ring, q->err = ps.err;
+  ps.cur ^= 1;
+  return grid;
+}
+static bool xy_ok(const PipeState& ps, int planes, size_t slot_elems) {
+  return ps.ring && 2 * planes + 1 <= ps.nctr && ps.ring_elems / slot_elems >= 4;
+}
+static bool xy_fwd(XYFwdArgs& a, int nfields, PipeState& ps, cudaStream_t st) {
+  using X = XYCfg<N>;
+  using C = ColCfg<N>;
+  const size_t plane_c = (size_t)N * a.nxp;
+  const int planes = nfields * a.nz;
+  if (!xy_ok(ps, planes, plane_c)) return false;
+  const int i2 = (a.nxp / C::W + C::TPC - 1) / C::TPC;
+  a.ring = ps.ring;
+  const int grid = xy_setup<0>(k_xy_fwd<N>, ps, &a.pipe, planes, X::XI, i2, plane_c);
+  k_xy_fwd<N><<<grid, dim3(C::W, C::WK, C::TPC), X::SMEM, st>>>(a);
+  return true;
+}
+template <int ID, int NF, class Epi> static bool yx_inv(YXInvArgs<NF>& a, const Epi& e, PipeState& ps, cudaStream_t st) {
+  using X = XYCfg<N>;
+  using C = ColCfg<N>;
+  const size_t plane_c = (size_t)N * a.nxp;
+  const int planes = (NF == 1 ? a.nfields : 1) * a.nz;
+  if (!xy_ok(ps, planes, plane_c * NF)) return false;
+  const int i1 = NF * ((a.nxp / C::W + C::TPC - 1) / C::TPC);
+  a.ring = ps.ring;
+  const int grid = xy_setup<10 + ID>(k_yx_inv<N, NF, Epi>, ps, &a.pipe, planes, i1, X::XI, plane_c * NF);
+  k_yx_inv<N, NF, Epi><<<grid, dim3(C::W, C::WK, C::TPC), X::SMEM, st>>>(a, e);
+  return true;
+}
+static bool yx_store(YXInvArgs<1>& a, const EpiStore& e, PipeState& ps, cudaStream_t st) { return yx_inv<0, 1>(a, e, ps, st); }
+static bool yx_add(YXInvArgs<1>& a, const EpiAdd& e, PipeState& ps, cudaStream_t st) { return yx_inv<1, 1>(a, e, ps, st); }
+static bool yx_velocity(YXInvArgs<1>& a, const EpiVelocity& e, PipeState& ps, cudaStream_t st) { return yx_inv<2, 1>(a, e, ps, st); }
+static bool yx_density(YXInvArgs<3>& a, const EpiDensity& e, PipeState& ps, cudaStream_t st) { return yx_inv<3, 3>(a, e, ps, st); }
+static bool yx_psum(YXInvArgs<2>& a, const EpiPressureSum& e, PipeState& ps, cudaStream_t st) { return yx_inv<4, 2>(a, e, ps, st); }
+
 static void zmid(const ZMidArgs& a, cudaStream_t st) {
   switch (a.axis) {
     case 0: zmid_axis<0>(a, st); break;
@@ -103,6 +163,8 @@ static void zmid(const ZMidArgs& a, cudaStream_t st) {
 #define KW_OPS_NAME2(n) fft_ops_##n
 #define KW_OPS_NAME(n) KW_OPS_NAME2(n)
 extern const FftOps KW_OPS_NAME(KW_N) = {KW_N, ColCfg<KW_N>::W, KW_CAT(inst_, KW_N)::xfwd, KW_CAT(inst_, KW_N)::xinv_store, KW_CAT(inst_, KW_N)::xinv_add, KW_CAT(inst_, KW_N)::xinv_velocity,
-                                            KW_CAT(inst_, KW_N)::xinv_density, KW_CAT(inst_, KW_N)::xinv_psum, KW_CAT(inst_, KW_N)::col, KW_CAT(inst_, KW_N)::zmid};
+                                            KW_CAT(inst_, KW_N)::xinv_density, KW_CAT(inst_, KW_N)::xinv_psum, KW_CAT(inst_, KW_N)::col, KW_CAT(inst_, KW_N)::zmid,
+                                            KW_CAT(inst_, KW_N)::xy_fwd, KW_CAT(inst_, KW_N)::yx_store, KW_CAT(inst_, KW_N)::yx_add, KW_CAT(inst_, KW_N)::yx_velocity,
+                                            KW_CAT(inst_, KW_N)::yx_density, KW_CAT(inst_, KW_N)::yx_psum};
 
 }  // namespace kw

@@ -165,6 +165,7 @@ struct kw_ctx {
   size_t nsens = 0;  // sensor points (index mask) or total cuboid points
   int ncuboids = 0;
   Stream streams[KW_STREAM_COUNT];
+  PipeState pipe;  // ring + counters of the plane-fused x/y kernels (Nx == Ny only)
   std::vector<void*> owned;
 
   Fld fld(int id) const { return Fld{count[id] > 1 ? d[id] : nullptr, scalar[id]}; }
@@ -194,6 +195,14 @@ template <class F> static void launch(kw_ctx* c, const char* name, double bytes,
   f();
   cudaEventRecord(p.e1, c->st);
   c->prof_pending.push_back(p);
+}
+// the plane-fused kernels flag a dependency wait that timed out (a scheduling bug); stream must be idle
+static int pipe_check(kw_ctx* c) {
+  if (!c->pipe.err) return KW_OK;
+  int e = 0;
+  KW_CUDA(cudaMemcpy(&e, c->pipe.err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (e) return fail(KW_ERR_CUDA, "plane-fused FFT pipeline: dependency wait timed out");
+  return KW_OK;
 }
 static void prof_resolve(kw_ctx* c) {  // stream must be idle
   for (auto& p : c->prof_pending) {
@@ -550,6 +559,21 @@ int kw_preprocess(kw_ctx* c) {
       c->count[id] = g.n;
     }
   for (int k = 0; k < 4; ++k) KW_TRY(dalloc(c, (void**)&c->S[k], g.nc * sizeof(float2)));
+  {  // plane-fused x/y passes (fft_xy.cuh): an L2-resident ring of spectrum planes + two sets of progress counters
+    static const long long ring_mb = getenv("KW_RING_MB") ? atoll(getenv("KW_RING_MB")) : 0;  // opt-in: the first version is correct but slower than the separate passes (profiles/r01_e)
+    if (g.nx == g.ny && ring_mb > 0) {
+      const size_t plane_c = (size_t)g.ny * g.nxp;
+      size_t slots = ((size_t)ring_mb << 20) / (plane_c * sizeof(float2));
+      if (slots < 12) slots = 12;  // at least four slots of three planes
+      if (slots > (size_t)3 * g.nz + 3) slots = (size_t)3 * g.nz + 3;
+      c->pipe.ring_elems = slots * plane_c;
+      c->pipe.nctr = 2 * 3 * g.nz + 1;
+      KW_TRY(dalloc(c, (void**)&c->pipe.ring, c->pipe.ring_elems * sizeof(float2)));
+      KW_TRY(dalloc(c, (void**)&c->pipe.ctr[0], c->pipe.nctr * sizeof(unsigned)));
+      KW_TRY(dalloc(c, (void**)&c->pipe.ctr[1], c->pipe.nctr * sizeof(unsigned)));
+      KW_TRY(dalloc(c, (void**)&c->pipe.err, sizeof(int)));
+    }
+  }
   if (cf.absorbing_flag) {
     KW_TRY(dalloc(c, (void**)&c->tA, g.n * sizeof(float)));
     KW_TRY(dalloc(c, (void**)&c->tB, g.n * sizeof(float)));
@@ -635,6 +659,14 @@ static int chunk_planes(const kw_ctx* c, int nf) {
 // forward x and y passes of `nf` real fields into spectral buffers
 static void forward_xy(kw_ctx* c, const float* const* in, float2* const* out, int nf) {
   const Geometry& g = c->g;
+  if (c->pipe.ring) {  // one kernel, the x-transformed planes stay in L2
+    XYFwdArgs fa{};
+    for (int f = 0; f < nf; ++f) fa.in[f] = in[f], fa.out[f] = out[f];
+    fa.tab = g.tx, fa.nz = g.nz, fa.nxp = g.nxp;
+    bool ok = true;
+    launch(c, "xy_fwd", nf * (4.0 * g.n + 8.0 * g.nc), [&] { ok = g.ox->xy_fwd(fa, nf, c->pipe, c->st); });
+    if (ok) return;
+  }
   XFwdArgs xa{};
   ColArgs ca{};
   for (int f = 0; f < nf; ++f) xa.in[f] = in[f], xa.out[f] = out[f], ca.data[f] = out[f];
@@ -650,8 +682,14 @@ static void forward_xy(kw_ctx* c, const float* const* in, float2* const* out, in
   }
 }
 // inverse y pass then the x inverse (with its fused epilogue) chunk by chunk; xinv(pair_begin, pair_end) launches it
-template <class F> static void inverse_yx(kw_ctx* c, float2* const* data, int nf, const char* name, double xinv_bytes, F&& xinv) {
+template <class F, class FF>
+static void inverse_yx(kw_ctx* c, float2* const* data, int nf, const char* name, const char* fused_name, double xinv_bytes, F&& xinv, FF&& fused) {
   const Geometry& g = c->g;
+  if (c->pipe.ring) {
+    bool ok = true;
+    launch(c, fused_name, xinv_bytes, [&] { ok = fused(); });
+    if (ok) return;
+  }
   ColArgs ca{};
   for (int f = 0; f < nf; ++f) ca.data[f] = data[f];
   ca.stride = g.nxp, ca.outer_stride = (size_t)g.ny * g.nxp, ca.ngroups = g.nxp / g.oy->col_w;
@@ -671,6 +709,12 @@ static void zmid_launch(kw_ctx* c, const ZField& f, int axis) {
   za.f = f, za.axis = axis;
   za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->col_w, za.ntiles = g.ny * za.ngroups, za.plane = (unsigned)((size_t)g.ny * g.nxp);
   launch(c, axis == 3 ? "zmid_grad" : "zmid", (axis == 3 ? 32.0 : 16.0) * g.nc + (f.mul ? 4.0 * g.nc : 0.0), [&] { g.oz->zmid(za, c->st); });
+}
+template <int NF> static YXInvArgs<NF> yx_args(kw_ctx* c, float2* const* in, int nfields = NF) {
+  YXInvArgs<NF> a{};
+  for (int f = 0; f < nfields; ++f) a.in[f] = in[f];
+  a.tab = c->g.tx, a.nz = c->g.nz, a.nxp = c->g.nxp, a.nfields = nfields;
+  return a;
 }
 template <int NF> static XInvArgs<NF> xinv_args(kw_ctx* c, float2* const* in, int pb, int pe, int nfields = NF) {
   XInvArgs<NF> a{};
@@ -702,8 +746,9 @@ static void add_scaled_source(kw_ctx* c, const float* signal, const uint64_t* in
   EpiAdd e{};
   for (int k = 0; k < ntargets; ++k) e.out[k] = targets[k];
   e.ntargets = ntargets;
-  inverse_yx(c, out, 1, "xinv_add_source", 8.0 * g.nc + 8.0 * g.n * ntargets,
-             [&](int pb, int pe) { g.ox->xinv_add(xinv_args<1>(c, out, pb, pe), e, c->st); });
+  inverse_yx(c, out, 1, "xinv_add_source", "yx_add_source", 8.0 * g.nc + 8.0 * g.n * ntargets,
+             [&](int pb, int pe) { g.ox->xinv_add(xinv_args<1>(c, out, pb, pe), e, c->st); },
+             [&] { auto a = yx_args<1>(c, out, 1); return g.ox->yx_add(a, e, c->pipe, c->st); });
 }
 
 static TermsArgs terms_args(kw_ctx* c) {
@@ -791,8 +836,9 @@ static int step(kw_ctx* c) {
     for (int k = 0; k < 3; ++k) e.u[k] = u[k], e.dtrho[k] = c->fld(KW_RHO0_SGX + k), e.pml_sg[k] = c->d[KW_PML_X_SGX + k];
     e.fd = fd, e.init = 0;
     const double het = c->count[KW_RHO0_SGX] > 1 ? 4.0 : 0.0;
-    inverse_yx(c, c->S, 3, "xinv_velocity", 3 * (8.0 * g.nc + (8.0 + het) * g.n),
-               [&](int pb, int pe) { g.ox->xinv_velocity(xinv_args<1>(c, c->S, pb, pe, 3), e, 3, c->st); });
+    inverse_yx(c, c->S, 3, "xinv_velocity", "yx_velocity", 3 * (8.0 * g.nc + (8.0 + het) * g.n),
+               [&](int pb, int pe) { g.ox->xinv_velocity(xinv_args<1>(c, c->S, pb, pe, 3), e, 3, c->st); },
+               [&] { auto a = yx_args<1>(c, c->S, 3); return g.ox->yx_velocity(a, e, c->pipe, c->st); });
   }
   // ---- addVelocitySource (cpp:2252-2303), transducer (cpp:894-897)
   const uint64_t uflag[3] = {cf.ux_source_flag, cf.uy_source_flag, cf.uz_source_flag};
@@ -836,8 +882,9 @@ static int step(kw_ctx* c) {
       if (cf.absorbing_flag) per += 4.0 + (e.defer_terms ? 0.0 : 4.0 + (cf.nonlinear_flag ? 4.0 : 0.0));  // A, B, NL
       else if (!e.defer_terms) per += 4.0 + (c->count[KW_C0] > 1 ? 4.0 : 0.0);                               // p, c2
       if (cf.nonlinear_flag && !e.defer_terms && c->count[KW_BONA] > 1) per += 4.0;
-      inverse_yx(c, c->S, 3, "xinv_density", 24.0 * g.nc + per * g.n + fused_bytes,
-                 [&](int pb, int pe) { g.ox->xinv_density(xinv_args<3>(c, c->S, pb, pe), e, c->st); });
+      inverse_yx(c, c->S, 3, "xinv_density", "yx_density", 24.0 * g.nc + per * g.n + fused_bytes,
+                 [&](int pb, int pe) { g.ox->xinv_density(xinv_args<3>(c, c->S, pb, pe), e, c->st); },
+                 [&] { auto a = yx_args<3>(c, c->S); return g.ox->yx_density(a, e, c->pipe, c->st); });
     }
     // ---- addPressureSource (cpp:2310-2334)
     if (p_src) {
@@ -871,8 +918,9 @@ static int step(kw_ctx* c) {
     const double per = 8.0 + (c->count[KW_C0] > 1 ? 4.0 : 0.0) + (c->count[KW_ABSORB_TAU] > 1 ? 8.0 : 0.0);
     double fused_bytes = 0;
     e.sample = fused_p_sample(c, &e.fs, &fused_bytes);
-    inverse_yx(c, c->S, 2, "xinv_pressure_sum", 16.0 * g.nc + per * g.n + fused_bytes,
-               [&](int pb, int pe) { g.ox->xinv_psum(xinv_args<2>(c, c->S, pb, pe), e, c->st); });
+    inverse_yx(c, c->S, 2, "xinv_pressure_sum", "yx_pressure_sum", 16.0 * g.nc + per * g.n + fused_bytes,
+               [&](int pb, int pe) { g.ox->xinv_psum(xinv_args<2>(c, c->S, pb, pe), e, c->st); },
+               [&] { auto a = yx_args<2>(c, c->S); return g.ox->yx_psum(a, e, c->pipe, c->st); });
   }
   // ---- addInitialPressureSource (cpp:2359-2396)
   if (t == 0 && cf.p0_source_flag == 1) {
@@ -883,8 +931,9 @@ static int step(kw_ctx* c) {
     EpiVelocity e{};
     for (int k = 0; k < 3; ++k) e.u[k] = u[k], e.dtrho[k] = c->fld(KW_RHO0_SGX + k), e.pml_sg[k] = c->d[KW_PML_X_SGX + k];
     e.fd = fd, e.init = 1;
-    inverse_yx(c, c->S, 3, "xinv_initial_velocity", 3 * (8.0 * g.nc + 8.0 * g.n),
-               [&](int pb, int pe) { g.ox->xinv_velocity(xinv_args<1>(c, c->S, pb, pe, 3), e, 3, c->st); });
+    inverse_yx(c, c->S, 3, "xinv_initial_velocity", "yx_initial_velocity", 3 * (8.0 * g.nc + 8.0 * g.n),
+               [&](int pb, int pe) { g.ox->xinv_velocity(xinv_args<1>(c, c->S, pb, pe, 3), e, 3, c->st); },
+               [&] { auto a = yx_args<1>(c, c->S, 3); return g.ox->yx_velocity(a, e, c->pipe, c->st); });
   }
   // ---- storeSensorData (cpp:1060-1093)
   if (t >= cf.sampling_start_index) sample_streams(c);
@@ -920,6 +969,7 @@ int kw_run(kw_ctx* c, uint64_t nsteps, uint64_t* steps_done, int sync) {
     KW_CUDA(cudaStreamSynchronize(c->st));
     KW_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
     prof_resolve(c);
+    KW_TRY(pipe_check(c));
   }
   return rc;
 }
@@ -935,6 +985,7 @@ int kw_synchronize(kw_ctx* c) {
   cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
   prof_resolve(c);
   KW_CUDA(cudaGetLastError());
+  KW_TRY(pipe_check(c));
   return KW_OK;
 }
 int kw_profile(kw_ctx* c, int enable, int reset) {
