@@ -150,6 +150,20 @@ int kw_set_source_row(kw_ctx* ctx, int array_id, uint64_t t_index, const float* 
 int kw_fft_r2c_3d(uint64_t nx, uint64_t ny, uint64_t nz, const float* host_real, float* host_complex);
 int kw_fft_c2r_3d(uint64_t nx, uint64_t ny, uint64_t nz, const float* host_complex, float* host_real);
 
+/* Slab decomposition over GPUs (no reference counterpart; the reference is single-GPU: MatrixContainer holds whole
+ * arrays, Containers/MatrixContainer.cpp:418-476).  One context per rank (one process per GPU); kw_config.rank/nranks and
+ * a ncclUniqueId created by ONE rank with kw_nccl_unique_id and distributed by the host (torch.distributed, MPI, a file).
+ * Rank r owns planes z in [z_begin, z_begin + z_count) of every Nx*Ny*Nz array: kw_set_array / kw_get_array take and
+ * return that slab (count = Nx*Ny*z_count) for full-grid arrays, and the complete data for 1-D vectors, signals and
+ * index lists (global 1-based indices; each rank keeps the points of its slab).  Every 3-D transform exchanges the
+ * half spectrum once with an all-to-all over NVLink (NCCL).  Stream rows hold the local sensor points only, in list
+ * order; kw_sensor_layout returns, for each of them, its position in the row of the undecomposed run. */
+int kw_nccl_unique_id(void* out128, uint64_t capacity);
+int kw_local_slab(kw_ctx* ctx, uint64_t* z_begin, uint64_t* z_count);
+int kw_sensor_layout(kw_ctx* ctx, uint64_t* total_points, uint64_t* local_points, uint64_t* positions, uint64_t capacity);
+/* Bytes this rank has sent through the all-to-all since the context was created (NVLink GB/s = bytes / exchange time). */
+int kw_comm_bytes(kw_ctx* ctx, double* bytes_sent);
+
 /* Timing of the device work of the last kw_run (CUDA events on the solver stream), milliseconds. */
 int kw_last_run_ms(kw_ctx* ctx, float* ms);
 /* Per-kernel device timing for roofline reports: when enabled, every launch of the time loop is bracketed by CUDA

@@ -13,5 +13,6 @@ from .capi import (  # noqa: F401
     fft_r2c_3d,
     library_path,
     load_library,
+    nccl_unique_id,
 )
-from . import synth  # noqa: F401
+from . import slab, synth  # noqa: F401

@@ -121,6 +121,10 @@ def load_library():
         "kw_launch_count": [vp, C.POINTER(u64)],
         "kw_profile": [vp, i32, i32],
         "kw_profile_report": [vp, C.c_char_p, u64],
+        "kw_nccl_unique_id": [vp, u64],
+        "kw_local_slab": [vp, C.POINTER(u64), C.POINTER(u64)],
+        "kw_sensor_layout": [vp, C.POINTER(u64), C.POINTER(u64), vp, u64],
+        "kw_comm_bytes": [vp, C.POINTER(C.c_double)],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -155,10 +159,21 @@ def fft_c2r_3d(xk, nx):
     return out
 
 
-class Simulation:
-    """One simulation == one kw_ctx.  ``cfg``/``arrays`` use the input-file names (see synth.make_case)."""
+def nccl_unique_id():
+    """128-byte ncclUniqueId for a slab-decomposed run: create on ONE rank, hand to all (e.g. dist.broadcast)."""
+    buf = C.create_string_buffer(128)
+    _check(load_library().kw_nccl_unique_id(buf, 128))
+    return bytes(buf.raw)
 
-    def __init__(self, cfg, arrays, streams=(), start_index=0, raw_rows_capacity=0, device=-1, compression=None):
+
+class Simulation:
+    """One simulation == one kw_ctx.  ``cfg``/``arrays`` use the input-file names (see synth.make_case).
+
+    Slab-decomposed runs (``nranks > 1``, one process per GPU): ``arrays`` may hold either the complete grids (they are
+    cut to this rank's z-slab here, see slab.slice_arrays) or slabs already; ``nccl_id`` is the shared ncclUniqueId."""
+
+    def __init__(self, cfg, arrays, streams=(), start_index=0, raw_rows_capacity=0, device=-1, compression=None,
+                 rank=0, nranks=1, nccl_id=None):
         self.lib = load_library()
         self.cfg = dict(cfg)
         kc = KwConfig()
@@ -174,14 +189,21 @@ class Simulation:
         kc.sampling_start_index = start_index
         kc.device = device
         kc.raw_rows_capacity = raw_rows_capacity
-        kc.rank, kc.nranks, kc.nccl_unique_id = 0, 1, None
+        kc.rank, kc.nranks = rank, nranks
+        self._nccl_id = C.create_string_buffer(bytes(nccl_id), 128) if nranks > 1 else None
+        kc.nccl_unique_id = C.cast(self._nccl_id, C.c_void_p) if nranks > 1 else None
+        self.rank, self.nranks = rank, nranks
         if compression:
             kc.c_period, kc.c_mos, kc.c_harmonics = compression["period"], compression.get("mos", 1), compression.get("harmonics", 1)
             kc.c_no_overlap, kc.c_40bit = int(compression.get("no_overlap", 0)), int(compression.get("c40", 0))
         self.ctx = C.c_void_p()
         _check(self.lib.kw_ctx_create(C.byref(kc), C.byref(self.ctx)))
         self.n = cfg["Nx"] * cfg["Ny"] * cfg["Nz"]
-        self.shape = (cfg["Nz"], cfg["Ny"], cfg["Nx"])
+        self.shape = (cfg["Nz"] // nranks, cfg["Ny"], cfg["Nx"])  # this rank's slab of every full-grid array
+        if nranks > 1:
+            from . import slab
+
+            arrays = slab.slice_arrays(cfg, arrays, rank, nranks)
         for name, arr in arrays.items():
             self.set_array(name, arr)
         self.streams = []
@@ -257,6 +279,25 @@ class Simulation:
         n = C.c_uint64()
         _check(self.lib.kw_launch_count(self.ctx, C.byref(n)))
         return n.value
+
+    def local_slab(self):
+        z0, nz = C.c_uint64(), C.c_uint64()
+        _check(self.lib.kw_local_slab(self.ctx, C.byref(z0), C.byref(nz)))
+        return z0.value, nz.value
+
+    def sensor_layout(self):
+        """(total points of the undecomposed row, positions of this rank's points in it)."""
+        total, local = C.c_uint64(), C.c_uint64()
+        _check(self.lib.kw_sensor_layout(self.ctx, C.byref(total), C.byref(local), None, 0))
+        pos = np.empty(local.value, dtype=np.uint64)
+        if local.value:
+            _check(self.lib.kw_sensor_layout(self.ctx, C.byref(total), C.byref(local), pos.ctypes.data, pos.size))
+        return total.value, pos
+
+    def comm_bytes(self):
+        b = C.c_double()
+        _check(self.lib.kw_comm_bytes(self.ctx, C.byref(b)))
+        return b.value
 
     @property
     def t_index(self):

@@ -75,12 +75,19 @@ template <int ID, class K> static int col_grid(K kernel, int ntiles, size_t smem
 static void col(const ColArgs& a, int dir, int nfields, cudaStream_t st) {
   using C = ColCfg<N>;
   const dim3 block(C::W, C::WK, C::TPC);
-  if (dir < 0) {
-    const int g = col_grid<0>(k_col<N, -1>, a.tile_end - a.tile_begin, C::SMEM);
-    k_col<N, -1><<<dim3(g, nfields), block, C::SMEM, st>>>(a);
+  const bool blocked = a.blk != 0;
+  if (dir < 0 && !blocked) {
+    const int g = col_grid<0>(k_col<N, -1, false>, a.tile_end - a.tile_begin, C::SMEM);
+    k_col<N, -1, false><<<dim3(g, nfields), block, C::SMEM, st>>>(a);
+  } else if (dir > 0 && !blocked) {
+    const int g = col_grid<1>(k_col<N, +1, false>, a.tile_end - a.tile_begin, C::SMEM);
+    k_col<N, +1, false><<<dim3(g, nfields), block, C::SMEM, st>>>(a);
+  } else if (dir < 0) {
+    const int g = col_grid<2>(k_col<N, -1, true>, a.tile_end - a.tile_begin, C::SMEM);
+    k_col<N, -1, true><<<dim3(g, nfields), block, C::SMEM, st>>>(a);
   } else {
-    const int g = col_grid<1>(k_col<N, +1>, a.tile_end - a.tile_begin, C::SMEM);
-    k_col<N, +1><<<dim3(g, nfields), block, C::SMEM, st>>>(a);
+    const int g = col_grid<3>(k_col<N, +1, true>, a.tile_end - a.tile_begin, C::SMEM);
+    k_col<N, +1, true><<<dim3(g, nfields), block, C::SMEM, st>>>(a);
   }
 }
 template <int AXIS> static void zmid_axis(const ZMidArgs& a, cudaStream_t st) {
@@ -162,7 +169,7 @@ static void zmid(const ZMidArgs& a, cudaStream_t st) {
 
 #define KW_OPS_NAME2(n) fft_ops_##n
 #define KW_OPS_NAME(n) KW_OPS_NAME2(n)
-extern const FftOps KW_OPS_NAME(KW_N) = {KW_N, ColCfg<KW_N>::W, KW_CAT(inst_, KW_N)::xfwd, KW_CAT(inst_, KW_N)::xinv_store, KW_CAT(inst_, KW_N)::xinv_add, KW_CAT(inst_, KW_N)::xinv_velocity,
+extern const FftOps KW_OPS_NAME(KW_N) = {KW_N, ColCfg<KW_N>::W, ColCfg<KW_N>::WK, KW_CAT(inst_, KW_N)::xfwd, KW_CAT(inst_, KW_N)::xinv_store, KW_CAT(inst_, KW_N)::xinv_add, KW_CAT(inst_, KW_N)::xinv_velocity,
                                             KW_CAT(inst_, KW_N)::xinv_density, KW_CAT(inst_, KW_N)::xinv_psum, KW_CAT(inst_, KW_N)::col, KW_CAT(inst_, KW_N)::zmid,
                                             KW_CAT(inst_, KW_N)::xy_fwd, KW_CAT(inst_, KW_N)::yx_store, KW_CAT(inst_, KW_N)::yx_add, KW_CAT(inst_, KW_N)::yx_velocity,
                                             KW_CAT(inst_, KW_N)::yx_density, KW_CAT(inst_, KW_N)::yx_psum};

@@ -19,17 +19,33 @@ constexpr int kMaxFields = 3;
 constexpr int kXThreads = 256;
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Where row (z, y) of a half-spectrum array lives.  Single GPU: [z][y][NXP], i.e. row * NXP.  Slab-decomposed runs keep
+// the x/y-local spectra in the y-blocked "exchange" layout [q][z_local][y_local][NXP] (q = rank that owns y after the
+// transpose, y = q*nyl + y_local), so that the block sent to rank q by the all-to-all is one contiguous range.
+struct RowMap {
+  int ny_log2;   // log2(Ny)
+  int ysh;       // log2(nyl), nyl = Ny / nranks  (== ny_log2 on one GPU)
+  size_t blk;    // elements of one block: nzl * nyl * NXP
+  __device__ __forceinline__ size_t off(size_t row, int nxp) const {
+    const size_t z = row >> ny_log2;
+    const unsigned y = (unsigned)row & ((1u << ny_log2) - 1u);
+    return (size_t)(y >> ysh) * blk + ((z << ysh) + (y & ((1u << ysh) - 1u))) * (size_t)nxp;
+  }
+};
+
 struct XFwdArgs {
   const float* in[kMaxFields];
   float2* out[kMaxFields];
   const float2* tab;  // forward twiddle table of length Nx
   int pair_begin, pair_end;  // range of row pairs (row = z*Ny + y) this launch transforms
   int nxp;
+  RowMap map;
 };
 
 // One row pair (rows row0, row0+1) of one field: real -> half spectrum.  T = N/8 threads cooperate through `ex`.
+// `out_off` = element offset of row0's spectrum row in `out` (row0 + 1 follows nxp elements later).
 template <int N, class EX> __device__ __forceinline__ void xfwd_rows(const float* __restrict__ in, float2* __restrict__ out, int nxp,
-                                                                     size_t row0, bool valid, int t, const RegTw& twp, EX& ex) {
+                                                                     size_t row0, size_t out_off, bool valid, int t, const RegTw& twp, EX& ex) {
   constexpr int T = N / 8;
   const float* ra = in + row0 * N;
   float2 v[1][8];
@@ -45,7 +61,7 @@ template <int N, class EX> __device__ __forceinline__ void xfwd_rows(const float
   for (int m = 0; m < 4; ++m) zp[m] = ex.get(0, (N - (t + m * T)) & (N - 1));
   ex.sync();
   if (valid) {
-    float2* oa = out + row0 * nxp;
+    float2* oa = out + out_off;
     float2* ob = oa + nxp;
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
@@ -77,7 +93,8 @@ template <int N> __global__ void __launch_bounds__(kXThreads, 3) k_xfwd(XFwdArgs
   for (int g = blockIdx.x; g * RP < npairs; g += gridDim.x) {
     const int pair = a.pair_begin + g * RP + rp;
     const bool valid = pair < a.pair_end;
-    xfwd_rows<N>(in, out, a.nxp, 2 * (size_t)(valid ? pair : a.pair_begin), valid, t, twp, ex);
+    const size_t row0 = 2 * (size_t)(valid ? pair : a.pair_begin);
+    xfwd_rows<N>(in, out, a.nxp, row0, a.map.off(row0, a.nxp), valid, t, twp, ex);
   }
 }
 
@@ -86,6 +103,7 @@ template <int NF> struct XInvArgs {
   const float2* in[kMaxFields];  // NF == 1: field selected by blockIdx.y; NF > 1: the NF fields of one voxel
   const float2* tab;
   int pair_begin, pair_end, nxp, ny;
+  RowMap map;
 };
 
 // One row pair of NF fields: half spectra -> real rows, then the epilogue on the registers.
@@ -98,7 +116,7 @@ __device__ __forceinline__ void xinv_rows(const XInvArgs<NF>& a, const Epi& epi,
 #pragma unroll
   for (int f = 0; f < NF; ++f) {
     const float2* __restrict__ in = (NF == 1) ? a.in[field] : a.in[f];
-    const float2* ia = in + row0 * a.nxp;
+    const float2* ia = in + a.map.off(row0, a.nxp);
     const float2* ib = ia + a.nxp;
     float2 v[1][8];
 #pragma unroll
@@ -202,10 +220,14 @@ struct ColArgs {
   size_t outer_stride;  // elements between consecutive "outer" tiles
   int ngroups;          // NXP / W
   int tile_begin, tile_end;  // range of tiles (tile = outer * ngroups + group) this launch transforms
+  // y-blocked exchange layout (slab-decomposed runs, see RowMap): point e of a worker (axis index w + WK*e) lives at
+  // (e >> blk_es) * blk + (e & ((1 << blk_es) - 1)) * WK * stride;  requires nyl >= WK.  Unused by k_col<.., false>.
+  int blk_es;
+  size_t blk;
 };
 
 #ifdef KW_N
-template <int N, int DIR> __global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MINB) k_col(ColArgs a) {
+template <int N, int DIR, bool BLOCKED> __global__ void __launch_bounds__(ColCfg<N>::THREADS, ColCfg<N>::MINB) k_col(ColArgs a) {
   using C = ColCfg<N>;
   using P = Plan2<N>;
   constexpr int W = C::W, WK = C::WK, E = P::E;
@@ -216,6 +238,10 @@ template <int N, int DIR> __global__ void __launch_bounds__(ColCfg<N>::THREADS, 
   const int ntiles = a.tile_end - a.tile_begin;
   const int niter = (ntiles + C::TPC - 1) / C::TPC;
   const size_t estride = (size_t)WK * a.stride;
+  auto poff = [&](int e) -> size_t {
+    if constexpr (BLOCKED) return (size_t)(e >> a.blk_es) * a.blk + (size_t)(e & ((1 << a.blk_es) - 1)) * estride;
+    else return e * estride;
+  };
   auto tile_ptr = [&](int it, bool& valid) -> float2* {
     const int tile = a.tile_begin + it * C::TPC + tz;
     valid = tile < a.tile_end;
@@ -230,7 +256,7 @@ template <int N, int DIR> __global__ void __launch_bounds__(ColCfg<N>::THREADS, 
       bool valid;
       const float2* p = tile_ptr(it, valid);
 #pragma unroll
-      for (int e = 0; e < E; ++e) cp_async8(ex.buf + (w + WK * e) * W, p + e * estride);
+      for (int e = 0; e < E; ++e) cp_async8(ex.buf + (w + WK * e) * W, p + poff(e));
       cp_async_commit();
     }
   };
@@ -247,7 +273,7 @@ template <int N, int DIR> __global__ void __launch_bounds__(ColCfg<N>::THREADS, 
       ex.sync();  // landing slots of other workers must be consumed before stage-1 outputs overwrite them
     } else {
 #pragma unroll
-      for (int e = 0; e < E; ++e) v[e] = p[e * estride];
+      for (int e = 0; e < E; ++e) v[e] = p[poff(e)];
     }
     const int nxt = it + gridDim.x;
     fft2_worker<N, DIR>(v, w, ex, ConstTab(), [&] {
@@ -255,7 +281,7 @@ template <int N, int DIR> __global__ void __launch_bounds__(ColCfg<N>::THREADS, 
     });
     if (valid) {
 #pragma unroll
-      for (int e = 0; e < E; ++e) p[e * estride] = v[e];
+      for (int e = 0; e < E; ++e) p[poff(e)] = v[e];
     }
   }
 }

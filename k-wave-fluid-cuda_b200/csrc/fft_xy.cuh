@@ -180,7 +180,8 @@ template <int N> __global__ void __launch_bounds__(XYCfg<N>::THREADS, ColCfg<N>:
       RegTw twp{twr};
       const int pair = it.sub * X::RP + rp;
       const bool valid = pair < N / 2;
-      xfwd_rows<N>(a.in[f] + (size_t)z * N * N, slot, a.nxp, 2 * (size_t)(valid ? pair : 0), valid, t, twp, rex);
+      const size_t rowl = 2 * (size_t)(valid ? pair : 0);
+      xfwd_rows<N>(a.in[f] + (size_t)z * N * N, slot, a.nxp, rowl, rowl * a.nxp, valid, t, twp, rex);
     } else {  // column tiles of the plane: ring slot -> final spectrum
       const int tile = it.sub * C::TPC + tz;
       const bool valid = tile < ngroups;

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/kwave_b200.h"
+#include "nccl_dl.h"
 #include "ops.h"
 
 namespace kw {
@@ -101,21 +102,41 @@ struct Stream {
   bool fused_this_step = false;  // accumulated by the kernel that produced the field
 };
 
+// Grid + slab decomposition.  Rank r of P owns the real-space planes z in [z0, z0 + nzl) of every
+// field ("x/y-local" side) and, after the all-to-all of a transform, the ky range [y0, y0 + nyl) of every spectrum for
+// all kz ("z-local" side).  P == 1: nzl = nz, nyl = ny, and every layout below reduces to the plain [z][y][x] one.
 struct Geometry {
   int nx = 0, ny = 0, nz = 0, nxr = 0, nxp = 0;
-  size_t n = 0, nc = 0;  // real voxels, padded complex elements
+  int rank = 0, nranks = 1;
+  int nzl = 0, nyl = 0, z0 = 0, y0 = 0;  // local extents / offsets
+  int ny_log2 = 0, ysh = 0;              // log2(ny), log2(nyl)
+  size_t n = 0, nc = 0;                  // LOCAL real voxels, LOCAL padded complex elements (nxp*ny*nzl == nxp*nyl*nz)
+  size_t ntot = 0;                       // global real voxels
+  size_t blk = 0;                        // complex elements exchanged with one peer per field: nxp*nyl*nzl
   const FftOps *ox = nullptr, *oy = nullptr, *oz = nullptr;
   const float2 *tx = nullptr, *ty = nullptr, *tz = nullptr;
-  int init(uint64_t nx_, uint64_t ny_, uint64_t nz_) {
+  RowMap row_map() const { return RowMap{ny_log2, ysh, blk}; }
+  int init(uint64_t nx_, uint64_t ny_, uint64_t nz_, int rank_ = 0, int nranks_ = 1) {
     nx = (int)nx_, ny = (int)ny_, nz = (int)nz_;
     ox = get_fft_ops(nx), oy = get_fft_ops(ny), oz = get_fft_ops(nz);
     if (!ox || !oy || !oz)
       return fail(KW_ERR_INVALID, "grid sizes must be powers of two in [16,1024] (hand-written FFT plan table); got " +
                                       std::to_string(nx_) + "x" + std::to_string(ny_) + "x" + std::to_string(nz_));
+    rank = rank_, nranks = nranks_ < 1 ? 1 : nranks_;
+    if (rank < 0 || rank >= nranks || (nranks & (nranks - 1)) || nz % nranks || ny % nranks)
+      return fail(KW_ERR_INVALID, "slab decomposition needs a power-of-two number of ranks dividing Ny and Nz");
+    nzl = nz / nranks, nyl = ny / nranks, z0 = rank * nzl, y0 = rank * nyl;
+    if (nranks > 1 && (nyl < oy->col_wk || (nyl & 1)))
+      return fail(KW_ERR_INVALID, "slab decomposition: Ny / nranks = " + std::to_string(nyl) + " is below the y-pass worker count " +
+                                      std::to_string(oy->col_wk) + " of this Ny (use fewer ranks)");
+    for (ny_log2 = 0; (1 << ny_log2) < ny; ++ny_log2) {}
+    for (ysh = 0; (1 << ysh) < nyl; ++ysh) {}
     nxr = nx / 2 + 1;
     nxp = (nxr + 15) / 16 * 16;
-    n = (size_t)nx * ny * nz;
-    nc = (size_t)nxp * ny * nz;
+    ntot = (size_t)nx * ny * nz;
+    n = (size_t)nx * ny * nzl;
+    nc = (size_t)nxp * ny * nzl;
+    blk = (size_t)nxp * nyl * nzl;
     KW_TRY(twiddle_table(nx, &tx));
     KW_TRY(twiddle_table(ny, &ty));
     KW_TRY(twiddle_table(nz, &tz));
@@ -160,10 +181,20 @@ struct kw_ctx {
   size_t count[KW_ARRAY_COUNT] = {};
   float scalar[KW_ARRAY_COUNT] = {};
   float2* S[4] = {};
+  float2* R[4] = {};  // receive side of the all-to-all (slab-decomposed runs only)
   float *tA = nullptr, *tB = nullptr, *tNL = nullptr, *tSrc = nullptr;
   uint64_t* cub_offsets = nullptr;
-  size_t nsens = 0;  // sensor points (index mask) or total cuboid points
+  uint64_t* cub_corners = nullptr;  // cuboid corners clipped to the local slab, local z
+  size_t nsens = 0;  // LOCAL sensor points (index mask) or LOCAL cuboid points
+  size_t nsens_total = 0;
   int ncuboids = 0;
+  // slab-decomposed runs: positions of the locally kept entries of each index list in the original list
+  uint64_t* dpos[KW_ARRAY_COUNT] = {};
+  size_t count_total[KW_ARRAY_COUNT] = {};
+  std::vector<uint64_t> sens_pos;     // index mask: position of every local sensor point in the global row
+  std::vector<uint64_t> sens_ranges;  // cuboid mask: (start in the global row, length) per cuboid part held locally
+  KwNcclComm comm = nullptr;
+  double comm_bytes = 0.0;
   Stream streams[KW_STREAM_COUNT];
   PipeState pipe;  // ring + counters of the plane-fused x/y kernels (Nx == Ny only)
   std::vector<void*> owned;
@@ -269,22 +300,24 @@ static void generate_k_operators(const kw_config& cf, const Geometry& g, std::ve
   const float nxRec = 1.0f / static_cast<float>(g.nx), nyRec = 1.0f / static_cast<float>(g.ny),
               nzRec = 1.0f / static_cast<float>(g.nz);
   const float ap = cf.alpha_power;
-  const size_t tot = (size_t)g.nxr * g.ny * g.nz;
-  if (kappa) kappa->resize(tot);
-  if (n1) n1->resize(tot), n2->resize(tot);
-  if (skappa) skappa->resize(tot);
+  // output: the z-local side of this rank, [kz][ky_local][NXP] (zero padded) -- what k_zmid multiplies with
+  const size_t tot = (size_t)g.nxp * g.nyl * g.nz;
+  if (kappa) kappa->assign(tot, 0.f);
+  if (n1) n1->assign(tot, 0.f), n2->assign(tot, 0.f);
+  if (skappa) skappa->assign(tot, 0.f);
 #pragma omp parallel for schedule(static)
   for (int z = 0; z < g.nz; z++) {
     float zPart = 0.5f - fabsf(0.5f - (float)z * nzRec);
     zPart = (zPart * zPart) * dz2;
-    for (int y = 0; y < g.ny; y++) {
+    for (int yl = 0; yl < g.nyl; yl++) {
+      const int y = g.y0 + yl;
       float yPart = 0.5f - fabsf(0.5f - (float)y * nyRec);
       yPart = (yPart * yPart) * dy2;
       const float yzPart = zPart + yPart;
       for (int x = 0; x < g.nxr; x++) {
         float xPart = 0.5f - fabsf(0.5f - (float)x * nxRec);
         xPart = (xPart * xPart) * dx2;
-        const size_t i = ((size_t)z * g.ny + y) * g.nxr + x;
+        const size_t i = ((size_t)z * g.nyl + yl) * g.nxp + x;
         const float root = sqrtf(xPart + yzPart);
         if (n1) {  // absorbing: kappa from pi2 * root * cRefDt2 (cpp:2556-2561)
           const float k = pi2 * root;
@@ -339,17 +372,33 @@ int kw_ctx_create(const kw_config* cfg, kw_ctx** out) {
   if (cfg->nz <= 1) return fail(KW_ERR_INVALID, "2-D simulations (Nz == 1) are not supported by this build");
   if (cfg->absorbing_flag && cfg->alpha_power == 1.0f)
     return fail(KW_ERR_INVALID, "alpha_power == 1 is not supported (Parameters.cpp:421-424)");
-  if (cfg->nranks > 1) return fail(KW_ERR_INVALID, "sharded runs are not available in this build");
+  if (cfg->nranks > 1 && !cfg->nccl_unique_id) return fail(KW_ERR_INVALID, "nranks > 1 needs the shared ncclUniqueId (kw_nccl_unique_id)");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) return fail(KW_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
   if (cfg->device >= 0) KW_CUDA(cudaSetDevice(cfg->device));
   kw_ctx* c = new kw_ctx();
   c->cfg = *cfg;
-  int r = c->g.init(cfg->nx, cfg->ny, cfg->nz);
+  int r = c->g.init(cfg->nx, cfg->ny, cfg->nz, cfg->rank, cfg->nranks);
   if (r != KW_OK) {
     delete c;
     return r;
+  }
+  if (c->g.nranks > 1) {  // one communicator per context, over NVLink / NVSwitch
+    NcclApi& nc = nccl_api();
+    if (!nc.ok) {
+      delete c;
+      return fail(KW_ERR_COMM, "NCCL unavailable: " + nc.error);
+    }
+    KwNcclUniqueId id;
+    memcpy(&id, cfg->nccl_unique_id, sizeof(id));
+    const int e = nc.CommInitRank(&c->comm, c->g.nranks, id, c->g.rank);
+    if (e != kNcclSuccess) {
+      const std::string msg = nc.GetErrorString(e);
+      delete c;
+      return fail(KW_ERR_COMM, "ncclCommInitRank: " + msg);
+    }
+    c->cfg.nccl_unique_id = nullptr;
   }
   KW_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
   KW_CUDA(cudaEventCreate(&c->ev0));
@@ -361,6 +410,7 @@ int kw_ctx_create(const kw_config* cfg, kw_ctx** out) {
 int kw_ctx_destroy(kw_ctx* c) {
   if (!c) return KW_OK;
   cudaStreamSynchronize(c->st);
+  if (c->comm) nccl_api().CommDestroy(c->comm);
   for (void* p : c->owned) cudaFree(p);
   prof_resolve(c);
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
@@ -394,6 +444,7 @@ int kw_set_array(kw_ctx* c, int id, const void* host, uint64_t count) {
   }
   const float* h = static_cast<const float*>(host);
   if (is_reduced_real(id)) {
+    if (g.nranks > 1) return fail(KW_ERR_INVALID, "kw_set_array: k-space operators are generated per rank in slab-decomposed runs");
     if (count != (size_t)g.nxr * g.ny * g.nz) return fail(KW_ERR_INVALID, "kw_set_array: wrong size for reduced-grid operator");
     return upload_reduced(c, id, h);
   }
@@ -473,10 +524,53 @@ int kw_preprocess(kw_ctx* c) {
     }
     if (id != KW_DELAY_MASK && id != KW_SENSOR_MASK_CORNERS)
       for (auto v : h)
-        if (v >= g.n) return fail(KW_ERR_INVALID, "index outside the grid in array " + std::to_string(id));
-    KW_TRY(dalloc(c, (void**)&c->di[id], h.size() * sizeof(uint64_t), false));
-    KW_CUDA(cudaMemcpyAsync(c->di[id], h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->st));
-    c->count[id] = h.size();
+        if (v >= g.ntot) return fail(KW_ERR_INVALID, "index outside the grid in array " + std::to_string(id));
+    c->count_total[id] = h.size();
+  }
+  // slab-decomposed runs keep the points of the local slab only (global 0-based linear index -> owner = z / nzl), with
+  // their position in the original list so that signals are looked up and rows are assembled in list order
+  {
+    const uint64_t lo = (uint64_t)g.z0 * g.nx * g.ny, hi = lo + g.n;
+    auto keep_local = [&](int id, std::vector<uint64_t>* pos) {
+      auto& h = c->h_idx[id];
+      std::vector<uint64_t> loc;
+      for (size_t j = 0; j < h.size(); ++j)
+        if (h[j] >= lo && h[j] < hi) loc.push_back(h[j] - lo), pos->push_back(j);
+      h.swap(loc);
+    };
+    if (g.nranks > 1) {
+      std::vector<uint64_t> pos;
+      auto upload_pos = [&](int id) -> int {
+        KW_TRY(dalloc(c, (void**)&c->dpos[id], pos.size() * sizeof(uint64_t), false));
+        KW_CUDA(cudaMemcpyAsync(c->dpos[id], pos.data(), pos.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->st));
+        KW_CUDA(cudaStreamSynchronize(c->st));
+        return KW_OK;
+      };
+      if (!c->h_idx[KW_P_SOURCE_INDEX].empty()) {
+        keep_local(KW_P_SOURCE_INDEX, &pos);
+        KW_TRY(upload_pos(KW_P_SOURCE_INDEX));
+      }
+      if (!c->h_idx[KW_U_SOURCE_INDEX].empty()) {
+        pos.clear();
+        keep_local(KW_U_SOURCE_INDEX, &pos);
+        KW_TRY(upload_pos(KW_U_SOURCE_INDEX));
+        auto& dm = c->h_idx[KW_DELAY_MASK];
+        if (!dm.empty()) {  // delay of every kept transducer point
+          std::vector<uint64_t> loc(pos.size());
+          for (size_t j = 0; j < pos.size(); ++j) loc[j] = dm[pos[j]];
+          dm.swap(loc);
+        }
+      }
+      if (!c->h_idx[KW_SENSOR_MASK_INDEX].empty()) keep_local(KW_SENSOR_MASK_INDEX, &c->sens_pos);
+    }
+    for (int id : {KW_SENSOR_MASK_INDEX, KW_P_SOURCE_INDEX, KW_U_SOURCE_INDEX, KW_DELAY_MASK}) {
+      auto& h = c->h_idx[id];
+      if (c->count_total[id] == 0) continue;
+      KW_TRY(dalloc(c, (void**)&c->di[id], h.size() * sizeof(uint64_t), false));
+      KW_CUDA(cudaMemcpyAsync(c->di[id], h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->st));
+      c->count[id] = h.size();
+    }
+    KW_CUDA(cudaStreamSynchronize(c->st));
   }
   // --- 2. dt / rho0_sg (cpp:825-830)
   for (int k = 0; k < 3; ++k) {
@@ -500,12 +594,17 @@ int kw_preprocess(kw_ctx* c) {
     if (need_kappa || need_nabla || need_sk)
       generate_k_operators(cf, g, need_kappa ? &kappa : nullptr, cf.absorbing_flag ? &n1 : nullptr,
                            cf.absorbing_flag ? &n2 : nullptr, need_sk ? &sk : nullptr);
-    if (need_kappa) KW_TRY(upload_reduced(c, KW_KAPPA, kappa.data()));
+    auto upload_padded = [&](int id, const std::vector<float>& h) -> int {
+      KW_TRY(upload_f(c, id, h.data(), h.size()));
+      c->count[id] = (size_t)g.nxr * g.nyl * g.nz;
+      return KW_OK;
+    };
+    if (need_kappa) KW_TRY(upload_padded(KW_KAPPA, kappa));
     if (need_nabla) {
-      KW_TRY(upload_reduced(c, KW_ABSORB_NABLA1, n1.data()));
-      KW_TRY(upload_reduced(c, KW_ABSORB_NABLA2, n2.data()));
+      KW_TRY(upload_padded(KW_ABSORB_NABLA1, n1));
+      KW_TRY(upload_padded(KW_ABSORB_NABLA2, n2));
     }
-    if (need_sk) KW_TRY(upload_reduced(c, KW_SOURCE_KAPPA, sk.data()));
+    if (need_sk) KW_TRY(upload_padded(KW_SOURCE_KAPPA, sk));
   }
   if (cf.absorbing_flag && c->count[KW_ABSORB_TAU] == 0) {  // tau, eta (cpp:2584-2643); c0 still unsquared here
     auto& al = c->h_in[KW_ALPHA_COEFF];
@@ -550,7 +649,7 @@ int kw_preprocess(kw_ctx* c) {
   if (cf.transducer_source_flag && (!c->d[KW_TRANSDUCER_SOURCE_INPUT] || !c->di[KW_DELAY_MASK]))
     return fail(KW_ERR_INVALID, "transducer source arrays missing");
   if (cf.p0_source_flag && !c->d[KW_P0_SOURCE_INPUT]) return fail(KW_ERR_INVALID, "p0_source_input missing");
-  if (cf.p_source_flag && cf.p_source_many && c->count[KW_P_SOURCE_INPUT] < cf.p_source_flag * c->count[KW_P_SOURCE_INDEX])
+  if (cf.p_source_flag && cf.p_source_many && c->count[KW_P_SOURCE_INPUT] < cf.p_source_flag * c->count_total[KW_P_SOURCE_INDEX])
     return fail(KW_ERR_INVALID, "p_source_input shorter than p_source_flag * Nsrc");
   // --- state and temporaries (state starts at zero, BaseFloatMatrix.cpp:144-145)
   for (int id : {KW_P, KW_RHOX, KW_RHOY, KW_RHOZ, KW_UX_SGX, KW_UY_SGY, KW_UZ_SGZ})
@@ -559,9 +658,11 @@ int kw_preprocess(kw_ctx* c) {
       c->count[id] = g.n;
     }
   for (int k = 0; k < 4; ++k) KW_TRY(dalloc(c, (void**)&c->S[k], g.nc * sizeof(float2)));
+  if (g.nranks > 1)
+    for (int k = 0; k < 4; ++k) KW_TRY(dalloc(c, (void**)&c->R[k], g.nc * sizeof(float2)));
   {  // plane-fused x/y passes (fft_xy.cuh): an L2-resident ring of spectrum planes + two sets of progress counters
     static const long long ring_mb = getenv("KW_RING_MB") ? atoll(getenv("KW_RING_MB")) : 0;  // opt-in: the first version is correct but slower than the separate passes (profiles/r01_e)
-    if (g.nx == g.ny && ring_mb > 0) {
+    if (g.nx == g.ny && ring_mb > 0 && g.nranks == 1) {
       const size_t plane_c = (size_t)g.ny * g.nxp;
       size_t slots = ((size_t)ring_mb << 20) / (plane_c * sizeof(float2));
       if (slots < 12) slots = 12;  // at least four slots of three planes
@@ -587,21 +688,42 @@ int kw_preprocess(kw_ctx* c) {
     if (cf.sensor_mask_type == 0) {
       if (!c->di[KW_SENSOR_MASK_INDEX]) return fail(KW_ERR_INVALID, "sensor_mask_index missing");
       c->nsens = c->count[KW_SENSOR_MASK_INDEX];
+      c->nsens_total = c->count_total[KW_SENSOR_MASK_INDEX];
     } else {
       auto& h = c->h_idx[KW_SENSOR_MASK_CORNERS];
       if (h.empty() || h.size() % 6) return fail(KW_ERR_INVALID, "sensor_mask_corners missing or not a multiple of 6");
       c->ncuboids = (int)(h.size() / 6);
-      std::vector<uint64_t> off(c->ncuboids + 1, 0);
+      // every cuboid is clipped to the local slab (a z-range of a cuboid is a contiguous range of its x-fastest buffer)
+      std::vector<uint64_t> off(c->ncuboids + 1, 0), loc(h.size(), 0);
+      uint64_t goff = 0;
       for (int k = 0; k < c->ncuboids; ++k) {
         const uint64_t* q = &h[6 * k];
         if (q[3] < q[0] || q[4] < q[1] || q[5] < q[2] || q[3] >= (uint64_t)g.nx || q[4] >= (uint64_t)g.ny || q[5] >= (uint64_t)g.nz)
           return fail(KW_ERR_INVALID, "sensor_mask_corners: cuboid outside the grid");
-        off[k + 1] = off[k] + (q[3] - q[0] + 1) * (q[4] - q[1] + 1) * (q[5] - q[2] + 1);
+        const uint64_t cxy = (q[3] - q[0] + 1) * (q[4] - q[1] + 1);
+        const uint64_t zlo = std::max<uint64_t>(q[2], (uint64_t)g.z0), zhi = std::min<uint64_t>(q[5], (uint64_t)(g.z0 + g.nzl - 1));
+        uint64_t* l = &loc[6 * k];
+        l[0] = q[0], l[1] = q[1], l[3] = q[3], l[4] = q[4];
+        if (zlo <= zhi) {
+          l[2] = zlo - g.z0, l[5] = zhi - g.z0;
+          off[k + 1] = off[k] + cxy * (zhi - zlo + 1);
+          c->sens_ranges.push_back(goff + cxy * (zlo - q[2]));
+          c->sens_ranges.push_back(cxy * (zhi - zlo + 1));
+        } else {
+          l[2] = l[5] = 0;  // empty part: zero length in the offsets, never addressed
+          off[k + 1] = off[k];
+        }
+        goff += cxy * (q[5] - q[2] + 1);
       }
       c->nsens = off.back();
+      c->nsens_total = goff;
       KW_TRY(dalloc(c, (void**)&c->cub_offsets, off.size() * sizeof(uint64_t), false));
+      KW_TRY(dalloc(c, (void**)&c->cub_corners, loc.size() * sizeof(uint64_t), false));
       KW_CUDA(cudaMemcpyAsync(c->cub_offsets, off.data(), off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->st));
+      KW_CUDA(cudaMemcpyAsync(c->cub_corners, loc.data(), loc.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->st));
       KW_CUDA(cudaStreamSynchronize(c->st));
+      c->h_idx[KW_SENSOR_MASK_CORNERS] = loc;  // fused_p_sample reads the (local) corners of a single cuboid from here
+      c->count[KW_SENSOR_MASK_CORNERS] = loc.size();
     }
   }
   const uint64_t nsamp = cf.nt > cf.sampling_start_index ? cf.nt - cf.sampling_start_index : 0;
@@ -635,28 +757,25 @@ int kw_preprocess(kw_ctx* c) {
 // =====================================================================================================================
 namespace kw {
 
-struct StepCtx {
-  kw_ctx* c;
-  const Geometry& g;
-  cudaStream_t st;
-};
+// ---- building blocks of a (possibly slab-decomposed) 3-D transform -------------------------------------------------
+// forward:  real slab --x pass, y pass--> x/y-local spectrum (y-blocked layout) --all-to-all--> z-local spectrum
+//           [kz][ky_local][NXP] --k_zmid (forward z, operator, inverse z)--> --all-to-all--> --y pass, x pass + epilogue
+// On one GPU the exchanges vanish and both layouts are the plain [z][y][NXP].
 
-// z-chunking: the x pass and the y pass of a transform are launched chunk by chunk over groups of z planes so that
-// the intermediate half-spectrum of a chunk is still in the 126 MB L2 when the next pass reads it (the two passes are
-// independent per z plane).  chunk_planes == nz means one launch per pass.
-static int chunk_planes(const kw_ctx* c, int nf) {
-  static const long long env = getenv("KW_ZCHUNK_MB") ? atoll(getenv("KW_ZCHUNK_MB")) : 0;
-  const Geometry& g = c->g;
-  if (env <= 0) return g.nz;
-  const double plane_mb = (double)g.ny * g.nxp * 8.0 * nf / (1 << 20);
-  int cz = (int)((double)env / plane_mb);
-  if (cz >= g.nz) return g.nz;
-  if (cz < 4) cz = 4;
-  while (g.nz % cz) --cz;  // nz is a power of two: ends at a divisor
-  return cz;
+static ColArgs ycol_args(const Geometry& g, float2* const* data, int nf) {
+  ColArgs ca{};
+  for (int f = 0; f < nf; ++f) ca.data[f] = data[f];
+  ca.stride = g.nxp, ca.outer_stride = (size_t)g.nyl * g.nxp, ca.ngroups = g.nxp / g.oy->col_w;
+  ca.tile_begin = 0, ca.tile_end = g.nzl * ca.ngroups;
+  if (g.nranks > 1) {
+    int wk_log2 = 0;
+    while ((1 << wk_log2) < g.oy->col_wk) ++wk_log2;
+    ca.blk_es = g.ysh - wk_log2, ca.blk = g.blk;
+  }
+  return ca;
 }
 
-// forward x and y passes of `nf` real fields into spectral buffers
+// forward x and y passes of `nf` real fields into spectral buffers (x/y-local side)
 static void forward_xy(kw_ctx* c, const float* const* in, float2* const* out, int nf) {
   const Geometry& g = c->g;
   if (c->pipe.ring) {  // one kernel, the x-transformed planes stay in L2
@@ -668,20 +787,14 @@ static void forward_xy(kw_ctx* c, const float* const* in, float2* const* out, in
     if (ok) return;
   }
   XFwdArgs xa{};
-  ColArgs ca{};
-  for (int f = 0; f < nf; ++f) xa.in[f] = in[f], xa.out[f] = out[f], ca.data[f] = out[f];
-  xa.tab = g.tx, xa.nxp = g.nxp;
-  ca.stride = g.nxp, ca.outer_stride = (size_t)g.ny * g.nxp, ca.ngroups = g.nxp / g.oy->col_w;
-  const int cz = chunk_planes(c, nf);
-  const double frac = (double)cz / g.nz;
-  for (int z0 = 0; z0 < g.nz; z0 += cz) {
-    xa.pair_begin = z0 * g.ny / 2, xa.pair_end = (z0 + cz) * g.ny / 2;
-    ca.tile_begin = z0 * ca.ngroups, ca.tile_end = (z0 + cz) * ca.ngroups;
-    launch(c, "xfwd", frac * nf * (4.0 * g.n + 8.0 * g.nc), [&] { g.ox->xfwd(xa, nf, c->st); });
-    launch(c, "ycol_fwd", frac * nf * 16.0 * g.nc, [&] { g.oy->col(ca, -1, nf, c->st); });
-  }
+  for (int f = 0; f < nf; ++f) xa.in[f] = in[f], xa.out[f] = out[f];
+  xa.tab = g.tx, xa.nxp = g.nxp, xa.map = g.row_map();
+  xa.pair_begin = 0, xa.pair_end = g.nzl * g.ny / 2;
+  const ColArgs ca = ycol_args(g, out, nf);
+  launch(c, "xfwd", nf * (4.0 * g.n + 8.0 * g.nc), [&] { g.ox->xfwd(xa, nf, c->st); });
+  launch(c, "ycol_fwd", nf * 16.0 * g.nc, [&] { g.oy->col(ca, -1, nf, c->st); });
 }
-// inverse y pass then the x inverse (with its fused epilogue) chunk by chunk; xinv(pair_begin, pair_end) launches it
+// inverse y pass then the x inverse with its fused epilogue; xinv(pair_begin, pair_end) launches it
 template <class F, class FF>
 static void inverse_yx(kw_ctx* c, float2* const* data, int nf, const char* name, const char* fused_name, double xinv_bytes, F&& xinv, FF&& fused) {
   const Geometry& g = c->g;
@@ -690,24 +803,47 @@ static void inverse_yx(kw_ctx* c, float2* const* data, int nf, const char* name,
     launch(c, fused_name, xinv_bytes, [&] { ok = fused(); });
     if (ok) return;
   }
-  ColArgs ca{};
-  for (int f = 0; f < nf; ++f) ca.data[f] = data[f];
-  ca.stride = g.nxp, ca.outer_stride = (size_t)g.ny * g.nxp, ca.ngroups = g.nxp / g.oy->col_w;
-  const int cz = chunk_planes(c, nf);
-  const double frac = (double)cz / g.nz;
-  for (int z0 = 0; z0 < g.nz; z0 += cz) {
-    ca.tile_begin = z0 * ca.ngroups, ca.tile_end = (z0 + cz) * ca.ngroups;
-    launch(c, "ycol_inv", frac * nf * 16.0 * g.nc, [&] { g.oy->col(ca, +1, nf, c->st); });
-    const int pb = z0 * g.ny / 2, pe = (z0 + cz) * g.ny / 2;
-    launch(c, name, frac * xinv_bytes, [&] { xinv(pb, pe); });
-  }
+  const ColArgs ca = ycol_args(g, data, nf);
+  launch(c, "ycol_inv", nf * 16.0 * g.nc, [&] { g.oy->col(ca, +1, nf, c->st); });
+  launch(c, name, xinv_bytes, [&] { xinv(0, g.nzl * g.ny / 2); });
 }
-// one fused z pass per field (axis < 0: no 1-D operator)
-static void zmid_launch(kw_ctx* c, const ZField& f, int axis) {
+
+// All-to-all of `nf` spectra between the x/y-local and the z-local side (the same contiguous-block exchange in both
+// directions: block q of the source goes to rank q, block q of the destination comes from rank q).  Returns the buffers
+// that hold the result: dst, or src itself on one GPU.
+static int exchange(kw_ctx* c, float2* const* src, float2* const* dst, int nf, float2** result) {
+  const Geometry& g = c->g;
+  if (g.nranks == 1) {
+    for (int f = 0; f < nf; ++f) result[f] = src[f];
+    return KW_OK;
+  }
+  NcclApi& nc = nccl_api();
+  int e = kNcclSuccess;
+  launch(c, "all_to_all", nf * 16.0 * (double)g.blk * (g.nranks - 1), [&] {
+    e = nc.GroupStart();
+    for (int f = 0; f < nf && e == kNcclSuccess; ++f)
+      for (int q = 0; q < g.nranks && e == kNcclSuccess; ++q) {
+        e = nc.Send(src[f] + (size_t)q * g.blk, 2 * g.blk, kNcclFloat, q, c->comm, c->st);
+        if (e == kNcclSuccess) e = nc.Recv(dst[f] + (size_t)q * g.blk, 2 * g.blk, kNcclFloat, q, c->comm, c->st);
+      }
+    const int e2 = nc.GroupEnd();
+    if (e == kNcclSuccess) e = e2;
+  });
+  if (e != kNcclSuccess) return fail(KW_ERR_COMM, std::string("NCCL all-to-all: ") + nc.GetErrorString(e));
+  c->comm_bytes += nf * 8.0 * (double)g.blk * (g.nranks - 1);
+  for (int f = 0; f < nf; ++f) result[f] = dst[f];
+  return KW_OK;
+}
+
+// one fused z pass per field on the z-local side (axis < 0: no 1-D operator)
+static void zmid_launch(kw_ctx* c, ZField f, int axis) {
   const Geometry& g = c->g;
   ZMidArgs za{};
+  // the ky-indexed operators are looked up with the local ky: shift them to this rank's range
+  if (axis == 1 && f.vec) f.vec += g.y0;
+  if (axis == 3 && f.vec_y) f.vec_y += g.y0;
   za.f = f, za.axis = axis;
-  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->col_w, za.ntiles = g.ny * za.ngroups, za.plane = (unsigned)((size_t)g.ny * g.nxp);
+  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->col_w, za.ntiles = g.nyl * za.ngroups, za.plane = (unsigned)((size_t)g.nyl * g.nxp);
   launch(c, axis == 3 ? "zmid_grad" : "zmid", (axis == 3 ? 32.0 : 16.0) * g.nc + (f.mul ? 4.0 * g.nc : 0.0), [&] { g.oz->zmid(za, c->st); });
 }
 template <int NF> static YXInvArgs<NF> yx_args(kw_ctx* c, float2* const* in, int nfields = NF) {
@@ -719,36 +855,46 @@ template <int NF> static YXInvArgs<NF> yx_args(kw_ctx* c, float2* const* in, int
 template <int NF> static XInvArgs<NF> xinv_args(kw_ctx* c, float2* const* in, int pb, int pe, int nfields = NF) {
   XInvArgs<NF> a{};
   for (int f = 0; f < nfields; ++f) a.in[f] = in[f];
-  a.tab = c->g.tx, a.pair_begin = pb, a.pair_end = pe, a.nxp = c->g.nxp, a.ny = c->g.ny;
+  a.tab = c->g.tx, a.pair_begin = pb, a.pair_end = pe, a.nxp = c->g.nxp, a.ny = c->g.ny, a.map = c->g.row_map();
   return a;
 }
 
-// F[p]*kappa*ddk_pos after the fused z pass; S0..S2 are ready for the inverse y and x passes  (cpp:2087-2101)
-static void pressure_gradient_spectra(kw_ctx* c) {
+// F[p]*kappa*ddk_pos after the fused z pass; grad[0..2] are ready for the inverse y and x passes  (cpp:2087-2101)
+static int pressure_gradient_spectra(kw_ctx* c, float2** grad) {
   const float* in[1] = {c->d[KW_P]};
   float2* out[1] = {c->S[3]};
   forward_xy(c, in, out, 1);
-  ZField zf{c->S[3], c->S[0], c->d[KW_KAPPA], 1.0f, reinterpret_cast<const float2*>(c->d[KW_DDX_K_SHIFT_POS_R]),
+  float2* zin[1];
+  KW_TRY(exchange(c, out, &c->R[3], 1, zin));
+  ZField zf{zin[0], c->S[0], c->d[KW_KAPPA], 1.0f, reinterpret_cast<const float2*>(c->d[KW_DDX_K_SHIFT_POS_R]),
             c->S[1], c->S[2], reinterpret_cast<const float2*>(c->d[KW_DDY_K_SHIFT_POS]),
             reinterpret_cast<const float2*>(c->d[KW_DDZ_K_SHIFT_POS])};
   zmid_launch(c, zf, 3);
+  return exchange(c, c->S, c->R, 3, grad);
 }
 
 // additive source: scaled = IFFT(FFT(scatter) * (source_kappa * fd)), added to the targets  (cpp:2339-2352)
-static void add_scaled_source(kw_ctx* c, const float* signal, const uint64_t* index, size_t nsrc, int many, float* const* targets, int ntargets) {
+static int add_scaled_source(kw_ctx* c, const float* signal, int index_id, int many, float* const* targets, int ntargets) {
   const Geometry& g = c->g;
+  const size_t nsrc = c->count[index_id];
   launch(c, "memset_source_grid", 4.0 * g.n, [&] { cudaMemsetAsync(c->tSrc, 0, g.n * sizeof(float), c->st); });
-  launch(c, "insert_source", 16.0 * nsrc, [&] { k_insert_source<<<ew_grid(nsrc), 256, 0, c->st>>>(c->tSrc, signal, index, nsrc, c->t, many); });
+  launch(c, "insert_source", 16.0 * nsrc, [&] {
+    k_insert_source<<<ew_grid(nsrc), 256, 0, c->st>>>(c->tSrc, signal, c->di[index_id], c->dpos[index_id], nsrc, c->count_total[index_id], c->t, many);
+  });
   const float* in[1] = {c->tSrc};
   float2* out[1] = {c->S[3]};
   forward_xy(c, in, out, 1);
-  zmid_launch(c, ZField{c->S[3], c->S[3], c->d[KW_SOURCE_KAPPA], 1.0f / (float)g.n, nullptr}, -1);
+  float2 *zb[1], *back[1];
+  KW_TRY(exchange(c, out, &c->R[3], 1, zb));
+  zmid_launch(c, ZField{zb[0], zb[0], c->d[KW_SOURCE_KAPPA], 1.0f / (float)g.ntot, nullptr}, -1);
+  KW_TRY(exchange(c, zb, &c->S[3], 1, back));
   EpiAdd e{};
   for (int k = 0; k < ntargets; ++k) e.out[k] = targets[k];
   e.ntargets = ntargets;
-  inverse_yx(c, out, 1, "xinv_add_source", "yx_add_source", 8.0 * g.nc + 8.0 * g.n * ntargets,
-             [&](int pb, int pe) { g.ox->xinv_add(xinv_args<1>(c, out, pb, pe), e, c->st); },
-             [&] { auto a = yx_args<1>(c, out, 1); return g.ox->yx_add(a, e, c->pipe, c->st); });
+  inverse_yx(c, back, 1, "xinv_add_source", "yx_add_source", 8.0 * g.nc + 8.0 * g.n * ntargets,
+             [&](int pb, int pe) { g.ox->xinv_add(xinv_args<1>(c, back, pb, pe), e, c->st); },
+             [&] { auto a = yx_args<1>(c, back, 1); return g.ox->yx_add(a, e, c->pipe, c->st); });
+  return KW_OK;
 }
 
 static TermsArgs terms_args(kw_ctx* c) {
@@ -765,11 +911,13 @@ template <int OP> static void sample_one(kw_ctx* c, Stream& s, const float* src,
   const double per = OP == kOpNone ? 8.0 : 12.0;  // src read + buffer write (+ buffer read for aggregates)
   if (s.all) {
     launch(c, "sample_all", per * g.n, [&] { k_sample_all<OP><<<ew_grid(g.n), 256, 0, c->st>>>(dst, src, g.n); });
+  } else if (c->nsens == 0) {
+    return;  // no sensor point in this slab
   } else if (c->cfg.sensor_mask_type == 0) {
     launch(c, "sample_index", (per + 8.0) * c->nsens,
            [&] { k_sample_index<OP><<<ew_grid(c->nsens), 256, 0, c->st>>>(dst, src, c->di[KW_SENSOR_MASK_INDEX], c->nsens); });
   } else {
-    CuboidArgs ca{c->di[KW_SENSOR_MASK_CORNERS], c->cub_offsets, c->ncuboids, g.nx, g.ny};
+    CuboidArgs ca{c->cub_corners, c->cub_offsets, c->ncuboids, g.nx, g.ny};
     launch(c, "sample_cuboid", per * c->nsens, [&] { k_sample_cuboid<OP><<<ew_grid(c->nsens), 256, 0, c->st>>>(dst, src, ca, c->nsens); });
   }
 }
@@ -789,12 +937,12 @@ static bool fused_p_sample(kw_ctx* c, FusedSample* fs, double* extra_bytes) {
   };
   take(KW_S_P_MAX_ALL, &fs->max_all, 8.0 * c->g.n);
   take(KW_S_P_MIN_ALL, &fs->min_all, 8.0 * c->g.n);
-  if (cf.sensor_mask_type == 1 && c->ncuboids == 1) {
+  if (cf.sensor_mask_type == 1 && c->ncuboids == 1 && c->nsens > 0) {
     take(KW_S_P_RMS, &fs->rms, 8.0 * c->nsens);
     take(KW_S_P_MAX, &fs->mx, 8.0 * c->nsens);
     take(KW_S_P_MIN, &fs->mn, 8.0 * c->nsens);
     if (fs->rms || fs->mx || fs->mn) {
-      const auto& h = c->h_idx[KW_SENSOR_MASK_CORNERS];
+      const auto& h = c->h_idx[KW_SENSOR_MASK_CORNERS];  // clipped to the slab, local z
       fs->x0 = (int)h[0], fs->y0 = (int)h[1], fs->z0 = (int)h[2], fs->x1 = (int)h[3], fs->y1 = (int)h[4], fs->z1 = (int)h[5];
       fs->cub = (c->nsens == c->g.n) ? 1 : 2;
     }
@@ -821,24 +969,31 @@ static void sample_streams(kw_ctx* c) {
   }
 }
 
+static EpiVelocity velocity_epilogue(kw_ctx* c, float* const* u, float fd, int init) {
+  EpiVelocity e{};
+  for (int k = 0; k < 3; ++k) e.u[k] = u[k], e.dtrho[k] = c->fld(KW_RHO0_SGX + k), e.pml_sg[k] = c->d[KW_PML_X_SGX + k];
+  e.pml_sg[2] += c->g.z0;  // the epilogues see local plane numbers
+  e.fd = fd, e.init = init;
+  return e;
+}
+
 static int step(kw_ctx* c) {
   const kw_config& cf = c->cfg;
   const Geometry& g = c->g;
   const uint64_t t = c->t;
-  const float fd = 1.0f / (float)g.n;  // fftDivider, CudaParameters.cpp:259
+  const float fd = 1.0f / (float)g.ntot;  // fftDivider, CudaParameters.cpp:259
   float* u[3] = {c->d[KW_UX_SGX], c->d[KW_UY_SGY], c->d[KW_UZ_SGZ]};
   float* rho[3] = {c->d[KW_RHOX], c->d[KW_RHOY], c->d[KW_RHOZ]};
+  float2* sp[3];  // spectra ready for the inverse y/x passes of the current stage
 
   // ---- computeVelocity (cpp:2087-2119)
-  pressure_gradient_spectra(c);
+  KW_TRY(pressure_gradient_spectra(c, sp));
   {
-    EpiVelocity e{};
-    for (int k = 0; k < 3; ++k) e.u[k] = u[k], e.dtrho[k] = c->fld(KW_RHO0_SGX + k), e.pml_sg[k] = c->d[KW_PML_X_SGX + k];
-    e.fd = fd, e.init = 0;
+    const EpiVelocity e = velocity_epilogue(c, u, fd, 0);
     const double het = c->count[KW_RHO0_SGX] > 1 ? 4.0 : 0.0;
-    inverse_yx(c, c->S, 3, "xinv_velocity", "yx_velocity", 3 * (8.0 * g.nc + (8.0 + het) * g.n),
-               [&](int pb, int pe) { g.ox->xinv_velocity(xinv_args<1>(c, c->S, pb, pe, 3), e, 3, c->st); },
-               [&] { auto a = yx_args<1>(c, c->S, 3); return g.ox->yx_velocity(a, e, c->pipe, c->st); });
+    inverse_yx(c, sp, 3, "xinv_velocity", "yx_velocity", 3 * (8.0 * g.nc + (8.0 + het) * g.n),
+               [&](int pb, int pe) { g.ox->xinv_velocity(xinv_args<1>(c, sp, pb, pe, 3), e, 3, c->st); },
+               [&] { auto a = yx_args<1>(c, sp, 3); return g.ox->yx_velocity(a, e, c->pipe, c->st); });
   }
   // ---- addVelocitySource (cpp:2252-2303), transducer (cpp:894-897)
   const uint64_t uflag[3] = {cf.ux_source_flag, cf.uy_source_flag, cf.uz_source_flag};
@@ -846,16 +1001,18 @@ static int step(kw_ctx* c) {
     if (uflag[k] <= t) continue;
     const size_t nsrc = c->count[KW_U_SOURCE_INDEX];
     if (cf.u_source_mode != KW_SRC_ADDITIVE) {
+      if (nsrc == 0) continue;
       SourceArgs sa{};
       sa.target[0] = u[k], sa.ntargets = 1, sa.signal = c->d[KW_UX_SOURCE_INPUT + k], sa.index = c->di[KW_U_SOURCE_INDEX];
-      sa.nsrc = nsrc, sa.t = t, sa.many = cf.u_source_many, sa.mode = cf.u_source_mode;
+      sa.pos = c->dpos[KW_U_SOURCE_INDEX], sa.nsrc = nsrc, sa.nsrc_total = c->count_total[KW_U_SOURCE_INDEX];
+      sa.t = t, sa.many = cf.u_source_many, sa.mode = cf.u_source_mode;
       launch(c, "add_u_source", 20.0 * nsrc, [&] { k_add_source<<<ew_grid(nsrc), 256, 0, c->st>>>(sa); });
     } else {
       float* tg[1] = {u[k]};
-      add_scaled_source(c, c->d[KW_UX_SOURCE_INPUT + k], c->di[KW_U_SOURCE_INDEX], nsrc, cf.u_source_many, tg, 1);
+      KW_TRY(add_scaled_source(c, c->d[KW_UX_SOURCE_INPUT + k], KW_U_SOURCE_INDEX, cf.u_source_many, tg, 1));
     }
   }
-  if (cf.transducer_source_flag > t) {
+  if (cf.transducer_source_flag > t && c->count[KW_U_SOURCE_INDEX] > 0) {
     const size_t nsrc = c->count[KW_U_SOURCE_INDEX];
     launch(c, "add_transducer", 28.0 * nsrc, [&] {
       k_add_transducer<<<ew_grid(nsrc), 256, 0, c->st>>>(u[0], c->di[KW_U_SOURCE_INDEX], c->d[KW_TRANSDUCER_SOURCE_INPUT],
@@ -865,12 +1022,16 @@ static int step(kw_ctx* c) {
   // ---- computeVelocityGradient (cpp:2126-2150) + computeDensity (cpp:2157/2169) [+ pressure terms / lossless p]
   {
     forward_xy(c, u, c->S, 3);
+    float2* zb[3];
+    KW_TRY(exchange(c, c->S, c->R, 3, zb));
     const int vec[3] = {KW_DDX_K_SHIFT_NEG_R, KW_DDY_K_SHIFT_NEG, KW_DDZ_K_SHIFT_NEG};
     for (int f = 0; f < 3; ++f)
-      zmid_launch(c, ZField{c->S[f], c->S[f], c->d[KW_KAPPA], fd, reinterpret_cast<const float2*>(c->d[vec[f]])}, f);
+      zmid_launch(c, ZField{zb[f], zb[f], c->d[KW_KAPPA], fd, reinterpret_cast<const float2*>(c->d[vec[f]])}, f);
+    KW_TRY(exchange(c, zb, c->S, 3, sp));
     const bool p_src = cf.p_source_flag > t;
     EpiDensity e{};
     for (int k = 0; k < 3; ++k) e.rho[k] = rho[k], e.pml[k] = c->d[KW_PML_X + k];
+    e.pml[2] += g.z0;
     e.rho0 = c->fld(KW_RHO0), e.bona = c->fld(KW_BONA), e.c2 = c->fld(KW_C0);
     e.dt = cf.dt, e.nonlinear = cf.nonlinear_flag, e.absorbing = cf.absorbing_flag;
     e.defer_terms = p_src && cf.p_source_mode == KW_SRC_ADDITIVE;
@@ -882,25 +1043,28 @@ static int step(kw_ctx* c) {
       if (cf.absorbing_flag) per += 4.0 + (e.defer_terms ? 0.0 : 4.0 + (cf.nonlinear_flag ? 4.0 : 0.0));  // A, B, NL
       else if (!e.defer_terms) per += 4.0 + (c->count[KW_C0] > 1 ? 4.0 : 0.0);                               // p, c2
       if (cf.nonlinear_flag && !e.defer_terms && c->count[KW_BONA] > 1) per += 4.0;
-      inverse_yx(c, c->S, 3, "xinv_density", "yx_density", 24.0 * g.nc + per * g.n + fused_bytes,
-                 [&](int pb, int pe) { g.ox->xinv_density(xinv_args<3>(c, c->S, pb, pe), e, c->st); },
-                 [&] { auto a = yx_args<3>(c, c->S); return g.ox->yx_density(a, e, c->pipe, c->st); });
+      inverse_yx(c, sp, 3, "xinv_density", "yx_density", 24.0 * g.nc + per * g.n + fused_bytes,
+                 [&](int pb, int pe) { g.ox->xinv_density(xinv_args<3>(c, sp, pb, pe), e, c->st); },
+                 [&] { auto a = yx_args<3>(c, sp); return g.ox->yx_density(a, e, c->pipe, c->st); });
     }
     // ---- addPressureSource (cpp:2310-2334)
     if (p_src) {
       const size_t nsrc = c->count[KW_P_SOURCE_INDEX];
       TermsArgs ta = terms_args(c);
       if (cf.p_source_mode != KW_SRC_ADDITIVE) {
-        SourceArgs sa{};
-        for (int k = 0; k < 3; ++k) sa.target[k] = rho[k];
-        sa.ntargets = 3, sa.signal = c->d[KW_P_SOURCE_INPUT], sa.index = c->di[KW_P_SOURCE_INDEX];
-        sa.nsrc = nsrc, sa.t = t, sa.many = cf.p_source_many, sa.mode = cf.p_source_mode;
-        launch(c, "add_p_source", 36.0 * nsrc, [&] { k_add_source<<<ew_grid(nsrc), 256, 0, c->st>>>(sa); });
-        // the fused epilogue computed the sum-of-density terms before the source landed: redo them at the source voxels
-        ta.index = c->di[KW_P_SOURCE_INDEX], ta.n = nsrc;
-        launch(c, "pressure_terms_fixup", 40.0 * nsrc, [&] { k_pressure_terms<<<ew_grid(nsrc), 256, 0, c->st>>>(ta); });
+        if (nsrc > 0) {
+          SourceArgs sa{};
+          for (int k = 0; k < 3; ++k) sa.target[k] = rho[k];
+          sa.ntargets = 3, sa.signal = c->d[KW_P_SOURCE_INPUT], sa.index = c->di[KW_P_SOURCE_INDEX];
+          sa.pos = c->dpos[KW_P_SOURCE_INDEX], sa.nsrc = nsrc, sa.nsrc_total = c->count_total[KW_P_SOURCE_INDEX];
+          sa.t = t, sa.many = cf.p_source_many, sa.mode = cf.p_source_mode;
+          launch(c, "add_p_source", 36.0 * nsrc, [&] { k_add_source<<<ew_grid(nsrc), 256, 0, c->st>>>(sa); });
+          // the fused epilogue computed the sum-of-density terms before the source landed: redo them at the source voxels
+          ta.index = c->di[KW_P_SOURCE_INDEX], ta.n = nsrc;
+          launch(c, "pressure_terms_fixup", 40.0 * nsrc, [&] { k_pressure_terms<<<ew_grid(nsrc), 256, 0, c->st>>>(ta); });
+        }
       } else {
-        add_scaled_source(c, c->d[KW_P_SOURCE_INPUT], c->di[KW_P_SOURCE_INDEX], nsrc, cf.p_source_many, rho, 3);
+        KW_TRY(add_scaled_source(c, c->d[KW_P_SOURCE_INPUT], KW_P_SOURCE_INDEX, cf.p_source_many, rho, 3));
         ta.index = nullptr, ta.n = g.n;
         launch(c, "pressure_terms", 28.0 * g.n, [&] { k_pressure_terms<<<ew_grid(g.n), 256, 0, c->st>>>(ta); });
       }
@@ -910,30 +1074,31 @@ static int step(kw_ctx* c) {
   if (cf.absorbing_flag) {
     const float* in[2] = {c->tA, c->tB};
     forward_xy(c, in, c->S, 2);
-    zmid_launch(c, ZField{c->S[0], c->S[0], c->d[KW_ABSORB_NABLA1], 1.0f, nullptr}, -1);
-    zmid_launch(c, ZField{c->S[1], c->S[1], c->d[KW_ABSORB_NABLA2], 1.0f, nullptr}, -1);
+    float2* zb[2];
+    KW_TRY(exchange(c, c->S, c->R, 2, zb));
+    zmid_launch(c, ZField{zb[0], zb[0], c->d[KW_ABSORB_NABLA1], 1.0f, nullptr}, -1);
+    zmid_launch(c, ZField{zb[1], zb[1], c->d[KW_ABSORB_NABLA2], 1.0f, nullptr}, -1);
+    KW_TRY(exchange(c, zb, c->S, 2, sp));
     EpiPressureSum e{};
     e.p = c->d[KW_P], e.base = cf.nonlinear_flag ? c->tNL : c->tB;
     e.c2 = c->fld(KW_C0), e.tau = c->fld(KW_ABSORB_TAU), e.eta = c->fld(KW_ABSORB_ETA), e.fd = fd;
     const double per = 8.0 + (c->count[KW_C0] > 1 ? 4.0 : 0.0) + (c->count[KW_ABSORB_TAU] > 1 ? 8.0 : 0.0);
     double fused_bytes = 0;
     e.sample = fused_p_sample(c, &e.fs, &fused_bytes);
-    inverse_yx(c, c->S, 2, "xinv_pressure_sum", "yx_pressure_sum", 16.0 * g.nc + per * g.n + fused_bytes,
-               [&](int pb, int pe) { g.ox->xinv_psum(xinv_args<2>(c, c->S, pb, pe), e, c->st); },
-               [&] { auto a = yx_args<2>(c, c->S); return g.ox->yx_psum(a, e, c->pipe, c->st); });
+    inverse_yx(c, sp, 2, "xinv_pressure_sum", "yx_pressure_sum", 16.0 * g.nc + per * g.n + fused_bytes,
+               [&](int pb, int pe) { g.ox->xinv_psum(xinv_args<2>(c, sp, pb, pe), e, c->st); },
+               [&] { auto a = yx_args<2>(c, sp); return g.ox->yx_psum(a, e, c->pipe, c->st); });
   }
   // ---- addInitialPressureSource (cpp:2359-2396)
   if (t == 0 && cf.p0_source_flag == 1) {
     launch(c, "initial_pressure", 24.0 * g.n, [&] {
       k_initial_pressure<<<ew_grid(g.n), 256, 0, c->st>>>(c->d[KW_P], rho[0], rho[1], rho[2], c->d[KW_P0_SOURCE_INPUT], c->fld(KW_C0), g.n);
     });
-    pressure_gradient_spectra(c);
-    EpiVelocity e{};
-    for (int k = 0; k < 3; ++k) e.u[k] = u[k], e.dtrho[k] = c->fld(KW_RHO0_SGX + k), e.pml_sg[k] = c->d[KW_PML_X_SGX + k];
-    e.fd = fd, e.init = 1;
-    inverse_yx(c, c->S, 3, "xinv_initial_velocity", "yx_initial_velocity", 3 * (8.0 * g.nc + 8.0 * g.n),
-               [&](int pb, int pe) { g.ox->xinv_velocity(xinv_args<1>(c, c->S, pb, pe, 3), e, 3, c->st); },
-               [&] { auto a = yx_args<1>(c, c->S, 3); return g.ox->yx_velocity(a, e, c->pipe, c->st); });
+    KW_TRY(pressure_gradient_spectra(c, sp));
+    const EpiVelocity e = velocity_epilogue(c, u, fd, 1);
+    inverse_yx(c, sp, 3, "xinv_initial_velocity", "yx_initial_velocity", 3 * (8.0 * g.nc + 8.0 * g.n),
+               [&](int pb, int pe) { g.ox->xinv_velocity(xinv_args<1>(c, sp, pb, pe, 3), e, 3, c->st); },
+               [&] { auto a = yx_args<1>(c, sp, 3); return g.ox->yx_velocity(a, e, c->pipe, c->st); });
   }
   // ---- storeSensorData (cpp:1060-1093)
   if (t >= cf.sampling_start_index) sample_streams(c);
@@ -1029,7 +1194,7 @@ int kw_get_array(kw_ctx* c, int id, void* host, uint64_t count) {
   KW_CUDA(cudaStreamSynchronize(c->st));
   if (is_reduced_real(id)) {
     if (!c->d[id]) return fail(KW_ERR_INVALID, "array not present");
-    const size_t rows = (size_t)g.ny * g.nz;
+    const size_t rows = (size_t)g.nyl * g.nz;  // z-local side: [kz][ky_local][kx]
     if (count < rows * g.nxr) return fail(KW_ERR_INVALID, "kw_get_array: buffer too small");
     KW_CUDA(cudaMemcpy2D(host, g.nxr * sizeof(float), c->d[id], g.nxp * sizeof(float), g.nxr * sizeof(float), rows, cudaMemcpyDeviceToHost));
     return KW_OK;
@@ -1043,6 +1208,44 @@ int kw_get_array(kw_ctx* c, int id, void* host, uint64_t count) {
   if (is_complex_vec(id)) n = std::min<size_t>(n, 2 * count);
   else if (count < n) return fail(KW_ERR_INVALID, "kw_get_array: buffer too small");
   KW_CUDA(cudaMemcpy(host, c->d[id], n * sizeof(float), cudaMemcpyDeviceToHost));
+  return KW_OK;
+}
+
+int kw_nccl_unique_id(void* out, uint64_t capacity) {
+  if (!out || capacity < sizeof(KwNcclUniqueId)) return fail(KW_ERR_INVALID, "kw_nccl_unique_id: need a 128-byte buffer");
+  NcclApi& nc = nccl_api();
+  if (!nc.ok) return fail(KW_ERR_COMM, "NCCL unavailable: " + nc.error);
+  KwNcclUniqueId id;
+  const int e = nc.GetUniqueId(&id);
+  if (e != kNcclSuccess) return fail(KW_ERR_COMM, std::string("ncclGetUniqueId: ") + nc.GetErrorString(e));
+  memcpy(out, &id, sizeof(id));
+  return KW_OK;
+}
+int kw_local_slab(kw_ctx* c, uint64_t* z_begin, uint64_t* z_count) {
+  if (!c) return fail(KW_ERR_INVALID, "null context");
+  if (z_begin) *z_begin = (uint64_t)c->g.z0;
+  if (z_count) *z_count = (uint64_t)c->g.nzl;
+  return KW_OK;
+}
+int kw_sensor_layout(kw_ctx* c, uint64_t* total, uint64_t* local, uint64_t* positions, uint64_t capacity) {
+  if (!c || !c->preprocessed) return fail(KW_ERR_STATE, "kw_sensor_layout before kw_preprocess");
+  if (total) *total = c->nsens_total;
+  if (local) *local = c->nsens;
+  if (!positions) return KW_OK;
+  if (capacity < c->nsens) return fail(KW_ERR_INVALID, "kw_sensor_layout: buffer too small");
+  if (c->cfg.sensor_mask_type == 0) {
+    if (c->g.nranks == 1) for (size_t j = 0; j < c->nsens; ++j) positions[j] = j;
+    else memcpy(positions, c->sens_pos.data(), c->nsens * sizeof(uint64_t));
+  } else {
+    size_t k = 0;
+    for (size_t r = 0; r + 1 < c->sens_ranges.size(); r += 2)
+      for (uint64_t j = 0; j < c->sens_ranges[r + 1]; ++j) positions[k++] = c->sens_ranges[r] + j;
+  }
+  return KW_OK;
+}
+int kw_comm_bytes(kw_ctx* c, double* bytes_sent) {
+  if (!c || !bytes_sent) return fail(KW_ERR_INVALID, "null argument");
+  *bytes_sent = c->comm_bytes;
   return KW_OK;
 }
 
@@ -1104,7 +1307,7 @@ static int fft3d_host(uint64_t nx, uint64_t ny, uint64_t nz, const float* in, fl
   if (forward) {
     KW_CUDA(cudaMemcpy(dreal, in, g.n * sizeof(float), cudaMemcpyHostToDevice));
     XFwdArgs xa{};
-    xa.in[0] = dreal, xa.out[0] = dspec, xa.tab = g.tx, xa.pair_begin = 0, xa.pair_end = (int)(rows / 2), xa.nxp = g.nxp;
+    xa.in[0] = dreal, xa.out[0] = dspec, xa.tab = g.tx, xa.pair_begin = 0, xa.pair_end = (int)(rows / 2), xa.nxp = g.nxp, xa.map = g.row_map();
     g.ox->xfwd(xa, 1, 0);
     g.oy->col(cy, -1, 1, 0);
     g.oz->col(cz, -1, 1, 0);
@@ -1117,7 +1320,7 @@ static int fft3d_host(uint64_t nx, uint64_t ny, uint64_t nz, const float* in, fl
     g.oz->col(cz, +1, 1, 0);
     g.oy->col(cy, +1, 1, 0);
     XInvArgs<1> xa{};
-    xa.in[0] = dspec, xa.tab = g.tx, xa.pair_begin = 0, xa.pair_end = (int)(rows / 2), xa.nxp = g.nxp, xa.ny = g.ny;
+    xa.in[0] = dspec, xa.tab = g.tx, xa.pair_begin = 0, xa.pair_end = (int)(rows / 2), xa.nxp = g.nxp, xa.ny = g.ny, xa.map = g.row_map();
     EpiStore e{};
     e.out[0] = dreal, e.scale = 1.0f;
     g.ox->xinv_store(xa, e, 1, 0);

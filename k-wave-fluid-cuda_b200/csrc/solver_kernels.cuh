@@ -293,19 +293,22 @@ static __global__ void k_pressure_terms(TermsArgs a) {
 // ---- sources -----------------------------------------------------------------------------------------------------
 // mode 0: '=' (Dirichlet), 1: '+=' (additive, no correction); many: signal[t*Nsrc + j] else signal[t]
 // (SolverCudaKernels.cu:504-527, :570-629).  ntargets = 1 (velocity component) or 3 (rhox, rhoy, rhoz).
+// Slab-decomposed runs keep only the source points of the local slab: index[] holds LOCAL voxel indices and pos[] the
+// position of each kept point in the original list (nullptr: identity), nsrc_total = length of the original list.
 struct SourceArgs {
   float* target[3];
   int ntargets;
   const float* signal;
   const uint64_t* index;
-  size_t nsrc;
+  const uint64_t* pos;
+  size_t nsrc, nsrc_total;
   size_t t;
   int many, mode;
 };
 static __global__ void k_add_source(SourceArgs a) {
-  const size_t base = a.many ? a.t * a.nsrc : a.t;
+  const size_t base = a.many ? a.t * a.nsrc_total : a.t;
   for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < a.nsrc; j += (size_t)gridDim.x * blockDim.x) {
-    const float s = a.many ? a.signal[base + j] : a.signal[base];
+    const float s = a.many ? a.signal[base + (a.pos ? a.pos[j] : j)] : a.signal[base];
     const size_t i = a.index[j];
     for (int k = 0; k < a.ntargets; ++k) {
       if (a.mode == 0) a.target[k][i] = s;
@@ -319,10 +322,11 @@ static __global__ void k_add_transducer(float* ux, const uint64_t* index, const 
     ux[index[j]] += signal[delay[j] + t];
 }
 // scaled[idx[j]] = s_j   into a zeroed grid (SolverCudaKernels.cu:679-697)
-static __global__ void k_insert_source(float* grid, const float* signal, const uint64_t* index, size_t nsrc, size_t t, int many) {
-  const size_t base = many ? t * nsrc : t;
+static __global__ void k_insert_source(float* grid, const float* signal, const uint64_t* index, const uint64_t* pos, size_t nsrc,
+                                       size_t nsrc_total, size_t t, int many) {
+  const size_t base = many ? t * nsrc_total : t;
   for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < nsrc; j += (size_t)gridDim.x * blockDim.x)
-    grid[index[j]] = many ? signal[base + j] : signal[base];
+    grid[index[j]] = many ? signal[base + (pos ? pos[j] : j)] : signal[base];
 }
 // p = p0 ; rho_i = p0 / (3*c2)   (SolverCudaKernels.cu:870-883)
 static __global__ void k_initial_pressure(float* p, float* rx, float* ry, float* rz, const float* p0, Fld c2, size_t n) {
