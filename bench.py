@@ -212,7 +212,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--size", type=int, default=0, help="grid edge; default 512 on one GPU (configs[3]), 1024 slab-decomposed on N > 1 (configs[4])")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: run N independent single-GPU replicas instead of one slab-decomposed grid")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -220,8 +221,13 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    sharded = world > 1 and not args.replicas
+    if not args.size:
+        args.size = 1024 if sharded else 512
     if args.impl == "reference":
         if rank == 0:
+            if world > 1:
+                args.size = min(args.size, 512)  # the reference is single-GPU: its largest one-GPU configuration
             run_reference(args)
         return
 
@@ -238,9 +244,21 @@ def main():
     KP = min(K, 10)  # profiled steps (per-kernel CUDA events) after the timed region
     nt = 2 * (K + W + KP) + 8
     # ---- workload: BASELINE.json configs[3]: 512^3 heterogeneous nonlinear absorbing, whole-domain p_max / p_rms
-    cfg, arrays = kw.synth.make_case(N, nt=nt, nonlinear=True, absorbing=True, source="p_plane", sensor="full_cuboid", pml_size=20 if N >= 128 else None)
+    # ---- N > 1: BASELINE.json configs[4]: ONE grid slab-decomposed along z over the ranks, all-to-all FFT transposes
+    pml = 20 if N >= 128 else None
+    slab_kw, sim_kw = {}, {}
+    if sharded:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(kw.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        z0, nzl = kw.slab.slab_extent(N, rank, world)
+        slab_kw = dict(medium="waves", z_range=(z0, nzl))
+        sim_kw = dict(rank=rank, nranks=world, nccl_id=bytes(idt.cpu().numpy().tobytes()))
+    cfg, arrays = kw.synth.make_case(N, nt=nt, nonlinear=True, absorbing=True, source="p_plane", sensor="full_cuboid", pml_size=pml, **slab_kw)
     streams = ["KW_S_P_RMS", "KW_S_P_MAX_ALL"]
-    sim = kw.Simulation(cfg, arrays, streams=streams, device=local_rank)
+    sim = kw.Simulation(cfg, arrays, streams=streams, device=local_rank, **sim_kw)
+    del arrays
 
     def barrier():
         torch.cuda.synchronize()
@@ -267,21 +285,25 @@ def main():
     sim.run(KP, sync=True)
     prof = sim.profile_report()
     sim.profile(False, False)
+    comm_bytes = sim.comm_bytes() if sharded else 0.0
+    comm_steps = W + K + KP
     sim.close()
     if world > 1:
         tmax = torch.tensor([dev_ms], device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dev_ms = float(tmax.item())
     ms_per_step = dev_ms / K
-    value = world * N**3 * K / (dev_ms * 1e-3) / 1e6
+    jobs = 1 if sharded else world  # one decomposed grid, or `world` replicas of the grid
+    value = jobs * N**3 * K / (dev_ms * 1e-3) / 1e6
 
     # ---- end to end: host-driven loop through the C ABI, host buffers in the timed region
     e2e = None
     if not args.no_e2e:
-        cfg2, arrays2 = kw.synth.make_case(N, nt=nt, nonlinear=True, absorbing=True, source="p_many", sensor="index", n_sensor=4096, pml_size=20 if N >= 128 else None)
+        cfg2, arrays2 = kw.synth.make_case(N, nt=nt, nonlinear=True, absorbing=True, source="p_many", sensor="index", n_sensor=4096, pml_size=pml, **slab_kw)
         nsrc = arrays2["p_source_index"].size
         sig = torch.from_numpy(np.ascontiguousarray(arrays2["p_source_input"]).reshape(nt, nsrc)).pin_memory()
-        s2 = kw.Simulation(cfg2, arrays2, streams=["KW_S_P_RAW", "KW_S_P_RMS", "KW_S_P_MAX_ALL"], raw_rows_capacity=4, device=local_rank)
+        s2 = kw.Simulation(cfg2, arrays2, streams=["KW_S_P_RAW", "KW_S_P_RMS", "KW_S_P_MAX_ALL"], raw_rows_capacity=4, device=local_rank, **sim_kw)
+        del arrays2
         out_rows = torch.empty((nt, 4096), dtype=torch.float32).pin_memory()
         import ctypes as C
 
@@ -306,14 +328,15 @@ def main():
             tm = torch.tensor([e2e_s], device="cuda")
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             e2e_s = float(tm.item())
-        e2e = {"value": world * N**3 * K / e2e_s / 1e6, "unit": "Mvoxel-steps/s", "h2d_bytes_per_step": int(nsrc * 4),
+        e2e = {"value": jobs * N**3 * K / e2e_s / 1e6, "unit": "Mvoxel-steps/s", "h2d_bytes_per_step": int(nsrc * 4),
                "d2h_bytes_per_step": 4096 * 4,
-               "how": "one kw_set_source_row + kw_run(1) + kw_stream_fetch(p_raw row) per step from pinned host buffers; wall clock"}  # fmt: skip
+               "how": "one kw_set_source_row + kw_run(1) + kw_stream_fetch(p_raw row) per step from pinned host buffers (on every rank); wall clock, max over ranks"}  # fmt: skip
 
     if rank != 0:
         return
     peak, peak_src = measured_peak()
-    top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else None
+    # dominant KERNEL (the NCCL exchange of sharded runs is reported separately under "nvlink")
+    top = max((kv for kv in prof.items() if kv[0] != "all_to_all"), key=lambda kv: kv[1]["ms"]) if prof else None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if top and os.path.exists(tp):
@@ -326,7 +349,7 @@ def main():
         name, st = top
         ach = st["bytes"] / st["launches"] / (st["ms"] / st["launches"] * 1e-3) / 1e9
         alg = ALG_BYTES[(nonlinear, absorbing)] + 16.0  # + p_max_all and full-cuboid p_rms
-        step_gbs = alg * N**3 / (ms_per_step * 1e-3) / 1e9
+        step_gbs = alg * N**3 / world / (ms_per_step * 1e-3) / 1e9 if sharded else alg * N**3 / (ms_per_step * 1e-3) / 1e9  # per GPU
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "peak_source": peak_src,
                     "kernel_share_of_step": st["ms"] / sum(v["ms"] for v in prof.values()),
@@ -336,15 +359,25 @@ def main():
                                     "GBps": v["bytes"] / max(v["ms"], 1e-9) / 1e6} for k, v in sorted(prof.items())}}  # fmt: skip
     line = {
         "metric": "Mvoxel-steps/s", "value": value, "unit": "Mvoxel-steps/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": f"{N}^3 synthetic heterogeneous medium, nonlinear (BonA) + power-law absorption, PML 20, plane pressure "
-                               f"source, whole-domain p_max_all + p_rms over a full-domain cuboid (BASELINE.json configs[3])",
-                   "grid": [N, N, N], "l2_policy": "inputs larger than L2 (every field >= 512 MiB at 512^3)" if N >= 512 else
-                   "working set partly L2 resident at this size", "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas",
+                               f"source, whole-domain p_max_all + p_rms over a full-domain cuboid (BASELINE.json "
+                               + (f"configs[4]: ONE grid slab-decomposed along z over {world} GPUs, NCCL all-to-all per 3-D transform)" if sharded
+                                  else "configs[3])"),
+                   "grid": [N, N, N], "l2_policy": "inputs larger than L2 (every field >= 512 MiB per GPU)" if N**3 // (world if sharded else 1) >= 512**3 else
+                   "working set partly L2 resident at this size",
+                   "parallelism": "1 GPU" if world == 1 else (f"z-slabs over {world} GPUs" if sharded else f"{world} independent replicas"),
                    "wall_ms_timed_region": wall_ms},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }  # fmt: skip
+    if sharded and "all_to_all" in prof:
+        a2a = prof["all_to_all"]
+        sent_per_step = comm_bytes / comm_steps  # bytes this rank sent per step (one direction)
+        line["nvlink"] = {"all_to_all_ms_per_step": a2a["ms"] / KP, "exchanges_per_step": a2a["launches"] / KP,
+                          "sent_bytes_per_gpu_per_step": sent_per_step,
+                          "GBps_per_gpu_per_direction": sent_per_step / (a2a["ms"] / KP * 1e-3) / 1e9,
+                          "how": "rank 0: bytes sent per step / CUDA-event time of the NCCL send/recv groups on the solver stream"}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_port_throughput(128, budget_s=12.0)
     print(json.dumps(line), flush=True)

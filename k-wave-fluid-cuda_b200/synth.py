@@ -59,6 +59,24 @@ def smooth_noise(shape, seed, sigma=8.0):
     return w
 
 
+def wave_field(shape, seed, z_range=None):
+    """Analytic smooth heterogeneity in [-1, 1]: mean of six products of low-frequency cosines with seeded phases.
+    Unlike smooth_noise it can be evaluated for any z-range on its own (slab-wise generation of 1024^3 inputs)."""
+    nz, ny, nx = shape
+    z0, nzl = (0, nz) if z_range is None else z_range
+    rng = np.random.default_rng(seed)
+    out = np.zeros((nzl, ny, nx), dtype=F32)
+    for _ in range(6):
+        f = rng.integers(1, 5, size=3)
+        ph = rng.uniform(0, 2 * np.pi, size=3)
+        cz = np.cos(2 * np.pi * f[0] * (np.arange(z0, z0 + nzl) / nz) + ph[0]).astype(F32)
+        cy = np.cos(2 * np.pi * f[1] * (np.arange(ny) / ny) + ph[1]).astype(F32)
+        cx = np.cos(2 * np.pi * f[2] * (np.arange(nx) / nx) + ph[2]).astype(F32)
+        out += cz[:, None, None] * cy[None, :, None] * cx[None, None, :]
+    out *= F32(1.0 / 6.0)
+    return out
+
+
 def make_case(
     nx,
     ny=None,
@@ -77,16 +95,45 @@ def make_case(
     period=50,
     shuffle_sensor=False,
     shifts=False,
+    medium="noise",  # noise: low-passed white noise; waves: analytic, can be generated slab by slab
+    z_range=None,  # (z0, nzl): full-grid arrays hold these planes only (medium="waves"); everything else stays global
 ):
     ny = nx if ny is None else ny
     nz = nx if nz is None else nz
     shape = (nz, ny, nx)
+    if z_range is not None and medium != "waves":
+        raise ValueError("slab-wise generation needs medium='waves'")
+    zs0, zsl = (0, nz) if z_range is None else z_range
     n = nx * ny * nz
     dx = dy = dz = 1e-4
     pml_size = pml_size if pml_size is not None else (20 if min(shape) >= 128 else max(2, min(shape) // 8))
     sig = 8.0 if min(shape) >= 64 else max(1.5, min(shape) / 8)
     arrays = {}
-    if heterogeneous:
+    if heterogeneous and medium == "waves":
+        zr = (zs0, zsl)
+        c0 = (1500.0 * (1.0 + 0.05 * wave_field(shape, seed, zr))).astype(F32)
+        zz, yy, xx = np.ogrid[zs0 : zs0 + zsl, :ny, :nx]
+        r = min(shape) // 8
+        c0[(xx - nx // 2) ** 2 + (yy - ny // 2) ** 2 + (zz - nz // 2) ** 2 <= r * r] = 1600.0
+        # one extra plane for the z-staggered density (the last plane of the grid copies itself)
+        ext = wave_field(shape, seed + 1, (zs0, min(zsl + 1, nz - zs0)))
+        rho_ext = (1000.0 * (1.0 + 0.05 * ext)).astype(F32)
+        if rho_ext.shape[0] == zsl:
+            rho_ext = np.concatenate([rho_ext, rho_ext[-1:]], axis=0)
+        rho0 = np.ascontiguousarray(rho_ext[:zsl])
+        sg = []
+        for ax in (2, 1):
+            nb = np.concatenate([np.take(rho0, range(1, shape[ax]), axis=ax), np.take(rho0, [-1], axis=ax)], axis=ax)
+            sg.append(((rho0 + nb) * F32(0.5)).astype(F32))
+        sg.append(((rho0 + rho_ext[1:]) * F32(0.5)).astype(F32))
+        del rho_ext, ext
+        arrays.update(c0=c0, rho0=rho0, rho0_sgx=sg[0], rho0_sgy=sg[1], rho0_sgz=sg[2])
+        if nonlinear:
+            arrays["BonA"] = (6.0 + wave_field(shape, seed + 2, zr)).astype(F32)
+        if absorbing:
+            arrays["alpha_coeff"] = (0.75 + 0.25 * wave_field(shape, seed + 3, zr)).astype(F32)
+        c_ref = 1600.0  # global bound of c0 (1500 * 1.05 < 1600 = the ball), known without seeing the other slabs
+    elif heterogeneous:
         g0, g1 = smooth_noise(shape, seed, sig), smooth_noise(shape, seed + 1, sig)
         c0 = (1500.0 * (1.0 + 0.05 * g0)).astype(F32)
         zz, yy, xx = np.ogrid[:nz, :ny, :nx]
@@ -167,7 +214,7 @@ def make_case(
         arrays["transducer_source_input"] = (0.05 * np.sin(2 * np.pi * tt2 / period)).astype(F32)
     elif source == "p0":
         cfg.update(p0_source_flag=1)
-        zz3, yy3, xx3 = np.ogrid[:nz, :ny, :nx]
+        zz3, yy3, xx3 = np.ogrid[zs0 : zs0 + zsl, :ny, :nx]
         s2 = 2.0 * (max(2.0, min(shape) / 32.0)) ** 2
         r2 = (xx3 - nx // 2) ** 2 + (yy3 - ny // 2) ** 2 + (zz3 - nz // 2) ** 2
         arrays["p0_source_input"] = (1.0e5 * np.exp(-r2 / s2)).astype(F32)
