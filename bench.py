@@ -286,6 +286,7 @@ def main():
     prof = sim.profile_report()
     sim.profile(False, False)
     comm_bytes = sim.comm_bytes() if sharded else 0.0
+    comm_mode = sim.comm_mode()
     comm_steps = W + K + KP
     sim.close()
     if world > 1:
@@ -376,7 +377,7 @@ def main():
         sent_per_step = comm_bytes / comm_steps  # bytes this rank sent per step (one direction)
         line["nvlink"] = {"all_to_all_ms_per_step": a2a["ms"] / KP, "exchanges_per_step": a2a["launches"] / KP,
                           "sent_bytes_per_gpu_per_step": sent_per_step,
-                          "GBps_per_gpu_per_direction": sent_per_step / (a2a["ms"] / KP * 1e-3) / 1e9,
+                          "GBps_per_gpu_per_direction": sent_per_step / (a2a["ms"] / KP * 1e-3) / 1e9, "path": comm_mode,
                           "how": "rank 0: bytes sent per step / CUDA-event time of the NCCL send/recv groups on the solver stream"}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_port_throughput(128, budget_s=12.0)

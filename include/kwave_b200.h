@@ -163,6 +163,9 @@ int kw_local_slab(kw_ctx* ctx, uint64_t* z_begin, uint64_t* z_count);
 int kw_sensor_layout(kw_ctx* ctx, uint64_t* total_points, uint64_t* local_points, uint64_t* positions, uint64_t capacity);
 /* Bytes this rank has sent through the all-to-all since the context was created (NVLink GB/s = bytes / exchange time). */
 int kw_comm_bytes(kw_ctx* ctx, double* bytes_sent);
+/* How the all-to-all runs: 0 = single GPU (none), 1 = NCCL send/recv groups, 2 = copy-engine pushes into IPC-mapped peer
+ * buffers ordered by stream memory operations (default on one node; KW_PEER=0 forces NCCL). */
+int kw_comm_mode(kw_ctx* ctx, int* mode);
 
 /* Timing of the device work of the last kw_run (CUDA events on the solver stream), milliseconds. */
 int kw_last_run_ms(kw_ctx* ctx, float* ms);

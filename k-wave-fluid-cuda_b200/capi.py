@@ -125,6 +125,7 @@ def load_library():
         "kw_local_slab": [vp, C.POINTER(u64), C.POINTER(u64)],
         "kw_sensor_layout": [vp, C.POINTER(u64), C.POINTER(u64), vp, u64],
         "kw_comm_bytes": [vp, C.POINTER(C.c_double)],
+        "kw_comm_mode": [vp, C.POINTER(C.c_int)],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -293,6 +294,11 @@ class Simulation:
         if local.value:
             _check(self.lib.kw_sensor_layout(self.ctx, C.byref(total), C.byref(local), pos.ctypes.data, pos.size))
         return total.value, pos
+
+    def comm_mode(self):
+        m = C.c_int()
+        _check(self.lib.kw_comm_mode(self.ctx, C.byref(m)))
+        return {0: "none", 1: "nccl", 2: "peer"}[m.value]
 
     def comm_bytes(self):
         b = C.c_double()

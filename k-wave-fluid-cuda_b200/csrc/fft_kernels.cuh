@@ -104,6 +104,7 @@ template <int NF> struct XInvArgs {
   const float2* tab;
   int pair_begin, pair_end, nxp, ny;
   RowMap map;
+  int field0;  // NF == 1: the launch covers fields field0 .. field0 + gridDim.y - 1 (per-field launches of pipelined runs)
 };
 
 // One row pair of NF fields: half spectra -> real rows, then the epilogue on the registers.
@@ -160,7 +161,7 @@ template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads,
   for (int g = blockIdx.x; g * RP < npairs; g += gridDim.x) {
     const int pair = a.pair_begin + g * RP + rp;
     const bool valid = pair < a.pair_end;
-    xinv_rows<N, NF>(a, epi, blockIdx.y, 2 * (size_t)(valid ? pair : a.pair_begin), valid, t, twp, ex);
+    xinv_rows<N, NF>(a, epi, blockIdx.y + a.field0, 2 * (size_t)(valid ? pair : a.pair_begin), valid, t, twp, ex);
   }
 }
 
@@ -173,7 +174,7 @@ template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads,
 // memory straight into registers and back; shared memory only carries the exchange.
 template <int N> struct ColCfg {
   using P = Plan2<N>;
-  static constexpr int W = 16;
+  static constexpr int W = (N >= 1024) ? 8 : 16;                              // 1024: 8 kx (64-byte segments) keep a slot at 256 threads, i.e. 254 registers for E = 32
   static constexpr int WK = P::WK;                                         // workers (threads per kx) of a tile
   static constexpr int SLOT = W * WK;                                      // threads of a tile slot
   static constexpr int TPC = (SLOT >= 256) ? 1 : 256 / SLOT;               // tile slots per CTA

@@ -1,0 +1,175 @@
+// Peer-memory all-to-all of slab-decomposed runs: copy-engine pushes into IPC-mapped peer buffers over NVLink / NVSwitch,
+// ordered by stream memory operations (cuStreamWriteValue32 / cuStreamWaitValue32) on flags in a POSIX shared-memory
+// segment that every rank of the node maps and registers with CUDA.  No SM is used for the exchange, so it overlaps the
+// compute kernels without competing for CTA slots (an NCCL send/recv kernel can only start at a kernel boundary of the
+// persistent compute grids, and then takes SMs away from them).  One node only (one process per GPU).
+//
+// The driver entry points are resolved at run time from libcuda.so.1 (the library links against the runtime only).
+#pragma once
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+
+namespace kw {
+
+constexpr int kPeerMaxRanks = 16;
+constexpr int kPeerBufs = 8;  // S[0..3], R[0..3]
+
+struct DrvApi {
+  // CUresult cuStreamWaitValue32(CUstream, CUdeviceptr, cuuint32_t value, unsigned flags)
+  int (*WaitValue32)(cudaStream_t, unsigned long long, uint32_t, unsigned) = nullptr;
+  int (*WriteValue32)(cudaStream_t, unsigned long long, uint32_t, unsigned) = nullptr;
+  bool ok = false;
+  std::string error;
+};
+enum { kWaitGeq = 0x0 /* CU_STREAM_WAIT_VALUE_GEQ */, kWriteDefault = 0x0 };
+
+inline DrvApi& drv_api() {
+  static DrvApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    api.error = "libcuda.so.1 not found";
+    return api;
+  }
+  const char* wait_names[] = {"cuStreamWaitValue32_v2", "cuStreamWaitValue32"};
+  const char* write_names[] = {"cuStreamWriteValue32_v2", "cuStreamWriteValue32"};
+  for (const char* n : wait_names)
+    if (!api.WaitValue32) api.WaitValue32 = reinterpret_cast<decltype(api.WaitValue32)>(dlsym(h, n));
+  for (const char* n : write_names)
+    if (!api.WriteValue32) api.WriteValue32 = reinterpret_cast<decltype(api.WriteValue32)>(dlsym(h, n));
+  if (!api.WaitValue32 || !api.WriteValue32) {
+    api.error = "cuStreamWaitValue32 / cuStreamWriteValue32 missing from the driver";
+    return api;
+  }
+  api.ok = true;
+  return api;
+}
+
+// what every rank of the run maps; plain integers only (lives in /dev/shm)
+struct PeerShm {
+  std::atomic<uint32_t> attached;                       // ranks that have written their handle
+  std::atomic<uint32_t> opened;                         // ranks that have opened every peer handle (or failed)
+  std::atomic<uint32_t> failed;                         // ranks whose set-up failed: everybody falls back to NCCL
+  std::atomic<uint32_t> detached;                       // ranks that are done with the segment
+  cudaIpcMemHandle_t handle[kPeerMaxRanks];             // arena of rank r
+  // arrived[dst][buf][src] = n: the n-th use of buffer `buf` of rank `dst` holds the block of rank `src`
+  volatile uint32_t arrived[kPeerMaxRanks][kPeerBufs][kPeerMaxRanks];
+  // credit[src][buf][dst] = n: rank `dst` no longer reads the n-th content of its buffer `buf` (src may push use n + 1)
+  volatile uint32_t credit[kPeerMaxRanks][kPeerBufs][kPeerMaxRanks];
+};
+
+struct PeerLink {
+  bool active = false;
+  int rank = 0, nranks = 1;
+  std::string shm_name;
+  PeerShm* shm = nullptr;        // host mapping
+  PeerShm* shm_dev = nullptr;    // device-side address of the same segment (stream memory operations)
+  char* peer_base[kPeerMaxRanks] = {};  // arena of every rank as seen from this process (own arena at [rank])
+  uint32_t use[kPeerBufs] = {};  // how often each buffer has been the destination of an exchange
+  std::string error;
+
+  static bool wait_count(std::atomic<uint32_t>& a, uint32_t want, double timeout_s) {
+    const auto t0 = std::chrono::steady_clock::now();
+    while (a.load(std::memory_order_acquire) < want) {
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s) return false;
+      std::this_thread::sleep_for(std::chrono::microseconds(200));
+    }
+    return true;
+  }
+
+  // `tag`: bytes shared by all ranks of this run and by nobody else (the ncclUniqueId); arena = this rank's cudaMalloc'ed
+  // block holding the kPeerBufs exchange buffers.  Collective over the ranks; returns false (with `error`) when the peer
+  // path is unavailable -- the caller then keeps the NCCL exchange.  All ranks take the same decision.
+  bool setup(const void* tag, size_t tag_bytes, int rank_, int nranks_, void* arena) {
+    rank = rank_, nranks = nranks_;
+    if (nranks > kPeerMaxRanks) return fail_local("more ranks than kPeerMaxRanks");
+    uint64_t hsh = 1469598103934665603ull;
+    for (size_t i = 0; i < tag_bytes; ++i) hsh = (hsh ^ static_cast<const unsigned char*>(tag)[i]) * 1099511628211ull;
+    char name[64];
+    snprintf(name, sizeof name, "/kwave_b200_%016llx", (unsigned long long)hsh);
+    shm_name = name;
+    const int fd = shm_open(name, O_CREAT | O_RDWR, 0600);
+    if (fd < 0) return fail_local("shm_open failed");
+    if (ftruncate(fd, sizeof(PeerShm)) != 0) {
+      close(fd);
+      return fail_local("ftruncate failed");
+    }
+    void* m = mmap(nullptr, sizeof(PeerShm), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return fail_local("mmap failed");
+    shm = static_cast<PeerShm*>(m);  // a fresh segment is zero filled
+    bool ok = drv_api().ok;
+    if (!ok) error = drv_api().error;
+    if (ok && cudaHostRegister(shm, sizeof(PeerShm), cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) {
+      cudaGetLastError();
+      ok = false, error = "cudaHostRegister of the flag segment failed";
+    }
+    void* dptr = nullptr;
+    if (ok && cudaHostGetDevicePointer(&dptr, shm, 0) != cudaSuccess) ok = false, error = "cudaHostGetDevicePointer failed";
+    shm_dev = static_cast<PeerShm*>(dptr);
+    if (ok && cudaIpcGetMemHandle(&shm->handle[rank], arena) != cudaSuccess) {
+      cudaGetLastError();
+      ok = false, error = "cudaIpcGetMemHandle failed";
+    }
+    if (!ok) shm->failed.fetch_add(1);
+    shm->attached.fetch_add(1, std::memory_order_release);
+    if (!wait_count(shm->attached, (uint32_t)nranks, 120.0)) return fail_local("timeout waiting for the other ranks (attach)");
+    if (shm->failed.load() == 0) {
+      peer_base[rank] = static_cast<char*>(arena);
+      for (int q = 0; q < nranks && ok; ++q) {
+        if (q == rank) continue;
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, shm->handle[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          ok = false, error = "cudaIpcOpenMemHandle failed for rank " + std::to_string(q);
+          shm->failed.fetch_add(1);
+        }
+        peer_base[q] = static_cast<char*>(p);
+      }
+    }
+    shm->opened.fetch_add(1, std::memory_order_release);
+    if (!wait_count(shm->opened, (uint32_t)nranks, 120.0)) return fail_local("timeout waiting for the other ranks (open)");
+    if (shm->failed.load() != 0) {
+      if (error.empty()) error = "another rank could not set up the peer path";
+      return false;
+    }
+    shm_unlink(name);  // every rank has it mapped: the name can go
+    active = true;
+    return true;
+  }
+  bool fail_local(const char* why) {
+    error = why;
+    if (shm) shm->failed.fetch_add(1);
+    return false;
+  }
+  void teardown() {
+    for (int q = 0; q < nranks; ++q)
+      if (q != rank && peer_base[q]) cudaIpcCloseMemHandle(peer_base[q]);
+    if (shm) {
+      cudaHostUnregister(shm);
+      munmap(shm, sizeof(PeerShm));
+      shm_unlink(shm_name.c_str());
+    }
+    shm = nullptr, active = false;
+  }
+  unsigned long long dev_addr(const volatile uint32_t* host_field) const {
+    return reinterpret_cast<unsigned long long>(reinterpret_cast<const char*>(shm_dev) +
+                                                (reinterpret_cast<const char*>(const_cast<const uint32_t*>(host_field)) - reinterpret_cast<const char*>(shm)));
+  }
+};
+
+}  // namespace kw

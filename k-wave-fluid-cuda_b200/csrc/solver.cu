@@ -15,6 +15,7 @@
 
 #include "../../include/kwave_b200.h"
 #include "nccl_dl.h"
+#include "peer_dl.h"
 #include "ops.h"
 
 namespace kw {
@@ -195,6 +196,13 @@ struct kw_ctx {
   std::vector<uint64_t> sens_ranges;  // cuboid mask: (start in the global row, length) per cuboid part held locally
   KwNcclComm comm = nullptr;
   double comm_bytes = 0.0;
+  // slab-decomposed runs: exchanges run on their own stream, ordered against the solver stream by events
+  cudaStream_t cs = nullptr;
+  std::vector<cudaEvent_t> ev_ring;
+  size_t ev_next = 0;
+  PeerLink peer;        // copy-engine pushes into peer memory (falls back to NCCL send/recv when unavailable)
+  char* arena = nullptr;  // S[0..3], R[0..3] in one allocation (one IPC handle per rank)
+  char nccl_id[128] = {};
   Stream streams[KW_STREAM_COUNT];
   PipeState pipe;  // ring + counters of the plane-fused x/y kernels (Nx == Ny only)
   std::vector<void*> owned;
@@ -215,17 +223,28 @@ static cudaEvent_t prof_event(kw_ctx* c) {
   return e;
 }
 // every kernel launch of the time loop goes through here: counts it and, in profiling mode, brackets it with events
-template <class F> static void launch(kw_ctx* c, const char* name, double bytes, F&& f) {
+template <class F> static void launch(kw_ctx* c, const char* name, double bytes, F&& f, cudaStream_t stream = nullptr) {
   c->launches++;
   if (!c->prof_on) {
     f();
     return;
   }
+  if (!stream) stream = c->st;
   ProfPending p{name, prof_event(c), prof_event(c), bytes};
-  cudaEventRecord(p.e0, c->st);
+  cudaEventRecord(p.e0, stream);
   f();
-  cudaEventRecord(p.e1, c->st);
+  cudaEventRecord(p.e1, stream);
   c->prof_pending.push_back(p);
+}
+// an event marking everything enqueued on `s` so far (ring of reusable events: a wait captures the record made before it)
+static cudaEvent_t mark(kw_ctx* c, cudaStream_t s) {
+  if (c->ev_ring.empty()) {
+    c->ev_ring.resize(256);
+    for (auto& e : c->ev_ring) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  }
+  cudaEvent_t e = c->ev_ring[c->ev_next++ % c->ev_ring.size()];
+  cudaEventRecord(e, s);
+  return e;
 }
 // the plane-fused kernels flag a dependency wait that timed out (a scheduling bug); stream must be idle
 static int pipe_check(kw_ctx* c) {
@@ -398,7 +417,9 @@ int kw_ctx_create(const kw_config* cfg, kw_ctx** out) {
       delete c;
       return fail(KW_ERR_COMM, "ncclCommInitRank: " + msg);
     }
+    memcpy(c->nccl_id, cfg->nccl_unique_id, sizeof(c->nccl_id));
     c->cfg.nccl_unique_id = nullptr;
+    KW_CUDA(cudaStreamCreateWithFlags(&c->cs, cudaStreamNonBlocking));
   }
   KW_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
   KW_CUDA(cudaEventCreate(&c->ev0));
@@ -410,7 +431,11 @@ int kw_ctx_create(const kw_config* cfg, kw_ctx** out) {
 int kw_ctx_destroy(kw_ctx* c) {
   if (!c) return KW_OK;
   cudaStreamSynchronize(c->st);
+  if (c->cs) cudaStreamSynchronize(c->cs);
+  if (c->peer.shm) c->peer.teardown();
   if (c->comm) nccl_api().CommDestroy(c->comm);
+  for (cudaEvent_t e : c->ev_ring) cudaEventDestroy(e);
+  if (c->cs) cudaStreamDestroy(c->cs);
   for (void* p : c->owned) cudaFree(p);
   prof_resolve(c);
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
@@ -657,9 +682,19 @@ int kw_preprocess(kw_ctx* c) {
       KW_TRY(dalloc(c, (void**)&c->d[id], g.n * sizeof(float)));
       c->count[id] = g.n;
     }
-  for (int k = 0; k < 4; ++k) KW_TRY(dalloc(c, (void**)&c->S[k], g.nc * sizeof(float2)));
-  if (g.nranks > 1)
-    for (int k = 0; k < 4; ++k) KW_TRY(dalloc(c, (void**)&c->R[k], g.nc * sizeof(float2)));
+  if (g.nranks == 1) {
+    for (int k = 0; k < 4; ++k) KW_TRY(dalloc(c, (void**)&c->S[k], g.nc * sizeof(float2)));
+  } else {  // one arena: S[0..3] then R[0..3], so that one IPC handle per rank maps every exchange buffer
+    const size_t per = (g.nc * sizeof(float2) + 255) / 256 * 256;
+    KW_TRY(dalloc(c, (void**)&c->arena, kPeerBufs * per));
+    for (int k = 0; k < 4; ++k) c->S[k] = reinterpret_cast<float2*>(c->arena + k * per), c->R[k] = reinterpret_cast<float2*>(c->arena + (4 + k) * per);
+    KW_CUDA(cudaStreamSynchronize(c->st));
+    const char* env = getenv("KW_PEER");
+    if (!env || atoi(env) != 0) {
+      if (!c->peer.setup(c->nccl_id, sizeof(c->nccl_id), g.rank, g.nranks, c->arena) && getenv("KW_PEER_VERBOSE"))
+        fprintf(stderr, "kwave_b200 rank %d: peer-memory exchange unavailable (%s); using NCCL send/recv\n", g.rank, c->peer.error.c_str());
+    }
+  }
   {  // plane-fused x/y passes (fft_xy.cuh): an L2-resident ring of spectrum planes + two sets of progress counters
     static const long long ring_mb = getenv("KW_RING_MB") ? atoll(getenv("KW_RING_MB")) : 0;  // opt-in: the first version is correct but slower than the separate passes (profiles/r01_e)
     if (g.nx == g.ny && ring_mb > 0 && g.nranks == 1) {
@@ -808,30 +843,94 @@ static void inverse_yx(kw_ctx* c, float2* const* data, int nf, const char* name,
   launch(c, name, xinv_bytes, [&] { xinv(0, g.nzl * g.ny / 2); });
 }
 
-// All-to-all of `nf` spectra between the x/y-local and the z-local side (the same contiguous-block exchange in both
-// directions: block q of the source goes to rank q, block q of the destination comes from rank q).  Returns the buffers
-// that hold the result: dst, or src itself on one GPU.
+// ---- all-to-all between the x/y-local and the z-local side --------------------------------------------------------
+// The same contiguous-block exchange in both directions: block q of the source goes to rank q, block q of the destination
+// comes from rank q.  Exchange buffers are addressed by id (S[k] -> k, R[k] -> 4 + k).  Exchanges run on the
+// communication stream `cs`; they start once everything enqueued on the solver stream so far has finished and hand back
+// an event the consumer waits for.
+//  * peer path (PeerLink): each rank pushes its blocks into the destination buffers of its peers with copy-engine copies
+//    over NVLink and announces them with stream memory operations on flags every rank maps; no SM is involved.  A rank
+//    may only be pushed to once it has said (release_buffer) that it no longer reads the previous content.
+//  * fallback: one NCCL group of send/recv pairs.
+static float2* xbuf(kw_ctx* c, int id) { return id < 4 ? c->S[id] : c->R[id - 4]; }
+static int xbuf_id(kw_ctx* c, const float2* p) {
+  for (int k = 0; k < 4; ++k) {
+    if (p == c->S[k]) return k;
+    if (p == c->R[k]) return 4 + k;
+  }
+  return -1;
+}
+static int exchange_async(kw_ctx* c, int src_id, int dst_id, cudaEvent_t* done) {
+  const Geometry& g = c->g;
+  const int me = g.rank, P = g.nranks;
+  float2 *src = xbuf(c, src_id), *dst = xbuf(c, dst_id);
+  const size_t bytes = g.blk * sizeof(float2);
+  cudaStreamWaitEvent(c->cs, mark(c, c->st), 0);
+  int e = 0;
+  std::string what;
+  const double moved = 16.0 * (double)g.blk * (P - 1);
+  if (c->peer.active) {
+    PeerLink& pl = c->peer;
+    DrvApi& d = drv_api();
+    const uint32_t n = ++pl.use[dst_id];
+    const size_t dst_off = reinterpret_cast<char*>(dst) - c->arena;
+    launch(c, "all_to_all", moved, [&] {
+      if (n > 1)  // every receiver has released the previous content of its destination buffer
+        for (int q = 0; q < P && !e; ++q)
+          if (q != me) e = d.WaitValue32(c->cs, pl.dev_addr(&pl.shm->credit[me][dst_id][q]), n - 1, kWaitGeq);
+      for (int k = 1; k < P && !e; ++k) {  // staggered: at any time every rank receives from one sender
+        const int q = (me + k) % P;
+        e = (int)cudaMemcpyAsync(pl.peer_base[q] + dst_off + (size_t)me * bytes, src + (size_t)q * g.blk, bytes, cudaMemcpyDeviceToDevice, c->cs);
+      }
+      if (!e && src != dst) e = (int)cudaMemcpyAsync(dst + (size_t)me * g.blk, src + (size_t)me * g.blk, bytes, cudaMemcpyDeviceToDevice, c->cs);
+      for (int q = 0; q < P && !e; ++q)
+        if (q != me) e = d.WriteValue32(c->cs, pl.dev_addr(&pl.shm->arrived[q][dst_id][me]), n, kWriteDefault);
+      for (int r = 0; r < P && !e; ++r)
+        if (r != me) e = d.WaitValue32(c->cs, pl.dev_addr(&pl.shm->arrived[me][dst_id][r]), n, kWaitGeq);
+    }, c->cs);
+    if (e) what = "peer-memory all-to-all: CUDA error " + std::to_string(e);
+  } else {
+    NcclApi& nc = nccl_api();
+    launch(c, "all_to_all", moved, [&] {
+      e = nc.GroupStart();
+      for (int q = 0; q < P && e == kNcclSuccess; ++q) {
+        e = nc.Send(src + (size_t)q * g.blk, 2 * g.blk, kNcclFloat, q, c->comm, c->cs);
+        if (e == kNcclSuccess) e = nc.Recv(dst + (size_t)q * g.blk, 2 * g.blk, kNcclFloat, q, c->comm, c->cs);
+      }
+      const int e2 = nc.GroupEnd();
+      if (e == kNcclSuccess) e = e2;
+    }, c->cs);
+    if (e != kNcclSuccess) what = std::string("NCCL all-to-all: ") + nc.GetErrorString(e);
+  }
+  if (e) return fail(KW_ERR_COMM, what);
+  c->comm_bytes += 8.0 * (double)g.blk * (P - 1);
+  *done = mark(c, c->cs);
+  return KW_OK;
+}
+// this rank has finished reading the current content of exchange buffer `id` (work enqueued on `s` so far): its peers may
+// push the next content.  Must follow every use of a buffer as a destination.
+static int release_buffer(kw_ctx* c, int id, cudaStream_t s) {
+  if (!c->peer.active) return KW_OK;
+  PeerLink& pl = c->peer;
+  const uint32_t n = pl.use[id];
+  for (int r = 0; r < pl.nranks; ++r)
+    if (r != pl.rank && drv_api().WriteValue32(s, pl.dev_addr(&pl.shm->credit[r][id][pl.rank]), n, kWriteDefault))
+      return fail(KW_ERR_COMM, "peer-memory all-to-all: cuStreamWriteValue32 failed");
+  return KW_OK;
+}
+// blocking form used by the rarely taken paths (additive sources): result[f] = the buffers that hold the exchanged spectra
 static int exchange(kw_ctx* c, float2* const* src, float2* const* dst, int nf, float2** result) {
   const Geometry& g = c->g;
   if (g.nranks == 1) {
     for (int f = 0; f < nf; ++f) result[f] = src[f];
     return KW_OK;
   }
-  NcclApi& nc = nccl_api();
-  int e = kNcclSuccess;
-  launch(c, "all_to_all", nf * 16.0 * (double)g.blk * (g.nranks - 1), [&] {
-    e = nc.GroupStart();
-    for (int f = 0; f < nf && e == kNcclSuccess; ++f)
-      for (int q = 0; q < g.nranks && e == kNcclSuccess; ++q) {
-        e = nc.Send(src[f] + (size_t)q * g.blk, 2 * g.blk, kNcclFloat, q, c->comm, c->st);
-        if (e == kNcclSuccess) e = nc.Recv(dst[f] + (size_t)q * g.blk, 2 * g.blk, kNcclFloat, q, c->comm, c->st);
-      }
-    const int e2 = nc.GroupEnd();
-    if (e == kNcclSuccess) e = e2;
-  });
-  if (e != kNcclSuccess) return fail(KW_ERR_COMM, std::string("NCCL all-to-all: ") + nc.GetErrorString(e));
-  c->comm_bytes += nf * 8.0 * (double)g.blk * (g.nranks - 1);
-  for (int f = 0; f < nf; ++f) result[f] = dst[f];
+  for (int f = 0; f < nf; ++f) {
+    cudaEvent_t ev;
+    KW_TRY(exchange_async(c, xbuf_id(c, src[f]), xbuf_id(c, dst[f]), &ev));
+    cudaStreamWaitEvent(c->st, ev, 0);
+    result[f] = dst[f];
+  }
   return KW_OK;
 }
 
@@ -888,12 +987,14 @@ static int add_scaled_source(kw_ctx* c, const float* signal, int index_id, int m
   KW_TRY(exchange(c, out, &c->R[3], 1, zb));
   zmid_launch(c, ZField{zb[0], zb[0], c->d[KW_SOURCE_KAPPA], 1.0f / (float)g.ntot, nullptr}, -1);
   KW_TRY(exchange(c, zb, &c->S[3], 1, back));
+  if (g.nranks > 1) KW_TRY(release_buffer(c, 7, c->cs));  // R[3] has been pushed back
   EpiAdd e{};
   for (int k = 0; k < ntargets; ++k) e.out[k] = targets[k];
   e.ntargets = ntargets;
   inverse_yx(c, back, 1, "xinv_add_source", "yx_add_source", 8.0 * g.nc + 8.0 * g.n * ntargets,
              [&](int pb, int pe) { g.ox->xinv_add(xinv_args<1>(c, back, pb, pe), e, c->st); },
              [&] { auto a = yx_args<1>(c, back, 1); return g.ox->yx_add(a, e, c->pipe, c->st); });
+  if (g.nranks > 1) KW_TRY(release_buffer(c, 3, c->st));
   return KW_OK;
 }
 
@@ -1106,6 +1207,177 @@ static int step(kw_ctx* c) {
   return KW_OK;
 }
 
+// ---- the pipelined step of slab-decomposed runs -------------------------------------------------------------------
+// Same arithmetic as step(), but every field travels on its own: x/y passes of field f, its exchange (on the communication
+// stream), its z pass, the exchange back, its inverse y pass.  While field f is on the wire the solver stream works on
+// the other fields, and the forward transform of u_f starts as soon as the velocity update of component f is done, i.e.
+// while the gradient components f+1.. are still arriving.
+static void ycol1(kw_ctx* c, float2* buf, int dir) {
+  float2* b[1] = {buf};
+  const ColArgs ca = ycol_args(c->g, b, 1);
+  launch(c, dir < 0 ? "ycol_fwd" : "ycol_inv", 16.0 * c->g.nc, [&] { c->g.oy->col(ca, dir, 1, c->st); });
+}
+static void forward1(kw_ctx* c, const float* in, float2* out) {
+  const float* i[1] = {in};
+  float2* o[1] = {out};
+  forward_xy(c, i, o, 1);
+}
+
+static int step_sharded(kw_ctx* c) {
+  const kw_config& cf = c->cfg;
+  const Geometry& g = c->g;
+  const uint64_t t = c->t;
+  const float fd = 1.0f / (float)g.ntot;
+  float* u[3] = {c->d[KW_UX_SGX], c->d[KW_UY_SGY], c->d[KW_UZ_SGZ]};
+  float* rho[3] = {c->d[KW_RHOX], c->d[KW_RHOY], c->d[KW_RHOZ]};
+  const int neg[3] = {KW_DDX_K_SHIFT_NEG_R, KW_DDY_K_SHIFT_NEG, KW_DDZ_K_SHIFT_NEG};
+  const uint64_t uflag[3] = {cf.ux_source_flag, cf.uy_source_flag, cf.uz_source_flag};
+  const int npairs = g.nzl * g.ny / 2;
+  cudaEvent_t ev, ef[3], eb[3];
+
+  // computeVelocity (cpp:2087-2119) [+ velocity sources + forward transforms of the new velocity]
+  auto velocity_phase = [&](int init, bool forward_u) -> int {
+    forward1(c, c->d[KW_P], c->S[3]);
+    KW_TRY(exchange_async(c, 3, 7, &ev));
+    cudaStreamWaitEvent(c->st, ev, 0);
+    ZField zf{c->R[3], c->S[0], c->d[KW_KAPPA], 1.0f, reinterpret_cast<const float2*>(c->d[KW_DDX_K_SHIFT_POS_R]),
+              c->S[1], c->S[2], reinterpret_cast<const float2*>(c->d[KW_DDY_K_SHIFT_POS]),
+              reinterpret_cast<const float2*>(c->d[KW_DDZ_K_SHIFT_POS])};
+    zmid_launch(c, zf, 3);
+    KW_TRY(release_buffer(c, 7, c->st));
+    cudaEvent_t eg[3];
+    for (int f = 0; f < 3; ++f) KW_TRY(exchange_async(c, f, 4 + f, &eg[f]));
+    const EpiVelocity e = velocity_epilogue(c, u, fd, init);
+    const double het = c->count[KW_RHO0_SGX] > 1 ? 4.0 : 0.0;
+    for (int f = 0; f < 3; ++f) {
+      cudaStreamWaitEvent(c->st, eg[f], 0);
+      ycol1(c, c->R[f], +1);
+      XInvArgs<1> xa = xinv_args<1>(c, c->R, 0, npairs, 3);
+      xa.field0 = f;
+      launch(c, init ? "xinv_initial_velocity" : "xinv_velocity", 8.0 * g.nc + (init ? 8.0 : 8.0 + het) * g.n,
+             [&] { g.ox->xinv_velocity(xa, e, 1, c->st); });
+      KW_TRY(release_buffer(c, 4 + f, c->st));
+      if (!forward_u) continue;
+      // addVelocitySource (cpp:2252-2303), transducer (cpp:894-897) of this component
+      if (uflag[f] > t) {
+        const size_t nsrc = c->count[KW_U_SOURCE_INDEX];
+        if (cf.u_source_mode != KW_SRC_ADDITIVE) {
+          if (nsrc > 0) {
+            SourceArgs sa{};
+            sa.target[0] = u[f], sa.ntargets = 1, sa.signal = c->d[KW_UX_SOURCE_INPUT + f], sa.index = c->di[KW_U_SOURCE_INDEX];
+            sa.pos = c->dpos[KW_U_SOURCE_INDEX], sa.nsrc = nsrc, sa.nsrc_total = c->count_total[KW_U_SOURCE_INDEX];
+            sa.t = t, sa.many = cf.u_source_many, sa.mode = cf.u_source_mode;
+            launch(c, "add_u_source", 20.0 * nsrc, [&] { k_add_source<<<ew_grid(nsrc), 256, 0, c->st>>>(sa); });
+          }
+        } else {
+          float* tg[1] = {u[f]};
+          KW_TRY(add_scaled_source(c, c->d[KW_UX_SOURCE_INPUT + f], KW_U_SOURCE_INDEX, cf.u_source_many, tg, 1));
+        }
+      }
+      if (f == 0 && cf.transducer_source_flag > t && c->count[KW_U_SOURCE_INDEX] > 0) {
+        const size_t nsrc = c->count[KW_U_SOURCE_INDEX];
+        launch(c, "add_transducer", 28.0 * nsrc, [&] {
+          k_add_transducer<<<ew_grid(nsrc), 256, 0, c->st>>>(u[0], c->di[KW_U_SOURCE_INDEX], c->d[KW_TRANSDUCER_SOURCE_INPUT],
+                                                              c->di[KW_DELAY_MASK], nsrc, t);
+        });
+      }
+      forward1(c, u[f], c->S[f]);  // computeVelocityGradient starts for this component
+      KW_TRY(exchange_async(c, f, 4 + f, &ef[f]));
+    }
+    return KW_OK;
+  };
+  KW_TRY(velocity_phase(0, true));
+
+  // ---- computeVelocityGradient (cpp:2126-2150) + computeDensity (cpp:2157/2169) [+ pressure terms / lossless p]
+  for (int f = 0; f < 3; ++f) {
+    cudaStreamWaitEvent(c->st, ef[f], 0);
+    zmid_launch(c, ZField{c->R[f], c->R[f], c->d[KW_KAPPA], fd, reinterpret_cast<const float2*>(c->d[neg[f]])}, f);
+    KW_TRY(exchange_async(c, 4 + f, f, &eb[f]));
+    KW_TRY(release_buffer(c, 4 + f, c->cs));
+  }
+  for (int f = 0; f < 3; ++f) {
+    cudaStreamWaitEvent(c->st, eb[f], 0);
+    ycol1(c, c->S[f], +1);
+  }
+  const bool p_src = cf.p_source_flag > t;
+  {
+    EpiDensity e{};
+    for (int k = 0; k < 3; ++k) e.rho[k] = rho[k], e.pml[k] = c->d[KW_PML_X + k];
+    e.pml[2] += g.z0;
+    e.rho0 = c->fld(KW_RHO0), e.bona = c->fld(KW_BONA), e.c2 = c->fld(KW_C0);
+    e.dt = cf.dt, e.nonlinear = cf.nonlinear_flag, e.absorbing = cf.absorbing_flag;
+    e.defer_terms = p_src && cf.p_source_mode == KW_SRC_ADDITIVE;
+    e.outA = c->tA, e.outB = c->tB, e.outNL = c->tNL, e.p = c->d[KW_P];
+    double fused_bytes = 0;
+    if (!cf.absorbing_flag && !p_src) e.sample = fused_p_sample(c, &e.fs, &fused_bytes);
+    double per = 24.0 + (c->count[KW_RHO0] > 1 ? 4.0 : 0.0);
+    if (cf.absorbing_flag) per += 4.0 + (e.defer_terms ? 0.0 : 4.0 + (cf.nonlinear_flag ? 4.0 : 0.0));
+    else if (!e.defer_terms) per += 4.0 + (c->count[KW_C0] > 1 ? 4.0 : 0.0);
+    if (cf.nonlinear_flag && !e.defer_terms && c->count[KW_BONA] > 1) per += 4.0;
+    launch(c, "xinv_density", 24.0 * g.nc + per * g.n + fused_bytes, [&] { g.ox->xinv_density(xinv_args<3>(c, c->S, 0, npairs), e, c->st); });
+    for (int f = 0; f < 3; ++f) KW_TRY(release_buffer(c, f, c->st));
+  }
+  // ---- addPressureSource (cpp:2310-2334)
+  if (p_src) {
+    const size_t nsrc = c->count[KW_P_SOURCE_INDEX];
+    TermsArgs ta = terms_args(c);
+    if (cf.p_source_mode != KW_SRC_ADDITIVE) {
+      if (nsrc > 0) {
+        SourceArgs sa{};
+        for (int k = 0; k < 3; ++k) sa.target[k] = rho[k];
+        sa.ntargets = 3, sa.signal = c->d[KW_P_SOURCE_INPUT], sa.index = c->di[KW_P_SOURCE_INDEX];
+        sa.pos = c->dpos[KW_P_SOURCE_INDEX], sa.nsrc = nsrc, sa.nsrc_total = c->count_total[KW_P_SOURCE_INDEX];
+        sa.t = t, sa.many = cf.p_source_many, sa.mode = cf.p_source_mode;
+        launch(c, "add_p_source", 36.0 * nsrc, [&] { k_add_source<<<ew_grid(nsrc), 256, 0, c->st>>>(sa); });
+        ta.index = c->di[KW_P_SOURCE_INDEX], ta.n = nsrc;
+        launch(c, "pressure_terms_fixup", 40.0 * nsrc, [&] { k_pressure_terms<<<ew_grid(nsrc), 256, 0, c->st>>>(ta); });
+      }
+    } else {
+      KW_TRY(add_scaled_source(c, c->d[KW_P_SOURCE_INPUT], KW_P_SOURCE_INDEX, cf.p_source_many, rho, 3));
+      ta.index = nullptr, ta.n = g.n;
+      launch(c, "pressure_terms", 28.0 * g.n, [&] { k_pressure_terms<<<ew_grid(g.n), 256, 0, c->st>>>(ta); });
+    }
+  }
+  // ---- computePressure, absorbing branch (cpp:2180-2246)
+  if (cf.absorbing_flag) {
+    const float* in[2] = {c->tA, c->tB};
+    const int nab[2] = {KW_ABSORB_NABLA1, KW_ABSORB_NABLA2};
+    for (int f = 0; f < 2; ++f) {
+      forward1(c, in[f], c->S[f]);
+      KW_TRY(exchange_async(c, f, 4 + f, &ef[f]));
+    }
+    for (int f = 0; f < 2; ++f) {
+      cudaStreamWaitEvent(c->st, ef[f], 0);
+      zmid_launch(c, ZField{c->R[f], c->R[f], c->d[nab[f]], 1.0f, nullptr}, -1);
+      KW_TRY(exchange_async(c, 4 + f, f, &eb[f]));
+      KW_TRY(release_buffer(c, 4 + f, c->cs));
+    }
+    for (int f = 0; f < 2; ++f) {
+      cudaStreamWaitEvent(c->st, eb[f], 0);
+      ycol1(c, c->S[f], +1);
+    }
+    EpiPressureSum e{};
+    e.p = c->d[KW_P], e.base = cf.nonlinear_flag ? c->tNL : c->tB;
+    e.c2 = c->fld(KW_C0), e.tau = c->fld(KW_ABSORB_TAU), e.eta = c->fld(KW_ABSORB_ETA), e.fd = fd;
+    const double per = 8.0 + (c->count[KW_C0] > 1 ? 4.0 : 0.0) + (c->count[KW_ABSORB_TAU] > 1 ? 8.0 : 0.0);
+    double fused_bytes = 0;
+    e.sample = fused_p_sample(c, &e.fs, &fused_bytes);
+    launch(c, "xinv_pressure_sum", 16.0 * g.nc + per * g.n + fused_bytes, [&] { g.ox->xinv_psum(xinv_args<2>(c, c->S, 0, npairs), e, c->st); });
+    for (int f = 0; f < 2; ++f) KW_TRY(release_buffer(c, f, c->st));
+  }
+  // ---- addInitialPressureSource (cpp:2359-2396)
+  if (t == 0 && cf.p0_source_flag == 1) {
+    launch(c, "initial_pressure", 24.0 * g.n, [&] {
+      k_initial_pressure<<<ew_grid(g.n), 256, 0, c->st>>>(c->d[KW_P], rho[0], rho[1], rho[2], c->d[KW_P0_SOURCE_INPUT], c->fld(KW_C0), g.n);
+    });
+    KW_TRY(velocity_phase(1, false));
+  }
+  // ---- storeSensorData (cpp:1060-1093)
+  if (t >= cf.sampling_start_index) sample_streams(c);
+  c->t++;
+  return KW_OK;
+}
+
 }  // namespace kw
 
 extern "C" {
@@ -1125,13 +1397,14 @@ int kw_run(kw_ctx* c, uint64_t nsteps, uint64_t* steps_done, int sync) {
       rc = fail(KW_ERR_STREAM_FULL, "a raw stream buffer is full: fetch it with kw_stream_fetch");
       break;
     }
-    KW_TRY(step(c));
+    KW_TRY(c->g.nranks > 1 ? step_sharded(c) : step(c));
   }
   KW_CUDA(cudaEventRecord(c->ev1, c->st));
   KW_CUDA(cudaGetLastError());
   if (steps_done) *steps_done = done;
   if (sync) {
     KW_CUDA(cudaStreamSynchronize(c->st));
+    if (c->cs) KW_CUDA(cudaStreamSynchronize(c->cs));
     KW_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
     prof_resolve(c);
     KW_TRY(pipe_check(c));
@@ -1147,6 +1420,7 @@ int kw_time_index(kw_ctx* c, uint64_t* t) {
 int kw_synchronize(kw_ctx* c) {
   if (!c) return fail(KW_ERR_INVALID, "null context");
   KW_CUDA(cudaStreamSynchronize(c->st));
+  if (c->cs) KW_CUDA(cudaStreamSynchronize(c->cs));
   cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
   prof_resolve(c);
   KW_CUDA(cudaGetLastError());
@@ -1156,6 +1430,7 @@ int kw_synchronize(kw_ctx* c) {
 int kw_profile(kw_ctx* c, int enable, int reset) {
   if (!c) return fail(KW_ERR_INVALID, "null context");
   KW_CUDA(cudaStreamSynchronize(c->st));
+  if (c->cs) KW_CUDA(cudaStreamSynchronize(c->cs));
   prof_resolve(c);
   c->prof_on = enable != 0;
   if (reset) c->prof.clear();
@@ -1241,6 +1516,11 @@ int kw_sensor_layout(kw_ctx* c, uint64_t* total, uint64_t* local, uint64_t* posi
     for (size_t r = 0; r + 1 < c->sens_ranges.size(); r += 2)
       for (uint64_t j = 0; j < c->sens_ranges[r + 1]; ++j) positions[k++] = c->sens_ranges[r] + j;
   }
+  return KW_OK;
+}
+int kw_comm_mode(kw_ctx* c, int* mode) {
+  if (!c || !mode) return fail(KW_ERR_INVALID, "null argument");
+  *mode = c->g.nranks == 1 ? 0 : (c->peer.active ? 2 : 1);
   return KW_OK;
 }
 int kw_comm_bytes(kw_ctx* c, double* bytes_sent) {

@@ -19,7 +19,7 @@ def run_rank(rank, world, nccl_id, shape, kwargs, nt, streams, start_index, q):
         out = {s: sim.fetch(s) for s in streams}
         out["p_final"] = sim.get_array("KW_P")
         out["ux_final"] = sim.get_array("KW_UX_SGX")
-        out.update(done=done, total=total, pos=pos, slab=sim.local_slab(), comm_bytes=sim.comm_bytes(), launches=sim.launch_count())
+        out.update(done=done, total=total, pos=pos, slab=sim.local_slab(), comm_bytes=sim.comm_bytes(), comm_mode=sim.comm_mode(), launches=sim.launch_count())
         sim.close()
         q.put((rank, out))
     except Exception as e:  # surface the failure in the parent instead of a hang

@@ -50,6 +50,7 @@ def run_sharded(kw, world, shape, kwargs, nt, streams, start_index=0):
     out["p_final"] = np.concatenate([res[r]["p_final"] for r in range(world)], axis=0)
     out["ux_final"] = np.concatenate([res[r]["ux_final"] for r in range(world)], axis=0)
     out["comm_bytes"] = [res[r]["comm_bytes"] for r in range(world)]
+    out["comm_mode"] = [res[r]["comm_mode"] for r in range(world)]
     return out
 
 
@@ -97,3 +98,19 @@ def test_sharded_run_matches_oracle_and_single_gpu(kw, synth, name, world):
         print(f"{name} P={world}: {s}: rel-L2 vs single GPU {err:.3e}")
         assert err <= TOL_SHARD, (name, s, err)
     assert all(b > 0 for b in got["comm_bytes"])
+    print(f"{name} P={world}: exchange path {got['comm_mode']}")
+    assert len(set(got["comm_mode"])) == 1
+
+
+def test_nccl_fallback_path(kw, synth, monkeypatch):
+    """KW_PEER=0: the exchange runs as NCCL send/recv groups instead of peer-memory pushes; same results."""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("KW_PEER", "0")
+    shape, kwargs = CASES["nonlinear_absorbing_index_shuffled"]
+    nt = 30
+    cfg, arrays = synth.make_case(*shape, nt=nt, **kwargs)
+    ref = ko.run(cfg, arrays, nt=nt, dtype=np.float64, record=("p_raw",))
+    got = run_sharded(kw, 2, shape, kwargs, nt, ["KW_S_P_RAW"])
+    assert got["comm_mode"] == ["nccl", "nccl"]
+    assert rel_l2(got["KW_S_P_RAW"], ref["p"]) <= TOL
