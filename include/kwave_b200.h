@@ -150,6 +150,15 @@ int kw_set_source_row(kw_ctx* ctx, int array_id, uint64_t t_index, const float* 
 int kw_fft_r2c_3d(uint64_t nx, uint64_t ny, uint64_t nz, const float* host_real, float* host_complex);
 int kw_fft_c2r_3d(uint64_t nx, uint64_t ny, uint64_t nz, const float* host_complex, float* host_real);
 
+/* Compression helpers.  kw_c40_encode / kw_c40_decode = CompressHelper::convertFloatCTo40b / convert40bToFloatC
+ * (Compression/CompressHelper.cpp:292-389 / :224-290) on n complex values (interleaved re, im <-> 5 bytes each), run by the
+ * device code the compressed streams use; max_exp = 138 (pressure) or 114 (velocity), CompressHelper.h:91-92.
+ * kw_compression_bases returns the windowed bases bE / bE_1 (harmonics x bSize complex values, CompressHelper::getBE /
+ * getBE_1 or their time-shifted variants) the context generated, with oSize and bSize (CompressHelper.cpp:48-65). */
+int kw_c40_encode(const float* complex_pairs, uint64_t n, int max_exp, uint8_t* bytes);
+int kw_c40_decode(const uint8_t* bytes, uint64_t n, int max_exp, float* complex_pairs);
+int kw_compression_bases(kw_ctx* ctx, int shifted, float* be, float* be1, uint64_t capacity_complex, uint64_t* osize, uint64_t* bsize);
+
 /* Slab decomposition over GPUs (no reference counterpart; the reference is single-GPU: MatrixContainer holds whole
  * arrays, Containers/MatrixContainer.cpp:418-476).  One context per rank (one process per GPU); kw_config.rank/nranks and
  * a ncclUniqueId created by ONE rank with kw_nccl_unique_id and distributed by the host (torch.distributed, MPI, a file).

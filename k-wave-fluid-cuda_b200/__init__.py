@@ -9,6 +9,8 @@ from .capi import (  # noqa: F401
     STREAM_IDS,
     KwError,
     Simulation,
+    c40_decode,
+    c40_encode,
     fft_c2r_3d,
     fft_r2c_3d,
     library_path,

@@ -126,6 +126,9 @@ def load_library():
         "kw_sensor_layout": [vp, C.POINTER(u64), C.POINTER(u64), vp, u64],
         "kw_comm_bytes": [vp, C.POINTER(C.c_double)],
         "kw_comm_mode": [vp, C.POINTER(C.c_int)],
+        "kw_c40_encode": [vp, u64, i32, vp],
+        "kw_c40_decode": [vp, u64, i32, vp],
+        "kw_compression_bases": [vp, i32, vp, vp, u64, C.POINTER(u64), C.POINTER(u64)],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -157,6 +160,22 @@ def fft_c2r_3d(xk, nx):
     assert nxr == nx // 2 + 1
     out = np.empty((nz, ny, nx), dtype=np.float32)
     _check(lib.kw_fft_c2r_3d(nx, ny, nz, xk.ctypes.data, out.ctypes.data))
+    return out
+
+
+def c40_encode(values, max_exp):
+    """CompressHelper::convertFloatCTo40b on the device: complex64 array -> uint8 array (..., 5)."""
+    v = np.ascontiguousarray(values, dtype=np.complex64)
+    out = np.empty(v.shape + (5,), dtype=np.uint8)
+    _check(load_library().kw_c40_encode(v.ctypes.data, v.size, max_exp, out.ctypes.data))
+    return out
+
+
+def c40_decode(packed, max_exp):
+    """CompressHelper::convert40bToFloatC on the device: uint8 array (..., 5) -> complex64 array."""
+    b = np.ascontiguousarray(packed, dtype=np.uint8)
+    out = np.empty(b.shape[:-1], dtype=np.complex64)
+    _check(load_library().kw_c40_decode(b.ctypes.data, out.size, max_exp, out.ctypes.data))
     return out
 
 
@@ -194,6 +213,7 @@ class Simulation:
         self._nccl_id = C.create_string_buffer(bytes(nccl_id), 128) if nranks > 1 else None
         kc.nccl_unique_id = C.cast(self._nccl_id, C.c_void_p) if nranks > 1 else None
         self.rank, self.nranks = rank, nranks
+        self._harmonics = (compression or {}).get("harmonics", 1)
         if compression:
             kc.c_period, kc.c_mos, kc.c_harmonics = compression["period"], compression.get("mos", 1), compression.get("harmonics", 1)
             kc.c_no_overlap, kc.c_40bit = int(compression.get("no_overlap", 0)), int(compression.get("c40", 0))
@@ -294,6 +314,16 @@ class Simulation:
         if local.value:
             _check(self.lib.kw_sensor_layout(self.ctx, C.byref(total), C.byref(local), pos.ctypes.data, pos.size))
         return total.value, pos
+
+    def compression_bases(self, shifted=False):
+        """(oSize, bSize, bE, bE_1) as generated by the context (complex64, shape (harmonics, bSize))."""
+        osz, bsz = C.c_uint64(), C.c_uint64()
+        _check(self.lib.kw_compression_bases(self.ctx, int(shifted), None, None, 0, C.byref(osz), C.byref(bsz)))
+        h = int(self._harmonics)
+        be = np.empty((h, bsz.value), np.complex64)
+        be1 = np.empty((h, bsz.value), np.complex64)
+        _check(self.lib.kw_compression_bases(self.ctx, int(shifted), be.ctypes.data, be1.ctypes.data, be.size, C.byref(osz), C.byref(bsz)))
+        return osz.value, bsz.value, be, be1
 
     def comm_mode(self):
         m = C.c_int()

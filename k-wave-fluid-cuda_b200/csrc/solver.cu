@@ -101,6 +101,15 @@ struct Stream {
   float* dbuf = nullptr;
   size_t row = 0, cap_rows = 0, rows = 0;
   bool fused_this_step = false;  // accumulated by the kernel that produced the field
+  // compressed streams (kOpC): two overlapped accumulators per (sensor, harmonic); frames are appended to dbuf
+  bool nosave = false;          // created only because an I_avg_c stream needs it (OutputStreamContainer.cpp:273-323)
+  bool shifted_bases = false;   // u*_non_staggered_c: time-shifted bases, exponent offset 114 (BaseOutputStream.cpp:63-102)
+  float* sbuf = nullptr;        // raw samples of the current step
+  void *acc1 = nullptr, *acc2 = nullptr;
+  void* cur = nullptr;          // the accumulator completed at this step (between flush and postSample2)
+  size_t acc_bytes = 0;
+  uint64_t sampled = 0, compressed = 0;
+  bool saving = false;
 };
 
 // Grid + slab decomposition.  Rank r of P owns the real-space planes z in [z0, z0 + nzl) of every
@@ -204,6 +213,13 @@ struct kw_ctx {
   char* arena = nullptr;  // S[0..3], R[0..3] in one allocation (one IPC handle per rank)
   char nccl_id[128] = {};
   Stream streams[KW_STREAM_COUNT];
+  // compression (Compression/CompressHelper.cpp:48-65): bases [0] plain, [1] time shifted
+  int c_osize = 0, c_bsize = 0, c_H = 0;
+  bool c_no_overlap = false;
+  float2 *d_be[2] = {}, *d_be1[2] = {};
+  // non-staggered velocity (cpp:2714-2735): shift operators extended to the full ky / kz range
+  float2* shift_full[3] = {};
+  bool need_shifted = false;
   PipeState pipe;  // ring + counters of the plane-fused x/y kernels (Nx == Ny only)
   std::vector<void*> owned;
 
@@ -465,6 +481,7 @@ int kw_set_array(kw_ctx* c, int id, const void* host, uint64_t count) {
     std::vector<float> tmp(2 * padded, 0.f);
     memcpy(tmp.data(), host, 2 * count * sizeof(float));
     KW_TRY(upload_f(c, id, tmp.data(), 2 * padded));
+    if (id >= KW_X_SHIFT_NEG_R && id <= KW_Z_SHIFT_NEG_R) c->h_in[id] = tmp;  // extended to full length by kw_preprocess
     return KW_OK;
   }
   const float* h = static_cast<const float*>(host);
@@ -506,20 +523,20 @@ int kw_set_source_row(kw_ctx* c, int id, uint64_t t, const float* row, uint64_t 
 }
 
 static const struct { int op; int src; bool all; bool supported; } kStreamTable[KW_STREAM_COUNT] = {
-    /* P_RAW */ {kOpNone, 0, false, true}, /* P_C */ {0, 0, false, false}, /* P_RMS */ {kOpRms, 0, false, true},
+    /* P_RAW */ {kOpNone, 0, false, true}, /* P_C */ {kOpC, 0, false, true}, /* P_RMS */ {kOpRms, 0, false, true},
     /* P_MAX */ {kOpMax, 0, false, true}, /* P_MIN */ {kOpMin, 0, false, true}, /* P_MAX_ALL */ {kOpMax, 0, true, true},
     /* P_MIN_ALL */ {kOpMin, 0, true, true},
     /* U*_RAW */ {kOpNone, 1, false, true}, {kOpNone, 2, false, true}, {kOpNone, 3, false, true},
-    /* U*_C */ {0, 1, false, false}, {0, 2, false, false}, {0, 3, false, false},
-    /* U*_NS_RAW */ {0, 4, false, false}, {0, 5, false, false}, {0, 6, false, false},
-    /* U*_NS_C */ {0, 4, false, false}, {0, 5, false, false}, {0, 6, false, false},
+    /* U*_C */ {kOpC, 1, false, true}, {kOpC, 2, false, true}, {kOpC, 3, false, true},
+    /* U*_NS_RAW */ {kOpNone, 4, false, true}, {kOpNone, 5, false, true}, {kOpNone, 6, false, true},
+    /* U*_NS_C */ {kOpC, 4, false, true}, {kOpC, 5, false, true}, {kOpC, 6, false, true},
     /* U*_RMS */ {kOpRms, 1, false, true}, {kOpRms, 2, false, true}, {kOpRms, 3, false, true},
     /* U*_MAX */ {kOpMax, 1, false, true}, {kOpMax, 2, false, true}, {kOpMax, 3, false, true},
     /* U*_MIN */ {kOpMin, 1, false, true}, {kOpMin, 2, false, true}, {kOpMin, 3, false, true},
     /* U*_MAX_ALL */ {kOpMax, 1, true, true}, {kOpMax, 2, true, true}, {kOpMax, 3, true, true},
     /* U*_MIN_ALL */ {kOpMin, 1, true, true}, {kOpMin, 2, true, true}, {kOpMin, 3, true, true},
     /* I*_AVG */ {0, 0, false, false}, {0, 0, false, false}, {0, 0, false, false},
-    /* I*_AVG_C */ {0, 0, false, false}, {0, 0, false, false}, {0, 0, false, false},
+    /* I*_AVG_C */ {kOpIAvgC, 0, false, true}, {kOpIAvgC, 1, false, true}, {kOpIAvgC, 2, false, true},
     /* Q_TERM */ {0, 0, false, false}, /* Q_TERM_C */ {0, 0, false, false}};
 
 int kw_stream_enable(kw_ctx* c, int sid) {
@@ -658,7 +675,8 @@ int kw_preprocess(kw_ctx* c) {
   for (auto& v : c0) v = v * v;
   if (c0.size() == 1) c->scalar[KW_C0] = c0[0], c->count[KW_C0] = 1;
   else KW_TRY(upload_f(c, KW_C0, c0.data(), c0.size()));
-  for (auto& v : c->h_in) std::vector<float>().swap(v);
+  for (int id = 0; id < KW_ARRAY_COUNT; ++id)
+    if (id < KW_X_SHIFT_NEG_R || id > KW_Z_SHIFT_NEG_R) std::vector<float>().swap(c->h_in[id]);  // the shift vectors are extended below
   // --- validation of what the loop needs
   if (c->count[KW_RHO0] == 0) return fail(KW_ERR_INVALID, "rho0 missing");
   if (cf.nonlinear_flag && c->count[KW_BONA] == 0) return fail(KW_ERR_INVALID, "BonA missing (nonlinear_flag = 1)");
@@ -716,6 +734,86 @@ int kw_preprocess(kw_ctx* c) {
     if (cf.nonlinear_flag) KW_TRY(dalloc(c, (void**)&c->tNL, g.n * sizeof(float)));
   }
   if (c->d[KW_SOURCE_KAPPA]) KW_TRY(dalloc(c, (void**)&c->tSrc, g.n * sizeof(float)));
+  // --- streams that exist only because others need them (OutputStreamContainer.cpp:273-323): I_avg_c reads the
+  //     frames of p_c and u*_non_staggered_c
+  for (int k = 0; k < 3; ++k)
+    if (c->streams[KW_S_IX_AVG_C + k].enabled)
+      for (int dep : {(int)KW_S_P_C, (int)KW_S_UX_NS_C + k}) {
+        Stream& d = c->streams[dep];
+        if (d.enabled) continue;
+        d.enabled = true, d.nosave = true, d.op = kStreamTable[dep].op, d.src = kStreamTable[dep].src, d.all = false;
+      }
+  bool any_c = false;
+  for (int sid = 0; sid < KW_STREAM_COUNT; ++sid) {
+    Stream& s = c->streams[sid];
+    if (!s.enabled) continue;
+    any_c |= s.op == kOpC;
+    c->need_shifted |= s.src >= 4 && s.op != kOpIAvgC;
+    s.shifted_bases = sid >= KW_S_UX_NS_C && sid <= KW_S_UZ_NS_C;
+  }
+  if (c->need_shifted) {  // non-staggered velocity (cpp:2714-2735)
+    const int nfull[3] = {g.nxp, g.ny, g.nz};
+    for (int k = 0; k < 3; ++k) {
+      auto& h = c->h_in[KW_X_SHIFT_NEG_R + k];
+      if (h.empty()) return fail(KW_ERR_INVALID, "x/y/z_shift_neg_r missing (needed by non-staggered velocity outputs, MatrixContainer.cpp:375-384)");
+      std::vector<float2> full(nfull[k], make_float2(0.f, 0.f));
+      if (k == 0) {
+        for (int i = 0; i < g.nxr; ++i) full[i] = make_float2(h[2 * i], h[2 * i + 1]);
+      } else {
+        // the reference transforms real lines (R2C / C2R along y or z): for the complex lines of the half spectrum the same
+        // operator is its Hermitian extension, with the real part only where C2R ignores the imaginary one (DC, Nyquist)
+        const int n = nfull[k], half = n / 2;
+        for (int i = 0; i <= half; ++i) {
+          const bool edge = i == 0 || (i == half && n % 2 == 0);
+          full[i] = make_float2(h[2 * i], edge ? 0.f : h[2 * i + 1]);
+          if (i > 0 && i < n - i) full[n - i] = make_float2(h[2 * i], -h[2 * i + 1]);
+        }
+      }
+      KW_TRY(dalloc(c, (void**)&c->shift_full[k], full.size() * sizeof(float2), false));
+      KW_CUDA(cudaMemcpyAsync(c->shift_full[k], full.data(), full.size() * sizeof(float2), cudaMemcpyHostToDevice, c->st));
+      KW_CUDA(cudaStreamSynchronize(c->st));
+      KW_TRY(dalloc(c, (void**)&c->d[KW_UX_SHIFTED + k], g.n * sizeof(float)));
+      c->count[KW_UX_SHIFTED + k] = g.n;
+    }
+  }
+  const uint64_t nsamp_c = cf.nt > cf.sampling_start_index ? cf.nt - cf.sampling_start_index : 0;
+  if (any_c) {  // CompressHelper::init + generateFunctions (Compression/CompressHelper.cpp:48-65, :672-778), FP32
+    if (!(cf.c_period > 0.f) || cf.c_mos == 0 || cf.c_harmonics == 0) return fail(KW_ERR_INVALID, "compression needs c_period > 0, c_mos >= 1, c_harmonics >= 1");
+    c->c_osize = (int)(cf.c_period * (float)cf.c_mos);
+    if (c->c_osize < 1) return fail(KW_ERR_INVALID, "compression: period * mos must be at least one step");
+    c->c_bsize = 2 * c->c_osize + 1;
+    c->c_H = (int)cf.c_harmonics;
+    c->c_no_overlap = cf.c_no_overlap != 0 || cf.c_period >= (float)nsamp_c;  // Parameters.cpp:141-145
+    const int os = c->c_osize, bs = c->c_bsize, H = c->c_H;
+    std::vector<float> win(bs);
+    for (int x = 0; x < bs; ++x) win[x] = x < os ? (float)x / (float)os : 2.0f - (float)x / (float)os;
+    for (int sh = 0; sh < 2; ++sh) {
+      std::vector<float2> e((size_t)H * bs), be((size_t)H * bs), be1((size_t)H * bs);
+      for (int ih = 0; ih < H; ++ih) {
+        const float w = 2.0f * (float)M_PI / (cf.c_period / (float)(ih + 1));
+        const float sa = (float)M_PI / (cf.c_period / (float)(ih + 1));
+        const float cs = cosf(sa), sn = sinf(sa);
+        for (int x = 0; x < bs; ++x) {
+          const float ang = w * (float)x;
+          float2 v = make_float2(cosf(ang), -sinf(ang));  // exp(-i w x)
+          if (sh) v = make_float2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);  // * exp(+i pi h / period)
+          e[(size_t)ih * bs + x] = v;
+        }
+        const float norm = 2.0f / (float)os;
+        for (int x = 0; x < bs; ++x) {
+          const int x1 = (x + os) % (bs - 1);
+          const float2 a = e[(size_t)ih * bs + x], b = e[(size_t)ih * bs + x1];
+          be[(size_t)ih * bs + x] = make_float2(win[x] * a.x * norm, win[x] * a.y * norm);
+          be1[(size_t)ih * bs + x] = make_float2(win[x1] * b.x * norm, win[x1] * b.y * norm);
+        }
+      }
+      KW_TRY(dalloc(c, (void**)&c->d_be[sh], be.size() * sizeof(float2), false));
+      KW_TRY(dalloc(c, (void**)&c->d_be1[sh], be1.size() * sizeof(float2), false));
+      KW_CUDA(cudaMemcpyAsync(c->d_be[sh], be.data(), be.size() * sizeof(float2), cudaMemcpyHostToDevice, c->st));
+      KW_CUDA(cudaMemcpyAsync(c->d_be1[sh], be1.data(), be1.size() * sizeof(float2), cudaMemcpyHostToDevice, c->st));
+      KW_CUDA(cudaStreamSynchronize(c->st));
+    }
+  }
   // --- sensors and streams
   bool any_sensor_stream = false;
   for (int s = 0; s < KW_STREAM_COUNT; ++s) any_sensor_stream |= c->streams[s].enabled && !c->streams[s].all;
@@ -766,7 +864,23 @@ int kw_preprocess(kw_ctx* c) {
     Stream& s = c->streams[sid];
     if (!s.enabled) continue;
     s.row = s.all ? g.n : c->nsens;
-    if (s.op == kOpNone) {
+    if (s.op == kOpC) {
+      const size_t H = c->c_H;
+      // BaseOutputStream.cpp:98-101 / IndexOutputStream.cpp:87-125: ceil(Nsens * complexSize) * harmonics floats per frame
+      s.row = cf.c_40bit ? (size_t)ceilf((float)c->nsens * 1.25f) * H : 2 * c->nsens * H;
+      s.acc_bytes = std::max<size_t>(s.row * sizeof(float), c->nsens * H * (cf.c_40bit ? 5 : 8));
+      KW_TRY(dalloc(c, (void**)&s.sbuf, c->nsens * sizeof(float)));
+      KW_TRY(dalloc(c, &s.acc1, s.acc_bytes));
+      if (c->c_no_overlap) s.acc2 = s.acc1;  // BaseOutputStream.cpp:246-257
+      else KW_TRY(dalloc(c, &s.acc2, s.acc_bytes));
+      const uint64_t nframes = std::max<uint64_t>(nsamp / (uint64_t)c->c_osize, 1);
+      uint64_t cap = cf.raw_rows_capacity ? cf.raw_rows_capacity : std::max<uint64_t>(1, std::min<uint64_t>(nframes, (256ull << 20) / (s.row * sizeof(float) + 1)));
+      s.cap_rows = s.nosave ? 0 : cap;
+      if (!s.nosave) KW_TRY(dalloc(c, (void**)&s.dbuf, s.cap_rows * s.row * sizeof(float)));
+    } else if (s.op == kOpIAvgC) {
+      s.cap_rows = 1;
+      KW_TRY(dalloc(c, (void**)&s.dbuf, s.row * sizeof(float)));
+    } else if (s.op == kOpNone) {
       uint64_t cap = cf.raw_rows_capacity;
       if (cap == 0) cap = std::max<uint64_t>(1, std::min<uint64_t>(nsamp ? nsamp : 1, (256ull << 20) / (s.row * sizeof(float) + 1)));
       s.cap_rows = cap;
@@ -1051,23 +1165,116 @@ static bool fused_p_sample(kw_ctx* c, FusedSample* fs, double* extra_bytes) {
   return any;
 }
 
-// OutputStreamContainer::sampleStreams (Containers/OutputStreamContainer.cpp:364-373): enum order
-static void sample_streams(kw_ctx* c) {
+// computeShiftedVelocity (cpp:2714-2735): u_i shifted by half a cell onto the pressure grid.  The reference runs 1-D
+// R2C / multiply / C2R along each axis; here the same multiplier is applied between the z transforms of the 3-D pipeline
+// (it commutes with the transforms along the other two axes), which also covers slab-decomposed grids.
+static int add_scaled_source(kw_ctx* c, const float* signal, int index_id, int many, float* const* targets, int ntargets);
+static int compute_shifted_velocity(kw_ctx* c) {
+  const Geometry& g = c->g;
+  const float fd = 1.0f / (float)g.ntot;
+  for (int f = 0; f < 3; ++f) {
+    const float* in[1] = {c->d[KW_UX_SGX + f]};
+    float2* out[1] = {c->S[3]};
+    forward_xy(c, in, out, 1);
+    float2 *zb[1], *back[1];
+    KW_TRY(exchange(c, out, &c->R[3], 1, zb));
+    zmid_launch(c, ZField{zb[0], zb[0], nullptr, fd, c->shift_full[f]}, f);
+    KW_TRY(exchange(c, zb, &c->S[3], 1, back));
+    if (g.nranks > 1) KW_TRY(release_buffer(c, 7, c->cs));
+    EpiStore e{};
+    e.out[0] = c->d[KW_UX_SHIFTED + f], e.scale = 1.0f;
+    inverse_yx(c, back, 1, "xinv_shifted_velocity", "yx_shifted_velocity", 8.0 * g.nc + 4.0 * g.n,
+               [&](int pb, int pe) { g.ox->xinv_store(xinv_args<1>(c, back, pb, pe), e, 1, c->st); },
+               [&] { auto a = yx_args<1>(c, back, 1); return g.ox->yx_store(a, e, c->pipe, c->st); });
+    if (g.nranks > 1) KW_TRY(release_buffer(c, 3, c->st));
+  }
+  return KW_OK;
+}
+
+static const float* stream_source(kw_ctx* c, const Stream& s) {
+  return s.src == 0 ? c->d[KW_P] : s.src <= 3 ? c->d[KW_UX_SGX + (s.src - 1)] : c->d[KW_UX_SHIFTED + (s.src - 4)];
+}
+
+// OutputStreamContainer::sampleStreams + flushRawStreams (Containers/OutputStreamContainer.cpp:364-403): sampling in enum
+// order; then, for the compressed streams, every flushRaw, every postSample (I_avg_c) and every postSample2 -- all on the
+// device, in the step that produced the samples (the reference does this on the host, one step later).
+static int sample_streams(kw_ctx* c) {
+  const kw_config& cf = c->cfg;
+  if (c->need_shifted) KW_TRY(compute_shifted_velocity(c));
+  const uint64_t nsamp = cf.nt - cf.sampling_start_index;
   for (int sid = 0; sid < KW_STREAM_COUNT; ++sid) {
     Stream& s = c->streams[sid];
-    if (!s.enabled) continue;
+    if (!s.enabled || s.op == kOpIAvgC) continue;
     if (s.fused_this_step) {
       s.fused_this_step = false;
       continue;
     }
-    const float* src = s.src == 0 ? c->d[KW_P] : c->d[KW_UX_SGX + (s.src - 1)];
+    const float* src = stream_source(c, s);
     switch (s.op) {
       case kOpNone: sample_one<kOpNone>(c, s, src, s.dbuf + s.rows * s.row); s.rows++; break;
       case kOpRms: sample_one<kOpRms>(c, s, src, s.dbuf); break;
       case kOpMax: sample_one<kOpMax>(c, s, src, s.dbuf); break;
-      default: sample_one<kOpMin>(c, s, src, s.dbuf); break;
+      case kOpMin: sample_one<kOpMin>(c, s, src, s.dbuf); break;
+      case kOpC: {  // IndexOutputStream::flushRaw :373-470 / CuboidOutputStream::flushRaw :431-532
+        sample_one<kOpNone>(c, s, src, s.sbuf);
+        const int step_local = (int)(s.sampled % (uint64_t)(c->c_bsize - 1));
+        s.saving = (step_local + 1) % c->c_osize == 0;
+        const bool odd = (s.compressed + 1) % 2 == 0;
+        const bool mirror = s.compressed == 0 && s.saving && !c->c_no_overlap;
+        const size_t n = c->nsens * (size_t)c->c_H;
+        if (n) {
+          CompressArgs a{};
+          a.x = s.sbuf, a.n = n, a.H = c->c_H, a.bsize = c->c_bsize, a.step_local = step_local, a.mirror = mirror;
+          a.be = c->d_be[s.shifted_bases], a.be1 = c->d_be1[s.shifted_bases];
+          a.e = s.shifted_bases ? 114 : 138;  // CompressHelper::kMaxExpU / kMaxExpP
+          if (cf.c_40bit) {
+            a.q1 = static_cast<uint8_t*>(s.acc1), a.q2 = static_cast<uint8_t*>(s.acc2);
+            launch(c, "compress", 4.0 * c->nsens + 20.0 * n, [&] { k_compress40<<<ew_grid(n), 256, 0, c->st>>>(a); });
+          } else {
+            a.acc1 = static_cast<float2*>(s.acc1), a.acc2 = static_cast<float2*>(s.acc2);
+            launch(c, "compress", 4.0 * c->nsens + 32.0 * n, [&] { k_compress<<<ew_grid(n), 256, 0, c->st>>>(a); });
+          }
+        }
+        const bool last = (nsamp - s.sampled == 1) && nsamp <= (uint64_t)c->c_osize;
+        if (s.saving || last) {
+          s.cur = odd ? s.acc1 : s.acc2;
+          if (!s.nosave) {
+            launch(c, "store_frame", 8.0 * s.row, [&] {
+              cudaMemcpyAsync(s.dbuf + s.rows * s.row, s.cur, s.row * sizeof(float), cudaMemcpyDeviceToDevice, c->st);
+            });
+            s.rows++;
+          }
+          s.compressed++;
+        }
+        s.sampled++;
+        break;
+      }
+      default: break;
     }
   }
+  // postSample: I_avg_c (IndexOutputStream.cpp:299-342)
+  for (int k = 0; k < 3; ++k) {
+    Stream& s = c->streams[KW_S_IX_AVG_C + k];
+    if (!s.enabled) continue;
+    Stream &sp = c->streams[KW_S_P_C], &su = c->streams[KW_S_UX_NS_C + k];
+    if (!sp.cur || !su.cur) continue;
+    if (c->nsens) {
+      const bool q = cf.c_40bit != 0;
+      launch(c, "intensity_c", (8.0 + 16.0 * c->c_H) * c->nsens, [&] {
+        k_intensity_c<<<ew_grid(c->nsens), 256, 0, c->st>>>(s.dbuf, q ? nullptr : static_cast<const float2*>(sp.cur), q ? nullptr : static_cast<const float2*>(su.cur),
+                                                            q ? static_cast<const uint8_t*>(sp.cur) : nullptr, q ? static_cast<const uint8_t*>(su.cur) : nullptr,
+                                                            c->nsens, c->c_H, 138, 114);
+      });
+    }
+    s.compressed++;
+  }
+  // postSample2: the completed accumulator starts the next frame from zero (BaseOutputStream.cpp:117-133)
+  for (auto& s : c->streams) {
+    if (!s.enabled || s.op != kOpC) continue;
+    if (s.saving && s.cur) launch(c, "zero_frame", 4.0 * s.row, [&] { cudaMemsetAsync(s.cur, 0, s.acc_bytes, c->st); });
+    s.cur = nullptr;
+  }
+  return KW_OK;
 }
 
 static EpiVelocity velocity_epilogue(kw_ctx* c, float* const* u, float fd, int init) {
@@ -1202,7 +1409,7 @@ static int step(kw_ctx* c) {
                [&] { auto a = yx_args<1>(c, sp, 3); return g.ox->yx_velocity(a, e, c->pipe, c->st); });
   }
   // ---- storeSensorData (cpp:1060-1093)
-  if (t >= cf.sampling_start_index) sample_streams(c);
+  if (t >= cf.sampling_start_index) KW_TRY(sample_streams(c));
   c->t++;
   return KW_OK;
 }
@@ -1373,7 +1580,7 @@ static int step_sharded(kw_ctx* c) {
     KW_TRY(velocity_phase(1, false));
   }
   // ---- storeSensorData (cpp:1060-1093)
-  if (t >= cf.sampling_start_index) sample_streams(c);
+  if (t >= cf.sampling_start_index) KW_TRY(sample_streams(c));
   c->t++;
   return KW_OK;
 }
@@ -1392,7 +1599,7 @@ int kw_run(kw_ctx* c, uint64_t nsteps, uint64_t* steps_done, int sync) {
   for (; done < nsteps && c->t < c->cfg.nt; ++done) {
     bool full = false;
     if (c->t >= c->cfg.sampling_start_index)
-      for (auto& s : c->streams) full |= s.enabled && s.op == kOpNone && s.rows >= s.cap_rows;
+      for (auto& s : c->streams) full |= s.enabled && !s.nosave && (s.op == kOpNone || s.op == kOpC) && s.rows >= s.cap_rows;
     if (full) {
       rc = fail(KW_ERR_STREAM_FULL, "a raw stream buffer is full: fetch it with kw_stream_fetch");
       break;
@@ -1518,6 +1725,44 @@ int kw_sensor_layout(kw_ctx* c, uint64_t* total, uint64_t* local, uint64_t* posi
   }
   return KW_OK;
 }
+// ---- compression helpers exposed for hosts and tests (CompressHelper's public statics) -----------------------------
+__global__ void k_c40_encode(const float2* in, uint8_t* out, size_t n, int e) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) c40_encode(in[i], out + 5 * i, e);
+}
+__global__ void k_c40_decode(const uint8_t* in, float2* out, size_t n, int e) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = c40_decode(in + 5 * i, e);
+}
+static int c40_host(const void* in, void* out, uint64_t n, int e, bool encode) {
+  if (!in || !out || n == 0) return fail(KW_ERR_INVALID, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(KW_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  void *din = nullptr, *dout = nullptr;
+  const size_t bin = encode ? n * sizeof(float2) : n * 5, bout = encode ? n * 5 : n * sizeof(float2);
+  KW_CUDA(cudaMalloc(&din, bin));
+  KW_CUDA(cudaMalloc(&dout, bout));
+  KW_CUDA(cudaMemcpy(din, in, bin, cudaMemcpyHostToDevice));
+  if (encode) k_c40_encode<<<ew_grid(n), 256>>>(static_cast<const float2*>(din), static_cast<uint8_t*>(dout), n, e);
+  else k_c40_decode<<<ew_grid(n), 256>>>(static_cast<const uint8_t*>(din), static_cast<float2*>(dout), n, e);
+  KW_CUDA(cudaGetLastError());
+  KW_CUDA(cudaMemcpy(out, dout, bout, cudaMemcpyDeviceToHost));
+  cudaFree(din), cudaFree(dout);
+  return KW_OK;
+}
+int kw_c40_encode(const float* complex_pairs, uint64_t n, int max_exp, uint8_t* bytes) { return c40_host(complex_pairs, bytes, n, max_exp, true); }
+int kw_c40_decode(const uint8_t* bytes, uint64_t n, int max_exp, float* complex_pairs) { return c40_host(bytes, complex_pairs, n, max_exp, false); }
+int kw_compression_bases(kw_ctx* c, int shifted, float* be, float* be1, uint64_t capacity_complex, uint64_t* osize, uint64_t* bsize) {
+  if (!c || !c->preprocessed || !c->d_be[0]) return fail(KW_ERR_STATE, "no compressed stream is enabled");
+  if (osize) *osize = (uint64_t)c->c_osize;
+  if (bsize) *bsize = (uint64_t)c->c_bsize;
+  const size_t n = (size_t)c->c_H * c->c_bsize;
+  if (!be && !be1) return KW_OK;
+  if (capacity_complex < n) return fail(KW_ERR_INVALID, "kw_compression_bases: buffer too small");
+  KW_CUDA(cudaStreamSynchronize(c->st));
+  if (be) KW_CUDA(cudaMemcpy(be, c->d_be[shifted ? 1 : 0], n * sizeof(float2), cudaMemcpyDeviceToHost));
+  if (be1) KW_CUDA(cudaMemcpy(be1, c->d_be1[shifted ? 1 : 0], n * sizeof(float2), cudaMemcpyDeviceToHost));
+  return KW_OK;
+}
+
 int kw_comm_mode(kw_ctx* c, int* mode) {
   if (!c || !mode) return fail(KW_ERR_INVALID, "null argument");
   *mode = c->g.nranks == 1 ? 0 : (c->peer.active ? 2 : 1);
@@ -1532,7 +1777,7 @@ int kw_comm_bytes(kw_ctx* c, double* bytes_sent) {
 int kw_stream_info(kw_ctx* c, int sid, uint64_t* row_floats, uint64_t* rows) {
   if (!c || sid < 0 || sid >= KW_STREAM_COUNT || !c->streams[sid].enabled) return fail(KW_ERR_INVALID, "stream not enabled");
   if (row_floats) *row_floats = c->streams[sid].row;
-  if (rows) *rows = c->streams[sid].op == kOpNone ? c->streams[sid].rows : 1;
+  if (rows) *rows = (c->streams[sid].op == kOpNone || c->streams[sid].op == kOpC) ? c->streams[sid].rows : 1;
   return KW_OK;
 }
 
@@ -1540,13 +1785,15 @@ int kw_stream_fetch(kw_ctx* c, int sid, float* host, uint64_t cap, uint64_t* row
   if (rows_fetched) *rows_fetched = 0;
   if (!c || !host || sid < 0 || sid >= KW_STREAM_COUNT || !c->streams[sid].enabled) return fail(KW_ERR_INVALID, "stream not enabled");
   Stream& s = c->streams[sid];
-  const uint64_t rows = s.op == kOpNone ? s.rows : 1;
+  if (s.nosave) return fail(KW_ERR_INVALID, "stream exists only as an input of I_avg_c (not stored)");
+  const bool series = s.op == kOpNone || s.op == kOpC;
+  const uint64_t rows = series ? s.rows : 1;
   if (cap < rows * s.row) return fail(KW_ERR_INVALID, "kw_stream_fetch: host buffer too small");
   if (rows) {
     KW_CUDA(cudaMemcpyAsync(host, s.dbuf, rows * s.row * sizeof(float), cudaMemcpyDeviceToHost, c->st));
     KW_CUDA(cudaStreamSynchronize(c->st));
   }
-  if (s.op == kOpNone) s.rows = 0;
+  if (series) s.rows = 0;
   if (rows_fetched) *rows_fetched = rows;
   return KW_OK;
 }
@@ -1559,6 +1806,10 @@ int kw_finish(kw_ctx* c) {
     if (s.enabled && s.op == kOpRms) {  // BaseOutputStream.cpp:172-178
       k_post_rms<<<ew_grid(s.row), 256, 0, c->st>>>(s.dbuf, 1.0f / (float)nsamp, s.row);
       c->launches++;
+    } else if (s.enabled && s.op == kOpIAvgC && s.compressed > 0) {  // IndexOutputStream::postProcess :477-490
+      k_divide<<<ew_grid(s.row), 256, 0, c->st>>>(s.dbuf, (float)s.compressed, s.row);
+      c->launches++;
+      s.compressed = 0;
     }
   KW_CUDA(cudaStreamSynchronize(c->st));
   KW_CUDA(cudaGetLastError());

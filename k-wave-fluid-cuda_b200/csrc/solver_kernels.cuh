@@ -340,7 +340,7 @@ static __global__ void k_initial_pressure(float* p, float* rx, float* ry, float*
 }
 
 // ---- sampling ----------------------------------------------------------------------------------------------------
-enum SampleOp { kOpNone = 0, kOpRms = 1, kOpMax = 2, kOpMin = 3 };  // BaseOutputStream::ReduceOperator
+enum SampleOp { kOpNone = 0, kOpRms = 1, kOpMax = 2, kOpMin = 3, kOpC = 4, kOpIAvgC = 5 };  // BaseOutputStream::ReduceOperator
 template <int OP> __device__ __forceinline__ void reduce_into(float* buf, size_t i, float x) {
   if (OP == kOpNone) buf[i] = x;
   else if (OP == kOpRms) buf[i] += x * x;
@@ -382,6 +382,113 @@ static __global__ void k_fill(float* buf, float v, size_t n) {
 static __global__ void k_post_rms(float* buf, float scaling, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     buf[i] = sqrtf(buf[i] * scaling);
+}
+
+// ---- on-the-fly harmonic compression (OutputStreams/IndexOutputStream.cpp:373-470, CuboidOutputStream.cpp:431-532) ---
+// Per sampled step and (sensor i, harmonic ih):  acc1 += bE[ih][stepLocal]*x_i ; acc2 += bE_1[ih][stepLocal]*x_i ;
+// first saving step (overlap mode): acc2 += acc1.  The products and sums are rounded separately (the reference's host
+// loop is SSE2 code without FMA contraction).  no_overlap: acc2 aliases acc1 (BaseOutputStream.cpp:246-257).
+__device__ __forceinline__ float2 c_axpy(float2 acc, float2 e, float x) {
+  return make_float2(__fadd_rn(acc.x, __fmul_rn(e.x, x)), __fadd_rn(acc.y, __fmul_rn(e.y, x)));
+}
+struct CompressArgs {
+  const float* x;  // the raw samples of this step, sensor order
+  float2 *acc1, *acc2;
+  uint8_t *q1, *q2;  // 40-bit mode: the accumulators are kept packed and re-quantised every step, as in the reference
+  const float2 *be, *be1;
+  size_t n;  // Nsens * H
+  int H, bsize, step_local, mirror, e;
+};
+static __global__ void k_compress(CompressArgs a) {
+  for (size_t ph = blockIdx.x * (size_t)blockDim.x + threadIdx.x; ph < a.n; ph += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = ph / a.H;
+    const int ih = (int)(ph % a.H);
+    const float x = a.x[i];
+    const float2 e = __ldg(a.be + (size_t)ih * a.bsize + a.step_local), e1 = __ldg(a.be1 + (size_t)ih * a.bsize + a.step_local);
+    const float2 c1 = c_axpy(a.acc1[ph], e, x);
+    a.acc1[ph] = c1;
+    float2 c2 = c_axpy(a.acc2 == a.acc1 ? c1 : a.acc2[ph], e1, x);
+    if (a.mirror) c2 = make_float2(__fadd_rn(c2.x, c1.x), __fadd_rn(c2.y, c1.y));
+    a.acc2[ph] = c2;
+  }
+}
+
+// 40-bit complex: byte0 = sR|sI|mR[16]|mI[16]|e[3:0], then two little-endian 16-bit mantissas; the shared 4-bit exponent
+// is offset by `e` (138 pressure, 114 velocity).  Integer arithmetic of CompressHelper::convert40bToFloatC /
+// convertFloatCTo40b (Compression/CompressHelper.cpp:224-389), bit-exact.
+__device__ __forceinline__ float2 c40_decode(const uint8_t* b, int e) {
+  const uint32_t b0 = b[0];
+  uint32_t mr = ((b0 & 0x20u) << 11) | (b[1] | ((uint32_t)b[2] << 8));
+  uint32_t mi = ((b0 & 0x10u) << 12) | (b[3] | ((uint32_t)b[4] << 8));
+  const uint32_t sr = b0 >> 7, si = (b0 & 0x40u) >> 6;
+  int er = (int)(b0 & 0xFu) + e, ei = er;
+  mr <<= 6, mi <<= 6;
+  if (mr) {
+    const int idx = 31 - __clz(mr);
+    mr <<= 23 - idx, er -= 22 - idx;
+  } else er = 0;
+  if (mi) {
+    const int idx = 31 - __clz(mi);
+    mi <<= 23 - idx, ei -= 22 - idx;
+  } else ei = 0;
+  return make_float2(__uint_as_float((sr << 31) | ((uint32_t)er << 23) | (mr & 0x007FFFFFu)),
+                     __uint_as_float((si << 31) | ((uint32_t)ei << 23) | (mi & 0x007FFFFFu)));
+}
+__device__ __forceinline__ void c40_encode(float2 c, uint8_t* b, int e) {
+  uint32_t mr = __float_as_uint(c.x), mi = __float_as_uint(c.y);
+  const uint32_t sr = mr >> 31, si = mi >> 31;
+  const int ers = (int)((mr & 0x7F800000u) >> 23) - e, eis = (int)((mi & 0x7F800000u) >> 23) - e;
+  int es = ers;
+  mr &= 0x007FFFFFu, mi &= 0x007FFFFFu;
+  int rsr = 6, rsi = 6;
+  if (ers > eis) rsi += ers - eis, es = ers;
+  else if (eis > ers) rsr += eis - ers, es = eis;
+  if (es < 0) rsr += -es, rsi += -es, es = 0;
+  rsr &= 0xFF, rsi &= 0xFF;  // the reference keeps the shifts in uint8_t
+  rsr = rsr > 23 ? 23 : rsr, rsi = rsi > 23 ? 23 : rsi;
+  mr >>= rsr, mi >>= rsi;
+  if (mr > 0 && mr != (0x7FFFFFu >> rsr)) mr += 1;
+  if (mi > 0 && mi != (0x7FFFFFu >> rsi)) mi += 1;
+  mr |= 1u << (23 - rsr), mr >>= 1;
+  mi |= 1u << (23 - rsi), mi >>= 1;
+  if (es > 0xF) mr = mi = 0xFFFFu, es = 0xF;
+  b[0] = (uint8_t)((sr << 7) | (si << 6) | ((mr & 0x10000u) >> 11) | ((mi & 0x10000u) >> 12) | ((uint32_t)es & 0xFu));
+  b[1] = (uint8_t)(mr & 0xFF), b[2] = (uint8_t)((mr >> 8) & 0xFF), b[3] = (uint8_t)(mi & 0xFF), b[4] = (uint8_t)((mi >> 8) & 0xFF);
+}
+static __global__ void k_compress40(CompressArgs a) {
+  for (size_t ph = blockIdx.x * (size_t)blockDim.x + threadIdx.x; ph < a.n; ph += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = ph / a.H;
+    const int ih = (int)(ph % a.H);
+    const float x = a.x[i];
+    const float2 e = __ldg(a.be + (size_t)ih * a.bsize + a.step_local), e1 = __ldg(a.be1 + (size_t)ih * a.bsize + a.step_local);
+    uint8_t *p1 = a.q1 + ph * 5, *p2 = a.q2 + ph * 5;
+    float2 c1 = c40_decode(p1, a.e);
+    if (a.q1 == a.q2) {  // no overlap: cc1 += bE*x + bE_1*x  (IndexOutputStream.cpp:419-423)
+      c1 = make_float2(__fadd_rn(c1.x, __fadd_rn(__fmul_rn(e.x, x), __fmul_rn(e1.x, x))), __fadd_rn(c1.y, __fadd_rn(__fmul_rn(e.y, x), __fmul_rn(e1.y, x))));
+      c40_encode(c1, p1, a.e);
+      continue;
+    }
+    float2 c2 = c40_decode(p2, a.e);
+    c1 = c_axpy(c1, e, x), c2 = c_axpy(c2, e1, x);
+    c40_encode(c1, p1, a.e);
+    if (a.mirror) c2 = make_float2(__fadd_rn(c2.x, c1.x), __fadd_rn(c2.y, c1.y));  // the unquantised cc1, as in the reference (:433-437)
+    c40_encode(c2, p2, a.e);
+  }
+}
+// I_avg_c: I[i] += sum_h Re(P_h * conj(U_h)) / 2 over the frames just completed (IndexOutputStream.cpp:299-342)
+static __global__ void k_intensity_c(float* I, const float2* pc, const float2* uc, const uint8_t* pq, const uint8_t* uq, size_t nsens, int H, int ep, int eu) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nsens; i += (size_t)gridDim.x * blockDim.x) {
+    float acc = I[i];
+    for (int ih = 0; ih < H; ++ih) {
+      const size_t ph = i * H + ih;
+      const float2 P = pq ? c40_decode(pq + ph * 5, ep) : pc[ph], U = uq ? c40_decode(uq + ph * 5, eu) : uc[ph];
+      acc = __fadd_rn(acc, __fadd_rn(__fmul_rn(P.x, U.x), __fmul_rn(P.y, U.y)) / 2.0f);
+    }
+    I[i] = acc;
+  }
+}
+static __global__ void k_divide(float* buf, float d, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = buf[i] / d;
 }
 
 // ---- layout helpers ------------------------------------------------------------------------------------------------

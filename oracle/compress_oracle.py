@@ -131,10 +131,18 @@ class CompressedStream:
     feed(x) takes the Nsens raw samples of one sampled step and returns the frame that the reference would write to the
     file at that step (complex64 array of shape (Nsens, harmonics)), or None."""
 
-    def __init__(self, nsens, period, mos=1, harmonics=1, shifted=False, no_overlap=False, nsteps_total=None, dtype=np.complex64):
+    def __init__(self, nsens, period, mos=1, harmonics=1, shifted=False, no_overlap=False, nsteps_total=None, dtype=np.complex64,
+                 c40=False, bases=None):
         self.osize, self.bsize, self.be, self.be1 = generate_bases(period, mos, harmonics, True, shifted)
+        if bases is not None:  # bases produced elsewhere (they depend on the libm's cosf/sinf to an ulp)
+            self.be, self.be1 = (np.asarray(b, np.complex64).reshape(harmonics, self.bsize) for b in bases)
         self.h = harmonics
         self.no_overlap = no_overlap
+        self.c40 = c40
+        self.e = K_MAX_EXP_U if shifted else K_MAX_EXP_P  # BaseOutputStream.cpp:63-102
+        if c40:  # the accumulators are kept packed (5 bytes per value) and re-quantised at every step
+            self.q1 = np.zeros((nsens, harmonics, 5), np.uint8)
+            self.q2 = self.q1 if no_overlap else np.zeros((nsens, harmonics, 5), np.uint8)
         self.buf1 = np.zeros((nsens, harmonics), dtype)
         self.buf2 = self.buf1 if no_overlap else np.zeros((nsens, harmonics), dtype)  # BaseOutputStream.cpp:246-257
         self.sampled = 0
@@ -142,17 +150,40 @@ class CompressedStream:
         self.nsteps_total = nsteps_total
         self.dtype = dtype
 
+    def _feed40(self, x, step_local, mirror):
+        """40-bit branch of flushRaw (IndexOutputStream.cpp:412-441): FP32, products and sums rounded separately."""
+        x = np.asarray(x, dtype=F32)
+        for i in range(self.q1.shape[0]):
+            for ih in range(self.h):
+                e, e1 = self.be[ih, step_local], self.be1[ih, step_local]
+                c1 = decode40(bytes(self.q1[i, ih]), self.e)
+                if self.no_overlap:
+                    re = F32(c1[0]) + (F32(e.real) * x[i] + F32(e1.real) * x[i])
+                    im = F32(c1[1]) + (F32(e.imag) * x[i] + F32(e1.imag) * x[i])
+                    self.q1[i, ih] = np.frombuffer(encode40(re, im, self.e), np.uint8)
+                    continue
+                c2 = decode40(bytes(self.q2[i, ih]), self.e)
+                r1, i1 = F32(c1[0]) + F32(e.real) * x[i], F32(c1[1]) + F32(e.imag) * x[i]
+                r2, i2 = F32(c2[0]) + F32(e1.real) * x[i], F32(c2[1]) + F32(e1.imag) * x[i]
+                self.q1[i, ih] = np.frombuffer(encode40(r1, i1, self.e), np.uint8)
+                if mirror:
+                    r2, i2 = r2 + r1, i2 + i1
+                self.q2[i, ih] = np.frombuffer(encode40(r2, i2, self.e), np.uint8)
+
     def feed(self, x):
         step_local = self.sampled % (self.bsize - 1)
         saving = (step_local + 1) % self.osize == 0
         odd = (self.compressed + 1) % 2 == 0
         mirror = self.compressed == 0 and saving and not self.no_overlap
-        x = np.asarray(x).astype(self.buf1.real.dtype)[:, None]
-        # NOTE with no_overlap buf1 is buf2: both updates land in the same accumulator, as in the reference
-        self.buf1 += self.be[:, step_local].astype(self.dtype)[None, :] * x
-        self.buf2 += self.be1[:, step_local].astype(self.dtype)[None, :] * x
-        if mirror:
-            self.buf2 += self.buf1
+        if self.c40:
+            self._feed40(x, step_local, mirror)
+        else:
+            x = np.asarray(x).astype(self.buf1.real.dtype)[:, None]
+            # NOTE with no_overlap buf1 is buf2: both updates land in the same accumulator, as in the reference
+            self.buf1 += self.be[:, step_local].astype(self.dtype)[None, :] * x
+            self.buf2 += self.be1[:, step_local].astype(self.dtype)[None, :] * x
+            if mirror:
+                self.buf2 += self.buf1
         out = None
         last = (
             self.nsteps_total is not None
@@ -160,10 +191,11 @@ class CompressedStream:
             and self.nsteps_total <= self.osize
         )
         if saving or last:
-            cur = self.buf1 if odd else self.buf2
-            out = cur.copy()
+            cur = (self.q1 if odd else self.q2) if self.c40 else (self.buf1 if odd else self.buf2)
+            out = cur.copy()  # c40: packed bytes (Nsens, harmonics, 5)
             self.compressed += 1
-            cur[...] = 0  # postSample2 (BaseOutputStream.cpp:117-133)
+            if saving:
+                cur[...] = 0  # postSample2 (BaseOutputStream.cpp:117-133): only after a regular saving step
         self.sampled += 1
         return out
 
@@ -171,3 +203,13 @@ class CompressedStream:
 def intensity_frame(pc, uc):
     """IndexOutputStream::postSample (:299-342): sum over harmonics of Re(P * conj(U)) / 2 for one saved frame."""
     return (pc * np.conj(uc)).real.sum(axis=1) / 2.0
+
+
+def unpack40(frame_bytes, e):
+    """Packed frame (Nsens, harmonics, 5) uint8 -> complex64 (Nsens, harmonics)."""
+    out = np.zeros(frame_bytes.shape[:2], np.complex64)
+    for i in range(frame_bytes.shape[0]):
+        for ih in range(frame_bytes.shape[1]):
+            re, im = decode40(bytes(frame_bytes[i, ih]), e)
+            out[i, ih] = complex(re, im)
+    return out
