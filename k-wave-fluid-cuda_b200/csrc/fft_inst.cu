@@ -33,8 +33,12 @@ static void xfwd(const XFwdArgs& a, int nfields, cudaStream_t st) {
   k_xfwd<N><<<dim3(x_grid(a.pair_end - a.pair_begin, per_sm), nfields), kXThreads, 0, st>>>(a);
 }
 template <int NF, class Epi> static void xinv(const XInvArgs<NF>& a, const Epi& e, int gy, cudaStream_t st) {
-  static const int per_sm = blocks_per_sm(k_xinv<N, NF, Epi>, kXThreads, 0);
-  k_xinv<N, NF, Epi><<<dim3(x_grid(a.pair_end - a.pair_begin, per_sm), gy), kXThreads, 0, st>>>(a, e);
+  constexpr size_t smem = (size_t)Epi::kStage * kXThreads * sizeof(float);  // staged epilogue operands
+  static const int per_sm = [] {
+    if (smem > 0) cudaFuncSetAttribute(k_xinv<N, NF, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return blocks_per_sm(k_xinv<N, NF, Epi>, kXThreads, smem);
+  }();
+  k_xinv<N, NF, Epi><<<dim3(x_grid(a.pair_end - a.pair_begin, per_sm), gy), kXThreads, smem, st>>>(a, e);
 }
 static void xinv_store(const XInvArgs<1>& a, const EpiStore& e, int nf, cudaStream_t st) { xinv<1>(a, e, nf, st); }
 static void xinv_add(const XInvArgs<1>& a, const EpiAdd& e, cudaStream_t st) { xinv<1>(a, e, 1, st); }

@@ -111,9 +111,16 @@ template <int NF> struct XInvArgs {
 // Epilogue contract:  epi.apply<N>(res, field, t, row0, y, z)  where res[f][m] = (row a, row b) values at x = t + m*T of
 // field f, row0 = flattened (z*Ny + y) index of row a (row b = row0 + 1, same z).
 template <int N, int NF, class Epi, class EX>
-__device__ __forceinline__ void xinv_rows(const XInvArgs<NF>& a, const Epi& epi, int field, size_t row0, bool valid, int t, const RegTw& twp, EX& ex) {
+__device__ __forceinline__ void xinv_rows(const XInvArgs<NF>& a, const Epi& epi, int field, size_t row0, bool valid, int t, const RegTw& twp, EX& ex,
+                                          float* stg = nullptr) {
   constexpr int T = N / 8;
   float2 res[NF][8];
+  // real-space operands of the epilogue start their way into (thread-private slots of) shared memory now and land while
+  // the transforms run: their latency is hidden without holding registers for them
+  if constexpr (Epi::kStage > 0) {
+    if (valid) epi.template stage<N>(stg, t, row0);
+    cp_async_commit();
+  }
 #pragma unroll
   for (int f = 0; f < NF; ++f) {
     const float2* __restrict__ in = (NF == 1) ? a.in[field] : a.in[f];
@@ -140,9 +147,11 @@ __device__ __forceinline__ void xinv_rows(const XInvArgs<NF>& a, const Epi& epi,
 #pragma unroll
     for (int m = 0; m < 8; ++m) res[f][m] = v[0][m];
   }
+  if constexpr (Epi::kStage > 0) cp_async_wait<0>();
   if (valid) {
     const int y = (int)(row0 % a.ny), z = (int)(row0 / a.ny);
-    epi.template apply<N>(res, field, t, row0, y, z);
+    if constexpr (Epi::kStage > 0) epi.template apply<N>(res, field, t, row0, y, z, stg);
+    else epi.template apply<N>(res, field, t, row0, y, z);
   }
 }
 
@@ -151,6 +160,7 @@ template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads,
   constexpr int T = P::T;
   constexpr int RP = kXThreads / T;
   __shared__ float2 sbuf[RP * N];
+  extern __shared__ float stage_smem[];  // Epi::kStage floats per thread (slot s of thread i at [s * kXThreads + i])
   const int t = threadIdx.x % T, rp = threadIdx.x / T;
   float2 twr[P::NTW > 0 ? P::NTW : 1];
   const float2* tab = a.tab;
@@ -161,7 +171,7 @@ template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads,
   for (int g = blockIdx.x; g * RP < npairs; g += gridDim.x) {
     const int pair = a.pair_begin + g * RP + rp;
     const bool valid = pair < a.pair_end;
-    xinv_rows<N, NF>(a, epi, blockIdx.y + a.field0, 2 * (size_t)(valid ? pair : a.pair_begin), valid, t, twp, ex);
+    xinv_rows<N, NF>(a, epi, blockIdx.y + a.field0, 2 * (size_t)(valid ? pair : a.pair_begin), valid, t, twp, ex, stage_smem + threadIdx.x);
   }
 }
 
@@ -172,9 +182,12 @@ template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads,
 // a thread owns E = 8..32 points of one kx in registers and the transform is two register-resident butterflies
 // (radix 8/16/32, compile-time twiddles) around ONE shared-memory exchange (fft_core2.cuh).  Points go from global
 // memory straight into registers and back; shared memory only carries the exchange.
+#ifndef KW_W1024
+#define KW_W1024 8
+#endif
 template <int N> struct ColCfg {
   using P = Plan2<N>;
-  static constexpr int W = (N >= 1024) ? 8 : 16;                              // 1024: 8 kx (64-byte segments) keep a slot at 256 threads, i.e. 254 registers for E = 32
+  static constexpr int W = (N >= 1024) ? KW_W1024 : 16;  // 1024: 8 kx (64-byte segments) keep a slot at 256 threads, i.e. 254 registers for E = 32
   static constexpr int WK = P::WK;                                         // workers (threads per kx) of a tile
   static constexpr int SLOT = W * WK;                                      // threads of a tile slot
   static constexpr int TPC = (SLOT >= 256) ? 1 : 256 / SLOT;               // tile slots per CTA
@@ -186,15 +199,6 @@ template <int N> struct ColCfg {
   // barrier flavour of a slot: whole CTA, named barrier (slot spans whole warps), or none (single-stage plans)
   static constexpr int BAR_THREADS = (P::R2 == 1) ? -1 : (TPC == 1 ? 0 : SLOT);
 };
-
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory"); }
 
 template <int W, int NTHREADS> struct ColExchange2 {
   float2* buf;  // tile buffer + lane

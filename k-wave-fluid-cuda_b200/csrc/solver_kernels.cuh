@@ -14,6 +14,7 @@
 namespace kw {
 
 // a medium property that is either a full-grid array or a scalar (homogeneous variants of the reference kernels)
+constexpr int kXThreadsStage = 256;  // = kXThreads: stride between the shared-memory slots of one thread (k_xinv)
 struct Fld {
   const float* p;
   float s;
@@ -49,6 +50,7 @@ struct FusedSample {
 // res[f][m] = (value in row a, value in row b) at x = t + m*T; row b = row a + 1 (same z, y+1).
 
 struct EpiStore {
+  static constexpr int kStage = 0;
   static constexpr int kMinBlocks = 3;  // CTAs per SM the register budget is sized for  // plain C2R:  out = scale * ifft
   float* out[3];
   float scale;
@@ -64,6 +66,7 @@ struct EpiStore {
 };
 
 struct EpiAdd {
+  static constexpr int kStage = 0;
   static constexpr int kMinBlocks = 3;  // CTAs per SM the register budget is sized for  // additive (k-space corrected) source: target_j += ifft   (SolverCudaKernels.cu:765-807)
   float* out[3];
   int ntargets;
@@ -83,6 +86,7 @@ struct EpiAdd {
 // u_i = (u_i*pml_i - (fd*g_i)*dtrho_i)*pml_i      (SolverCudaKernels.cu:199-212; homogeneous :287-305)
 // init: u_i = g_i * (dtrho_i * (fd*0.5))            (SolverCudaKernels.cu:971-980)
 struct EpiVelocity {
+  static constexpr int kStage = 0;
   static constexpr int kMinBlocks = 3;  // CTAs per SM the register budget is sized for
   float* u[3];
   Fld dtrho[3];
@@ -126,6 +130,24 @@ struct EpiVelocity {
 //  lossless:  p = c2*(B + BonA*(B*B)/(2 rho0))  |  p = c2*B                            (:2079-2082, :2229-2235)
 struct EpiDensity {
   static constexpr int kMinBlocks = 2;  // CTAs per SM the register budget is sized for
+#ifndef KW_STAGE_DENSITY
+#define KW_STAGE_DENSITY 1
+#endif
+  // shared-memory slots per thread: rho_x, rho_y, rho_z, rho0, BonA at the thread's 16 voxels (slot = k*16 + v)
+  static constexpr int kStage = KW_STAGE_DENSITY ? 5 * 16 : 0;
+  template <int N> __device__ __forceinline__ void stage(float* stg, int t, size_t row0) const {
+    constexpr int T = N / 8;
+    const bool need_bona = nonlinear && !defer_terms && bona.p;
+#pragma unroll
+    for (int v = 0; v < 16; ++v) {
+      const size_t i = row0 * N + (v & 1) * N + t + (v >> 1) * T;
+      cp_async4(stg + (0 * 16 + v) * kXThreadsStage, rho[0] + i);
+      cp_async4(stg + (1 * 16 + v) * kXThreadsStage, rho[1] + i);
+      cp_async4(stg + (2 * 16 + v) * kXThreadsStage, rho[2] + i);
+      if (rho0.p) cp_async4(stg + (3 * 16 + v) * kXThreadsStage, rho0.p + i);
+      if (need_bona) cp_async4(stg + (4 * 16 + v) * kXThreadsStage, bona.p + i);
+    }
+  }
   float* rho[3];
   Fld rho0, bona, c2;
   const float* pml[3];
@@ -138,7 +160,7 @@ struct EpiDensity {
   float* p;
   FusedSample fs;  // sampling of p when this epilogue produces the final pressure of the step (lossless)
   int sample;
-  template <int N> __device__ __forceinline__ void apply(float2 (&res)[3][8], int, int t, size_t row0, int y, int z) const {
+  template <int N> __device__ __forceinline__ void apply(float2 (&res)[3][8], int, int t, size_t row0, int y, int z, const float* stg = nullptr) const {
     constexpr int T = N / 8;
     // restrict-qualified locals: the arrays never alias, which lets the loads of all voxels be issued ahead of the stores
     float* __restrict__ rxp = rho[0];
@@ -155,7 +177,13 @@ struct EpiDensity {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const size_t i = row0 * N + (q & 1) * N + t + (h * 4 + (q >> 1)) * T;
-        rx[q] = rxp[i], ry[q] = ryp[i], rz[q] = rzp[i], r0[q] = rho0.at(i);
+        if (kStage > 0 && stg) {
+          const int v = h * 8 + q;  // = 2*m + row, the slot order of stage()
+          rx[q] = stg[(0 * 16 + v) * kXThreadsStage], ry[q] = stg[(1 * 16 + v) * kXThreadsStage], rz[q] = stg[(2 * 16 + v) * kXThreadsStage];
+          r0[q] = rho0.p ? stg[(3 * 16 + v) * kXThreadsStage] : rho0.s;
+        } else {
+          rx[q] = rxp[i], ry[q] = ryp[i], rz[q] = rzp[i], r0[q] = rho0.at(i);
+        }
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -181,11 +209,12 @@ struct EpiDensity {
         if (absorbing) oA[i] = r0[q] * (dux + duy + duz);
         if (!defer_terms) {
           const float sum = ax + ay + az;
+          const float bq = !nonlinear ? 0.f : (kStage > 0 && stg && bona.p) ? stg[(4 * 16 + h * 8 + q) * kXThreadsStage] : bona.at(i);
           if (absorbing) {
             oB[i] = sum;
-            if (nonlinear) oNL[i] = ((bona.at(i) * sum * sum) / (2.0f * r0[q])) + sum;
+            if (nonlinear) oNL[i] = ((bq * sum * sum) / (2.0f * r0[q])) + sum;
           } else {
-            const float pv = nonlinear ? c2.at(i) * (sum + (bona.at(i) * (sum * sum) / (2.0f * r0[q]))) : c2.at(i) * sum;
+            const float pv = nonlinear ? c2.at(i) * (sum + (bq * (sum * sum) / (2.0f * r0[q]))) : c2.at(i) * sum;
             pp[i] = pv;
             if (sample) fs(i, x, y + (q & 1), z, pv);
           }
@@ -199,13 +228,29 @@ struct EpiDensity {
 // p = c2*(B  + fd*(ta*tau - tb*eta))       linear     (:1973-1979)
 struct EpiPressureSum {
   static constexpr int kMinBlocks = 2;  // CTAs per SM the register budget is sized for
+#ifndef KW_STAGE_PSUM
+#define KW_STAGE_PSUM 1
+#endif
+  // shared-memory slots per thread: base (NL or B), c2, tau, eta at the thread's 16 voxels
+  static constexpr int kStage = KW_STAGE_PSUM ? 4 * 16 : 0;
+  template <int N> __device__ __forceinline__ void stage(float* stg, int t, size_t row0) const {
+    constexpr int T = N / 8;
+#pragma unroll
+    for (int v = 0; v < 16; ++v) {
+      const size_t i = row0 * N + (v & 1) * N + t + (v >> 1) * T;
+      cp_async4(stg + (0 * 16 + v) * kXThreadsStage, base + i);
+      if (c2.p) cp_async4(stg + (1 * 16 + v) * kXThreadsStage, c2.p + i);
+      if (tau.p) cp_async4(stg + (2 * 16 + v) * kXThreadsStage, tau.p + i);
+      if (eta.p) cp_async4(stg + (3 * 16 + v) * kXThreadsStage, eta.p + i);
+    }
+  }
   float* p;
   const float* base;  // NL (nonlinear) or B (linear)
   Fld c2, tau, eta;
   float fd;
   FusedSample fs;
   int sample;
-  template <int N> __device__ __forceinline__ void apply(float2 (&res)[2][8], int, int t, size_t row0, int y, int z) const {
+  template <int N> __device__ __forceinline__ void apply(float2 (&res)[2][8], int, int t, size_t row0, int y, int z, const float* stg = nullptr) const {
     constexpr int T = N / 8;
     float* __restrict__ pp = p;
     float pv[16];
@@ -214,7 +259,15 @@ struct EpiPressureSum {
       const int m = q >> 1;
       const size_t i = row0 * N + (q & 1) * N + t + m * T;
       const float ta = (q & 1) ? res[0][m].y : res[0][m].x, tb = (q & 1) ? res[1][m].y : res[1][m].x;
-      pv[q] = c2.at(i) * (__ldg(base + i) + fd * ((ta * tau.at(i)) - (tb * eta.at(i))));
+      if (kStage > 0 && stg) {
+        const float bv = stg[(0 * 16 + q) * kXThreadsStage];
+        const float cv = c2.p ? stg[(1 * 16 + q) * kXThreadsStage] : c2.s;
+        const float tv = tau.p ? stg[(2 * 16 + q) * kXThreadsStage] : tau.s;
+        const float ev = eta.p ? stg[(3 * 16 + q) * kXThreadsStage] : eta.s;
+        pv[q] = cv * (bv + fd * ((ta * tv) - (tb * ev)));
+      } else {
+        pv[q] = c2.at(i) * (__ldg(base + i) + fd * ((ta * tau.at(i)) - (tb * eta.at(i))));
+      }
     }
     if (sample) {
       float* __restrict__ mxa = fs.max_all;
