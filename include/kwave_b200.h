@@ -107,6 +107,8 @@ int kw_abi_version(void);
 const char* kw_last_error(void);
 /* SolverCudaKernels::getCudaCodeVersion (SolverCudaKernels.cuh:77): __CUDA_ARCH__/10 of the loaded kernels (100). */
 int kw_cuda_code_version(int* version);
+/* KSpaceFirstOrderSolver::getDeviceMemoryUsage / getAvailableDeviceMemory (cpp:470-492): cudaMemGetInfo of the current device. */
+int kw_device_memory(size_t* free_bytes, size_t* total_bytes);
 
 /* Context lifetime (KSpaceFirstOrderSolver ctor / allocateMemory / freeMemory, KSpaceFirstOrderSolver.cpp:91-151). */
 int kw_ctx_create(const kw_config* cfg, kw_ctx** out);

@@ -399,6 +399,14 @@ int kw_cuda_code_version(int* version) {
   return KW_OK;
 }
 
+int kw_device_memory(size_t* free_bytes, size_t* total_bytes) {
+  size_t f = 0, t = 0;
+  KW_CUDA(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
+  return KW_OK;
+}
+
 int kw_ctx_create(const kw_config* cfg, kw_ctx** out) {
   if (!cfg || !out) return fail(KW_ERR_INVALID, "null argument");
   if (cfg->abi_version != KW_ABI_VERSION || cfg->struct_size != sizeof(kw_config))

@@ -1,0 +1,481 @@
+#include "KSpaceFirstOrderSolver.h"
+
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <new>
+#include <stdexcept>
+#include <thread>
+
+namespace kwhost {
+
+namespace {
+struct NamedArray {
+  const char* name;  // dataset name in the input file (Utils/MatrixNames.h)
+  int id;            // kw_array
+  bool isIndex;
+};
+// MatrixContainer::init (Containers/MatrixContainer.cpp:94-410): what is loaded from the input file
+const NamedArray kMedium[] = {{"c0", KW_C0, false}, {"rho0", KW_RHO0, false}, {"rho0_sgx", KW_RHO0_SGX, false},
+                              {"rho0_sgy", KW_RHO0_SGY, false}, {"rho0_sgz", KW_RHO0_SGZ, false}};
+const NamedArray kOperators[] = {{"ddx_k_shift_pos_r", KW_DDX_K_SHIFT_POS_R, false}, {"ddy_k_shift_pos", KW_DDY_K_SHIFT_POS, false},
+                                 {"ddz_k_shift_pos", KW_DDZ_K_SHIFT_POS, false}, {"ddx_k_shift_neg_r", KW_DDX_K_SHIFT_NEG_R, false},
+                                 {"ddy_k_shift_neg", KW_DDY_K_SHIFT_NEG, false}, {"ddz_k_shift_neg", KW_DDZ_K_SHIFT_NEG, false},
+                                 {"pml_x_sgx", KW_PML_X_SGX, false}, {"pml_y_sgy", KW_PML_Y_SGY, false}, {"pml_z_sgz", KW_PML_Z_SGZ, false},
+                                 {"pml_x", KW_PML_X, false}, {"pml_y", KW_PML_Y, false}, {"pml_z", KW_PML_Z, false}};
+const NamedArray kShifts[] = {{"x_shift_neg_r", KW_X_SHIFT_NEG_R, false}, {"y_shift_neg_r", KW_Y_SHIFT_NEG_R, false},
+                              {"z_shift_neg_r", KW_Z_SHIFT_NEG_R, false}};
+
+std::string formatSeconds(double s) {
+  char buf[64];
+  snprintf(buf, sizeof buf, "%8.2fs", s);
+  return buf;
+}
+}  // namespace
+
+KSpaceFirstOrderSolver::KSpaceFirstOrderSolver(const CommandLine& commandLine) : mCmd(commandLine) { mTotalTime.start(); }
+
+KSpaceFirstOrderSolver::~KSpaceFirstOrderSolver() { freeMemory(); }
+
+void KSpaceFirstOrderSolver::log(int level, const char* fmt, ...) const {
+  if (mCmd.verbose + 1 < level) return;  // 0 basic, 1 advanced, 2 full (Logger/Logger.h)
+  va_list ap;
+  va_start(ap, fmt);
+  vfprintf(stdout, fmt, ap);
+  va_end(ap);
+  fflush(stdout);
+}
+
+// the C ABI reports status codes; the host turns them into the exceptions the reference throws
+void KSpaceFirstOrderSolver::check(int status) const {
+  if (status == KW_OK) return;
+  const std::string msg = std::string("Error: ") + kw_last_error();
+  switch (status) {
+    case KW_ERR_ALLOC: throw std::bad_alloc();
+    case KW_ERR_INVALID: throw std::invalid_argument(msg);
+    default: throw std::runtime_error(msg);
+  }
+}
+
+void KSpaceFirstOrderSolver::printFullCodeNameAndLicense() const {
+  printf("+---------------------------------------------------------------+\n");
+  printf("| %-61s |\n", getCodeName().c_str());
+  printf("| B200-native time-step engine behind the k-Wave CUDA interface |\n");
+  printf("| Input/output files, flags and outputs as kspaceFirstOrder-CUDA|\n");
+  int version = 0;
+  if (kw_cuda_code_version(&version) == KW_OK) printf("| GPU code built for compute capability %d.%d                     |\n", version / 10, version % 10);
+  printf("+---------------------------------------------------------------+\n");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+void KSpaceFirstOrderSolver::readScalars() {  // Parameters::readScalarsFromInputFile (Parameters.cpp:194-553)
+  const hid_t root = mInputFile.root();
+  const std::string type = mInputFile.getStringAttribute(root, "/", "file_type");
+  if (!type.empty() && type != "input") throw std::ios::failure("Error: The input file has not a valid format (file_type = \"" + type + "\").");
+  const std::string major = mInputFile.getStringAttribute(root, "/", "major_version"), minor = mInputFile.getStringAttribute(root, "/", "minor_version");
+  if (!major.empty() && (major != "1" || (minor != "0" && minor != "1")))
+    throw std::ios::failure("Error: Unsupported file format version " + major + "." + minor + " (1.0 and 1.1 are supported).");
+  FileScalars& s = mScalars;
+  auto u = [&](const char* n) { return mInputFile.readIndexScalar(root, n); };
+  auto f = [&](const char* n) { return mInputFile.readFloatScalar(root, n); };
+  s.nx = u("Nx"), s.ny = u("Ny"), s.nz = u("Nz"), s.nt = u("Nt");
+  s.dt = f("dt"), s.dx = f("dx"), s.dy = f("dy");
+  if (s.nz > 1) s.dz = f("dz");
+  s.cRef = f("c_ref");
+  s.pmlXSize = u("pml_x_size"), s.pmlYSize = u("pml_y_size"), s.pmlXAlpha = f("pml_x_alpha"), s.pmlYAlpha = f("pml_y_alpha");
+  if (s.nz > 1) s.pmlZSize = u("pml_z_size"), s.pmlZAlpha = f("pml_z_alpha");
+  s.sensorMaskType = u("sensor_mask_type");
+  if (s.sensorMaskType > 1) throw std::ios::failure("Error: The sensor mask type specified in the input file is not supported.");
+  s.uxSourceFlag = u("ux_source_flag"), s.uySourceFlag = u("uy_source_flag");
+  if (s.nz > 1) s.uzSourceFlag = u("uz_source_flag");
+  s.transducerSourceFlag = u("transducer_source_flag"), s.pSourceFlag = u("p_source_flag"), s.p0SourceFlag = u("p0_source_flag");
+  s.nonuniformGridFlag = u("nonuniform_grid_flag"), s.absorbingFlag = u("absorbing_flag"), s.nonlinearFlag = u("nonlinear_flag");
+  if (s.uxSourceFlag || s.uySourceFlag || s.uzSourceFlag) s.uSourceMany = u("u_source_many"), s.uSourceMode = u("u_source_mode");
+  if (s.pSourceFlag) s.pSourceMany = u("p_source_many"), s.pSourceMode = u("p_source_mode");
+  if (s.absorbingFlag) {
+    s.alphaPower = f("alpha_power");
+    if (s.alphaPower == 1.0f) throw std::invalid_argument("Error: The value of alpha_power = 1.0 is not supported (Parameters.cpp:421-424).");
+  }
+  if (s.nonuniformGridFlag) throw std::invalid_argument("Error: Non-uniform grids are not supported (main.cpp:460).");
+}
+
+void KSpaceFirstOrderSolver::allocateMemory() {
+  mInputFile.open(mCmd.inputFile, true);
+  readScalars();
+  FileScalars& s = mScalars;
+  if (mCmd.benchmark) s.nt = mCmd.benchmarkSteps;  // Parameters.cpp:130-133
+  if (mCmd.samplingStartIndex >= s.nt) throw std::invalid_argument("Error: The beginning of data sampling is out of the simulation time span <1, " + std::to_string(s.nt) + ">.");
+  mSamplingSteps = s.nt - mCmd.samplingStartIndex;
+
+  kw_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.abi_version = KW_ABI_VERSION, cfg.struct_size = sizeof cfg;
+  cfg.nx = s.nx, cfg.ny = s.ny, cfg.nz = s.nz, cfg.nt = s.nt;
+  cfg.dt = s.dt, cfg.dx = s.dx, cfg.dy = s.dy, cfg.dz = s.dz, cfg.c_ref = s.cRef, cfg.alpha_power = s.alphaPower;
+  cfg.nonlinear_flag = (int)s.nonlinearFlag, cfg.absorbing_flag = (int)s.absorbingFlag, cfg.nonuniform_grid_flag = (int)s.nonuniformGridFlag;
+  cfg.p_source_flag = s.pSourceFlag, cfg.ux_source_flag = s.uxSourceFlag, cfg.uy_source_flag = s.uySourceFlag, cfg.uz_source_flag = s.uzSourceFlag;
+  cfg.transducer_source_flag = s.transducerSourceFlag, cfg.p0_source_flag = (int)s.p0SourceFlag;
+  cfg.p_source_mode = (int)s.pSourceMode, cfg.p_source_many = (int)s.pSourceMany, cfg.u_source_mode = (int)s.uSourceMode, cfg.u_source_many = (int)s.uSourceMany;
+  cfg.sensor_mask_type = (int)s.sensorMaskType;
+  cfg.sampling_start_index = mCmd.samplingStartIndex;
+  if (mCmd.anyCompressed()) {
+    // CompressHelper is initialised with the period in time steps; --frequency is converted with dt (main.cpp)
+    cfg.c_period = mCmd.period > 0.f ? mCmd.period : 1.0f / (mCmd.frequency * s.dt);
+    cfg.c_mos = (uint32_t)mCmd.mos, cfg.c_harmonics = (uint32_t)mCmd.harmonics;
+    cfg.c_no_overlap = mCmd.noOverlap, cfg.c_40bit = mCmd.c40bit;
+    const uint64_t oSize = (uint64_t)(cfg.c_period * (float)cfg.c_mos);
+    mCompressedSteps = oSize ? std::max<uint64_t>(mSamplingSteps / oSize, 1) : 1;
+  }
+  cfg.device = mCmd.gpuDevice;
+  cfg.raw_rows_capacity = 0;  // the library sizes the device-side row buffers (<= 256 MB per stream)
+  cfg.rank = 0, cfg.nranks = 1;
+  check(kw_ctx_create(&cfg, &mCtx));
+}
+
+void KSpaceFirstOrderSolver::freeMemory() {
+  for (auto& st : mStreams) {
+    if (st.dataset >= 0) mOutputFile.closeDataset(st.dataset);
+    for (hid_t d : st.cuboidDatasets) mOutputFile.closeDataset(d);
+    if (st.group >= 0) mOutputFile.closeGroup(st.group);
+  }
+  mStreams.clear();
+  if (mCtx) kw_ctx_destroy(mCtx);
+  mCtx = nullptr;
+  mInputFile.close();
+  mOutputFile.close();
+}
+
+void KSpaceFirstOrderSolver::loadArray(const std::string& name, int arrayId, bool isIndex, bool required) {
+  const hid_t root = mInputFile.root();
+  if (!mInputFile.exists(root, name)) {
+    if (required) throw std::ios::failure("Error: dataset \"" + name + "\" is missing in the input file.");
+    return;
+  }
+  if (isIndex) {
+    const auto v = mInputFile.readIndices(root, name);
+    mHostBytes = std::max(mHostBytes, v.size() * sizeof(uint64_t));
+    check(kw_set_array(mCtx, arrayId, v.data(), v.size()));
+    if (arrayId == KW_SENSOR_MASK_CORNERS) mCorners = v;
+    if (arrayId == KW_SENSOR_MASK_INDEX) mSensorPoints = v.size();
+  } else {
+    const auto v = mInputFile.readFloats(root, name);
+    mHostBytes = std::max(mHostBytes, v.size() * sizeof(float));
+    const std::string domain = mInputFile.getStringAttribute(root, name, "domain_type");
+    const bool isComplex = domain == "complex";
+    check(kw_set_array(mCtx, arrayId, v.data(), isComplex ? v.size() / 2 : v.size()));
+  }
+}
+
+void KSpaceFirstOrderSolver::loadInputData() {
+  mDataLoadTime.start();
+  const FileScalars& s = mScalars;
+  for (const auto& a : kMedium) loadArray(a.name, a.id, a.isIndex, true);
+  if (s.nonlinearFlag) loadArray("BonA", KW_BONA, false, true);
+  if (s.absorbingFlag) loadArray("alpha_coeff", KW_ALPHA_COEFF, false, true);
+  for (const auto& a : kOperators) loadArray(a.name, a.id, a.isIndex, true);
+  const bool needShift = mCmd.uNonStaggeredRaw || mCmd.uNonStaggeredC || mCmd.iAvgC;
+  for (const auto& a : kShifts) loadArray(a.name, a.id, a.isIndex, needShift);
+  if (s.sensorMaskType == 0) loadArray("sensor_mask_index", KW_SENSOR_MASK_INDEX, true, true);
+  else loadArray("sensor_mask_corners", KW_SENSOR_MASK_CORNERS, true, true);
+  if (s.p0SourceFlag) loadArray("p0_source_input", KW_P0_SOURCE_INPUT, false, true);
+  if (s.pSourceFlag) {
+    loadArray("p_source_index", KW_P_SOURCE_INDEX, true, true);
+    loadArray("p_source_input", KW_P_SOURCE_INPUT, false, true);
+  }
+  if (s.uxSourceFlag || s.uySourceFlag || s.uzSourceFlag || s.transducerSourceFlag) loadArray("u_source_index", KW_U_SOURCE_INDEX, true, true);
+  if (s.uxSourceFlag) loadArray("ux_source_input", KW_UX_SOURCE_INPUT, false, true);
+  if (s.uySourceFlag) loadArray("uy_source_input", KW_UY_SOURCE_INPUT, false, true);
+  if (s.uzSourceFlag) loadArray("uz_source_input", KW_UZ_SOURCE_INPUT, false, true);
+  if (s.transducerSourceFlag) {
+    loadArray("delay_mask", KW_DELAY_MASK, true, true);
+    loadArray("transducer_source_input", KW_TRANSDUCER_SOURCE_INPUT, false, true);
+  }
+  if (s.sensorMaskType == 1) {
+    if (mCorners.empty() || mCorners.size() % 6) throw std::ios::failure("Error: sensor_mask_corners has not a valid format.");
+    mSensorPoints = 0;
+    for (size_t k = 0; k < mCorners.size(); k += 6)
+      mSensorPoints += (mCorners[k + 3] - mCorners[k] + 1) * (mCorners[k + 4] - mCorners[k + 1] + 1) * (mCorners[k + 5] - mCorners[k + 2] + 1);
+  }
+  mOutputFile.create(mCmd.outputFile);  // cpp:230-235
+  mDataLoadTime.stop();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+void KSpaceFirstOrderSolver::createStreams() {  // OutputStreamContainer::init (Containers/OutputStreamContainer.cpp:70-325)
+  using K = OutputStream::Kind;
+  auto add = [&](bool on, int id, const std::string& name, K kind, bool shifted = false) {
+    if (!on) return;
+    check(kw_stream_enable(mCtx, id));
+    OutputStream st{};
+    st.id = id, st.name = name, st.kind = kind, st.shifted = shifted;
+    mStreams.push_back(st);
+  };
+  const char* axes[3] = {"x", "y", "z"};
+  add(mCmd.pRaw, KW_S_P_RAW, "p", K::kSeries);
+  add(mCmd.pC, KW_S_P_C, "p_c", K::kCompressed);
+  add(mCmd.pRms, KW_S_P_RMS, "p_rms", K::kAggregate);
+  add(mCmd.pMax, KW_S_P_MAX, "p_max", K::kAggregate);
+  add(mCmd.pMin, KW_S_P_MIN, "p_min", K::kAggregate);
+  add(mCmd.pMaxAll, KW_S_P_MAX_ALL, "p_max_all", K::kWholeDomain);
+  add(mCmd.pMinAll, KW_S_P_MIN_ALL, "p_min_all", K::kWholeDomain);
+  for (int k = 0; k < 3; ++k) {
+    const std::string u = std::string("u") + axes[k];
+    add(mCmd.uRaw, KW_S_UX_RAW + k, u, K::kSeries);
+    add(mCmd.uC, KW_S_UX_C + k, u + "_c", K::kCompressed);
+    add(mCmd.uNonStaggeredRaw, KW_S_UX_NS_RAW + k, u + "_non_staggered", K::kSeries);
+    add(mCmd.uNonStaggeredC, KW_S_UX_NS_C + k, u + "_non_staggered_c", K::kCompressed, true);
+    add(mCmd.uRms, KW_S_UX_RMS + k, u + "_rms", K::kAggregate);
+    add(mCmd.uMax, KW_S_UX_MAX + k, u + "_max", K::kAggregate);
+    add(mCmd.uMin, KW_S_UX_MIN + k, u + "_min", K::kAggregate);
+    add(mCmd.uMaxAll, KW_S_UX_MAX_ALL + k, u + "_max_all", K::kWholeDomain);
+    add(mCmd.uMinAll, KW_S_UX_MIN_ALL + k, u + "_min_all", K::kWholeDomain);
+    add(mCmd.iAvgC, KW_S_IX_AVG_C + k, std::string("I") + axes[k] + "_avg_c", K::kAggregate);
+  }
+  // flush order = OutputStreamIdx order (Containers/OutputStreamContainer.h:59-150)
+  std::stable_sort(mStreams.begin(), mStreams.end(), [](const OutputStream& a, const OutputStream& b) { return a.id < b.id; });
+}
+
+void KSpaceFirstOrderSolver::createOutputDatasets() {
+  using K = OutputStream::Kind;
+  const hid_t root = mOutputFile.root();
+  const bool cuboids = mScalars.sensorMaskType == 1;
+  const unsigned deflate = mCmd.compressionLevel;
+  for (auto& st : mStreams) {
+    uint64_t rowFloats = 0, rows = 0;
+    check(kw_stream_info(mCtx, st.id, &rowFloats, &rows));
+    st.rowFloats = rowFloats;
+    if (st.kind == K::kWholeDomain) continue;  // written at the end (WholeDomainOutputStream::create :78-99)
+    const bool series = st.kind == K::kSeries || st.kind == K::kCompressed;
+    const uint64_t nRows = st.kind == K::kSeries ? mSamplingSteps : st.kind == K::kCompressed ? mCompressedSteps : 0;
+    auto compressionAttributes = [&](hid_t loc, const std::string& name) {  // IndexOutputStream.cpp:147-157
+      mOutputFile.setLongLongAttribute(loc, name, "c_harmonics", (long long)mCmd.harmonics);
+      mOutputFile.setStringAttribute(loc, name, "c_type", "c");
+      float period = mCmd.period > 0.f ? mCmd.period : 1.0f / (mCmd.frequency * mScalars.dt);
+      mOutputFile.setFloatAttribute(loc, name, "c_period", period);
+      mOutputFile.setLongLongAttribute(loc, name, "c_mos", (long long)mCmd.mos);
+      mOutputFile.setLongLongAttribute(loc, name, "c_shift", st.shifted ? 1 : 0);
+      mOutputFile.setFloatAttribute(loc, name, "c_complex_size", mCmd.c40bit ? 1.25f : 2.0f);
+      mOutputFile.setLongLongAttribute(loc, name, "c_max_exp", st.shifted ? 114 : 138);
+    };
+    if (!cuboids) {  // IndexOutputStream::create (:87-160): (Nsens, Nt - s, 1), i.e. [1][rows][Nsens] on disk
+      const hsize_t width = rowFloats;
+      const std::vector<hsize_t> dims = series ? std::vector<hsize_t>{1, nRows, width} : std::vector<hsize_t>{1, 1, width};
+      std::vector<hsize_t> chunk = {1, 1, width > (1ull << 23) ? (1ull << 20) : width};
+      st.dataset = mOutputFile.createDataset(root, st.name, dims, chunk, true, deflate);
+      if (st.kind == K::kCompressed) compressionAttributes(root, st.name);
+    } else {  // CuboidOutputStream::create (:80-150): group /<name>, one dataset per cuboid named 1..Ncub
+      if (st.kind == K::kCompressed && mCmd.c40bit)
+        throw std::invalid_argument("Error: --40-bit_complex with a cuboid sensor mask is not available in this build.");
+      st.group = mOutputFile.createGroup(root, st.name);
+      const uint64_t factor = st.kind == K::kCompressed ? 2 * mCmd.harmonics : 1;
+      for (size_t k = 0; k < mCorners.size() / 6; ++k) {
+        const uint64_t* c = &mCorners[6 * k];
+        const hsize_t cx = (c[3] - c[0] + 1) * factor, cy = c[4] - c[1] + 1, cz = c[5] - c[2] + 1;
+        const std::string name = std::to_string(k + 1);
+        std::vector<hsize_t> dims, chunk;
+        if (series) dims = {nRows, cz, cy, cx}, chunk = {1, cz, cy, cx};
+        else dims = {cz, cy, cx}, chunk = {cz, cy, cx};
+        if (cx * cy * cz > (1ull << 23)) {  // >= 32 MB per step: ~4 MB slabs (CuboidOutputStream.cpp:676-684)
+          hsize_t slabs = 1;
+          while (slabs * cx * cy < (1ull << 20)) ++slabs;
+          chunk[series ? 1 : 0] = std::min<hsize_t>(slabs, cz);
+        }
+        st.cuboidDatasets.push_back(mOutputFile.createDataset(st.group, name, dims, chunk, true, deflate));
+        if (st.kind == K::kCompressed) compressionAttributes(st.group, name);
+      }
+    }
+  }
+}
+
+// rows buffered on the device -> output file (IndexOutputStream::flushBufferToFile :583-591, CuboidOutputStream :560-620)
+void KSpaceFirstOrderSolver::flushSeries(bool final) {
+  using K = OutputStream::Kind;
+  (void)final;
+  for (auto& st : mStreams) {
+    if (st.kind != K::kSeries && st.kind != K::kCompressed) continue;
+    uint64_t rowFloats = 0, rows = 0;
+    check(kw_stream_info(mCtx, st.id, &rowFloats, &rows));
+    if (rows == 0) continue;
+    if (mRowBuffer.size() < rows * rowFloats) mRowBuffer.resize(rows * rowFloats);
+    uint64_t got = 0;
+    check(kw_stream_fetch(mCtx, st.id, mRowBuffer.data(), mRowBuffer.size(), &got));
+    if (st.dataset >= 0) {
+      mOutputFile.writeHyperslab(st.dataset, {0, st.rowsWritten, 0}, {1, got, rowFloats}, mRowBuffer.data());
+    } else {
+      const uint64_t factor = st.kind == K::kCompressed ? 2 * mCmd.harmonics : 1;
+      uint64_t offset = 0;
+      std::vector<float> part;
+      for (size_t k = 0; k < st.cuboidDatasets.size(); ++k) {
+        const uint64_t* c = &mCorners[6 * k];
+        const hsize_t cx = (c[3] - c[0] + 1) * factor, cy = c[4] - c[1] + 1, cz = c[5] - c[2] + 1;
+        const uint64_t n = cx * cy * cz;
+        part.resize(got * n);
+        for (uint64_t r = 0; r < got; ++r) memcpy(&part[r * n], &mRowBuffer[r * rowFloats + offset], n * sizeof(float));
+        mOutputFile.writeHyperslab(st.cuboidDatasets[k], {st.rowsWritten, 0, 0, 0}, {got, cz, cy, cx}, part.data());
+        offset += n;
+      }
+    }
+    st.rowsWritten += got;
+  }
+}
+
+void KSpaceFirstOrderSolver::writeAggregates() {
+  using K = OutputStream::Kind;
+  const FileScalars& s = mScalars;
+  const hid_t root = mOutputFile.root();
+  for (auto& st : mStreams) {
+    if (st.kind != K::kAggregate && st.kind != K::kWholeDomain) continue;
+    std::vector<float> buf(st.rowFloats);
+    uint64_t got = 0;
+    check(kw_stream_fetch(mCtx, st.id, buf.data(), buf.size(), &got));
+    if (st.kind == K::kWholeDomain) {
+      mOutputFile.writeWhole(root, st.name, {s.nz, s.ny, s.nx}, {1, s.ny, s.nx}, buf.data(), true, mCmd.compressionLevel);
+    } else if (st.dataset >= 0) {
+      mOutputFile.writeHyperslab(st.dataset, {0, 0, 0}, {1, 1, st.rowFloats}, buf.data());
+    } else {
+      uint64_t offset = 0;
+      for (size_t k = 0; k < st.cuboidDatasets.size(); ++k) {
+        const uint64_t* c = &mCorners[6 * k];
+        const hsize_t cx = c[3] - c[0] + 1, cy = c[4] - c[1] + 1, cz = c[5] - c[2] + 1;
+        mOutputFile.writeHyperslab(st.cuboidDatasets[k], {0, 0, 0}, {cz, cy, cx}, &buf[offset]);
+        offset += cx * cy * cz;
+      }
+    }
+  }
+  // p_final / u*_final (cpp:952-973; RealMatrix::writeData :88-121)
+  std::vector<float> field;
+  auto final_field = [&](bool on, int id, const char* name) {
+    if (!on) return;
+    field.resize(s.nx * s.ny * s.nz);
+    check(kw_get_array(mCtx, id, field.data(), field.size()));
+    mOutputFile.writeWhole(root, name, {s.nz, s.ny, s.nx}, {1, s.ny, s.nx}, field.data(), true, mCmd.compressionLevel);
+  };
+  final_field(mCmd.pFinal, KW_P, "p_final");
+  final_field(mCmd.uFinal, KW_UX_SGX, "ux_final");
+  final_field(mCmd.uFinal, KW_UY_SGY, "uy_final");
+  final_field(mCmd.uFinal, KW_UZ_SGZ, "uz_final");
+}
+
+void KSpaceFirstOrderSolver::saveScalarsToOutputFile() {  // Parameters::saveScalarsToOutputFile (Parameters.cpp:559-650)
+  const FileScalars& s = mScalars;
+  const hid_t root = mOutputFile.root();
+  Hdf5File& o = mOutputFile;
+  o.writeScalar(root, "Nx", s.nx), o.writeScalar(root, "Ny", s.ny), o.writeScalar(root, "Nz", s.nz), o.writeScalar(root, "Nt", s.nt);
+  o.writeScalar(root, "dt", s.dt), o.writeScalar(root, "dx", s.dx), o.writeScalar(root, "dy", s.dy), o.writeScalar(root, "dz", s.dz);
+  o.writeScalar(root, "c_ref", s.cRef);
+  o.writeScalar(root, "pml_x_size", s.pmlXSize), o.writeScalar(root, "pml_y_size", s.pmlYSize), o.writeScalar(root, "pml_z_size", s.pmlZSize);
+  o.writeScalar(root, "pml_x_alpha", s.pmlXAlpha), o.writeScalar(root, "pml_y_alpha", s.pmlYAlpha), o.writeScalar(root, "pml_z_alpha", s.pmlZAlpha);
+  o.writeScalar(root, "p_source_flag", s.pSourceFlag), o.writeScalar(root, "p0_source_flag", s.p0SourceFlag);
+  o.writeScalar(root, "transducer_source_flag", s.transducerSourceFlag);
+  o.writeScalar(root, "ux_source_flag", s.uxSourceFlag), o.writeScalar(root, "uy_source_flag", s.uySourceFlag), o.writeScalar(root, "uz_source_flag", s.uzSourceFlag);
+  o.writeScalar(root, "nonuniform_grid_flag", s.nonuniformGridFlag), o.writeScalar(root, "absorbing_flag", s.absorbingFlag);
+  o.writeScalar(root, "nonlinear_flag", s.nonlinearFlag);
+  if (s.uxSourceFlag || s.uySourceFlag || s.uzSourceFlag) o.writeScalar(root, "u_source_many", s.uSourceMany), o.writeScalar(root, "u_source_mode", s.uSourceMode);
+  if (s.pSourceFlag) o.writeScalar(root, "p_source_many", s.pSourceMany), o.writeScalar(root, "p_source_mode", s.pSourceMode);
+  if (s.absorbingFlag) o.writeScalar(root, "alpha_power", s.alphaPower);
+  o.writeScalar(root, "t_index", (uint64_t)timeIndex());
+  if (mCmd.copySensorMask) {  // cpp:1100-1116
+    o.writeScalar(root, "sensor_mask_type", s.sensorMaskType);
+    if (s.sensorMaskType == 0) {
+      const auto idx = mInputFile.readIndices(mInputFile.root(), "sensor_mask_index");
+      o.writeWhole(root, "sensor_mask_index", {1, 1, idx.size()}, {}, idx.data(), false, 0);
+    } else {
+      o.writeWhole(root, "sensor_mask_corners", {1, mCorners.size() / 6, 6}, {}, mCorners.data(), false, 0);
+    }
+  }
+}
+
+void KSpaceFirstOrderSolver::writeOutputHeader() {  // Hdf5FileHeader (Hdf5/Hdf5FileHeader.cpp:70-87); statistics cpp:1132-1168
+  const hid_t root = mOutputFile.root();
+  Hdf5File& o = mOutputFile;
+  char host[256] = "unknown";
+  gethostname(host, sizeof host - 1);
+  char date[64];
+  const time_t now = time(nullptr);
+  strftime(date, sizeof date, "%d-%b-%Y-%H-%M-%S", localtime(&now));
+  o.setStringAttribute(root, "/", "created_by", getCodeName());
+  o.setStringAttribute(root, "/", "creation_date", date);
+  o.setStringAttribute(root, "/", "file_description", "Output data created by the B200 time-step engine");
+  o.setStringAttribute(root, "/", "file_type", "output");
+  o.setStringAttribute(root, "/", "major_version", "1");
+  o.setStringAttribute(root, "/", "minor_version", "1");
+  o.setStringAttribute(root, "/", "host_names", host);
+  o.setStringAttribute(root, "/", "number_of_cpu_cores", std::to_string(mCmd.numberOfThreads > 0 ? mCmd.numberOfThreads : (long)std::thread::hardware_concurrency()));
+  o.setStringAttribute(root, "/", "total_memory_in_use", std::to_string(getHostMemoryUsage() >> 20) + " MB");
+  o.setStringAttribute(root, "/", "peak_core_memory_in_use", std::to_string(getDeviceMemoryUsage() >> 20) + " MB");
+  o.setStringAttribute(root, "/", "total_execution_time", formatSeconds(getTotalTime()));
+  o.setStringAttribute(root, "/", "data_load_phase_execution_time", formatSeconds(getDataLoadTime()));
+  o.setStringAttribute(root, "/", "pre-processing_phase_execution_time", formatSeconds(getPreProcessingTime()));
+  o.setStringAttribute(root, "/", "simulation_phase_execution_time", formatSeconds(getSimulationTime()));
+  o.setStringAttribute(root, "/", "post-processing_phase_execution_time", formatSeconds(getPostProcessingTime()));
+}
+
+uint64_t KSpaceFirstOrderSolver::timeIndex() const {
+  uint64_t t = 0;
+  if (mCtx) kw_time_index(mCtx, &t);
+  return t;
+}
+
+size_t KSpaceFirstOrderSolver::getHostMemoryUsage() const { return mHostBytes + mRowBuffer.size() * sizeof(float); }
+size_t KSpaceFirstOrderSolver::getAvailableDeviceMemory() const {
+  size_t freeB = 0, total = 0;
+  kw_device_memory(&freeB, &total);
+  return freeB;
+}
+size_t KSpaceFirstOrderSolver::getDeviceMemoryUsage() const {
+  size_t freeB = 0, total = 0;
+  kw_device_memory(&freeB, &total);
+  return total - freeB;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+void KSpaceFirstOrderSolver::compute() {
+  // preProcessing (cpp:784-857)
+  mPreProcessingTime.start();
+  createStreams();
+  check(kw_preprocess(mCtx));
+  createOutputDatasets();
+  mPreProcessingTime.stop();
+  log(1, "Pre-processing phase: %s, device memory in use: %zu MB\n", formatSeconds(getPreProcessingTime()).c_str(), getDeviceMemoryUsage() >> 20);
+
+  // computeMainLoop (cpp:864-943): the library runs until Nt or until a device-side row buffer is full
+  mSimulationTime.start();
+  const uint64_t nt = mScalars.nt;
+  uint64_t nextReport = 0;
+  while (timeIndex() < nt) {
+    uint64_t done = 0;
+    const uint64_t chunk = std::max<uint64_t>(1, nt * (uint64_t)mCmd.progressInterval / 100);
+    const int status = kw_run(mCtx, std::min<uint64_t>(chunk, nt - timeIndex()), &done, 1);
+    if (status == KW_ERR_STREAM_FULL) {
+      flushSeries(false);
+      continue;
+    }
+    check(status);
+    if (mCmd.verbose > 0 && timeIndex() >= nextReport) {
+      log(2, "  %3llu%% done, step %llu of %llu\n", (unsigned long long)(100 * timeIndex() / nt), (unsigned long long)timeIndex(), (unsigned long long)nt);
+      nextReport = timeIndex() + chunk;
+    }
+  }
+  check(kw_synchronize(mCtx));
+  flushSeries(true);
+  mSimulationTime.stop();
+  log(1, "Simulation phase: %s (%llu steps)\n", formatSeconds(getSimulationTime()).c_str(), (unsigned long long)nt);
+
+  // postProcessing (cpp:950-973) + writeOutputDataInfo (cpp:1099-1168)
+  mPostProcessingTime.start();
+  check(kw_finish(mCtx));
+  writeAggregates();
+  saveScalarsToOutputFile();
+  mPostProcessingTime.stop();
+  mTotalTime.stop();
+  writeOutputHeader();
+  mOutputFile.close();
+  log(1, "Post-processing phase: %s, total: %s\n", formatSeconds(getPostProcessingTime()).c_str(), formatSeconds(getTotalTime()).c_str());
+}
+
+}  // namespace kwhost

@@ -1,0 +1,104 @@
+"""The C++ host (k-wave-fluid-cuda_b200/host: KSpaceFirstOrderSolver interface, command line and file layout of the
+reference) end to end: the same input FILE and the same FLAGS given to kspaceFirstOrder-B200 and to the reference's own
+binary (its unmodified sources + cuFFT, oracle/_ref/ref_kspace), every dataset of the two output files compared --
+names and shapes exactly, values to rel-L2 <= 1e-5 (max-abs printed).  For the components of a vector quantity (ux, uy, uz
+and their derived outputs) the error of each component is taken relative to the largest component of that quantity: the
+three travel through the same FP32 transforms, so a component two orders below the main one carries the same absolute
+rounding noise in both codes (e.g. uz at 4 % of ux differs by 1.7e-8, exactly like ux)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import kwh5  # noqa: E402
+
+OURS = os.path.join(ROOT, "k-wave-fluid-cuda_b200", "kspaceFirstOrder-B200")
+REF = os.path.join(ROOT, "oracle", "_ref", "ref_kspace")
+SCALARS = {"Nx", "Ny", "Nz", "Nt", "dt", "dx", "dy", "dz", "c_ref", "t_index"}
+
+CASES = {
+    "index_raw_and_aggregates": (dict(nonlinear=True, absorbing=True, source="p_plane", n_sensor=96, shuffle_sensor=True),
+                                 ["-p", "--p_rms", "--p_max", "--p_min", "--p_max_all", "--p_min_all", "--p_final", "-u", "--u_max", "--u_final", "-s", "6"]),
+    "cuboids": (dict(nonlinear=False, absorbing=False, source="p0", sensor="cuboid"), ["-p", "--p_rms", "--p_max", "--u_min_all", "--copy_sensor_mask"]),
+    "compressed": (dict(nonlinear=False, absorbing=False, source="p_plane", n_sensor=64, period=20, shifts=True),
+                   ["--p_c", "--u_non_staggered_c", "--I_avg_c", "--u_non_staggered_raw", "--period", "20", "--mos", "1", "--harmonics", "2"]),
+    "transducer_u_sources": (dict(nonlinear=True, absorbing=True, source="transducer", n_sensor=32), ["-p", "-u", "--u_rms"]),
+    "no_output_flags": (dict(nonlinear=False, absorbing=False, source="p0", n_sensor=8), []),
+}
+
+
+def run(binary, fin, fout, flags):
+    r = subprocess.run([binary, "-i", fin, "-o", fout, "-t", "4", "--verbose", "0"] + flags, capture_output=True, text=True)
+    assert r.returncode == 0, f"{os.path.basename(binary)} failed:\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"
+    return kwh5.read_file(fout)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES))
+def test_same_file_same_flags_same_output(synth, tmp_path, name):
+    if not os.path.exists(REF):
+        pytest.skip("reference binary not built (oracle/ref_build)")
+    assert os.path.exists(OURS), "kspaceFirstOrder-B200 not built (__graft_entry__.build())"
+    kwargs, flags = CASES[name]
+    nt = 120
+    cfg, arrays = synth.make_case(32, nt=nt, **kwargs)
+    fin = str(tmp_path / "in.h5")
+    kwh5.write_input(fin, cfg, arrays)
+    ref = run(REF, fin, str(tmp_path / "ref.h5"), flags)
+    got = run(OURS, fin, str(tmp_path / "out.h5"), flags)
+    ref_ds = {p: o for p, o in ref.items() if o["kind"] != "group"}
+    got_ds = {p: o for p, o in got.items() if o["kind"] != "group"}
+    assert set(ref_ds) == set(got_ds), (sorted(set(ref_ds) ^ set(got_ds)))
+    assert {p for p, o in ref.items() if o["kind"] == "group"} == {p for p, o in got.items() if o["kind"] == "group"}
+    compared = 0
+    for p, o in sorted(ref_ds.items()):
+        a, b = got_ds[p]["data"], o["data"]
+        assert a.shape == b.shape and got_ds[p]["kind"] == o["kind"], (p, a.shape, b.shape)
+        for k in ("data_type", "domain_type", "c_harmonics", "c_type", "c_mos", "c_shift", "c_max_exp", "c_period", "c_complex_size"):
+            assert got_ds[p]["attrs"].get(k) == o["attrs"].get(k), (p, k)
+        if o["kind"] == "u64" or p.strip("/") in SCALARS or a.size == 1:
+            assert np.array_equal(a, b), p
+            continue
+        nb = np.linalg.norm(b.astype(np.float64).ravel())
+        base = p.strip("/")
+        if base[:2] in ("ux", "uy", "uz", "Ix", "Iy", "Iz"):  # vector quantity: norm of its largest component
+            sib = ["/" + base[0] + c + base[2:] for c in "xyz"]
+            nb = max(np.linalg.norm(ref_ds[q]["data"].astype(np.float64).ravel()) for q in sib if q in ref_ds)
+        err = np.linalg.norm((a.astype(np.float64) - b).ravel()) / max(nb, 1e-300)
+        print(f"{name}: {p} {a.shape}: rel-L2 {err:.3e}, max-abs {np.abs(a - b).max():.3e} (scale {np.abs(b).max():.3e})")
+        assert err <= 1e-5, (p, err)
+        compared += 1
+    assert compared >= 1 or not flags
+    for k in ("file_type", "major_version", "minor_version"):
+        assert got["/"]["attrs"].get(k) == ref["/"]["attrs"].get(k)
+
+
+def test_command_line_errors_exit_like_the_reference(tmp_path):
+    """Boxed message on stderr + EXIT_FAILURE (Logger/Logger.cpp:82-89); -s is 1-based; unsupported features say so."""
+    assert os.path.exists(OURS), "kspaceFirstOrder-B200 not built (__graft_entry__.build())"
+    for args, needle in (([], "Input file was not specified"), (["-i", "a"], "Output file was not specified"),
+                         (["-i", "a", "-o", "b", "--checkpoint_interval", "5"], "not available in this build"),
+                         (["-i", "a", "-o", "b", "--p_c"], "--period or --frequency"), (["-i", "a", "-o", "b", "-s", "0"], "Invalid value"),
+                         (["-i", "a", "-o", "b", "-c", "12"], "Invalid value"),
+                         (["-i", str(tmp_path / "missing.h5"), "-o", "b"], "could not be opened")):  # fmt: skip
+        r = subprocess.run([OURS] + args, capture_output=True, text=True)
+        assert r.returncode == 1, args
+        assert "K-Wave experienced a fatal error" in r.stderr and needle in r.stderr, (args, r.stderr)
+    r = subprocess.run([OURS, "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "--p_max_all" in r.stdout
+
+
+def test_no_gpu_means_error_exit_not_cpu_fallback(synth, tmp_path):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    cfg, arrays = synth.make_case(16, nt=4, source="p0")
+    fin = str(tmp_path / "in.h5")
+    kwh5.write_input(fin, cfg, arrays)
+    r = subprocess.run([OURS, "-i", fin, "-o", str(tmp_path / "o.h5")], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
