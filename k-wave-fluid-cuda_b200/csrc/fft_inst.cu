@@ -95,7 +95,7 @@ static void col(const ColArgs& a, int dir, int nfields, cudaStream_t st) {
   }
 }
 template <int AXIS> static void zmid_axis(const ZMidArgs& a, cudaStream_t st) {
-  using C = ColCfg<N>;
+  using C = ZCfg<N>;
   const int g = col_grid<10 + AXIS>(k_zmid<N, AXIS>, a.ntiles, C::SMEM_ZMID);
   k_zmid<N, AXIS><<<g, dim3(C::W, C::WK, C::TPC), C::SMEM_ZMID, st>>>(a);
 }
@@ -173,7 +173,7 @@ static void zmid(const ZMidArgs& a, cudaStream_t st) {
 
 #define KW_OPS_NAME2(n) fft_ops_##n
 #define KW_OPS_NAME(n) KW_OPS_NAME2(n)
-extern const FftOps KW_OPS_NAME(KW_N) = {KW_N, ColCfg<KW_N>::W, ColCfg<KW_N>::WK, KW_CAT(inst_, KW_N)::xfwd, KW_CAT(inst_, KW_N)::xinv_store, KW_CAT(inst_, KW_N)::xinv_add, KW_CAT(inst_, KW_N)::xinv_velocity,
+extern const FftOps KW_OPS_NAME(KW_N) = {KW_N, ColCfg<KW_N>::W, ColCfg<KW_N>::WK, ZCfg<KW_N>::W, KW_CAT(inst_, KW_N)::xfwd, KW_CAT(inst_, KW_N)::xinv_store, KW_CAT(inst_, KW_N)::xinv_add, KW_CAT(inst_, KW_N)::xinv_velocity,
                                             KW_CAT(inst_, KW_N)::xinv_density, KW_CAT(inst_, KW_N)::xinv_psum, KW_CAT(inst_, KW_N)::col, KW_CAT(inst_, KW_N)::zmid,
                                             KW_CAT(inst_, KW_N)::xy_fwd, KW_CAT(inst_, KW_N)::yx_store, KW_CAT(inst_, KW_N)::yx_add, KW_CAT(inst_, KW_N)::yx_velocity,
                                             KW_CAT(inst_, KW_N)::yx_density, KW_CAT(inst_, KW_N)::yx_psum};

@@ -182,12 +182,12 @@ template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads,
 // a thread owns E = 8..32 points of one kx in registers and the transform is two register-resident butterflies
 // (radix 8/16/32, compile-time twiddles) around ONE shared-memory exchange (fft_core2.cuh).  Points go from global
 // memory straight into registers and back; shared memory only carries the exchange.
-#ifndef KW_W1024
-#define KW_W1024 8
-#endif
-template <int N> struct ColCfg {
+// WV = kx values per tile.  16 (128-byte segments) everywhere, except the fused z pass of N = 1024 (ZCfg below): its
+// 32 points per thread need ~250 registers, i.e. a 256-thread slot, i.e. 8 kx per tile (measured on B200, isolated:
+// fused z pass 1024: W=8 2.2 TB/s vs W=16 (128 registers, spilling) 1.5 TB/s; plain passes: W=16 3.9-4.0 vs W=8 2.9-3.5).
+template <int N, int WV = 16> struct ColCfg {
   using P = Plan2<N>;
-  static constexpr int W = (N >= 1024) ? KW_W1024 : 16;  // 1024: 8 kx (64-byte segments) keep a slot at 256 threads, i.e. 254 registers for E = 32
+  static constexpr int W = WV;
   static constexpr int WK = P::WK;                                         // workers (threads per kx) of a tile
   static constexpr int SLOT = W * WK;                                      // threads of a tile slot
   static constexpr int TPC = (SLOT >= 256) ? 1 : 256 / SLOT;               // tile slots per CTA
@@ -199,6 +199,8 @@ template <int N> struct ColCfg {
   // barrier flavour of a slot: whole CTA, named barrier (slot spans whole warps), or none (single-stage plans)
   static constexpr int BAR_THREADS = (P::R2 == 1) ? -1 : (TPC == 1 ? 0 : SLOT);
 };
+template <int N> using ZCfg = ColCfg<N, (N >= 1024) ? 8 : 16>;  // tiles of the fused z pass
+
 
 template <int W, int NTHREADS> struct ColExchange2 {
   float2* buf;  // tile buffer + lane
@@ -319,13 +321,13 @@ struct ZMidArgs {
 #ifndef KW_ZMID_MINB
 // E = 32 points per thread need ~150 registers to stay spill free (ncu/ptxas: 128 registers spill 300+ bytes and run
 // 25-55% slower than one CTA per SM at 254 registers)
-#define KW_ZMID_MINB ((Plan2<N>::E >= 32 || AXIS == 3) ? 1 : ColCfg<N>::MINB)
+#define KW_ZMID_MINB ((Plan2<N>::E >= 32 || AXIS == 3) ? 1 : ZCfg<N>::MINB)
 #endif
 #ifndef KW_ZMID_MULMODE
 #define KW_ZMID_MULMODE 0  // 0: multiplier lands in shared memory through cp.async; 1: plain loads at the point of use
 #endif
-template <int N, int AXIS> __global__ void __launch_bounds__(ColCfg<N>::THREADS, KW_ZMID_MINB) k_zmid(ZMidArgs a) {
-  using C = ColCfg<N>;
+template <int N, int AXIS> __global__ void __launch_bounds__(ZCfg<N>::THREADS, KW_ZMID_MINB) k_zmid(ZMidArgs a) {
+  using C = ZCfg<N>;
   using P = Plan2<N>;
   constexpr int W = C::W, WK = C::WK, E = P::E;
   extern __shared__ float2 smem[];

@@ -20,7 +20,8 @@ struct PipeState {
 struct FftOps {
   int n;
   int col_w;  // kx values per column tile of this length (ColCfg<N>::W)
-  int col_wk; // workers per column transform (ColCfg<N>::WK); the y-blocked layout needs Ny / nranks >= col_wk
+  int col_wk;  // workers per column transform (ColCfg<N>::WK); the y-blocked layout needs Ny / nranks >= col_wk
+  int zmid_w;  // kx values per tile of the fused z pass (ZCfg<N>::W)
   void (*xfwd)(const XFwdArgs&, int nfields, cudaStream_t);
   void (*xinv_store)(const XInvArgs<1>&, const EpiStore&, int nfields, cudaStream_t);
   void (*xinv_add)(const XInvArgs<1>&, const EpiAdd&, cudaStream_t);

@@ -167,6 +167,7 @@ struct ProfPending {
   const char* name;
   cudaEvent_t e0, e1;
   double bytes;
+  bool solver_stream;  // launched on the solver stream: gaps between consecutive ones are reported as "idle before <name>"
 };
 
 struct kw_ctx {
@@ -207,6 +208,7 @@ struct kw_ctx {
   double comm_bytes = 0.0;
   // slab-decomposed runs: exchanges run on their own stream, ordered against the solver stream by events
   cudaStream_t cs = nullptr;
+  cudaStream_t ws = nullptr;  // arrival waits (peer path): a rank keeps pushing its next blocks while it waits for its peers
   std::vector<cudaEvent_t> ev_ring;
   size_t ev_next = 0;
   PeerLink peer;        // copy-engine pushes into peer memory (falls back to NCCL send/recv when unavailable)
@@ -240,13 +242,13 @@ static cudaEvent_t prof_event(kw_ctx* c) {
 }
 // every kernel launch of the time loop goes through here: counts it and, in profiling mode, brackets it with events
 template <class F> static void launch(kw_ctx* c, const char* name, double bytes, F&& f, cudaStream_t stream = nullptr) {
-  c->launches++;
+  if (!stream || stream == c->st) c->launches++;  // kernels (and the few copies) of the solver stream; exchanges are not kernels
   if (!c->prof_on) {
     f();
     return;
   }
   if (!stream) stream = c->st;
-  ProfPending p{name, prof_event(c), prof_event(c), bytes};
+  ProfPending p{name, prof_event(c), prof_event(c), bytes, stream == c->st};
   cudaEventRecord(p.e0, stream);
   f();
   cudaEventRecord(p.e1, stream);
@@ -271,14 +273,25 @@ static int pipe_check(kw_ctx* c) {
   return KW_OK;
 }
 static void prof_resolve(kw_ctx* c) {  // stream must be idle
+  const ProfPending* prev = nullptr;
   for (auto& p : c->prof_pending) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, p.e0, p.e1);
     ProfStat& st = c->prof[p.name];
     st.launches++, st.ms += ms, st.bytes += p.bytes;
-    c->prof_pool.push_back(p.e0);
-    c->prof_pool.push_back(p.e1);
+    if (p.solver_stream && c->g.nranks > 1) {  // time the solver stream spent waiting (for an exchange) before this launch
+      if (prev) {
+        float gap = 0.f;
+        cudaEventElapsedTime(&gap, prev->e1, p.e0);
+        if (gap > 0.002f) {
+          ProfStat& idle = c->prof[std::string("idle_before_") + p.name];
+          idle.launches++, idle.ms += gap;
+        }
+      }
+      prev = &p;
+    }
   }
+  for (auto& p : c->prof_pending) c->prof_pool.push_back(p.e0), c->prof_pool.push_back(p.e1);
   c->prof_pending.clear();
 }
 
@@ -444,6 +457,8 @@ int kw_ctx_create(const kw_config* cfg, kw_ctx** out) {
     memcpy(c->nccl_id, cfg->nccl_unique_id, sizeof(c->nccl_id));
     c->cfg.nccl_unique_id = nullptr;
     KW_CUDA(cudaStreamCreateWithFlags(&c->cs, cudaStreamNonBlocking));
+    static const bool split = getenv("KW_ARRIVAL_STREAM") && atoi(getenv("KW_ARRIVAL_STREAM")) != 0;  // measured at 8 GPUs: 19.8 vs 19.0 ms/step without -> off
+    if (split) KW_CUDA(cudaStreamCreateWithFlags(&c->ws, cudaStreamNonBlocking));
   }
   KW_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
   KW_CUDA(cudaEventCreate(&c->ev0));
@@ -456,6 +471,7 @@ int kw_ctx_destroy(kw_ctx* c) {
   if (!c) return KW_OK;
   cudaStreamSynchronize(c->st);
   if (c->cs) cudaStreamSynchronize(c->cs);
+  if (c->ws) cudaStreamSynchronize(c->ws), cudaStreamDestroy(c->ws);
   if (c->peer.shm) c->peer.teardown();
   if (c->comm) nccl_api().CommDestroy(c->comm);
   for (cudaEvent_t e : c->ev_ring) cudaEventDestroy(e);
@@ -1007,9 +1023,22 @@ static int exchange_async(kw_ctx* c, int src_id, int dst_id, cudaEvent_t* done) 
       if (!e && src != dst) e = (int)cudaMemcpyAsync(dst + (size_t)me * g.blk, src + (size_t)me * g.blk, bytes, cudaMemcpyDeviceToDevice, c->cs);
       for (int q = 0; q < P && !e; ++q)
         if (q != me) e = d.WriteValue32(c->cs, pl.dev_addr(&pl.shm->arrived[q][dst_id][me]), n, kWriteDefault);
-      for (int r = 0; r < P && !e; ++r)
-        if (r != me) e = d.WaitValue32(c->cs, pl.dev_addr(&pl.shm->arrived[me][dst_id][r]), n, kWaitGeq);
+      if (!c->ws)
+        for (int r = 0; r < P && !e; ++r)
+          if (r != me) e = d.WaitValue32(c->cs, pl.dev_addr(&pl.shm->arrived[me][dst_id][r]), n, kWaitGeq);
     }, c->cs);
+    if (!e && c->ws) {  // the consumer needs my own block (copied on cs) and the blocks of my peers; cs itself moves on
+      cudaStreamWaitEvent(c->ws, mark(c, c->cs), 0);
+      launch(c, "all_to_all_arrival", 0.0, [&] {
+        for (int r = 0; r < P && !e; ++r)
+          if (r != me) e = d.WaitValue32(c->ws, pl.dev_addr(&pl.shm->arrived[me][dst_id][r]), n, kWaitGeq);
+      }, c->ws);
+      if (!e) {
+        c->comm_bytes += 8.0 * (double)g.blk * (P - 1);
+        *done = mark(c, c->ws);
+        return KW_OK;
+      }
+    }
     if (e) what = "peer-memory all-to-all: CUDA error " + std::to_string(e);
   } else {
     NcclApi& nc = nccl_api();
@@ -1064,7 +1093,7 @@ static void zmid_launch(kw_ctx* c, ZField f, int axis) {
   if (axis == 1 && f.vec) f.vec += g.y0;
   if (axis == 3 && f.vec_y) f.vec_y += g.y0;
   za.f = f, za.axis = axis;
-  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->col_w, za.ntiles = g.nyl * za.ngroups, za.plane = (unsigned)((size_t)g.nyl * g.nxp);
+  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->zmid_w, za.ntiles = g.nyl * za.ngroups, za.plane = (unsigned)((size_t)g.nyl * g.nxp);
   launch(c, axis == 3 ? "zmid_grad" : "zmid", (axis == 3 ? 32.0 : 16.0) * g.nc + (f.mul ? 4.0 * g.nc : 0.0), [&] { g.oz->zmid(za, c->st); });
 }
 template <int NF> static YXInvArgs<NF> yx_args(kw_ctx* c, float2* const* in, int nfields = NF) {
@@ -1620,6 +1649,7 @@ int kw_run(kw_ctx* c, uint64_t nsteps, uint64_t* steps_done, int sync) {
   if (sync) {
     KW_CUDA(cudaStreamSynchronize(c->st));
     if (c->cs) KW_CUDA(cudaStreamSynchronize(c->cs));
+    if (c->ws) KW_CUDA(cudaStreamSynchronize(c->ws));
     KW_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
     prof_resolve(c);
     KW_TRY(pipe_check(c));
@@ -1636,6 +1666,7 @@ int kw_synchronize(kw_ctx* c) {
   if (!c) return fail(KW_ERR_INVALID, "null context");
   KW_CUDA(cudaStreamSynchronize(c->st));
   if (c->cs) KW_CUDA(cudaStreamSynchronize(c->cs));
+  if (c->ws) KW_CUDA(cudaStreamSynchronize(c->ws));
   cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
   prof_resolve(c);
   KW_CUDA(cudaGetLastError());
@@ -1646,6 +1677,7 @@ int kw_profile(kw_ctx* c, int enable, int reset) {
   if (!c) return fail(KW_ERR_INVALID, "null context");
   KW_CUDA(cudaStreamSynchronize(c->st));
   if (c->cs) KW_CUDA(cudaStreamSynchronize(c->cs));
+  if (c->ws) KW_CUDA(cudaStreamSynchronize(c->ws));
   prof_resolve(c);
   c->prof_on = enable != 0;
   if (reset) c->prof.clear();
@@ -1889,7 +1921,7 @@ int kw_bench_col(uint64_t nx, uint64_t ny, uint64_t nz, int axis, int fused, int
   else ca.stride = (size_t)g.ny * g.nxp, ca.outer_stride = g.nxp, ca.ngroups = g.nxp / op->col_w, ca.tile_end = g.ny * ca.ngroups;
   ZMidArgs za{};
   za.f = ZField{d, d, mul, 1.0f, nullptr}, za.axis = -1;
-  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->col_w, za.ntiles = g.ny * za.ngroups, za.plane = (unsigned)((size_t)g.ny * g.nxp);
+  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->zmid_w, za.ntiles = g.ny * za.ngroups, za.plane = (unsigned)((size_t)g.ny * g.nxp);
   for (int i = 0; i < iters + 2; ++i) {
     if (i == 2) cudaEventRecord(e0);
     if (fused) g.oz->zmid(za, 0);
