@@ -25,12 +25,36 @@ template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 
 
+// Complex arithmetic on the packed FP32x2 pipe of sm_100 (FADD2 / FMUL2 / FFMA2: one instruction per complex add, two
+// per complex multiply; half swaps, per-half negation and scalar broadcast are operand modifiers, so the make_float2
+// shuffles below cost nothing).  The butterflies are issue-bound, not FLOP-bound: halving their instruction count is what
+// shortens them.  Measured on B200 (profiles/r01_l_*): the fused z pass of N = 512 gains 4-5 % (1.97 -> 1.88 ms per step),
+// but the radix-32 x 32 plan of N = 1024 LOSES 30 % (2.29 -> 1.60 TB/s) and N = 256 loses 3 %: with two warps per scheduler
+// the passes are bound by dependent-issue latency, and the packed instructions have the longer one.  Hence packed forms
+// only in the N = 512 translation unit (fft_inst.cu is compiled once per length); KW_PACKED=0/1 overrides.
+#ifndef KW_PACKED
+#ifdef KW_N
+#define KW_PACKED (KW_N == 512)
+#else
+#define KW_PACKED 0
+#endif
+#endif
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+#if KW_PACKED
+  return __ffma2_rn(make_float2(a.y, a.x), make_float2(-b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
+#else
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+#endif
 }
+#if KW_PACKED
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+#else
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+#endif
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 // multiply by DIR * i  (DIR = -1: forward e^{-i..}, multiply by -i;  DIR = +1: inverse, multiply by +i)
 template <int DIR> __device__ __forceinline__ float2 mul_di(float2 a) {
@@ -61,14 +85,9 @@ template <int DIR> __device__ __forceinline__ void dft8(float2 (&v)[8]) {
   dft4<DIR>(v[0], v[2], v[4], v[6]);
   dft4<DIR>(v[1], v[3], v[5], v[7]);
   // odd outputs times W8^k
-  float2 o1, o3;
-  if (DIR < 0) {
-    o1 = make_float2((v[3].x + v[3].y) * R, (v[3].y - v[3].x) * R);    // * (1 - i)/sqrt2
-    o3 = make_float2((-v[7].x + v[7].y) * R, (-v[7].y - v[7].x) * R);  // * (-1 - i)/sqrt2
-  } else {
-    o1 = make_float2((v[3].x - v[3].y) * R, (v[3].y + v[3].x) * R);    // * (1 + i)/sqrt2
-    o3 = make_float2((-v[7].x - v[7].y) * R, (-v[7].y + v[7].x) * R);  // * (-1 + i)/sqrt2
-  }
+  // odd outputs times W8^k:  W8 = (1 - i)/sqrt2, W8^3 = (-1 - i)/sqrt2 (conjugated for the inverse)
+  const float2 o1 = cmul(v[3], make_float2(R, DIR < 0 ? -R : R));
+  const float2 o3 = cmul(v[7], make_float2(-R, DIR < 0 ? -R : R));
   float2 o0 = v[1], o2 = mul_di<DIR>(v[5]);
   float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
   v[0] = cadd(e0, o0);

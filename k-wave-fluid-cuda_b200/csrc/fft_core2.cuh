@@ -25,52 +25,44 @@ template <int... Is, class F> KW_HD void static_for_impl(std::integer_sequence<i
 }
 template <int N, class F> KW_HD void static_for(F&& f) { static_for_impl(std::make_integer_sequence<int, N>{}, f); }
 
-template <int DIR> KW_HD float2 cmulc(float2 a, cf2 w) {  // a * w (forward) or a * conj(w) (inverse), w compile-time
-  return DIR < 0 ? make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x)
-                 : make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
+// The butterflies below run on the device only; they are written with the (packed) complex helpers of fft_core.cuh.
+template <int DIR> __device__ __forceinline__ float2 cmulc(float2 a, cf2 w) {  // a * w (forward) or a * conj(w) (inverse), w compile-time
+  return cmul(a, make_float2(w.x, DIR < 0 ? w.y : -w.y));
 }
-template <int DIR> KW_HD float2 mul_di_hd(float2 a) { return DIR < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x); }
-
-template <int DIR> KW_HD void dft4r(float2& a0, float2& a1, float2& a2, float2& a3) {
-  const float2 s02 = make_float2(a0.x + a2.x, a0.y + a2.y), d02 = make_float2(a0.x - a2.x, a0.y - a2.y);
-  const float2 s13 = make_float2(a1.x + a3.x, a1.y + a3.y), d13 = mul_di_hd<DIR>(make_float2(a1.x - a3.x, a1.y - a3.y));
-  a0 = make_float2(s02.x + s13.x, s02.y + s13.y);
-  a2 = make_float2(s02.x - s13.x, s02.y - s13.y);
-  a1 = make_float2(d02.x + d13.x, d02.y + d13.y);
-  a3 = make_float2(d02.x - d13.x, d02.y - d13.y);
+template <int DIR> __device__ __forceinline__ void dft4r(float2& a0, float2& a1, float2& a2, float2& a3) {
+  const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2);
+  const float2 s13 = cadd(a1, a3), d13 = mul_di<DIR>(csub(a1, a3));
+  a0 = cadd(s02, s13);
+  a2 = csub(s02, s13);
+  a1 = cadd(d02, d13);
+  a3 = csub(d02, d13);
 }
 // 8-point DFT on references, natural order in and out
-template <int DIR> KW_HD void dft8r(float2& v0, float2& v1, float2& v2, float2& v3, float2& v4, float2& v5, float2& v6, float2& v7) {
+template <int DIR> __device__ __forceinline__ void dft8r(float2& v0, float2& v1, float2& v2, float2& v3, float2& v4, float2& v5, float2& v6, float2& v7) {
   constexpr float R = 0.70710678118654752440f;
   dft4r<DIR>(v0, v2, v4, v6);
   dft4r<DIR>(v1, v3, v5, v7);
-  float2 o1, o3;
-  if (DIR < 0) {
-    o1 = make_float2((v3.x + v3.y) * R, (v3.y - v3.x) * R);
-    o3 = make_float2((-v7.x + v7.y) * R, (-v7.y - v7.x) * R);
-  } else {
-    o1 = make_float2((v3.x - v3.y) * R, (v3.y + v3.x) * R);
-    o3 = make_float2((-v7.x - v7.y) * R, (-v7.y + v7.x) * R);
-  }
-  const float2 o0 = v1, o2 = mul_di_hd<DIR>(v5);
+  const float2 o1 = cmul(v3, make_float2(R, DIR < 0 ? -R : R));
+  const float2 o3 = cmul(v7, make_float2(-R, DIR < 0 ? -R : R));
+  const float2 o0 = v1, o2 = mul_di<DIR>(v5);
   const float2 e0 = v0, e1 = v2, e2 = v4, e3 = v6;
-  v0 = make_float2(e0.x + o0.x, e0.y + o0.y);
-  v4 = make_float2(e0.x - o0.x, e0.y - o0.y);
-  v1 = make_float2(e1.x + o1.x, e1.y + o1.y);
-  v5 = make_float2(e1.x - o1.x, e1.y - o1.y);
-  v2 = make_float2(e2.x + o2.x, e2.y + o2.y);
-  v6 = make_float2(e2.x - o2.x, e2.y - o2.y);
-  v3 = make_float2(e3.x + o3.x, e3.y + o3.y);
-  v7 = make_float2(e3.x - o3.x, e3.y - o3.y);
+  v0 = cadd(e0, o0);
+  v4 = csub(e0, o0);
+  v1 = cadd(e1, o1);
+  v5 = csub(e1, o1);
+  v2 = cadd(e2, o2);
+  v6 = csub(e2, o2);
+  v3 = cadd(e3, o3);
+  v7 = csub(e3, o3);
 }
 
 // R-point DFT of v[off + str*j], j < R, natural order in and out (R = 1, 2, 4, 8, 16, 32); all indices compile time.
-template <int R, int DIR, int STR, int OFF, int LEN> KW_HD void dftR(float2 (&v)[LEN]) {
+template <int R, int DIR, int STR, int OFF, int LEN> __device__ __forceinline__ void dftR(float2 (&v)[LEN]) {
 #define KW_V(j) v[OFF + STR * (j)]
   if constexpr (R == 2) {
     const float2 t = KW_V(0);
-    KW_V(0) = make_float2(t.x + KW_V(1).x, t.y + KW_V(1).y);
-    KW_V(1) = make_float2(t.x - KW_V(1).x, t.y - KW_V(1).y);
+    KW_V(0) = cadd(t, KW_V(1));
+    KW_V(1) = csub(t, KW_V(1));
   } else if constexpr (R == 4) {
     dft4r<DIR>(KW_V(0), KW_V(1), KW_V(2), KW_V(3));
   } else if constexpr (R == 8) {
