@@ -275,7 +275,9 @@ def main():
         l0 = sim.launch_count()
         barrier()
         t0 = time.perf_counter()
-        sim.run(K, sync=True)  # timed region: K steps, CUDA events on the solver stream around them
+        sim.run(K, sync=False)  # timed region: K steps, CUDA events on the solver stream around them
+        host_enqueue_ms = (time.perf_counter() - t0) * 1e3 / K  # how long the host needs to enqueue one step
+        sim.synchronize()
         barrier()
         t1 = time.perf_counter()
         clk.window(t0, t1)
@@ -380,16 +382,19 @@ def main():
                    "grid": [N, N, N], "l2_policy": "inputs larger than L2 (every field >= 512 MiB per GPU)" if N**3 // (world if sharded else 1) >= 512**3 else
                    "working set partly L2 resident at this size",
                    "parallelism": "1 GPU" if world == 1 else (f"z-slabs over {world} GPUs" if sharded else f"{world} independent replicas"),
-                   "wall_ms_timed_region": wall_ms},
+                   "wall_ms_timed_region": wall_ms, "host_enqueue_ms_per_step": host_enqueue_ms},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }  # fmt: skip
     if sharded and "all_to_all" in prof:
         a2a = prof["all_to_all"]
         sent_per_step = comm_bytes / comm_steps  # bytes this rank sent per step (one direction)
         line["nvlink"] = {"all_to_all_ms_per_step": a2a["ms"] / KP, "exchanges_per_step": a2a["launches"] / KP,
+                          "credit_wait_ms_per_step": prof.get("all_to_all_credit_wait", {}).get("ms", 0.0) / KP,
+                          "arrival_wait_ms_per_step": prof.get("all_to_all_arrival_wait", {}).get("ms", 0.0) / KP,
                           "sent_bytes_per_gpu_per_step": sent_per_step,
                           "GBps_per_gpu_per_direction": sent_per_step / (a2a["ms"] / KP * 1e-3) / 1e9, "path": comm_mode,
-                          "how": "rank 0: bytes sent per step / CUDA-event time of the NCCL send/recv groups on the solver stream"}
+                          "how": "rank 0: bytes sent per step / CUDA-event time of the pushes (peer path: the copies alone; waits for credits and "
+                                 "arrivals are listed beside them) on the communication stream"}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_port_throughput(128, budget_s=12.0)
     print(json.dumps(line), flush=True)

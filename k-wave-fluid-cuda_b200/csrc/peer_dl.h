@@ -6,6 +6,7 @@
 //
 // The driver entry points are resolved at run time from libcuda.so.1 (the library links against the runtime only).
 #pragma once
+#include <cuda.h>  // driver API TYPES only (CUstreamBatchMemOpParams); entry points are resolved with dlsym
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <fcntl.h>
@@ -30,6 +31,9 @@ struct DrvApi {
   // CUresult cuStreamWaitValue32(CUstream, CUdeviceptr, cuuint32_t value, unsigned flags)
   int (*WaitValue32)(cudaStream_t, unsigned long long, uint32_t, unsigned) = nullptr;
   int (*WriteValue32)(cudaStream_t, unsigned long long, uint32_t, unsigned) = nullptr;
+  // CUresult cuStreamBatchMemOp(CUstream, unsigned count, CUstreamBatchMemOpParams*, unsigned flags): one driver call for the
+  // P-1 waits or writes of an exchange (the host enqueues ~40 operations per exchange at 8 ranks otherwise)
+  int (*BatchMemOp)(cudaStream_t, unsigned, CUstreamBatchMemOpParams*, unsigned) = nullptr;
   bool ok = false;
   std::string error;
 };
@@ -51,6 +55,10 @@ inline DrvApi& drv_api() {
     if (!api.WaitValue32) api.WaitValue32 = reinterpret_cast<decltype(api.WaitValue32)>(dlsym(h, n));
   for (const char* n : write_names)
     if (!api.WriteValue32) api.WriteValue32 = reinterpret_cast<decltype(api.WriteValue32)>(dlsym(h, n));
+  const char* batch_names[] = {"cuStreamBatchMemOp_v2", "cuStreamBatchMemOp"};
+  for (const char* n : batch_names)
+    if (!api.BatchMemOp) api.BatchMemOp = reinterpret_cast<decltype(api.BatchMemOp)>(dlsym(h, n));
+  if (getenv("KW_BATCH_MEMOPS") && atoi(getenv("KW_BATCH_MEMOPS")) == 0) api.BatchMemOp = nullptr;
   if (!api.WaitValue32 || !api.WriteValue32) {
     api.error = "cuStreamWaitValue32 / cuStreamWriteValue32 missing from the driver";
     return api;
@@ -165,6 +173,37 @@ struct PeerLink {
       shm_unlink(shm_name.c_str());
     }
     shm = nullptr, active = false;
+  }
+  // `count` 32-bit waits (>= value) or writes on the flags flag(r), r != rank, in one driver call when available
+  template <class F> int flag_ops(cudaStream_t stream, bool wait, uint32_t value, F&& flag) const {
+    DrvApi& d = drv_api();
+    if (d.BatchMemOp) {
+      CUstreamBatchMemOpParams ops[kPeerMaxRanks];
+      unsigned n = 0;
+      for (int r = 0; r < nranks; ++r) {
+        if (r == rank) continue;
+        memset(&ops[n], 0, sizeof(ops[n]));
+        if (wait) {
+          ops[n].waitValue.operation = CU_STREAM_MEM_OP_WAIT_VALUE_32;
+          ops[n].waitValue.address = (CUdeviceptr)dev_addr(flag(r));
+          ops[n].waitValue.value = value;
+          ops[n].waitValue.flags = CU_STREAM_WAIT_VALUE_GEQ;
+        } else {
+          ops[n].writeValue.operation = CU_STREAM_MEM_OP_WRITE_VALUE_32;
+          ops[n].writeValue.address = (CUdeviceptr)dev_addr(flag(r));
+          ops[n].writeValue.value = value;
+          ops[n].writeValue.flags = CU_STREAM_WRITE_VALUE_DEFAULT;
+        }
+        ++n;
+      }
+      return n ? d.BatchMemOp(stream, n, ops, 0) : 0;
+    }
+    for (int r = 0; r < nranks; ++r) {
+      if (r == rank) continue;
+      const int e = wait ? d.WaitValue32(stream, dev_addr(flag(r)), value, kWaitGeq) : d.WriteValue32(stream, dev_addr(flag(r)), value, kWriteDefault);
+      if (e) return e;
+    }
+    return 0;
   }
   unsigned long long dev_addr(const volatile uint32_t* host_field) const {
     return reinterpret_cast<unsigned long long>(reinterpret_cast<const char*>(shm_dev) +

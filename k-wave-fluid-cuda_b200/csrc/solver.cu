@@ -208,7 +208,7 @@ struct kw_ctx {
   double comm_bytes = 0.0;
   // slab-decomposed runs: exchanges run on their own stream, ordered against the solver stream by events
   cudaStream_t cs = nullptr;
-  cudaStream_t ws = nullptr;  // arrival waits (peer path): a rank keeps pushing its next blocks while it waits for its peers
+  cudaStream_t ws = nullptr;  // local copy of the own block (peer path): keeps the copy stream for the NVLink pushes
   std::vector<cudaEvent_t> ev_ring;
   size_t ev_next = 0;
   PeerLink peer;        // copy-engine pushes into peer memory (falls back to NCCL send/recv when unavailable)
@@ -457,8 +457,8 @@ int kw_ctx_create(const kw_config* cfg, kw_ctx** out) {
     memcpy(c->nccl_id, cfg->nccl_unique_id, sizeof(c->nccl_id));
     c->cfg.nccl_unique_id = nullptr;
     KW_CUDA(cudaStreamCreateWithFlags(&c->cs, cudaStreamNonBlocking));
-    static const bool split = getenv("KW_ARRIVAL_STREAM") && atoi(getenv("KW_ARRIVAL_STREAM")) != 0;  // measured at 8 GPUs: 19.8 vs 19.0 ms/step without -> off
-    if (split) KW_CUDA(cudaStreamCreateWithFlags(&c->ws, cudaStreamNonBlocking));
+    static const bool own = !getenv("KW_SELF_COPY_STREAM") || atoi(getenv("KW_SELF_COPY_STREAM")) != 0;
+    if (own) KW_CUDA(cudaStreamCreateWithFlags(&c->ws, cudaStreamNonBlocking));  // local copy of the own block of every exchange
   }
   KW_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
   KW_CUDA(cudaEventCreate(&c->ev0));
@@ -1003,42 +1003,38 @@ static int exchange_async(kw_ctx* c, int src_id, int dst_id, cudaEvent_t* done) 
   const int me = g.rank, P = g.nranks;
   float2 *src = xbuf(c, src_id), *dst = xbuf(c, dst_id);
   const size_t bytes = g.blk * sizeof(float2);
-  cudaStreamWaitEvent(c->cs, mark(c, c->st), 0);
+  const cudaEvent_t start = mark(c, c->st);
+  cudaStreamWaitEvent(c->cs, start, 0);
   int e = 0;
   std::string what;
   const double moved = 16.0 * (double)g.blk * (P - 1);
   if (c->peer.active) {
     PeerLink& pl = c->peer;
-    DrvApi& d = drv_api();
     const uint32_t n = ++pl.use[dst_id];
     const size_t dst_off = reinterpret_cast<char*>(dst) - c->arena;
-    launch(c, "all_to_all", moved, [&] {
+    // (profiling brackets the four parts separately: credit wait / copies / signal / arrival wait)
+    launch(c, "all_to_all_credit_wait", 0.0, [&] {
       if (n > 1)  // every receiver has released the previous content of its destination buffer
-        for (int q = 0; q < P && !e; ++q)
-          if (q != me) e = d.WaitValue32(c->cs, pl.dev_addr(&pl.shm->credit[me][dst_id][q]), n - 1, kWaitGeq);
+        e = pl.flag_ops(c->cs, true, n - 1, [&](int q) { return &pl.shm->credit[me][dst_id][q]; });
+    }, c->cs);
+    cudaEvent_t self_done = nullptr;
+    if (!e && c->ws && src != dst) {  // the own block is a local copy: off the copy stream that feeds NVLink
+      cudaStreamWaitEvent(c->ws, start, 0);
+      e = (int)cudaMemcpyAsync(dst + (size_t)me * g.blk, src + (size_t)me * g.blk, bytes, cudaMemcpyDeviceToDevice, c->ws);
+      self_done = mark(c, c->ws);
+    }
+    launch(c, "all_to_all", moved, [&] {
       for (int k = 1; k < P && !e; ++k) {  // staggered: at any time every rank receives from one sender
         const int q = (me + k) % P;
         e = (int)cudaMemcpyAsync(pl.peer_base[q] + dst_off + (size_t)me * bytes, src + (size_t)q * g.blk, bytes, cudaMemcpyDeviceToDevice, c->cs);
       }
-      if (!e && src != dst) e = (int)cudaMemcpyAsync(dst + (size_t)me * g.blk, src + (size_t)me * g.blk, bytes, cudaMemcpyDeviceToDevice, c->cs);
-      for (int q = 0; q < P && !e; ++q)
-        if (q != me) e = d.WriteValue32(c->cs, pl.dev_addr(&pl.shm->arrived[q][dst_id][me]), n, kWriteDefault);
-      if (!c->ws)
-        for (int r = 0; r < P && !e; ++r)
-          if (r != me) e = d.WaitValue32(c->cs, pl.dev_addr(&pl.shm->arrived[me][dst_id][r]), n, kWaitGeq);
+      if (!e && !c->ws && src != dst) e = (int)cudaMemcpyAsync(dst + (size_t)me * g.blk, src + (size_t)me * g.blk, bytes, cudaMemcpyDeviceToDevice, c->cs);
     }, c->cs);
-    if (!e && c->ws) {  // the consumer needs my own block (copied on cs) and the blocks of my peers; cs itself moves on
-      cudaStreamWaitEvent(c->ws, mark(c, c->cs), 0);
-      launch(c, "all_to_all_arrival", 0.0, [&] {
-        for (int r = 0; r < P && !e; ++r)
-          if (r != me) e = d.WaitValue32(c->ws, pl.dev_addr(&pl.shm->arrived[me][dst_id][r]), n, kWaitGeq);
-      }, c->ws);
-      if (!e) {
-        c->comm_bytes += 8.0 * (double)g.blk * (P - 1);
-        *done = mark(c, c->ws);
-        return KW_OK;
-      }
-    }
+    launch(c, "all_to_all_arrival_wait", 0.0, [&] {
+      e = pl.flag_ops(c->cs, false, n, [&](int q) { return &pl.shm->arrived[q][dst_id][me]; });
+      if (!e) e = pl.flag_ops(c->cs, true, n, [&](int r) { return &pl.shm->arrived[me][dst_id][r]; });
+      if (self_done) cudaStreamWaitEvent(c->cs, self_done, 0);
+    }, c->cs);
     if (e) what = "peer-memory all-to-all: CUDA error " + std::to_string(e);
   } else {
     NcclApi& nc = nccl_api();
@@ -1064,9 +1060,8 @@ static int release_buffer(kw_ctx* c, int id, cudaStream_t s) {
   if (!c->peer.active) return KW_OK;
   PeerLink& pl = c->peer;
   const uint32_t n = pl.use[id];
-  for (int r = 0; r < pl.nranks; ++r)
-    if (r != pl.rank && drv_api().WriteValue32(s, pl.dev_addr(&pl.shm->credit[r][id][pl.rank]), n, kWriteDefault))
-      return fail(KW_ERR_COMM, "peer-memory all-to-all: cuStreamWriteValue32 failed");
+  if (pl.flag_ops(s, false, n, [&](int r) { return &pl.shm->credit[r][id][pl.rank]; }))
+    return fail(KW_ERR_COMM, "peer-memory all-to-all: cuStreamWriteValue32 failed");
   return KW_OK;
 }
 // blocking form used by the rarely taken paths (additive sources): result[f] = the buffers that hold the exchanged spectra
