@@ -152,6 +152,17 @@ int kw_set_source_row(kw_ctx* ctx, int array_id, uint64_t t_index, const float* 
 int kw_fft_r2c_3d(uint64_t nx, uint64_t ny, uint64_t nz, const float* host_real, float* host_complex);
 int kw_fft_c2r_3d(uint64_t nx, uint64_t ny, uint64_t nz, const float* host_complex, float* host_real);
 
+/* Checkpoint / restart (KSpaceFirstOrderSolver::saveCheckpointData cpp:1176-1224, recovery in loadInputData :186-228).
+ * The state of a run is t_index, the seven state arrays (kw_get_array / kw_set_array of KW_P, KW_RHO{X,Y,Z}, KW_U?_SG?, valid
+ * after kw_preprocess too) and, per enabled stream, what BaseOutputStream::checkpoint stores (OutputStreams/
+ * BaseOutputStream.cpp:528-606): the aggregate buffer, or the two compression accumulators (the reference's
+ * Temp_<name>_1/_2 datasets) with the sampled / compressed step counters.  The state blob is opaque; size 0 = the stream is
+ * not part of this run (internal do-not-save streams of I_avg_c DO have a state).  Buffered raw rows must be fetched first. */
+int kw_set_time_index(kw_ctx* ctx, uint64_t t_index);
+int kw_stream_state_size(kw_ctx* ctx, int stream_id, uint64_t* bytes);
+int kw_stream_state_get(kw_ctx* ctx, int stream_id, void* buffer, uint64_t bytes);
+int kw_stream_state_set(kw_ctx* ctx, int stream_id, const void* buffer, uint64_t bytes);
+
 /* Compression helpers.  kw_c40_encode / kw_c40_decode = CompressHelper::convertFloatCTo40b / convert40bToFloatC
  * (Compression/CompressHelper.cpp:292-389 / :224-290) on n complex values (interleaved re, im <-> 5 bytes each), run by the
  * device code the compressed streams use; max_exp = 138 (pressure) or 114 (velocity), CompressHelper.h:91-92.

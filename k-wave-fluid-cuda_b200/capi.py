@@ -126,6 +126,11 @@ def load_library():
         "kw_sensor_layout": [vp, C.POINTER(u64), C.POINTER(u64), vp, u64],
         "kw_comm_bytes": [vp, C.POINTER(C.c_double)],
         "kw_comm_mode": [vp, C.POINTER(C.c_int)],
+        "kw_set_time_index": [vp, u64],
+        "kw_stream_state_size": [vp, i32, C.POINTER(u64)],
+        "kw_stream_state_get": [vp, i32, vp, u64],
+        "kw_stream_state_set": [vp, i32, vp, u64],
+        "kw_device_memory": [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)],
         "kw_c40_encode": [vp, u64, i32, vp],
         "kw_c40_decode": [vp, u64, i32, vp],
         "kw_compression_bases": [vp, i32, vp, vp, u64, C.POINTER(u64), C.POINTER(u64)],
@@ -314,6 +319,29 @@ class Simulation:
         if local.value:
             _check(self.lib.kw_sensor_layout(self.ctx, C.byref(total), C.byref(local), pos.ctypes.data, pos.size))
         return total.value, pos
+
+    # -- checkpoint / restart -----------------------------------------------------------------------------------------
+    def save_state(self):
+        """Everything a restart needs (cpp:1176-1224): t_index, the seven state arrays, the state of every stream."""
+        st = {"t_index": self.t_index, "arrays": {n: self.get_array(n) for n in ("KW_P", "KW_RHOX", "KW_RHOY", "KW_RHOZ", "KW_UX_SGX", "KW_UY_SGY", "KW_UZ_SGZ")},
+              "streams": {}}
+        for name, sid in STREAM_IDS.items():
+            if name == "KW_STREAM_COUNT":
+                continue
+            n = C.c_uint64()
+            _check(self.lib.kw_stream_state_size(self.ctx, sid, C.byref(n)))
+            if n.value:
+                buf = np.empty(n.value, dtype=np.uint8)
+                _check(self.lib.kw_stream_state_get(self.ctx, sid, buf.ctypes.data, buf.size))
+                st["streams"][sid] = buf
+        return st
+
+    def load_state(self, st):
+        for n, a in st["arrays"].items():
+            self.set_array(n, a)
+        _check(self.lib.kw_set_time_index(self.ctx, st["t_index"]))
+        for sid, buf in st["streams"].items():
+            _check(self.lib.kw_stream_state_set(self.ctx, sid, buf.ctypes.data, buf.size))
 
     def compression_bases(self, shifted=False):
         """(oSize, bSize, bE, bE_1) as generated by the context (complex64, shape (harmonics, bSize))."""

@@ -1657,6 +1657,71 @@ int kw_time_index(kw_ctx* c, uint64_t* t) {
   *t = c->t;
   return KW_OK;
 }
+// ---- checkpoint / restart support (KSpaceFirstOrderSolver::saveCheckpointData cpp:1176-1224, loadInputData :186-228;
+//      BaseOutputStream::checkpoint / reopen, OutputStreams/BaseOutputStream.cpp:528-606) ------------------------------
+int kw_set_time_index(kw_ctx* c, uint64_t t) {
+  if (!c) return fail(KW_ERR_INVALID, "null context");
+  if (!c->preprocessed) return fail(KW_ERR_STATE, "kw_set_time_index before kw_preprocess");
+  if (t > c->cfg.nt) return fail(KW_ERR_INVALID, "time index beyond Nt");
+  c->t = t;
+  return KW_OK;
+}
+namespace {
+struct StreamStateHeader {
+  uint64_t magic, op, sampled, compressed, payload_bytes, reserved;
+};
+constexpr uint64_t kStateMagic = 0x4b57535452454d31ull;  // "KWSTREM1"
+size_t stream_payload_bytes(const kw_ctx* c, const Stream& s) {
+  if (s.op == kOpC) return s.acc_bytes * (s.acc2 != s.acc1 ? 2 : 1);
+  if (s.op == kOpNone) return 0;  // raw rows are flushed before a checkpoint
+  return s.row * sizeof(float);   // rms / max / min (+ _all) accumulators, I_avg_c
+}
+}  // namespace
+int kw_stream_state_size(kw_ctx* c, int sid, uint64_t* bytes) {
+  if (!c || !bytes || sid < 0 || sid >= KW_STREAM_COUNT) return fail(KW_ERR_INVALID, "bad argument");
+  if (!c->preprocessed) return fail(KW_ERR_STATE, "stream state before kw_preprocess");
+  const Stream& s = c->streams[sid];
+  *bytes = s.enabled ? sizeof(StreamStateHeader) + stream_payload_bytes(c, s) : 0;  // 0: stream does not exist in this run
+  return KW_OK;
+}
+int kw_stream_state_get(kw_ctx* c, int sid, void* buf, uint64_t bytes) {
+  uint64_t need = 0;
+  KW_TRY(kw_stream_state_size(c, sid, &need));
+  if (!buf || need == 0 || bytes < need) return fail(KW_ERR_INVALID, "kw_stream_state_get: stream not enabled or buffer too small");
+  Stream& s = c->streams[sid];
+  if (s.rows) return fail(KW_ERR_STATE, "kw_stream_state_get: fetch the buffered rows first");
+  KW_CUDA(cudaStreamSynchronize(c->st));
+  StreamStateHeader h{kStateMagic, (uint64_t)s.op, s.sampled, s.compressed, need - sizeof(StreamStateHeader), 0};
+  memcpy(buf, &h, sizeof h);
+  char* out = static_cast<char*>(buf) + sizeof h;
+  if (s.op == kOpC) {
+    KW_CUDA(cudaMemcpy(out, s.acc1, s.acc_bytes, cudaMemcpyDeviceToHost));
+    if (s.acc2 != s.acc1) KW_CUDA(cudaMemcpy(out + s.acc_bytes, s.acc2, s.acc_bytes, cudaMemcpyDeviceToHost));
+  } else if (h.payload_bytes) {
+    KW_CUDA(cudaMemcpy(out, s.dbuf, h.payload_bytes, cudaMemcpyDeviceToHost));
+  }
+  return KW_OK;
+}
+int kw_stream_state_set(kw_ctx* c, int sid, const void* buf, uint64_t bytes) {
+  uint64_t need = 0;
+  KW_TRY(kw_stream_state_size(c, sid, &need));
+  if (!buf || need == 0 || bytes < need) return fail(KW_ERR_INVALID, "kw_stream_state_set: stream not enabled or state too short");
+  Stream& s = c->streams[sid];
+  StreamStateHeader h;
+  memcpy(&h, buf, sizeof h);
+  if (h.magic != kStateMagic || h.op != (uint64_t)s.op || h.payload_bytes != need - sizeof h)
+    return fail(KW_ERR_INVALID, "kw_stream_state_set: the state was saved by a different stream configuration");
+  s.sampled = h.sampled, s.compressed = h.compressed, s.rows = 0;
+  const char* in = static_cast<const char*>(buf) + sizeof h;
+  if (s.op == kOpC) {
+    KW_CUDA(cudaMemcpy(s.acc1, in, s.acc_bytes, cudaMemcpyHostToDevice));
+    if (s.acc2 != s.acc1) KW_CUDA(cudaMemcpy(s.acc2, in + s.acc_bytes, s.acc_bytes, cudaMemcpyHostToDevice));
+  } else if (h.payload_bytes) {
+    KW_CUDA(cudaMemcpy(s.dbuf, in, h.payload_bytes, cudaMemcpyHostToDevice));
+  }
+  return KW_OK;
+}
+
 int kw_synchronize(kw_ctx* c) {
   if (!c) return fail(KW_ERR_INVALID, "null context");
   KW_CUDA(cudaStreamSynchronize(c->st));

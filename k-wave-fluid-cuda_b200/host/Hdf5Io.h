@@ -5,6 +5,8 @@
 #include <hdf5.h>
 #include <hdf5_hl.h>
 
+#include <unistd.h>
+
 #include <cstdint>
 #include <ios>
 #include <string>
@@ -43,7 +45,18 @@ class Hdf5File {
     if (g < 0) throw std::ios::failure("Error: cannot create group \"" + name + "\".");
     return g;
   }
+  hid_t openGroup(hid_t loc, const std::string& name) {
+    const hid_t g = H5Gopen(loc, name.c_str(), H5P_DEFAULT);
+    if (g < 0) throw std::ios::failure("Error: cannot open group \"" + name + "\" of \"" + mName + "\".");
+    return g;
+  }
   void closeGroup(hid_t g) { H5Gclose(g); }
+  hid_t openDataset(hid_t loc, const std::string& name) {
+    const hid_t d = H5Dopen(loc, name.c_str(), H5P_DEFAULT);
+    if (d < 0) throw std::ios::failure("Error: cannot open dataset \"" + name + "\" of \"" + mName + "\".");
+    return d;
+  }
+  static bool canAccess(const std::string& name) { return access(name.c_str(), F_OK) == 0; }  // Hdf5File::canAccess
 
   // number of elements of a dataset (any rank)
   uint64_t elementCount(hid_t loc, const std::string& name) const {

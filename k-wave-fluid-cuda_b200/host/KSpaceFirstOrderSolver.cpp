@@ -201,7 +201,17 @@ void KSpaceFirstOrderSolver::loadInputData() {
     for (size_t k = 0; k < mCorners.size(); k += 6)
       mSensorPoints += (mCorners[k + 3] - mCorners[k] + 1) * (mCorners[k + 4] - mCorners[k + 1] + 1) * (mCorners[k + 5] - mCorners[k + 2] + 1);
   }
-  mOutputFile.create(mCmd.outputFile);  // cpp:230-235
+  // cpp:185-240: a run with checkpointing enabled whose checkpoint file exists continues that run
+  mRecover = mCmd.isCheckpointEnabled() && Hdf5File::canAccess(mCmd.checkpointFile);
+  if (mRecover) {
+    if (!Hdf5File::canAccess(mCmd.outputFile)) throw std::ios::failure("Error: The output file of the checkpointed run \"" + mCmd.outputFile + "\" is missing.");
+    mOutputFile.open(mCmd.outputFile, false);
+    const std::string type = mOutputFile.getStringAttribute(mOutputFile.root(), "/", "file_type");
+    if (type != "output") throw std::ios::failure("Error: \"" + mCmd.outputFile + "\" is not an output file of a checkpointed run.");
+  } else {
+    mOutputFile.create(mCmd.outputFile);  // cpp:230-235
+  }
+  mStepsToCheckpoint = mCmd.checkpointTimeSteps ? mCmd.checkpointTimeSteps : ~0ull;  // Parameters.cpp:147-151
   mDataLoadTime.stop();
 }
 
@@ -266,12 +276,16 @@ void KSpaceFirstOrderSolver::createOutputDatasets() {
       const hsize_t width = rowFloats;
       const std::vector<hsize_t> dims = series ? std::vector<hsize_t>{1, nRows, width} : std::vector<hsize_t>{1, 1, width};
       std::vector<hsize_t> chunk = {1, 1, width > (1ull << 23) ? (1ull << 20) : width};
-      st.dataset = mOutputFile.createDataset(root, st.name, dims, chunk, true, deflate);
-      if (st.kind == K::kCompressed) compressionAttributes(root, st.name);
+      if (mRecover) {
+        st.dataset = mOutputFile.openDataset(root, st.name);  // IndexOutputStream::reopen (:177-247)
+      } else {
+        st.dataset = mOutputFile.createDataset(root, st.name, dims, chunk, true, deflate);
+        if (st.kind == K::kCompressed) compressionAttributes(root, st.name);
+      }
     } else {  // CuboidOutputStream::create (:80-150): group /<name>, one dataset per cuboid named 1..Ncub
       if (st.kind == K::kCompressed && mCmd.c40bit)
         throw std::invalid_argument("Error: --40-bit_complex with a cuboid sensor mask is not available in this build.");
-      st.group = mOutputFile.createGroup(root, st.name);
+      st.group = mRecover ? mOutputFile.openGroup(root, st.name) : mOutputFile.createGroup(root, st.name);
       const uint64_t factor = st.kind == K::kCompressed ? 2 * mCmd.harmonics : 1;
       for (size_t k = 0; k < mCorners.size() / 6; ++k) {
         const uint64_t* c = &mCorners[6 * k];
@@ -284,6 +298,10 @@ void KSpaceFirstOrderSolver::createOutputDatasets() {
           hsize_t slabs = 1;
           while (slabs * cx * cy < (1ull << 20)) ++slabs;
           chunk[series ? 1 : 0] = std::min<hsize_t>(slabs, cz);
+        }
+        if (mRecover) {
+          st.cuboidDatasets.push_back(mOutputFile.openDataset(st.group, name));  // CuboidOutputStream::reopen (:156-257)
+          continue;
         }
         st.cuboidDatasets.push_back(mOutputFile.createDataset(st.group, name, dims, chunk, true, deflate));
         if (st.kind == K::kCompressed) compressionAttributes(st.group, name);
@@ -415,6 +433,77 @@ void KSpaceFirstOrderSolver::writeOutputHeader() {  // Hdf5FileHeader (Hdf5/Hdf5
   o.setStringAttribute(root, "/", "post-processing_phase_execution_time", formatSeconds(getPostProcessingTime()));
 }
 
+bool KSpaceFirstOrderSolver::isTimeToCheckpoint() const {  // Parameters::isTimeToCheckpoint (Parameters.cpp:683-692)
+  if (!mCmd.isCheckpointEnabled()) return false;
+  TimeMeasure t = mTotalTime;
+  t.stop();
+  return mStepsToCheckpoint == 0 || (mCmd.checkpointInterval > 0 && t.getElapsedTime() > (double)mCmd.checkpointInterval);
+}
+
+namespace {
+const struct { const char* name; int id; } kCheckpointArrays[] = {  // the kCheckpoint records, Containers/MatrixContainer.cpp:101-115
+    {"p", KW_P}, {"ux_sgx", KW_UX_SGX}, {"uy_sgy", KW_UY_SGY}, {"uz_sgz", KW_UZ_SGZ}, {"rhox", KW_RHOX}, {"rhoy", KW_RHOY}, {"rhoz", KW_RHOZ}};
+}
+
+void KSpaceFirstOrderSolver::saveCheckpointData() {
+  const FileScalars& s = mScalars;
+  Hdf5File ck;
+  ck.create(mCmd.checkpointFile);  // overwrites the one of the previous leg
+  const hid_t root = ck.root();
+  std::vector<float> field(s.nx * s.ny * s.nz);
+  for (const auto& a : kCheckpointArrays) {
+    check(kw_get_array(mCtx, a.id, field.data(), field.size()));
+    ck.writeWhole(root, a.name, {s.nz, s.ny, s.nx}, {1, s.ny, s.nx}, field.data(), true, mCmd.compressionLevel);
+  }
+  ck.writeScalar(root, "t_index", (uint64_t)timeIndex());
+  ck.writeScalar(root, "Nx", s.nx), ck.writeScalar(root, "Ny", s.ny), ck.writeScalar(root, "Nz", s.nz);
+  // stream state (OutputStreamContainer::checkpointStreams): aggregate buffers, compression accumulators, step counters,
+  // and how many rows of each series are already in the output file
+  for (int sid = 0; sid < KW_STREAM_COUNT; ++sid) {
+    uint64_t bytes = 0;
+    check(kw_stream_state_size(mCtx, sid, &bytes));
+    if (!bytes) continue;
+    std::vector<float> blob((bytes + 3) / 4, 0.f);
+    check(kw_stream_state_get(mCtx, sid, blob.data(), bytes));
+    const std::string name = "Temp_stream_" + std::to_string(sid);
+    ck.writeWhole(root, name, {1, 1, blob.size()}, {}, blob.data(), true, 0);
+    ck.setLongLongAttribute(root, name, "state_bytes", (long long)bytes);
+  }
+  for (const auto& st : mStreams) ck.writeScalar(root, "Temp_rows_" + std::to_string(st.id), (uint64_t)st.rowsWritten);
+  ck.setStringAttribute(root, "/", "created_by", getCodeName());
+  ck.setStringAttribute(root, "/", "file_type", "checkpoint");
+  ck.setStringAttribute(root, "/", "major_version", "1");
+  ck.setStringAttribute(root, "/", "minor_version", "1");
+  ck.close();
+}
+
+void KSpaceFirstOrderSolver::recoverFromCheckpoint() {
+  const FileScalars& s = mScalars;
+  Hdf5File ck;
+  ck.open(mCmd.checkpointFile, true);
+  const hid_t root = ck.root();
+  if (ck.getStringAttribute(root, "/", "file_type") != "checkpoint") throw std::ios::failure("Error: \"" + mCmd.checkpointFile + "\" is not a checkpoint file.");
+  if (ck.readIndexScalar(root, "Nx") != s.nx || ck.readIndexScalar(root, "Ny") != s.ny || ck.readIndexScalar(root, "Nz") != s.nz)
+    throw std::ios::failure("Error: The checkpoint file was created for a different domain size (cpp:2846-2890).");
+  for (const auto& a : kCheckpointArrays) {
+    const auto v = ck.readFloats(root, a.name);
+    check(kw_set_array(mCtx, a.id, v.data(), v.size()));
+  }
+  check(kw_set_time_index(mCtx, ck.readIndexScalar(root, "t_index")));
+  for (int sid = 0; sid < KW_STREAM_COUNT; ++sid) {
+    uint64_t bytes = 0;
+    check(kw_stream_state_size(mCtx, sid, &bytes));
+    if (!bytes) continue;
+    const std::string name = "Temp_stream_" + std::to_string(sid);
+    if (!ck.exists(root, name)) throw std::ios::failure("Error: The checkpoint file was created with different output flags (" + name + " is missing).");
+    const auto blob = ck.readFloats(root, name);
+    check(kw_stream_state_set(mCtx, sid, blob.data(), blob.size() * sizeof(float)));
+  }
+  for (auto& st : mStreams) st.rowsWritten = ck.readIndexScalar(root, "Temp_rows_" + std::to_string(st.id));
+  ck.close();
+  log(1, "Recovered from the checkpoint at time step %llu\n", (unsigned long long)timeIndex());
+}
+
 uint64_t KSpaceFirstOrderSolver::timeIndex() const {
   uint64_t t = 0;
   if (mCtx) kw_time_index(mCtx, &t);
@@ -443,14 +532,20 @@ void KSpaceFirstOrderSolver::compute() {
   mPreProcessingTime.stop();
   log(1, "Pre-processing phase: %s, device memory in use: %zu MB\n", formatSeconds(getPreProcessingTime()).c_str(), getDeviceMemoryUsage() >> 20);
 
-  // computeMainLoop (cpp:864-943): the library runs until Nt or until a device-side row buffer is full
+  if (mRecover) recoverFromCheckpoint();
+
+  // computeMainLoop (cpp:864-943): the library runs until Nt, until a device-side row buffer is full, or until it is time
+  // to checkpoint (cpp:885)
   mSimulationTime.start();
   const uint64_t nt = mScalars.nt;
   uint64_t nextReport = 0;
-  while (timeIndex() < nt) {
+  while (timeIndex() < nt && !isTimeToCheckpoint()) {
     uint64_t done = 0;
-    const uint64_t chunk = std::max<uint64_t>(1, nt * (uint64_t)mCmd.progressInterval / 100);
-    const int status = kw_run(mCtx, std::min<uint64_t>(chunk, nt - timeIndex()), &done, 1);
+    uint64_t chunk = std::max<uint64_t>(1, nt * (uint64_t)mCmd.progressInterval / 100);
+    chunk = std::min<uint64_t>(chunk, nt - timeIndex());
+    if (mCmd.checkpointTimeSteps) chunk = std::min<uint64_t>(chunk, mStepsToCheckpoint);
+    const int status = kw_run(mCtx, chunk, &done, 1);
+    mStepsToCheckpoint -= std::min<uint64_t>(done, mStepsToCheckpoint);  // Parameters::incrementTimeIndex (:698-702)
     if (status == KW_ERR_STREAM_FULL) {
       flushSeries(false);
       continue;
@@ -464,7 +559,18 @@ void KSpaceFirstOrderSolver::compute() {
   check(kw_synchronize(mCtx));
   flushSeries(true);
   mSimulationTime.stop();
-  log(1, "Simulation phase: %s (%llu steps)\n", formatSeconds(getSimulationTime()).c_str(), (unsigned long long)nt);
+  log(1, "Simulation phase: %s (%llu of %llu steps)\n", formatSeconds(getSimulationTime()).c_str(), (unsigned long long)timeIndex(), (unsigned long long)nt);
+
+  if (timeIndex() < nt) {  // interrupted to checkpoint (cpp:373-398): store the state, keep the output file for the next leg
+    mPostProcessingTime.start();
+    saveCheckpointData();
+    mPostProcessingTime.stop();
+    mTotalTime.stop();
+    writeOutputHeader();
+    mOutputFile.close();
+    log(1, "Checkpoint created after %llu time steps; run the same command again to continue.\n", (unsigned long long)timeIndex());
+    return;
+  }
 
   // postProcessing (cpp:950-973) + writeOutputDataInfo (cpp:1099-1168)
   mPostProcessingTime.start();
@@ -475,6 +581,7 @@ void KSpaceFirstOrderSolver::compute() {
   mTotalTime.stop();
   writeOutputHeader();
   mOutputFile.close();
+  if (mCmd.isCheckpointEnabled()) std::remove(mCmd.checkpointFile.c_str());  // cpp:409-413
   log(1, "Post-processing phase: %s, total: %s\n", formatSeconds(getPostProcessingTime()).c_str(), formatSeconds(getTotalTime()).c_str());
 }
 

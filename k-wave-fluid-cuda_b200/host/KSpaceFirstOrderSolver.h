@@ -84,6 +84,9 @@ class KSpaceFirstOrderSolver {
   void loadArray(const std::string& name, int arrayId, bool isIndex, bool required);
   void createStreams();
   void createOutputDatasets();
+  bool isTimeToCheckpoint() const;   // Parameters::isTimeToCheckpoint (Parameters.cpp:683-692)
+  void saveCheckpointData();         // cpp:1176-1224
+  void recoverFromCheckpoint();      // cpp:186-228 (state) + OutputStreamContainer::reopenStreams
   void flushSeries(bool final);
   void writeAggregates();
   void writeOutputHeader();
@@ -101,6 +104,9 @@ class KSpaceFirstOrderSolver {
   uint64_t mCompressedSteps = 0;
   uint64_t mRowsCapacity = 0;
   std::vector<float> mRowBuffer;
+  bool mRecover = false;             // a checkpoint file exists: continue that run
+  uint64_t mStepsToCheckpoint = 0;   // Parameters::mTimeStepsToCheckpoint
+  double mElapsedBefore[5] = {};     // total, load, pre-processing, simulation, post-processing of the previous legs
   size_t mHostBytes = 0;
   TimeMeasure mTotalTime, mPreProcessingTime, mDataLoadTime, mSimulationTime, mPostProcessingTime;
 };

@@ -14,8 +14,9 @@ std::string CommandLine::usage() {
          "  -p|--p_raw --p_c --p_rms --p_max --p_min --p_max_all --p_min_all --p_final\n"
          "  -u|--u_raw --u_c --u_non_staggered_raw --u_non_staggered_c --u_rms --u_max --u_min --u_max_all --u_min_all --u_final\n"
          "  --I_avg_c  --period <steps> | --frequency <Hz>  --mos <n>  --harmonics <n>  --no_overlap  --40-bit_complex\n"
+         "  --checkpoint_file <file> with --checkpoint_interval <seconds> and/or --checkpoint_timesteps <steps>\n"
          "  -h|--help  --version\n"
-         "Not available in this build: --checkpoint_file/_interval/_timesteps, --I_avg, --Q_term, --Q_term_c, --post\n";
+         "Not available in this build: --I_avg, --Q_term, --Q_term_c, --post\n";
 }
 
 static long toLong(const char* s, const char* what, long minValue) {
@@ -71,7 +72,9 @@ void CommandLine::parse(int argc, char** argv) {
       case 's': samplingStartIndex = (uint64_t)toLong(optarg, "-s (must be >= 1)", 1) - 1; break;  // 1-based on the command line
       case 1: benchmark = true; benchmarkSteps = (uint64_t)toLong(optarg, "--benchmark", 1); break;
       case 2: copySensorMask = true; break;
-      case 3: case 4: case 5: throw std::invalid_argument("Error: checkpoint / restart (--checkpoint_*) is not available in this build.");
+      case 3: checkpointFile = optarg; break;
+      case 4: checkpointInterval = (uint64_t)toLong(optarg, "--checkpoint_interval", 1); break;
+      case 5: checkpointTimeSteps = (uint64_t)toLong(optarg, "--checkpoint_timesteps", 1); break;
       case 6: verbose = (int)toLong(optarg, "--verbose (0-2)", 0); if (verbose > 2) throw std::invalid_argument("Error: Invalid value of --verbose (0-2)."); break;
       case 7: printVersion = true; break;
       case 9: pC = true; break;
@@ -107,6 +110,9 @@ void CommandLine::parse(int argc, char** argv) {
   // validation (CommandLineParameters.cpp:888-947)
   if (inputFile.empty()) throw std::invalid_argument("Error: Input file was not specified.");
   if (outputFile.empty()) throw std::invalid_argument("Error: Output file was not specified.");
+  if (isCheckpointEnabled() && checkpointFile.empty()) throw std::invalid_argument("Error: Checkpoint file was not specified.");  // :905-913
+  if (!checkpointFile.empty() && !isCheckpointEnabled())
+    throw std::invalid_argument("Error: Checkpoint interval or the number of time steps to checkpoint was not specified.");
   if (anyCompressed() && period == 0.f && frequency == 0.f)
     throw std::invalid_argument("Error: Compression (--p_c, --u_c, --u_non_staggered_c, --I_avg_c) needs --period or --frequency.");
   // nothing selected: this fork of the reference stores nothing (CommandLineParameters.cpp:938-947 sets

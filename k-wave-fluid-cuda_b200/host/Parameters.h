@@ -1,7 +1,7 @@
 // Command-line flags and input-file scalars of the solver.  Flag names, meaning and validation follow the reference
 // (Parameters/CommandLineParameters.cpp:264-292, :888-964; Parameters/Parameters.cpp:111-163, :194-553): a run
 // scripted for kspaceFirstOrder-CUDA is accepted unchanged.  Flags whose feature lies outside the time-step hot path
-// (checkpointing, raw-series post-processing) are recognised and rejected with an explicit message.
+// (raw-series post-processing: --I_avg, --Q_term, --Q_term_c, --post) are recognised and rejected with an explicit message.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -14,6 +14,9 @@ struct CommandLine {
   int gpuDevice = -1;         // -g
   long progressInterval = 5;  // -r
   unsigned compressionLevel = 0;  // -c
+  uint64_t checkpointInterval = 0;   // --checkpoint_interval <seconds>
+  uint64_t checkpointTimeSteps = 0;  // --checkpoint_timesteps <steps>
+  bool isCheckpointEnabled() const { return checkpointInterval > 0 || checkpointTimeSteps > 0; }  // CommandLineParameters.h:348
   bool benchmark = false;
   uint64_t benchmarkSteps = 0;
   uint64_t samplingStartIndex = 0;  // -s, stored 0-based (CommandLineParameters.cpp:424)

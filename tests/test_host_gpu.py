@@ -102,3 +102,41 @@ def test_no_gpu_means_error_exit_not_cpu_fallback(synth, tmp_path):
     kwh5.write_input(fin, cfg, arrays)
     r = subprocess.run([OURS, "-i", fin, "-o", str(tmp_path / "o.h5")], capture_output=True, text=True)
     assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sensor", ["index", "cuboid"])
+def test_checkpoint_restart_is_bit_identical(synth, tmp_path, sensor):
+    """--checkpoint_file / --checkpoint_timesteps (KSpaceFirstOrderSolver.cpp:1176-1224, :186-228): a run interrupted twice and
+    resumed with the same command line writes the same output file, bit for bit, as the uninterrupted run -- raw series,
+    aggregates, compressed frames (accumulators live across the interruption), intensities, final fields."""
+    assert os.path.exists(OURS), "kspaceFirstOrder-B200 not built (__graft_entry__.build())"
+    nt = 130
+    kwargs = dict(nonlinear=True, absorbing=True, source="p_plane", n_sensor=48, period=20, shifts=True)
+    if sensor == "cuboid":
+        kwargs["sensor"] = "cuboid"
+    cfg, arrays = synth.make_case(32, nt=nt, **kwargs)
+    fin = str(tmp_path / "in.h5")
+    kwh5.write_input(fin, cfg, arrays)
+    flags = ["-p", "--p_rms", "--p_max", "--p_max_all", "--p_final", "--u_final", "--p_c", "--I_avg_c", "--u_non_staggered_raw", "--u_max",
+             "--period", "20", "--harmonics", "2", "-s", "4"]  # fmt: skip
+    whole = run(OURS, fin, str(tmp_path / "whole.h5"), flags)
+    ck, out = str(tmp_path / "ck.h5"), str(tmp_path / "legs.h5")
+    legs = 0
+    while True:
+        r = subprocess.run([OURS, "-i", fin, "-o", out, "-t", "4", "--verbose", "0", "--checkpoint_file", ck, "--checkpoint_timesteps", "47"] + flags,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        legs += 1
+        if not os.path.exists(ck):
+            break
+        assert legs < 5
+        assert kwh5.read_root_attrs(ck)["file_type"] == "checkpoint"
+    assert legs == 3  # 47 + 47 + 36 steps
+    got = kwh5.read_file(out)
+    assert set(got) == set(whole)
+    for p, o in whole.items():
+        if o["kind"] == "group":
+            continue
+        assert np.array_equal(got[p]["data"].view(np.uint32) if o["kind"] == "f32" else got[p]["data"],
+                              o["data"].view(np.uint32) if o["kind"] == "f32" else o["data"]), p
