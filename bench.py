@@ -247,6 +247,8 @@ def main():
     # ---- N > 1: BASELINE.json configs[4]: ONE grid slab-decomposed along z over the ranks, all-to-all FFT transposes
     pml = 20 if N >= 128 else None
     slab_kw, sim_kw = {}, {}
+    if N >= 1024 and not sharded:
+        slab_kw = dict(medium="waves")  # the analytic medium: the low-passed noise of 1024^3 needs > 100 GB of host memory and minutes
 
     def fresh_comm_id():  # one ncclUniqueId per context: created on rank 0, handed to every rank
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -382,7 +384,9 @@ def main():
                    "grid": [N, N, N], "l2_policy": "inputs larger than L2 (every field >= 512 MiB per GPU)" if N**3 // (world if sharded else 1) >= 512**3 else
                    "working set partly L2 resident at this size",
                    "parallelism": "1 GPU" if world == 1 else (f"z-slabs over {world} GPUs" if sharded else f"{world} independent replicas"),
-                   "wall_ms_timed_region": wall_ms, "host_enqueue_ms_per_step": host_enqueue_ms},
+                   "wall_ms_timed_region": wall_ms, "host_enqueue_ms_per_step": host_enqueue_ms,
+                   "same_grid_on_one_gpu": ("1024^3 on ONE B200 (python bench.py --size 1024): 113.3 ms/step = 9475 Mvoxel-steps/s, "
+                                            "profiles/r01_o_bench_1024_1gpu.json" if sharded and N == 1024 else None)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }  # fmt: skip
     if sharded and "all_to_all" in prof:
