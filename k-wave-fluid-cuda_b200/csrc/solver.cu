@@ -128,8 +128,10 @@ struct Geometry {
   RowMap row_map() const { return RowMap{ny_log2, ysh, blk}; }
   int init(uint64_t nx_, uint64_t ny_, uint64_t nz_, int rank_ = 0, int nranks_ = 1) {
     nx = (int)nx_, ny = (int)ny_, nz = (int)nz_;
-    ox = get_fft_ops(nx), oy = get_fft_ops(ny), oz = get_fft_ops(nz);
-    if (!ox || !oy || !oz)
+    // Nz == 1 (2-D simulations, Parameters.h:88-94): the z transforms are identities; everything else is the 3-D path with a
+    // z extent of one (the z components stay exactly zero, so the sums of the reference's 2-D kernels are reproduced)
+    ox = get_fft_ops(nx), oy = get_fft_ops(ny), oz = nz == 1 ? nullptr : get_fft_ops(nz);
+    if (!ox || !oy || (!oz && nz != 1))
       return fail(KW_ERR_INVALID, "grid sizes must be powers of two in [16,1024] (hand-written FFT plan table); got " +
                                       std::to_string(nx_) + "x" + std::to_string(ny_) + "x" + std::to_string(nz_));
     rank = rank_, nranks = nranks_ < 1 ? 1 : nranks_;
@@ -149,7 +151,7 @@ struct Geometry {
     blk = (size_t)nxp * nyl * nzl;
     KW_TRY(twiddle_table(nx, &tx));
     KW_TRY(twiddle_table(ny, &ty));
-    KW_TRY(twiddle_table(nz, &tz));
+    if (nz > 1) KW_TRY(twiddle_table(nz, &tz));
     return KW_OK;
   }
 };
@@ -425,7 +427,8 @@ int kw_ctx_create(const kw_config* cfg, kw_ctx** out) {
   if (cfg->abi_version != KW_ABI_VERSION || cfg->struct_size != sizeof(kw_config))
     return fail(KW_ERR_INVALID, "kw_config ABI mismatch");
   if (cfg->nonuniform_grid_flag) return fail(KW_ERR_INVALID, "nonuniform_grid_flag must be 0 (main.cpp:460)");
-  if (cfg->nz <= 1) return fail(KW_ERR_INVALID, "2-D simulations (Nz == 1) are not supported by this build");
+  if (cfg->nz < 1) return fail(KW_ERR_INVALID, "Nz must be at least 1");
+  if (cfg->nz == 1 && cfg->nranks > 1) return fail(KW_ERR_INVALID, "2-D simulations (Nz == 1) run on one GPU");
   if (cfg->absorbing_flag && cfg->alpha_power == 1.0f)
     return fail(KW_ERR_INVALID, "alpha_power == 1 is not supported (Parameters.cpp:421-424)");
   if (cfg->nranks > 1 && !cfg->nccl_unique_id) return fail(KW_ERR_INVALID, "nranks > 1 needs the shared ncclUniqueId (kw_nccl_unique_id)");
@@ -637,6 +640,16 @@ int kw_preprocess(kw_ctx* c) {
       c->count[id] = h.size();
     }
     KW_CUDA(cudaStreamSynchronize(c->st));
+  }
+  // --- Nz == 1: the input file of a 2-D simulation has no z arrays (main.cpp:446-563); give the 3-D path neutral ones
+  if (g.nz == 1) {
+    const float one = 1.0f, zero2[2] = {0.f, 0.f};
+    for (int id : {KW_PML_Z, KW_PML_Z_SGZ})
+      if (!c->d[id]) KW_TRY(upload_f(c, id, &one, 1));
+    for (int id : {KW_DDZ_K_SHIFT_POS, KW_DDZ_K_SHIFT_NEG})
+      if (!c->d[id]) KW_TRY(upload_f(c, id, zero2, 2));
+    if (c->h_in[KW_RHO0_SGZ].empty()) c->h_in[KW_RHO0_SGZ].assign(1, 1.0f);
+    if (c->h_in[KW_Z_SHIFT_NEG_R].empty() && !c->h_in[KW_X_SHIFT_NEG_R].empty()) c->h_in[KW_Z_SHIFT_NEG_R] = {1.0f, 0.0f};
   }
   // --- 2. dt / rho0_sg (cpp:825-830)
   for (int k = 0; k < 3; ++k) {
@@ -1080,9 +1093,35 @@ static int exchange(kw_ctx* c, float2* const* src, float2* const* dst, int nf, f
   return KW_OK;
 }
 
+// Nz == 1: out = (in * (mul * scal)) (x) vec[coordinate of the axis]; the z-indexed operator has one entry
+struct ZMulArgs {
+  ZField f;
+  int axis, nxp;
+  size_t n;  // NXP * Ny
+};
+static __global__ void k_zmul(ZMulArgs a) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) {
+    const int kx = (int)(i % a.nxp), y = (int)(i / a.nxp);
+    const float2 e = cscale(a.f.in[i], a.f.mul ? a.f.mul[i] * a.f.scal : a.f.scal);
+    if (a.axis == 3) {
+      a.f.out[i] = cmul(e, a.f.vec[kx]);
+      a.f.out_y[i] = cmul(e, a.f.vec_y[y]);
+      a.f.out_z[i] = cmul(e, a.f.vec_z[0]);
+    } else {
+      a.f.out[i] = a.axis < 0 ? e : cmul(e, a.f.vec[a.axis == 0 ? kx : a.axis == 1 ? y : 0]);
+    }
+  }
+}
+
 // one fused z pass per field on the z-local side (axis < 0: no 1-D operator)
 static void zmid_launch(kw_ctx* c, ZField f, int axis) {
   const Geometry& g = c->g;
+  if (g.nz == 1) {  // 2-D: forward z, operator, inverse z collapse to the operator
+    ZMulArgs ma{f, axis, g.nxp, (size_t)g.nxp * g.ny};
+    launch(c, axis == 3 ? "zmul_grad" : "zmul", (axis == 3 ? 32.0 : 16.0) * g.nc + (f.mul ? 4.0 * g.nc : 0.0),
+           [&] { k_zmul<<<ew_grid(ma.n), 256, 0, c->st>>>(ma); });
+    return;
+  }
   ZMidArgs za{};
   // the ky-indexed operators are looked up with the local ky: shift them to this rank's range
   if (axis == 1 && f.vec) f.vec += g.y0;
@@ -1432,7 +1471,7 @@ static int step(kw_ctx* c) {
   // ---- addInitialPressureSource (cpp:2359-2396)
   if (t == 0 && cf.p0_source_flag == 1) {
     launch(c, "initial_pressure", 24.0 * g.n, [&] {
-      k_initial_pressure<<<ew_grid(g.n), 256, 0, c->st>>>(c->d[KW_P], rho[0], rho[1], rho[2], c->d[KW_P0_SOURCE_INPUT], c->fld(KW_C0), g.n);
+      k_initial_pressure<<<ew_grid(g.n), 256, 0, c->st>>>(c->d[KW_P], rho[0], rho[1], rho[2], c->d[KW_P0_SOURCE_INPUT], c->fld(KW_C0), g.n, g.nz == 1 ? 2 : 3);
     });
     KW_TRY(pressure_gradient_spectra(c, sp));
     const EpiVelocity e = velocity_epilogue(c, u, fd, 1);
@@ -1607,7 +1646,7 @@ static int step_sharded(kw_ctx* c) {
   // ---- addInitialPressureSource (cpp:2359-2396)
   if (t == 0 && cf.p0_source_flag == 1) {
     launch(c, "initial_pressure", 24.0 * g.n, [&] {
-      k_initial_pressure<<<ew_grid(g.n), 256, 0, c->st>>>(c->d[KW_P], rho[0], rho[1], rho[2], c->d[KW_P0_SOURCE_INPUT], c->fld(KW_C0), g.n);
+      k_initial_pressure<<<ew_grid(g.n), 256, 0, c->st>>>(c->d[KW_P], rho[0], rho[1], rho[2], c->d[KW_P0_SOURCE_INPUT], c->fld(KW_C0), g.n, g.nz == 1 ? 2 : 3);
     });
     KW_TRY(velocity_phase(1, false));
   }
@@ -1934,21 +1973,21 @@ static int fft3d_host(uint64_t nx, uint64_t ny, uint64_t nz, const float* in, fl
   ColArgs cy{}, cz{};
   cy.data[0] = cz.data[0] = dspec;
   cy.stride = g.nxp, cy.outer_stride = (size_t)g.ny * g.nxp, cy.ngroups = g.nxp / g.oy->col_w, cy.tile_begin = 0, cy.tile_end = g.nz * cy.ngroups;
-  cz.stride = (size_t)g.ny * g.nxp, cz.outer_stride = g.nxp, cz.ngroups = g.nxp / g.oz->col_w, cz.tile_begin = 0, cz.tile_end = g.ny * cz.ngroups;
+  if (g.nz > 1) cz.stride = (size_t)g.ny * g.nxp, cz.outer_stride = g.nxp, cz.ngroups = g.nxp / g.oz->col_w, cz.tile_begin = 0, cz.tile_end = g.ny * cz.ngroups;
   if (forward) {
     KW_CUDA(cudaMemcpy(dreal, in, g.n * sizeof(float), cudaMemcpyHostToDevice));
     XFwdArgs xa{};
     xa.in[0] = dreal, xa.out[0] = dspec, xa.tab = g.tx, xa.pair_begin = 0, xa.pair_end = (int)(rows / 2), xa.nxp = g.nxp, xa.map = g.row_map();
     g.ox->xfwd(xa, 1, 0);
     g.oy->col(cy, -1, 1, 0);
-    g.oz->col(cz, -1, 1, 0);
+    if (g.nz > 1) g.oz->col(cz, -1, 1, 0);
     k_pad_complex<<<ew_grid(g.nc), 256>>>(dnat, dspec, g.nxr, g.nxp, rows, 0);
     KW_CUDA(cudaGetLastError());
     KW_CUDA(cudaMemcpy(out, dnat, rows * g.nxr * sizeof(float2), cudaMemcpyDeviceToHost));
   } else {
     KW_CUDA(cudaMemcpy(dnat, in, rows * g.nxr * sizeof(float2), cudaMemcpyHostToDevice));
     k_pad_complex<<<ew_grid(g.nc), 256>>>(dspec, dnat, g.nxr, g.nxp, rows, 1);
-    g.oz->col(cz, +1, 1, 0);
+    if (g.nz > 1) g.oz->col(cz, +1, 1, 0);
     g.oy->col(cy, +1, 1, 0);
     XInvArgs<1> xa{};
     xa.in[0] = dspec, xa.tab = g.tx, xa.pair_begin = 0, xa.pair_end = (int)(rows / 2), xa.nxp = g.nxp, xa.ny = g.ny, xa.map = g.row_map();

@@ -382,13 +382,15 @@ static __global__ void k_insert_source(float* grid, const float* signal, const u
     grid[index[j]] = many ? signal[base + (pos ? pos[j] : j)] : signal[base];
 }
 // p = p0 ; rho_i = p0 / (3*c2)   (SolverCudaKernels.cu:870-883)
-static __global__ void k_initial_pressure(float* p, float* rx, float* ry, float* rz, const float* p0, Fld c2, size_t n) {
+// dims = 3, or 2 for Nz == 1 where rho = p0 / (2*c2) and there is no z component (SolverCudaKernels.cu:870-883)
+static __global__ void k_initial_pressure(float* p, float* rx, float* ry, float* rz, const float* p0, Fld c2, size_t n, int dims) {
+  const float d = (float)dims;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float tmp = p[i] = p0[i];
-    tmp = tmp / (3.0f * c2.at(i));
+    tmp = tmp / (d * c2.at(i));
     rx[i] = tmp;
     ry[i] = tmp;
-    rz[i] = tmp;
+    rz[i] = dims == 3 ? tmp : 0.f;
   }
 }
 

@@ -174,12 +174,16 @@ void KSpaceFirstOrderSolver::loadArray(const std::string& name, int arrayId, boo
 void KSpaceFirstOrderSolver::loadInputData() {
   mDataLoadTime.start();
   const FileScalars& s = mScalars;
-  for (const auto& a : kMedium) loadArray(a.name, a.id, a.isIndex, true);
+  const bool is3D = s.nz > 1;  // the input file of a 2-D simulation carries no z arrays (main.cpp:446-563)
+  auto isZArray = [](int id) {
+    return id == KW_RHO0_SGZ || id == KW_DDZ_K_SHIFT_POS || id == KW_DDZ_K_SHIFT_NEG || id == KW_PML_Z || id == KW_PML_Z_SGZ || id == KW_Z_SHIFT_NEG_R;
+  };
+  for (const auto& a : kMedium) loadArray(a.name, a.id, a.isIndex, is3D || !isZArray(a.id));
   if (s.nonlinearFlag) loadArray("BonA", KW_BONA, false, true);
   if (s.absorbingFlag) loadArray("alpha_coeff", KW_ALPHA_COEFF, false, true);
-  for (const auto& a : kOperators) loadArray(a.name, a.id, a.isIndex, true);
+  for (const auto& a : kOperators) loadArray(a.name, a.id, a.isIndex, is3D || !isZArray(a.id));
   const bool needShift = mCmd.uNonStaggeredRaw || mCmd.uNonStaggeredC || mCmd.iAvgC;
-  for (const auto& a : kShifts) loadArray(a.name, a.id, a.isIndex, needShift);
+  for (const auto& a : kShifts) loadArray(a.name, a.id, a.isIndex, needShift && (is3D || !isZArray(a.id)));
   if (s.sensorMaskType == 0) loadArray("sensor_mask_index", KW_SENSOR_MASK_INDEX, true, true);
   else loadArray("sensor_mask_corners", KW_SENSOR_MASK_CORNERS, true, true);
   if (s.p0SourceFlag) loadArray("p0_source_input", KW_P0_SOURCE_INPUT, false, true);
@@ -233,7 +237,8 @@ void KSpaceFirstOrderSolver::createStreams() {  // OutputStreamContainer::init (
   add(mCmd.pMin, KW_S_P_MIN, "p_min", K::kAggregate);
   add(mCmd.pMaxAll, KW_S_P_MAX_ALL, "p_max_all", K::kWholeDomain);
   add(mCmd.pMinAll, KW_S_P_MIN_ALL, "p_min_all", K::kWholeDomain);
-  for (int k = 0; k < 3; ++k) {
+  const int ncomp = mScalars.nz > 1 ? 3 : 2;  // 2-D: no z component streams (OutputStreamContainer.cpp: is3DSimulation)
+  for (int k = 0; k < ncomp; ++k) {
     const std::string u = std::string("u") + axes[k];
     add(mCmd.uRaw, KW_S_UX_RAW + k, u, K::kSeries);
     add(mCmd.uC, KW_S_UX_C + k, u + "_c", K::kCompressed);
@@ -376,7 +381,7 @@ void KSpaceFirstOrderSolver::writeAggregates() {
   final_field(mCmd.pFinal, KW_P, "p_final");
   final_field(mCmd.uFinal, KW_UX_SGX, "ux_final");
   final_field(mCmd.uFinal, KW_UY_SGY, "uy_final");
-  final_field(mCmd.uFinal, KW_UZ_SGZ, "uz_final");
+  final_field(mCmd.uFinal && s.nz > 1, KW_UZ_SGZ, "uz_final");
 }
 
 void KSpaceFirstOrderSolver::saveScalarsToOutputFile() {  // Parameters::saveScalarsToOutputFile (Parameters.cpp:559-650)
@@ -384,13 +389,18 @@ void KSpaceFirstOrderSolver::saveScalarsToOutputFile() {  // Parameters::saveSca
   const hid_t root = mOutputFile.root();
   Hdf5File& o = mOutputFile;
   o.writeScalar(root, "Nx", s.nx), o.writeScalar(root, "Ny", s.ny), o.writeScalar(root, "Nz", s.nz), o.writeScalar(root, "Nt", s.nt);
-  o.writeScalar(root, "dt", s.dt), o.writeScalar(root, "dx", s.dx), o.writeScalar(root, "dy", s.dy), o.writeScalar(root, "dz", s.dz);
+  const bool is3D = s.nz > 1;
+  o.writeScalar(root, "dt", s.dt), o.writeScalar(root, "dx", s.dx), o.writeScalar(root, "dy", s.dy);
+  if (is3D) o.writeScalar(root, "dz", s.dz);
   o.writeScalar(root, "c_ref", s.cRef);
-  o.writeScalar(root, "pml_x_size", s.pmlXSize), o.writeScalar(root, "pml_y_size", s.pmlYSize), o.writeScalar(root, "pml_z_size", s.pmlZSize);
-  o.writeScalar(root, "pml_x_alpha", s.pmlXAlpha), o.writeScalar(root, "pml_y_alpha", s.pmlYAlpha), o.writeScalar(root, "pml_z_alpha", s.pmlZAlpha);
+  o.writeScalar(root, "pml_x_size", s.pmlXSize), o.writeScalar(root, "pml_y_size", s.pmlYSize);
+  if (is3D) o.writeScalar(root, "pml_z_size", s.pmlZSize);
+  o.writeScalar(root, "pml_x_alpha", s.pmlXAlpha), o.writeScalar(root, "pml_y_alpha", s.pmlYAlpha);
+  if (is3D) o.writeScalar(root, "pml_z_alpha", s.pmlZAlpha);
   o.writeScalar(root, "p_source_flag", s.pSourceFlag), o.writeScalar(root, "p0_source_flag", s.p0SourceFlag);
   o.writeScalar(root, "transducer_source_flag", s.transducerSourceFlag);
-  o.writeScalar(root, "ux_source_flag", s.uxSourceFlag), o.writeScalar(root, "uy_source_flag", s.uySourceFlag), o.writeScalar(root, "uz_source_flag", s.uzSourceFlag);
+  o.writeScalar(root, "ux_source_flag", s.uxSourceFlag), o.writeScalar(root, "uy_source_flag", s.uySourceFlag);
+  if (is3D) o.writeScalar(root, "uz_source_flag", s.uzSourceFlag);
   o.writeScalar(root, "nonuniform_grid_flag", s.nonuniformGridFlag), o.writeScalar(root, "absorbing_flag", s.absorbingFlag);
   o.writeScalar(root, "nonlinear_flag", s.nonlinearFlag);
   if (s.uxSourceFlag || s.uySourceFlag || s.uzSourceFlag) o.writeScalar(root, "u_source_many", s.uSourceMany), o.writeScalar(root, "u_source_mode", s.uSourceMode);

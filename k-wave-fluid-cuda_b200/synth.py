@@ -106,8 +106,10 @@ def make_case(
     zs0, zsl = (0, nz) if z_range is None else z_range
     n = nx * ny * nz
     dx = dy = dz = 1e-4
-    pml_size = pml_size if pml_size is not None else (20 if min(shape) >= 128 else max(2, min(shape) // 8))
-    sig = 8.0 if min(shape) >= 64 else max(1.5, min(shape) / 8)
+    two_d = nz == 1  # 2-D simulation: the file carries no z arrays (main.cpp:446-563)
+    ext = min(shape[1:]) if two_d else min(shape)
+    pml_size = pml_size if pml_size is not None else (20 if ext >= 128 else max(2, ext // 8))
+    sig = 8.0 if ext >= 64 else max(1.5, ext / 8)
     arrays = {}
     if heterogeneous and medium == "waves":
         zr = (zs0, zsl)
@@ -137,7 +139,7 @@ def make_case(
         g0, g1 = smooth_noise(shape, seed, sig), smooth_noise(shape, seed + 1, sig)
         c0 = (1500.0 * (1.0 + 0.05 * g0)).astype(F32)
         zz, yy, xx = np.ogrid[:nz, :ny, :nx]
-        r = min(shape) // 8
+        r = ext // 8
         ball = (xx - nx // 2) ** 2 + (yy - ny // 2) ** 2 + (zz - nz // 2) ** 2 <= r * r
         c0[ball] = 1600.0
         rho0 = (1000.0 * (1.0 + 0.05 * g1)).astype(F32)
@@ -180,8 +182,15 @@ def make_case(
     if shifts:
         arrays.update(x_shift_neg_r=sx[: nx // 2 + 1], y_shift_neg_r=sy[: ny // 2 + 1], z_shift_neg_r=sz[: nz // 2 + 1])
     for a, nn, d in (("x", nx, dx), ("y", ny, dy), ("z", nz, dz)):
+        if two_d and a == "z":
+            continue
         arrays[f"pml_{a}_sg{a}"] = pml_vec(nn, d, dt, c_ref, pml_size, 2.0, True)
         arrays[f"pml_{a}"] = pml_vec(nn, d, dt, c_ref, pml_size, 2.0, False)
+    if two_d:  # what a 2-D input file does not contain
+        for k in ("ddz_k_shift_pos", "ddz_k_shift_neg", "z_shift_neg_r", "rho0_sgz"):
+            arrays.pop(k, None)
+        for k in ("pml_z_size", "pml_z_alpha", "uz_source_flag"):  # dz stays in cfg for the callers' convenience; nothing reads it
+            cfg.pop(k, None)
     # sources
     tt = np.arange(nt, dtype=np.float64)
     tone = np.sin(2 * np.pi * tt / period)
@@ -230,8 +239,9 @@ def make_case(
     elif sensor == "cuboid":
         a0, a1 = int(0.3 * nx), int(0.7 * nx) - 1
         b0, b1 = max(1, nx // 12), max(2, nx // 6)
+        zb0, zb1 = (0, 0) if two_d else (b0, nz - b0 - 1)
         arrays["sensor_mask_corners"] = np.array(
-            [[a0, a0 * ny // nx, a0 * nz // nx, a1, a1 * ny // nx, a1 * nz // nx], [b0, b0, b0, b1, b1, nz - b0 - 1]],
+            [[a0, a0 * ny // nx, a0 * nz // nx, a1, a1 * ny // nx, a1 * nz // nx], [b0, b0, zb0, b1, b1, zb1]],
             dtype=np.uint64,
         ) + 1
     elif sensor == "full_cuboid":

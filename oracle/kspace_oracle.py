@@ -127,6 +127,17 @@ class KSpaceOracle:
         self.t = 0
         a = {k: np.asarray(v) for k, v in arrays.items()}
         T = self.dt.type
+        if self.nz == 1:
+            # 2-D simulation (Parameters.h:88-94): the input file has no z arrays; every z term of the 3-D formulas is dropped
+            # by the reference's k2D branches (e.g. SolverCudaKernels.cu:197,1147).  Neutral z operators reproduce that exactly:
+            # the z gradient is 0, u_z and rho_z stay 0 and add exact zeros to the sums.
+            a.setdefault("ddz_k_shift_pos", np.zeros(1, np.complex64))
+            a.setdefault("ddz_k_shift_neg", np.zeros(1, np.complex64))
+            a.setdefault("pml_z", np.ones(1, F32))
+            a.setdefault("pml_z_sgz", np.ones(1, F32))
+            a.setdefault("rho0_sgz", np.ones(1, F32))
+            if "x_shift_neg_r" in a:
+                a.setdefault("z_shift_neg_r", np.ones(1, np.complex64))
 
         def field(x):
             x = np.asarray(x, dtype=F32)
@@ -298,8 +309,12 @@ class KSpaceOracle:
         # addInitialPressureSource (cpp:2359-2396; SolverCudaKernels.cu:870-883, :971-980)
         if t == 0 and c.get("p0_source_flag", 0) == 1:
             self.p = self.p0.copy() if isinstance(self.p0, np.ndarray) else np.full(self.shape, self.p0, self.dt)
-            r = self.p / (3 * self.c2)
-            self.rho = [r.copy(), r.copy(), r.copy()]
+            if self.nz == 1:  # SolverCudaKernels.cu:873: rho_x = rho_y = p0 / (2 c^2), no z component
+                r = self.p / (2 * self.c2)
+                self.rho = [r.copy(), r.copy(), np.zeros_like(r)]
+            else:
+                r = self.p / (3 * self.c2)
+                self.rho = [r.copy(), r.copy(), r.copy()]
             g = self._pressure_gradient()
             half_fd = fd * self.dt.type(0.5)
             for i in range(3):

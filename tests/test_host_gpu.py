@@ -28,6 +28,9 @@ CASES = {
                    ["--p_c", "--u_non_staggered_c", "--I_avg_c", "--u_non_staggered_raw", "--period", "20", "--mos", "1", "--harmonics", "2"]),
     "transducer_u_sources": (dict(nonlinear=True, absorbing=True, source="transducer", n_sensor=32), ["-p", "-u", "--u_rms"]),
     "no_output_flags": (dict(nonlinear=False, absorbing=False, source="p0", n_sensor=8), []),
+    "2d": (dict(ny=64, nz=1, nonlinear=True, absorbing=True, source="p_plane", n_sensor=80, period=20, shifts=True),
+           ["-p", "--p_rms", "--p_max_all", "--p_final", "-u", "--u_final", "--u_non_staggered_raw", "--p_c", "--I_avg_c", "--period", "20", "--harmonics", "2"]),
+    "2d_p0": (dict(ny=32, nz=1, nonlinear=False, absorbing=False, source="p0", sensor="cuboid"), ["-p", "--p_min", "--u_max_all"]),
 }
 
 
@@ -45,7 +48,9 @@ def test_same_file_same_flags_same_output(synth, tmp_path, name):
     assert os.path.exists(OURS), "kspaceFirstOrder-B200 not built (__graft_entry__.build())"
     kwargs, flags = CASES[name]
     nt = 120
-    cfg, arrays = synth.make_case(32, nt=nt, **kwargs)
+    kwargs = dict(kwargs)
+    ny, nz = kwargs.pop("ny", None), kwargs.pop("nz", None)
+    cfg, arrays = synth.make_case(32, ny, nz, nt=nt, **kwargs)
     fin = str(tmp_path / "in.h5")
     kwh5.write_input(fin, cfg, arrays)
     ref = run(REF, fin, str(tmp_path / "ref.h5"), flags)
@@ -81,7 +86,9 @@ def test_command_line_errors_exit_like_the_reference(tmp_path):
     """Boxed message on stderr + EXIT_FAILURE (Logger/Logger.cpp:82-89); -s is 1-based; unsupported features say so."""
     assert os.path.exists(OURS), "kspaceFirstOrder-B200 not built (__graft_entry__.build())"
     for args, needle in (([], "Input file was not specified"), (["-i", "a"], "Output file was not specified"),
-                         (["-i", "a", "-o", "b", "--checkpoint_interval", "5"], "not available in this build"),
+                         (["-i", "a", "-o", "b", "--checkpoint_interval", "5"], "Checkpoint file was not specified"),
+                         (["-i", "a", "-o", "b", "--checkpoint_file", "c"], "Checkpoint interval or the number of time steps"),
+                         (["-i", "a", "-o", "b", "--Q_term"], "not available in this build"),
                          (["-i", "a", "-o", "b", "--p_c"], "--period or --frequency"), (["-i", "a", "-o", "b", "-s", "0"], "Invalid value"),
                          (["-i", "a", "-o", "b", "-c", "12"], "Invalid value"),
                          (["-i", str(tmp_path / "missing.h5"), "-o", "b"], "could not be opened")):  # fmt: skip

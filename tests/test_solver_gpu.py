@@ -40,6 +40,10 @@ CASES = {
     "homogeneous_scalars": ((32, 32, 32), dict(nonlinear=True, absorbing=True, heterogeneous=False, source="p_plane")),
     "non_cubic": ((64, 32, 16), dict(nonlinear=True, absorbing=True, source="p_plane", shuffle_sensor=True)),
     "n64": ((64, 64, 64), dict(nonlinear=True, absorbing=True, source="p_plane")),
+    # 2-D simulations (Nz == 1, Parameters.h:88-94): no z arrays in the input
+    "2d_nonlinear_absorbing": ((64, 32, 1), dict(nonlinear=True, absorbing=True, source="p_plane", n_sensor=100, shuffle_sensor=True)),
+    "2d_p0_cuboid": ((64, 64, 1), dict(nonlinear=False, absorbing=False, source="p0", sensor="cuboid")),
+    "2d_additive_u_source": ((32, 64, 1), dict(nonlinear=True, absorbing=False, source="u_plane", source_mode=2, n_sensor=64)),
 }
 
 
