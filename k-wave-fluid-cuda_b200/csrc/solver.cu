@@ -343,7 +343,8 @@ static int upload_reduced(kw_ctx* c, int id, const float* h) {
 // KSpaceFirstOrderSolver.cpp:2404-2452 (kappa), :2460-2506 (source kappa), :2514-2577 (kappa + nablas)
 static void generate_k_operators(const kw_config& cf, const Geometry& g, std::vector<float>* kappa, std::vector<float>* n1,
                                  std::vector<float>* n2, std::vector<float>* skappa) {
-  const float dx2 = 1.0f / (cf.dx * cf.dx), dy2 = 1.0f / (cf.dy * cf.dy), dz2 = 1.0f / (cf.dz * cf.dz);
+  // 2-D (Nz == 1): dz is not part of the input file and the z term is dropped (cpp:2404-2452, k2D branches)
+  const float dx2 = 1.0f / (cf.dx * cf.dx), dy2 = 1.0f / (cf.dy * cf.dy), dz2 = g.nz == 1 ? 0.0f : 1.0f / (cf.dz * cf.dz);
   const float cRefDtPi = cf.c_ref * cf.dt * static_cast<float>(M_PI);
   const float cRefDt2 = cf.c_ref * cf.dt * 0.5f;
   const float pi2 = static_cast<float>(M_PI) * 2.0f;
@@ -1434,7 +1435,7 @@ static int step(kw_ctx* c) {
         if (nsrc > 0) {
           SourceArgs sa{};
           for (int k = 0; k < 3; ++k) sa.target[k] = rho[k];
-          sa.ntargets = 3, sa.signal = c->d[KW_P_SOURCE_INPUT], sa.index = c->di[KW_P_SOURCE_INDEX];
+          sa.ntargets = g.nz == 1 ? 2 : 3 /* 2-D: rhox, rhoy only (SolverCudaKernels.cu:570-629) */, sa.signal = c->d[KW_P_SOURCE_INPUT], sa.index = c->di[KW_P_SOURCE_INDEX];
           sa.pos = c->dpos[KW_P_SOURCE_INDEX], sa.nsrc = nsrc, sa.nsrc_total = c->count_total[KW_P_SOURCE_INDEX];
           sa.t = t, sa.many = cf.p_source_many, sa.mode = cf.p_source_mode;
           launch(c, "add_p_source", 36.0 * nsrc, [&] { k_add_source<<<ew_grid(nsrc), 256, 0, c->st>>>(sa); });
@@ -1443,7 +1444,7 @@ static int step(kw_ctx* c) {
           launch(c, "pressure_terms_fixup", 40.0 * nsrc, [&] { k_pressure_terms<<<ew_grid(nsrc), 256, 0, c->st>>>(ta); });
         }
       } else {
-        KW_TRY(add_scaled_source(c, c->d[KW_P_SOURCE_INPUT], KW_P_SOURCE_INDEX, cf.p_source_many, rho, 3));
+        KW_TRY(add_scaled_source(c, c->d[KW_P_SOURCE_INPUT], KW_P_SOURCE_INDEX, cf.p_source_many, rho, g.nz == 1 ? 2 : 3));
         ta.index = nullptr, ta.n = g.n;
         launch(c, "pressure_terms", 28.0 * g.n, [&] { k_pressure_terms<<<ew_grid(g.n), 256, 0, c->st>>>(ta); });
       }
@@ -1603,7 +1604,7 @@ static int step_sharded(kw_ctx* c) {
       if (nsrc > 0) {
         SourceArgs sa{};
         for (int k = 0; k < 3; ++k) sa.target[k] = rho[k];
-        sa.ntargets = 3, sa.signal = c->d[KW_P_SOURCE_INPUT], sa.index = c->di[KW_P_SOURCE_INDEX];
+        sa.ntargets = g.nz == 1 ? 2 : 3 /* 2-D: rhox, rhoy only (SolverCudaKernels.cu:570-629) */, sa.signal = c->d[KW_P_SOURCE_INPUT], sa.index = c->di[KW_P_SOURCE_INDEX];
         sa.pos = c->dpos[KW_P_SOURCE_INDEX], sa.nsrc = nsrc, sa.nsrc_total = c->count_total[KW_P_SOURCE_INDEX];
         sa.t = t, sa.many = cf.p_source_many, sa.mode = cf.p_source_mode;
         launch(c, "add_p_source", 36.0 * nsrc, [&] { k_add_source<<<ew_grid(nsrc), 256, 0, c->st>>>(sa); });
@@ -1611,7 +1612,7 @@ static int step_sharded(kw_ctx* c) {
         launch(c, "pressure_terms_fixup", 40.0 * nsrc, [&] { k_pressure_terms<<<ew_grid(nsrc), 256, 0, c->st>>>(ta); });
       }
     } else {
-      KW_TRY(add_scaled_source(c, c->d[KW_P_SOURCE_INPUT], KW_P_SOURCE_INDEX, cf.p_source_many, rho, 3));
+      KW_TRY(add_scaled_source(c, c->d[KW_P_SOURCE_INPUT], KW_P_SOURCE_INDEX, cf.p_source_many, rho, g.nz == 1 ? 2 : 3));
       ta.index = nullptr, ta.n = g.n;
       launch(c, "pressure_terms", 28.0 * g.n, [&] { k_pressure_terms<<<ew_grid(g.n), 256, 0, c->st>>>(ta); });
     }

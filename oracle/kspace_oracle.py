@@ -279,12 +279,13 @@ class KSpaceOracle:
         if c.get("p_source_flag", 0) > t:
             pmode, pmany = c.get("p_source_mode", 0), c.get("p_source_many", 0)
             s = self._src_values(self.p_src_in, self.p_src_idx.size, pmany)
+            ndim = 2 if self.nz == 1 else 3  # 2-D: rhox and rhoy only (SolverCudaKernels.cu:570-629, :795-807)
             if pmode == 2:
                 f = self._scale_source(s, self.p_src_idx)
-                for i in range(3):
+                for i in range(ndim):
                     self.rho[i] = self.rho[i] + f
             else:
-                for i in range(3):
+                for i in range(ndim):
                     flat = self.rho[i].reshape(-1)
                     if pmode == 0:
                         flat[self.p_src_idx] = s

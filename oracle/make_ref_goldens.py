@@ -46,6 +46,10 @@ CASES = {
                            ["-p"], ["p"]),
     "n64_long": ((64, 64, 64), dict(nonlinear=True, absorbing=True, source="p_plane", n_sensor=64), 300,
                  ["-p", "--p_rms"], ["p", "p_rms"]),
+    "two_d_p_source": ((64, 32, 1), dict(nonlinear=True, absorbing=True, source="p_plane", n_sensor=64), 150,
+                       ["-p", "--p_rms", "-u"], ["p", "p_rms", "ux"]),
+    "two_d_p0_cuboid": ((32, 32, 1), dict(nonlinear=False, absorbing=False, source="p0", sensor="cuboid"), 100,
+                        ["-p", "--p_max"], ["p/1", "p/2", "p_max/1"]),
     "compressed_p_and_intensity": ((32, 32, 32), dict(nonlinear=False, absorbing=False, source="p_plane", n_sensor=64, period=20, shifts=True), 200,
                                    ["--p_c", "--u_non_staggered_c", "--I_avg_c", "--u_non_staggered_raw", "--period", "20", "--mos", "1", "--harmonics", "2"],
                                    ["p_c", "ux_non_staggered_c", "Ix_avg_c", "Iy_avg_c", "Iz_avg_c", "ux_non_staggered", "uy_non_staggered", "uz_non_staggered"]),
