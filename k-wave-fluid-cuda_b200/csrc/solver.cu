@@ -565,7 +565,7 @@ static const struct { int op; int src; bool all; bool supported; } kStreamTable[
     /* U*_MIN_ALL */ {kOpMin, 1, true, true}, {kOpMin, 2, true, true}, {kOpMin, 3, true, true},
     /* I*_AVG */ {0, 0, false, false}, {0, 0, false, false}, {0, 0, false, false},
     /* I*_AVG_C */ {kOpIAvgC, 0, false, true}, {kOpIAvgC, 1, false, true}, {kOpIAvgC, 2, false, true},
-    /* Q_TERM */ {0, 0, false, false}, /* Q_TERM_C */ {0, 0, false, false}};
+    /* Q_TERM */ {0, 0, false, false}, /* Q_TERM_C */ {kOpQTermC, 0, false, true}};
 
 int kw_stream_enable(kw_ctx* c, int sid) {
   if (!c || sid < 0 || sid >= KW_STREAM_COUNT) return fail(KW_ERR_INVALID, "kw_stream_enable: bad stream id");
@@ -774,6 +774,12 @@ int kw_preprocess(kw_ctx* c) {
   if (c->d[KW_SOURCE_KAPPA]) KW_TRY(dalloc(c, (void**)&c->tSrc, g.n * sizeof(float)));
   // --- streams that exist only because others need them (OutputStreamContainer.cpp:273-323): I_avg_c reads the
   //     frames of p_c and u*_non_staggered_c
+  if (c->streams[KW_S_Q_TERM_C].enabled)  // Q_term_c is computed from the three I_avg_c (cpp:1013-1020)
+    for (int k = 0; k < (g.nz == 1 ? 2 : 3); ++k) {
+      Stream& d = c->streams[KW_S_IX_AVG_C + k];
+      if (d.enabled) continue;
+      d.enabled = true, d.nosave = true, d.op = kOpIAvgC, d.src = k, d.all = false;
+    }
   for (int k = 0; k < 3; ++k)
     if (c->streams[KW_S_IX_AVG_C + k].enabled)
       for (int dep : {(int)KW_S_P_C, (int)KW_S_UX_NS_C + k}) {
@@ -915,7 +921,7 @@ int kw_preprocess(kw_ctx* c) {
       uint64_t cap = cf.raw_rows_capacity ? cf.raw_rows_capacity : std::max<uint64_t>(1, std::min<uint64_t>(nframes, (256ull << 20) / (s.row * sizeof(float) + 1)));
       s.cap_rows = s.nosave ? 0 : cap;
       if (!s.nosave) KW_TRY(dalloc(c, (void**)&s.dbuf, s.cap_rows * s.row * sizeof(float)));
-    } else if (s.op == kOpIAvgC) {
+    } else if (s.op == kOpIAvgC || s.op == kOpQTermC) {
       s.cap_rows = 1;
       KW_TRY(dalloc(c, (void**)&s.dbuf, s.row * sizeof(float)));
     } else if (s.op == kOpNone) {
@@ -1276,7 +1282,7 @@ static int sample_streams(kw_ctx* c) {
   const uint64_t nsamp = cf.nt - cf.sampling_start_index;
   for (int sid = 0; sid < KW_STREAM_COUNT; ++sid) {
     Stream& s = c->streams[sid];
-    if (!s.enabled || s.op == kOpIAvgC) continue;
+    if (!s.enabled || s.op == kOpIAvgC || s.op == kOpQTermC) continue;
     if (s.fused_this_step) {
       s.fused_this_step = false;
       continue;
@@ -1657,6 +1663,70 @@ static int step_sharded(kw_ctx* c) {
   return KW_OK;
 }
 
+// Q_term_c = -(dIx/dx + dIy/dy + dIz/dz) of the time-averaged intensity (computeQTerm, KSpaceFirstOrderSolver.cpp:1783-2080):
+// the I_avg_c values are scattered onto a zero grid, differentiated spectrally along their own axis (multiplier i*k,
+// k = 2 pi / d * shift / N; the reference runs 1-D R2C / C2R per axis, here the multiplier sits between the z transforms of
+// the 3-D pipeline like the other operators), summed in the order x, y, z, negated and gathered at the sensor points.
+static int compute_q_term_c(kw_ctx* c) {
+  const Geometry& g = c->g;
+  const kw_config& cf = c->cfg;
+  Stream& q = c->streams[KW_S_Q_TERM_C];
+  float *grid = nullptr, *acc = nullptr;
+  KW_TRY(dalloc(c, (void**)&grid, g.n * sizeof(float)));
+  KW_TRY(dalloc(c, (void**)&acc, g.n * sizeof(float)));
+  const int ncomp = g.nz == 1 ? 2 : 3;
+  const int len[3] = {g.nxp, g.ny, g.nz}, n[3] = {g.nx, g.ny, g.nz};
+  const float d[3] = {cf.dx, cf.dy, cf.dz};
+  const float fd = 1.0f / (float)g.ntot;
+  for (int f = 0; f < ncomp; ++f) {
+    // i*k of this axis: the half range for x, the full (Hermitian) range for y and z; the Nyquist entry multiplies a
+    // value whose imaginary part C2R ignores, i.e. it contributes nothing (cpp:1903-1921)
+    std::vector<float2> ik(len[f], make_float2(0.f, 0.f));
+    const int count = f == 0 ? g.nxr : n[f];
+    const float pi2 = static_cast<float>(M_PI) * 2.0f;
+    for (int i = 0; i < count; ++i) {
+      const long long shift = (long long)((i + n[f] / 2) % n[f]) - n[f] / 2;
+      const bool nyquist = n[f] % 2 == 0 && i == n[f] / 2;
+      ik[i] = make_float2(0.f, nyquist && f != 0 ? 0.f : (pi2 / d[f]) * ((float)shift / (float)n[f]));
+    }
+    float2* dik = nullptr;
+    KW_TRY(dalloc(c, (void**)&dik, ik.size() * sizeof(float2), false));
+    KW_CUDA(cudaMemcpyAsync(dik, ik.data(), ik.size() * sizeof(float2), cudaMemcpyHostToDevice, c->st));
+    KW_CUDA(cudaStreamSynchronize(c->st));
+    const float* I = c->streams[KW_S_IX_AVG_C + f].dbuf;
+    KW_CUDA(cudaMemsetAsync(grid, 0, g.n * sizeof(float), c->st));
+    if (c->nsens) {
+      if (cf.sensor_mask_type == 0) {
+        k_scatter_index<<<ew_grid(c->nsens), 256, 0, c->st>>>(grid, I, c->di[KW_SENSOR_MASK_INDEX], c->nsens);
+      } else {
+        CuboidArgs ca{c->cub_corners, c->cub_offsets, c->ncuboids, g.nx, g.ny};
+        k_scatter_cuboid<<<ew_grid(c->nsens), 256, 0, c->st>>>(grid, I, ca, c->nsens);
+      }
+      c->launches++;
+    }
+    const float* in[1] = {grid};
+    float2* out[1] = {c->S[3]};
+    forward_xy(c, in, out, 1);
+    float2 *zb[1], *back[1];
+    KW_TRY(exchange(c, out, &c->R[3], 1, zb));
+    zmid_launch(c, ZField{zb[0], zb[0], nullptr, fd, dik}, f);
+    KW_TRY(exchange(c, zb, &c->S[3], 1, back));
+    if (g.nranks > 1) KW_TRY(release_buffer(c, 7, c->cs));
+    EpiAdd e{};
+    e.out[0] = acc, e.ntargets = 1;
+    inverse_yx(c, back, 1, "xinv_q_term", "yx_q_term", 8.0 * g.nc + 8.0 * g.n,
+               [&](int pb, int pe) { g.ox->xinv_add(xinv_args<1>(c, back, pb, pe), e, c->st); },
+               [&] { auto a = yx_args<1>(c, back, 1); return g.ox->yx_add(a, e, c->pipe, c->st); });
+    if (g.nranks > 1) KW_TRY(release_buffer(c, 3, c->st));
+  }
+  if (c->nsens) {
+    sample_one<kOpNone>(c, q, acc, q.dbuf);
+    k_negate<<<ew_grid(c->nsens), 256, 0, c->st>>>(q.dbuf, c->nsens);
+    c->launches++;
+  }
+  return KW_OK;
+}
+
 }  // namespace kw
 
 extern "C" {
@@ -1951,7 +2021,9 @@ int kw_finish(kw_ctx* c) {
       c->launches++;
       s.compressed = 0;
     }
+  if (c->streams[KW_S_Q_TERM_C].enabled) KW_TRY(compute_q_term_c(c));
   KW_CUDA(cudaStreamSynchronize(c->st));
+  if (c->cs) KW_CUDA(cudaStreamSynchronize(c->cs));
   KW_CUDA(cudaGetLastError());
   c->finished = true;
   return KW_OK;

@@ -395,7 +395,7 @@ static __global__ void k_initial_pressure(float* p, float* rx, float* ry, float*
 }
 
 // ---- sampling ----------------------------------------------------------------------------------------------------
-enum SampleOp { kOpNone = 0, kOpRms = 1, kOpMax = 2, kOpMin = 3, kOpC = 4, kOpIAvgC = 5 };  // BaseOutputStream::ReduceOperator
+enum SampleOp { kOpNone = 0, kOpRms = 1, kOpMax = 2, kOpMin = 3, kOpC = 4, kOpIAvgC = 5, kOpQTermC = 6 };  // BaseOutputStream::ReduceOperator
 template <int OP> __device__ __forceinline__ void reduce_into(float* buf, size_t i, float x) {
   if (OP == kOpNone) buf[i] = x;
   else if (OP == kOpRms) buf[i] += x * x;
@@ -429,6 +429,24 @@ template <int OP> static __global__ void k_sample_cuboid(float* buf, const float
 template <int OP> static __global__ void k_sample_all(float* buf, const float* __restrict__ src, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     reduce_into<OP>(buf, i, __ldg(src + i));
+}
+// inverse of the gathers: grid[voxel of sensor point j] = buf[j]  (computeQTerm, KSpaceFirstOrderSolver.cpp:1799-1863)
+static __global__ void k_scatter_index(float* grid, const float* __restrict__ buf, const uint64_t* __restrict__ mask, size_t n) {
+  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) grid[mask[j]] = buf[j];
+}
+static __global__ void k_scatter_cuboid(float* grid, const float* __restrict__ buf, CuboidArgs a, size_t total) {
+  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < total; j += (size_t)gridDim.x * blockDim.x) {
+    int c = 0;
+    while (c + 1 < a.ncuboids && j >= a.offsets[c + 1]) ++c;
+    const uint64_t* k = a.corners + 6 * c;
+    const size_t l = j - a.offsets[c];
+    const size_t cx = k[3] - k[0] + 1, cy = k[4] - k[1] + 1;
+    const size_t x = l % cx, y = (l / cx) % cy, z = l / (cx * cy);
+    grid[((z + k[2]) * a.ny + (y + k[1])) * a.nx + (x + k[0])] = buf[j];
+  }
+}
+static __global__ void k_negate(float* buf, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = -buf[i];
 }
 static __global__ void k_fill(float* buf, float v, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = v;

@@ -182,7 +182,7 @@ void KSpaceFirstOrderSolver::loadInputData() {
   if (s.nonlinearFlag) loadArray("BonA", KW_BONA, false, true);
   if (s.absorbingFlag) loadArray("alpha_coeff", KW_ALPHA_COEFF, false, true);
   for (const auto& a : kOperators) loadArray(a.name, a.id, a.isIndex, is3D || !isZArray(a.id));
-  const bool needShift = mCmd.uNonStaggeredRaw || mCmd.uNonStaggeredC || mCmd.iAvgC;
+  const bool needShift = mCmd.uNonStaggeredRaw || mCmd.uNonStaggeredC || mCmd.iAvgC || mCmd.qTermC;
   for (const auto& a : kShifts) loadArray(a.name, a.id, a.isIndex, needShift && (is3D || !isZArray(a.id)));
   if (s.sensorMaskType == 0) loadArray("sensor_mask_index", KW_SENSOR_MASK_INDEX, true, true);
   else loadArray("sensor_mask_corners", KW_SENSOR_MASK_CORNERS, true, true);
@@ -251,6 +251,7 @@ void KSpaceFirstOrderSolver::createStreams() {  // OutputStreamContainer::init (
     add(mCmd.uMinAll, KW_S_UX_MIN_ALL + k, u + "_min_all", K::kWholeDomain);
     add(mCmd.iAvgC, KW_S_IX_AVG_C + k, std::string("I") + axes[k] + "_avg_c", K::kAggregate);
   }
+  add(mCmd.qTermC, KW_S_Q_TERM_C, "Q_term_c", K::kAggregate);
   // flush order = OutputStreamIdx order (Containers/OutputStreamContainer.h:59-150)
   std::stable_sort(mStreams.begin(), mStreams.end(), [](const OutputStream& a, const OutputStream& b) { return a.id < b.id; });
 }

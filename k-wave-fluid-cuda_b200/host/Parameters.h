@@ -26,7 +26,7 @@ struct CommandLine {
   // outputs
   bool pRaw = false, pC = false, pRms = false, pMax = false, pMin = false, pMaxAll = false, pMinAll = false, pFinal = false;
   bool uRaw = false, uC = false, uRms = false, uMax = false, uMin = false, uMaxAll = false, uMinAll = false, uFinal = false;
-  bool uNonStaggeredRaw = false, uNonStaggeredC = false, iAvgC = false;
+  bool uNonStaggeredRaw = false, uNonStaggeredC = false, iAvgC = false, qTermC = false;
   // compression
   float frequency = 0.f, period = 0.f;
   uint64_t mos = 1, harmonics = 1;
@@ -35,7 +35,7 @@ struct CommandLine {
 
   // throws std::invalid_argument with the message to print (the caller prints usage and exits with EXIT_FAILURE)
   void parse(int argc, char** argv);
-  bool anyCompressed() const { return pC || uC || uNonStaggeredC || iAvgC; }
+  bool anyCompressed() const { return pC || uC || uNonStaggeredC || iAvgC || qTermC; }
   static std::string usage();
 };
 

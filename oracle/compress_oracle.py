@@ -213,3 +213,25 @@ def unpack40(frame_bytes, e):
             re, im = decode40(bytes(frame_bytes[i, ih]), e)
             out[i, ih] = complex(re, im)
     return out
+
+
+def q_term(cfg, intensities, lin_index):
+    """computeQTerm (KSpaceFirstOrderSolver.cpp:1783-2080): Q = -(dIx/dx + dIy/dy [+ dIz/dz]) with the intensities scattered
+    onto a zero grid at the (0-based linear) sensor indices, each differentiated spectrally along its own axis
+    (1-D R2C, * i*k / N, C2R; k = 2 pi / d * shift / N, shift = (i + N/2) % N - N/2), gathered at the same indices."""
+    nx, ny, nz = cfg["Nx"], cfg["Ny"], cfg["Nz"]
+    idx = np.asarray(lin_index, dtype=np.int64)
+    total = np.zeros((nz, ny, nx), np.float64)
+    for comp, (ax, n, d) in enumerate(((2, nx, cfg["dx"]), (1, ny, cfg["dy"]), (0, nz, cfg.get("dz", 1.0)))):
+        if comp >= len(intensities) or (nz == 1 and comp == 2):
+            break
+        grid = np.zeros(nx * ny * nz, np.float64)
+        grid[idx] = np.asarray(intensities[comp], np.float64)
+        i = np.arange(n // 2 + 1)
+        shift = (i + n // 2) % n - n // 2
+        ik = 1j * (2.0 * np.pi / float(F32(d))) * (shift / n)
+        shp = [1, 1, 1]
+        shp[ax] = -1
+        xk = np.fft.rfft(grid.reshape(nz, ny, nx), axis=ax) * ik.reshape(shp)
+        total += np.fft.irfft(xk, n=n, axis=ax)
+    return (-total).reshape(-1)[idx]

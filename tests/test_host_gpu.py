@@ -30,6 +30,10 @@ CASES = {
     "no_output_flags": (dict(nonlinear=False, absorbing=False, source="p0", n_sensor=8), []),
     "2d": (dict(ny=64, nz=1, nonlinear=True, absorbing=True, source="p_plane", n_sensor=80, period=20, shifts=True),
            ["-p", "--p_rms", "--p_max_all", "--p_final", "-u", "--u_final", "--u_non_staggered_raw", "--p_c", "--I_avg_c", "--period", "20", "--harmonics", "2"]),
+    "q_term_c": (dict(nonlinear=True, absorbing=True, source="p_plane", n_sensor=300, period=20, shifts=True),
+                 ["--Q_term_c", "--I_avg_c", "--period", "20", "--harmonics", "2"]),
+    "q_term_c_only_cuboid": (dict(nonlinear=False, absorbing=True, source="p_plane", sensor="cuboid", period=20, shifts=True),
+                             ["--Q_term_c", "--period", "20"]),
     "2d_p0": (dict(ny=32, nz=1, nonlinear=False, absorbing=False, source="p0", sensor="cuboid"), ["-p", "--p_min", "--u_max_all"]),
 }
 
@@ -88,7 +92,7 @@ def test_command_line_errors_exit_like_the_reference(tmp_path):
     for args, needle in (([], "Input file was not specified"), (["-i", "a"], "Output file was not specified"),
                          (["-i", "a", "-o", "b", "--checkpoint_interval", "5"], "Checkpoint file was not specified"),
                          (["-i", "a", "-o", "b", "--checkpoint_file", "c"], "Checkpoint interval or the number of time steps"),
-                         (["-i", "a", "-o", "b", "--Q_term"], "not available in this build"),
+                         (["-i", "a", "-o", "b", "--Q_term"], "not available in this build"), (["-i", "a", "-o", "b", "--Q_term_c"], "--period or --frequency"),
                          (["-i", "a", "-o", "b", "--p_c"], "--period or --frequency"), (["-i", "a", "-o", "b", "-s", "0"], "Invalid value"),
                          (["-i", "a", "-o", "b", "-c", "12"], "Invalid value"),
                          (["-i", str(tmp_path / "missing.h5"), "-o", "b"], "could not be opened")):  # fmt: skip

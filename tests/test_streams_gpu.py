@@ -178,3 +178,23 @@ def test_40bit_codec_bit_exact_against_reference_vectors(kw):
         dec = kw.c40_decode(want, e)
         want_bits = np.array([[c["dre"], c["dim"]] for c in cs], dtype=np.uint32)
         assert np.array_equal(dec.view(np.uint32).reshape(-1, 2), want_bits)
+
+
+@pytest.mark.parametrize("shape", [(32, 32, 32), (64, 32, 1)])
+def test_q_term_c_matches_oracle(kw, synth, shape):
+    """--Q_term_c (cpp:1013-1020, :1783-2080): the divergence of the compressed time-averaged intensity, 3-D and 2-D, against
+    the NumPy restatement applied to this run's own I_avg_c."""
+    nt = 100
+    cfg, arrays = synth.make_case(*shape, nt=nt, nonlinear=True, absorbing=True, source="p_plane", n_sensor=200, period=20, shifts=True)
+    comps = ["X", "Y"] + (["Z"] if shape[2] > 1 else [])
+    streams = [f"KW_S_I{a}_AVG_C" for a in comps] + ["KW_S_Q_TERM_C"]
+    sim = kw.Simulation(cfg, arrays, streams=streams, compression=dict(period=20.0, harmonics=2))
+    assert sim.run(nt) == nt
+    sim.finish()
+    got = {s: sim.fetch(s)[0] for s in streams}
+    sim.close()
+    idx = arrays["sensor_mask_index"].astype(np.int64) - 1
+    ref = co.q_term(cfg, [got[f"KW_S_I{a}_AVG_C"] for a in comps], idx)
+    err = rel_l2(got["KW_S_Q_TERM_C"], ref)
+    print(f"Q_term_c {shape}: rel-L2 {err:.3e}, scale {np.abs(ref).max():.3e}")
+    assert np.abs(ref).max() > 0 and err <= TOL
