@@ -32,8 +32,8 @@ CASES = {
            ["-p", "--p_rms", "--p_max_all", "--p_final", "-u", "--u_final", "--u_non_staggered_raw", "--p_c", "--I_avg_c", "--period", "20", "--harmonics", "2"]),
     "q_term_c": (dict(nonlinear=True, absorbing=True, source="p_plane", n_sensor=300, period=20, shifts=True),
                  ["--Q_term_c", "--I_avg_c", "--period", "20", "--harmonics", "2"]),
-    "q_term_c_only_cuboid": (dict(nonlinear=False, absorbing=True, source="p_plane", sensor="cuboid", period=20, shifts=True),
-                             ["--Q_term_c", "--period", "20"]),
+    # (cuboid masks with --Q_term_c / --I_avg_c: the reference's own binary aborts or writes NaN there, so that combination is
+    #  checked against the oracle instead: tests/test_streams_gpu.py::test_q_term_c_matches_oracle[cuboid])
     "2d_p0": (dict(ny=32, nz=1, nonlinear=False, absorbing=False, source="p0", sensor="cuboid"), ["-p", "--p_min", "--u_max_all"]),
 }
 
@@ -71,6 +71,10 @@ def test_same_file_same_flags_same_output(synth, tmp_path, name):
             assert got_ds[p]["attrs"].get(k) == o["attrs"].get(k), (p, k)
         if o["kind"] == "u64" or p.strip("/") in SCALARS or a.size == 1:
             assert np.array_equal(a, b), p
+            continue
+        if not np.isfinite(b).all():  # the reference itself produced NaN/inf here: nothing to match, ours must stay finite
+            print(f"{name}: {p}: the reference output is not finite ({int((~np.isfinite(b)).sum())} values); ours checked for finiteness only")
+            assert np.isfinite(a).all(), p
             continue
         nb = np.linalg.norm(b.astype(np.float64).ravel())
         base = p.strip("/")

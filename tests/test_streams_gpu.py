@@ -180,12 +180,21 @@ def test_40bit_codec_bit_exact_against_reference_vectors(kw):
         assert np.array_equal(dec.view(np.uint32).reshape(-1, 2), want_bits)
 
 
-@pytest.mark.parametrize("shape", [(32, 32, 32), (64, 32, 1)])
-def test_q_term_c_matches_oracle(kw, synth, shape):
+def cuboid_linear_indices(corners_1based, nx, ny):
+    """0-based linear indices of all cuboid points: x fastest inside a cuboid, cuboids concatenated (the row order)."""
+    out = []
+    for x0, y0, z0, x1, y1, z1 in np.asarray(corners_1based, np.int64).reshape(-1, 6) - 1:
+        z, y, x = np.meshgrid(np.arange(z0, z1 + 1), np.arange(y0, y1 + 1), np.arange(x0, x1 + 1), indexing="ij")
+        out.append(((z * ny + y) * nx + x).reshape(-1))
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("shape,sensor", [((32, 32, 32), "index"), ((64, 32, 1), "index"), ((32, 32, 32), "cuboid")], ids=["3d", "2d", "cuboid"])
+def test_q_term_c_matches_oracle(kw, synth, shape, sensor):
     """--Q_term_c (cpp:1013-1020, :1783-2080): the divergence of the compressed time-averaged intensity, 3-D and 2-D, against
     the NumPy restatement applied to this run's own I_avg_c."""
     nt = 100
-    cfg, arrays = synth.make_case(*shape, nt=nt, nonlinear=True, absorbing=True, source="p_plane", n_sensor=200, period=20, shifts=True)
+    cfg, arrays = synth.make_case(*shape, nt=nt, nonlinear=True, absorbing=True, source="p_plane", n_sensor=200, period=20, shifts=True, sensor=sensor)
     comps = ["X", "Y"] + (["Z"] if shape[2] > 1 else [])
     streams = [f"KW_S_I{a}_AVG_C" for a in comps] + ["KW_S_Q_TERM_C"]
     sim = kw.Simulation(cfg, arrays, streams=streams, compression=dict(period=20.0, harmonics=2))
@@ -193,7 +202,10 @@ def test_q_term_c_matches_oracle(kw, synth, shape):
     sim.finish()
     got = {s: sim.fetch(s)[0] for s in streams}
     sim.close()
-    idx = arrays["sensor_mask_index"].astype(np.int64) - 1
+    if sensor == "index":
+        idx = arrays["sensor_mask_index"].astype(np.int64) - 1
+    else:
+        idx = cuboid_linear_indices(arrays["sensor_mask_corners"], shape[0], shape[1])
     ref = co.q_term(cfg, [got[f"KW_S_I{a}_AVG_C"] for a in comps], idx)
     err = rel_l2(got["KW_S_Q_TERM_C"], ref)
     print(f"Q_term_c {shape}: rel-L2 {err:.3e}, scale {np.abs(ref).max():.3e}")
