@@ -163,6 +163,15 @@ int kw_stream_state_size(kw_ctx* ctx, int stream_id, uint64_t* bytes);
 int kw_stream_state_get(kw_ctx* ctx, int stream_id, void* buffer, uint64_t bytes);
 int kw_stream_state_set(kw_ctx* ctx, int stream_id, const void* buffer, uint64_t bytes);
 
+/* Post-processing of stored raw series (--I_avg, --Q_term; the reference re-reads them block-wise from the output file).
+ * kw_intensity_avg_block = the block body of KSpaceFirstOrderSolver::computeAverageIntensities (cpp:1231-1534): p and the
+ * ncomp non-staggered velocity components of n sensor points over `steps` stored samples, laid out [step][point] as in
+ * the file; the velocity is shifted by half a time step spectrally, intensity[f][i] = sum_t p * u_shifted / steps.
+ * kw_q_term = computeQTerm (cpp:1783-2080) on per-sensor intensities in mask order (local points of this rank);
+ * kw_stream KW_S_Q_TERM_C does the same for the compressed intensities inside kw_finish. */
+int kw_intensity_avg_block(const float* p, const float* const* u, int ncomp, uint64_t n, uint64_t steps, float* const* intensity);
+int kw_q_term(kw_ctx* ctx, const float* const* intensity, int ncomp, float* q_out, uint64_t capacity);
+
 /* Compression helpers.  kw_c40_encode / kw_c40_decode = CompressHelper::convertFloatCTo40b / convert40bToFloatC
  * (Compression/CompressHelper.cpp:292-389 / :224-290) on n complex values (interleaved re, im <-> 5 bytes each), run by the
  * device code the compressed streams use; max_exp = 138 (pressure) or 114 (velocity), CompressHelper.h:91-92.

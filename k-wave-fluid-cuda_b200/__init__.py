@@ -12,6 +12,7 @@ from .capi import (  # noqa: F401
     c40_decode,
     c40_encode,
     fft_c2r_3d,
+    intensity_avg_block,
     fft_r2c_3d,
     library_path,
     load_library,

@@ -127,6 +127,8 @@ def load_library():
         "kw_comm_bytes": [vp, C.POINTER(C.c_double)],
         "kw_comm_mode": [vp, C.POINTER(C.c_int)],
         "kw_set_time_index": [vp, u64],
+        "kw_intensity_avg_block": [vp, vp, i32, u64, u64, vp],
+        "kw_q_term": [vp, vp, i32, vp, u64],
         "kw_stream_state_size": [vp, i32, C.POINTER(u64)],
         "kw_stream_state_get": [vp, i32, vp, u64],
         "kw_stream_state_set": [vp, i32, vp, u64],
@@ -182,6 +184,18 @@ def c40_decode(packed, max_exp):
     out = np.empty(b.shape[:-1], dtype=np.complex64)
     _check(load_library().kw_c40_decode(b.ctypes.data, out.size, max_exp, out.ctypes.data))
     return out
+
+
+def intensity_avg_block(p, u_list):
+    """computeAverageIntensities on one block: p and every u of shape (steps, n) -> list of intensities of shape (n,)."""
+    p = np.ascontiguousarray(p, dtype=np.float32)
+    us = [np.ascontiguousarray(u, dtype=np.float32) for u in u_list]
+    steps, n = p.shape
+    outs = [np.zeros(n, np.float32) for _ in us]
+    up = (C.c_void_p * len(us))(*[u.ctypes.data for u in us])
+    op = (C.c_void_p * len(us))(*[o.ctypes.data for o in outs])
+    _check(load_library().kw_intensity_avg_block(p.ctypes.data, up, len(us), n, steps, op))
+    return outs
 
 
 def nccl_unique_id():
@@ -342,6 +356,14 @@ class Simulation:
         _check(self.lib.kw_set_time_index(self.ctx, st["t_index"]))
         for sid, buf in st["streams"].items():
             _check(self.lib.kw_stream_state_set(self.ctx, sid, buf.ctypes.data, buf.size))
+
+    def q_term(self, intensities):
+        """computeQTerm on per-sensor intensities (mask order)."""
+        ins = [np.ascontiguousarray(i, dtype=np.float32) for i in intensities]
+        out = np.zeros(ins[0].size, np.float32)
+        ip = (C.c_void_p * len(ins))(*[i.ctypes.data for i in ins])
+        _check(self.lib.kw_q_term(self.ctx, ip, len(ins), out.ctypes.data, out.size))
+        return out
 
     def compression_bases(self, shifted=False):
         """(oSize, bSize, bE, bE_1) as generated by the context (complex64, shape (harmonics, bSize))."""

@@ -1667,10 +1667,10 @@ static int step_sharded(kw_ctx* c) {
 // the I_avg_c values are scattered onto a zero grid, differentiated spectrally along their own axis (multiplier i*k,
 // k = 2 pi / d * shift / N; the reference runs 1-D R2C / C2R per axis, here the multiplier sits between the z transforms of
 // the 3-D pipeline like the other operators), summed in the order x, y, z, negated and gathered at the sensor points.
-static int compute_q_term_c(kw_ctx* c) {
+static int compute_q_term(kw_ctx* c, const float* const* intensity, float* q_out) {
   const Geometry& g = c->g;
   const kw_config& cf = c->cfg;
-  Stream& q = c->streams[KW_S_Q_TERM_C];
+  Stream& q = c->streams[KW_S_P_RAW];  // only its "not whole-domain" flag matters to sample_one below
   float *grid = nullptr, *acc = nullptr;
   KW_TRY(dalloc(c, (void**)&grid, g.n * sizeof(float)));
   KW_TRY(dalloc(c, (void**)&acc, g.n * sizeof(float)));
@@ -1693,7 +1693,7 @@ static int compute_q_term_c(kw_ctx* c) {
     KW_TRY(dalloc(c, (void**)&dik, ik.size() * sizeof(float2), false));
     KW_CUDA(cudaMemcpyAsync(dik, ik.data(), ik.size() * sizeof(float2), cudaMemcpyHostToDevice, c->st));
     KW_CUDA(cudaStreamSynchronize(c->st));
-    const float* I = c->streams[KW_S_IX_AVG_C + f].dbuf;
+    const float* I = intensity[f];
     KW_CUDA(cudaMemsetAsync(grid, 0, g.n * sizeof(float), c->st));
     if (c->nsens) {
       if (cf.sensor_mask_type == 0) {
@@ -1720,11 +1720,42 @@ static int compute_q_term_c(kw_ctx* c) {
     if (g.nranks > 1) KW_TRY(release_buffer(c, 3, c->st));
   }
   if (c->nsens) {
-    sample_one<kOpNone>(c, q, acc, q.dbuf);
-    k_negate<<<ew_grid(c->nsens), 256, 0, c->st>>>(q.dbuf, c->nsens);
+    Stream gather = q;
+    gather.all = false;
+    sample_one<kOpNone>(c, gather, acc, q_out);
+    k_negate<<<ew_grid(c->nsens), 256, 0, c->st>>>(q_out, c->nsens);
     c->launches++;
   }
   return KW_OK;
+}
+static int compute_q_term_c(kw_ctx* c) {
+  const float* I[3] = {c->streams[KW_S_IX_AVG_C].dbuf, c->streams[KW_S_IY_AVG_C].dbuf, c->streams[KW_S_IZ_AVG_C].dbuf};
+  return compute_q_term(c, I, c->streams[KW_S_Q_TERM_C].dbuf);
+}
+
+// computeAverageIntensities (KSpaceFirstOrderSolver.cpp:1231-1534) for a block of n sensor points with `steps` stored samples
+// each (series laid out [step][point], as in the output file): the velocity is shifted by half a time step -- the
+// reference's R2C / * exp(i pi shift / steps) / C2R along time is a circular convolution with the real kernel h built
+// below in double precision (any number of steps, no FFT length restriction) -- and I = sum_t p * u_shifted / steps.
+static __global__ void k_intensity_avg(const float* __restrict__ p, const float* __restrict__ u, const float* __restrict__ h, float* I, size_t n,
+                                       int steps, int tchunk) {
+  extern __shared__ float sh[];  // the kernel h
+  for (int m = threadIdx.x; m < steps; m += blockDim.x) sh[m] = h[m];
+  __syncthreads();
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t0 = blockIdx.y * tchunk, t1 = min(steps, t0 + tchunk);
+  float acc = 0.f;
+  for (int t = t0; t < t1; ++t) {
+    float us = 0.f;
+    int m = t;  // (t - s) mod steps, walked downwards
+    for (int s = 0; s < steps; ++s) {
+      us = fmaf(__ldg(u + (size_t)s * n + i), sh[m], us);
+      m = m == 0 ? steps - 1 : m - 1;
+    }
+    acc = fmaf(__ldg(p + (size_t)t * n + i), us, acc);
+  }
+  atomicAdd(I + i, acc);
 }
 
 }  // namespace kw
@@ -1970,6 +2001,65 @@ int kw_compression_bases(kw_ctx* c, int shifted, float* be, float* be1, uint64_t
   KW_CUDA(cudaStreamSynchronize(c->st));
   if (be) KW_CUDA(cudaMemcpy(be, c->d_be[shifted ? 1 : 0], n * sizeof(float2), cudaMemcpyDeviceToHost));
   if (be1) KW_CUDA(cudaMemcpy(be1, c->d_be1[shifted ? 1 : 0], n * sizeof(float2), cudaMemcpyDeviceToHost));
+  return KW_OK;
+}
+
+// ---- post-processing of stored raw series (--I_avg, --Q_term): cpp:1231-1534, :1783-2080 ----------------------------------
+int kw_intensity_avg_block(const float* p, const float* const* u, int ncomp, uint64_t n, uint64_t steps, float* const* intensity) {
+  if (!p || !u || !intensity || ncomp < 1 || ncomp > 3 || n == 0 || steps == 0) return fail(KW_ERR_INVALID, "kw_intensity_avg_block: bad argument");
+  if (steps > 12000) return fail(KW_ERR_INVALID, "kw_intensity_avg_block: more than 12000 stored steps are not supported");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(KW_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  std::vector<float> h(steps);
+  {  // h[m] = (1 + 2 sum_{k=1}^{(steps-1)/2} cos(2 pi k m / steps + pi k / steps)) / steps; the Nyquist bin contributes nothing
+    const long long K = ((long long)steps - 1) / 2;
+#pragma omp parallel for schedule(static)
+    for (long long m = 0; m < (long long)steps; ++m) {
+      double acc = 1.0;
+      for (long long k = 1; k <= K; ++k) acc += 2.0 * cos((2.0 * M_PI * (double)k * (double)m + M_PI * (double)k) / (double)steps);
+      h[m] = (float)(acc / (double)steps);
+    }
+  }
+  float *dp = nullptr, *du = nullptr, *dh = nullptr, *dI = nullptr;
+  const size_t bytes = n * steps * sizeof(float);
+  KW_CUDA(cudaMalloc(&dp, bytes));
+  KW_CUDA(cudaMalloc(&du, bytes));
+  KW_CUDA(cudaMalloc(&dh, steps * sizeof(float)));
+  KW_CUDA(cudaMalloc(&dI, n * sizeof(float)));
+  KW_CUDA(cudaMemcpy(dp, p, bytes, cudaMemcpyHostToDevice));
+  KW_CUDA(cudaMemcpy(dh, h.data(), steps * sizeof(float), cudaMemcpyHostToDevice));
+  const int tchunk = 32;
+  const dim3 grid((unsigned)((n + 127) / 128), (unsigned)((steps + tchunk - 1) / tchunk));
+  KW_CUDA(cudaFuncSetAttribute(k_intensity_avg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(steps * sizeof(float))));
+  for (int f = 0; f < ncomp; ++f) {
+    KW_CUDA(cudaMemcpy(du, u[f], bytes, cudaMemcpyHostToDevice));
+    KW_CUDA(cudaMemset(dI, 0, n * sizeof(float)));
+    k_intensity_avg<<<grid, 128, steps * sizeof(float)>>>(dp, du, dh, dI, n, (int)steps, tchunk);
+    KW_CUDA(cudaGetLastError());
+    k_divide<<<ew_grid(n), 256>>>(dI, (float)steps, n);
+    KW_CUDA(cudaMemcpy(intensity[f], dI, n * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  cudaFree(dp), cudaFree(du), cudaFree(dh), cudaFree(dI);
+  return KW_OK;
+}
+int kw_q_term(kw_ctx* c, const float* const* intensity, int ncomp, float* q_out, uint64_t capacity) {
+  if (!c || !intensity || !q_out) return fail(KW_ERR_INVALID, "null argument");
+  if (!c->preprocessed) return fail(KW_ERR_STATE, "kw_q_term before kw_preprocess");
+  if (ncomp != (c->g.nz == 1 ? 2 : 3)) return fail(KW_ERR_INVALID, "kw_q_term: one intensity per dimension");
+  if (capacity < c->nsens) return fail(KW_ERR_INVALID, "kw_q_term: buffer too small");
+  if (c->nsens == 0) return KW_OK;
+  float* dI[3] = {};
+  float* dq = nullptr;
+  for (int f = 0; f < ncomp; ++f) {
+    KW_TRY(dalloc(c, (void**)&dI[f], c->nsens * sizeof(float), false));
+    KW_CUDA(cudaMemcpyAsync(dI[f], intensity[f], c->nsens * sizeof(float), cudaMemcpyHostToDevice, c->st));
+  }
+  KW_TRY(dalloc(c, (void**)&dq, c->nsens * sizeof(float)));
+  KW_CUDA(cudaStreamSynchronize(c->st));
+  KW_TRY(compute_q_term(c, dI, dq));
+  KW_CUDA(cudaMemcpyAsync(q_out, dq, c->nsens * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+  KW_CUDA(cudaStreamSynchronize(c->st));
+  if (c->cs) KW_CUDA(cudaStreamSynchronize(c->cs));
   return KW_OK;
 }
 

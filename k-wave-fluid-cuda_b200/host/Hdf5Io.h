@@ -119,6 +119,16 @@ class Hdf5File {
     H5Sclose(fspace);
     if (e < 0) throw std::ios::failure("Error: cannot write to the output file.");
   }
+  // read `count` elements at `start` (dataset dimension order) into a dense buffer (Hdf5File::readHyperSlab, Hdf5File.cpp:559-600)
+  void readHyperslab(hid_t dataset, const std::vector<hsize_t>& start, const std::vector<hsize_t>& count, float* data) const {
+    const hid_t fspace = H5Dget_space(dataset);
+    H5Sselect_hyperslab(fspace, H5S_SELECT_SET, start.data(), nullptr, count.data(), nullptr);
+    const hid_t mspace = H5Screate_simple((int)count.size(), count.data(), nullptr);
+    const herr_t e = H5Dread(dataset, H5T_NATIVE_FLOAT, mspace, fspace, H5P_DEFAULT, data);
+    H5Sclose(mspace);
+    H5Sclose(fspace);
+    if (e < 0) throw std::ios::failure("Error: cannot read from \"" + mName + "\".");
+  }
   void writeWhole(hid_t loc, const std::string& name, const std::vector<hsize_t>& dims, const std::vector<hsize_t>& chunk, const void* data,
                   bool isFloat, unsigned deflate) {
     const hid_t d = createDataset(loc, name, dims, chunk, isFloat, deflate);

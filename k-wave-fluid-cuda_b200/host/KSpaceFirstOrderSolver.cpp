@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <ctime>
+#include <functional>
 #include <new>
 #include <stdexcept>
 #include <thread>
@@ -182,7 +183,7 @@ void KSpaceFirstOrderSolver::loadInputData() {
   if (s.nonlinearFlag) loadArray("BonA", KW_BONA, false, true);
   if (s.absorbingFlag) loadArray("alpha_coeff", KW_ALPHA_COEFF, false, true);
   for (const auto& a : kOperators) loadArray(a.name, a.id, a.isIndex, is3D || !isZArray(a.id));
-  const bool needShift = mCmd.uNonStaggeredRaw || mCmd.uNonStaggeredC || mCmd.iAvgC || mCmd.qTermC;
+  const bool needShift = mCmd.uNonStaggeredRaw || mCmd.uNonStaggeredC || mCmd.iAvgC || mCmd.qTermC || mCmd.iAvg || mCmd.qTerm;
   for (const auto& a : kShifts) loadArray(a.name, a.id, a.isIndex, needShift && (is3D || !isZArray(a.id)));
   if (s.sensorMaskType == 0) loadArray("sensor_mask_index", KW_SENSOR_MASK_INDEX, true, true);
   else loadArray("sensor_mask_corners", KW_SENSOR_MASK_CORNERS, true, true);
@@ -383,6 +384,84 @@ void KSpaceFirstOrderSolver::writeAggregates() {
   final_field(mCmd.uFinal, KW_UX_SGX, "ux_final");
   final_field(mCmd.uFinal, KW_UY_SGY, "uy_final");
   final_field(mCmd.uFinal && s.nz > 1, KW_UZ_SGZ, "uz_final");
+}
+
+// one value per sensor point in the layout of an aggregated stream: (Nsens,1,1), or one 3-D dataset per cuboid in a group
+void KSpaceFirstOrderSolver::writeSensorValues(const std::string& name, const float* data) {
+  const hid_t root = mOutputFile.root();
+  if (mScalars.sensorMaskType == 0) {
+    mOutputFile.writeWhole(root, name, {1, 1, mSensorPoints}, {1, 1, mSensorPoints}, data, true, mCmd.compressionLevel);
+    return;
+  }
+  const hid_t group = mOutputFile.createGroup(root, name);
+  uint64_t offset = 0;
+  for (size_t k = 0; k < mCorners.size() / 6; ++k) {
+    const uint64_t* c = &mCorners[6 * k];
+    const hsize_t cx = c[3] - c[0] + 1, cy = c[4] - c[1] + 1, cz = c[5] - c[2] + 1;
+    mOutputFile.writeWhole(group, std::to_string(k + 1), {cz, cy, cx}, {cz, cy, cx}, data + offset, true, mCmd.compressionLevel);
+    offset += cx * cy * cz;
+  }
+  mOutputFile.closeGroup(group);
+}
+
+// Average intensity from the stored raw series (computeAverageIntensities, cpp:1231-1534): p and the non-staggered velocity
+// are read back from the output file block by block (all stored steps of a block of sensor points), the device shifts the
+// velocity by half a time step and accumulates p * u; then the Q term from the three intensities (computeQTerm, :1783-2080).
+void KSpaceFirstOrderSolver::computeAverageIntensities() {
+  const int ncomp = mScalars.nz > 1 ? 3 : 2;
+  const uint64_t steps = mSamplingSteps;
+  const OutputStream* sp = nullptr;
+  const OutputStream* su[3] = {};
+  for (const auto& st : mStreams) {
+    if (st.id == KW_S_P_RAW) sp = &st;
+    for (int k = 0; k < ncomp; ++k)
+      if (st.id == KW_S_UX_NS_RAW + k) su[k] = &st;
+  }
+  if (!sp || !su[0] || !su[1] || (ncomp == 3 && !su[2])) throw std::runtime_error("Error: the raw series needed by --I_avg / --Q_term were not stored.");
+  std::vector<std::vector<float>> intensity(ncomp, std::vector<float>(mSensorPoints, 0.f));
+  // block size: --block_size points, else what keeps the five host / device buffers of a block near 1 GB (cpp:1281-1300)
+  uint64_t maxPoints = mCmd.blockSize ? mCmd.blockSize : std::max<uint64_t>(1, (48ull << 20) / steps);
+  std::vector<float> bp, bu[3];
+  auto process = [&](uint64_t first, uint64_t n, const std::function<void(const OutputStream&, float*)>& read) {
+    bp.resize(n * steps);
+    read(*sp, bp.data());
+    const float* up[3] = {};
+    float* ip[3] = {};
+    for (int k = 0; k < ncomp; ++k) {
+      bu[k].resize(n * steps);
+      read(*su[k], bu[k].data());
+      up[k] = bu[k].data(), ip[k] = intensity[k].data() + first;
+    }
+    check(kw_intensity_avg_block(bp.data(), up, ncomp, n, steps, ip));
+  };
+  if (mScalars.sensorMaskType == 0) {
+    for (uint64_t i = 0; i < mSensorPoints; i += maxPoints) {
+      const uint64_t n = std::min<uint64_t>(maxPoints, mSensorPoints - i);
+      process(i, n, [&](const OutputStream& st, float* dst) { mOutputFile.readHyperslab(st.dataset, {0, 0, i}, {1, steps, n}, dst); });
+    }
+  } else {
+    uint64_t offset = 0;
+    for (size_t k = 0; k < mCorners.size() / 6; ++k) {
+      const uint64_t* c = &mCorners[6 * k];
+      const hsize_t cx = c[3] - c[0] + 1, cy = c[4] - c[1] + 1, cz = c[5] - c[2] + 1;
+      const uint64_t slab = std::max<uint64_t>(1, maxPoints / (cx * cy));  // whole z slices of the cuboid per block
+      for (uint64_t z = 0; z < cz; z += slab) {
+        const uint64_t zc = std::min<uint64_t>(slab, cz - z);
+        process(offset + z * cx * cy, zc * cx * cy,
+                [&](const OutputStream& st, float* dst) { mOutputFile.readHyperslab(st.cuboidDatasets[k], {0, z, 0, 0}, {steps, zc, cy, cx}, dst); });
+      }
+      offset += cx * cy * cz;
+    }
+  }
+  const char* names[3] = {"Ix_avg", "Iy_avg", "Iz_avg"};
+  if (mCmd.iAvg)
+    for (int k = 0; k < ncomp; ++k) writeSensorValues(names[k], intensity[k].data());
+  if (mCmd.qTerm) {
+    std::vector<float> q(mSensorPoints, 0.f);
+    const float* ip[3] = {intensity[0].data(), intensity[1].data(), ncomp == 3 ? intensity[2].data() : nullptr};
+    check(kw_q_term(mCtx, ip, ncomp, q.data(), q.size()));
+    writeSensorValues("Q_term", q.data());
+  }
 }
 
 void KSpaceFirstOrderSolver::saveScalarsToOutputFile() {  // Parameters::saveScalarsToOutputFile (Parameters.cpp:559-650)
@@ -587,6 +666,7 @@ void KSpaceFirstOrderSolver::compute() {
   mPostProcessingTime.start();
   check(kw_finish(mCtx));
   writeAggregates();
+  if (mCmd.iAvg || mCmd.qTerm) computeAverageIntensities();
   saveScalarsToOutputFile();
   mPostProcessingTime.stop();
   mTotalTime.stop();

@@ -89,6 +89,8 @@ class KSpaceFirstOrderSolver {
   void recoverFromCheckpoint();      // cpp:186-228 (state) + OutputStreamContainer::reopenStreams
   void flushSeries(bool final);
   void writeAggregates();
+  void computeAverageIntensities();  // cpp:1231-1534 (+ computeQTerm :1783-2080): --I_avg / --Q_term from the stored series
+  void writeSensorValues(const std::string& name, const float* data);
   void writeOutputHeader();
   void saveScalarsToOutputFile();
   void log(int level, const char* fmt, ...) const;

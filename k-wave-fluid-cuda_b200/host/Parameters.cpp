@@ -13,10 +13,11 @@ std::string CommandLine::usage() {
          "  -t <n>  -g <id>  -r <pct>  -c <0-9>  -s <step>  --benchmark <steps>  --verbose <0-2>  --copy_sensor_mask\n"
          "  -p|--p_raw --p_c --p_rms --p_max --p_min --p_max_all --p_min_all --p_final\n"
          "  -u|--u_raw --u_c --u_non_staggered_raw --u_non_staggered_c --u_rms --u_max --u_min --u_max_all --u_min_all --u_final\n"
+         "  --I_avg  --Q_term  --block_size <n>  (from the stored raw series)\n"
          "  --I_avg_c  --Q_term_c  --period <steps> | --frequency <Hz>  --mos <n>  --harmonics <n>  --no_overlap  --40-bit_complex\n"
          "  --checkpoint_file <file> with --checkpoint_interval <seconds> and/or --checkpoint_timesteps <steps>\n"
          "  -h|--help  --version\n"
-         "Not available in this build: --I_avg, --Q_term, --post\n";
+         "Not available in this build: --post\n";
 }
 
 static long toLong(const char* s, const char* what, long minValue) {
@@ -99,8 +100,9 @@ void CommandLine::parse(int argc, char** argv) {
       case 28: uNonStaggeredC = true; break;
       case 30: iAvgC = true; break;
       case 32: qTermC = true; break;
-      case 29: case 31: case 33:
-        throw std::invalid_argument("Error: --I_avg, --Q_term and --post (post-processing of stored raw series) are not available in this build.");
+      case 29: iAvg = true; break;
+      case 31: qTerm = true; break;
+      case 33: throw std::invalid_argument("Error: --post (post-processing of an existing output file only) is not available in this build.");
       case 34: blockSize = (uint64_t)toLong(optarg, "--block_size", 1); break;
       case 35: noOverlap = true; break;
       case 36: c40bit = true; break;
@@ -116,6 +118,9 @@ void CommandLine::parse(int argc, char** argv) {
     throw std::invalid_argument("Error: Checkpoint interval or the number of time steps to checkpoint was not specified.");
   if (anyCompressed() && period == 0.f && frequency == 0.f)
     throw std::invalid_argument("Error: Compression (--p_c, --u_c, --u_non_staggered_c, --I_avg_c, --Q_term_c) needs --period or --frequency.");
+  // --I_avg / --Q_term are computed from the stored raw series of p and the non-staggered velocity, which are therefore
+  // stored too (OutputStreamContainer.cpp:229-262)
+  if (iAvg || qTerm) pRaw = uNonStaggeredRaw = true;
   // nothing selected: this fork of the reference stores nothing (CommandLineParameters.cpp:938-947 sets
   // mStorePressureRawFlag = false where upstream k-Wave defaults to --p_raw); the scalars and the header are still written
 }

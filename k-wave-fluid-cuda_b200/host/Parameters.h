@@ -26,7 +26,7 @@ struct CommandLine {
   // outputs
   bool pRaw = false, pC = false, pRms = false, pMax = false, pMin = false, pMaxAll = false, pMinAll = false, pFinal = false;
   bool uRaw = false, uC = false, uRms = false, uMax = false, uMin = false, uMaxAll = false, uMinAll = false, uFinal = false;
-  bool uNonStaggeredRaw = false, uNonStaggeredC = false, iAvgC = false, qTermC = false;
+  bool uNonStaggeredRaw = false, uNonStaggeredC = false, iAvgC = false, qTermC = false, iAvg = false, qTerm = false;
   // compression
   float frequency = 0.f, period = 0.f;
   uint64_t mos = 1, harmonics = 1;

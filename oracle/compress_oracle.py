@@ -235,3 +235,24 @@ def q_term(cfg, intensities, lin_index):
         xk = np.fft.rfft(grid.reshape(nz, ny, nx), axis=ax) * ik.reshape(shp)
         total += np.fft.irfft(xk, n=n, axis=ax)
     return (-total).reshape(-1)[idx]
+
+
+def intensity_avg(p, u):
+    """computeAverageIntensities (KSpaceFirstOrderSolver.cpp:1231-1534) for series of shape (steps, n): the velocity is shifted by
+    half a time step spectrally -- R2C along time, * exp(i*pi*shift/steps) / steps with shift = (k + steps/2) % steps - steps/2,
+    C2R (which ignores the imaginary part of the Nyquist bin) -- and I = sum_t p * u_shifted / steps."""
+    p = np.asarray(p, np.float64)
+    u = np.asarray(u, np.float64)
+    steps = p.shape[0]
+    k = np.arange(steps // 2 + 1)
+    shift = (k + steps // 2) % steps - steps // 2
+    kx = np.exp(1j * np.pi * shift / steps)
+    us = np.fft.irfft(np.fft.rfft(u, axis=0) * kx[:, None], n=steps, axis=0)
+    return (p * us).sum(axis=0) / steps
+
+
+def half_step_kernel(steps):
+    """The same shift as a circular convolution kernel: u_shifted[t] = sum_s u[s] * h[(t - s) % steps]."""
+    m = np.arange(steps)
+    kk = np.arange(1, (steps - 1) // 2 + 1)
+    return (1.0 + 2.0 * np.cos(2.0 * np.pi * np.outer(m, kk) / steps + np.pi * kk / steps).sum(axis=1)) / steps

@@ -34,6 +34,7 @@ CASES = {
                  ["--Q_term_c", "--I_avg_c", "--period", "20", "--harmonics", "2"]),
     # (cuboid masks with --Q_term_c / --I_avg_c: the reference's own binary aborts or writes NaN there, so that combination is
     #  checked against the oracle instead: tests/test_streams_gpu.py::test_q_term_c_matches_oracle[cuboid])
+    "i_avg_q_term_raw": (dict(nonlinear=True, absorbing=True, source="p_plane", n_sensor=120, shifts=True), ["--I_avg", "--Q_term", "--block_size", "50"]),
     "2d_p0": (dict(ny=32, nz=1, nonlinear=False, absorbing=False, source="p0", sensor="cuboid"), ["-p", "--p_min", "--u_max_all"]),
 }
 
@@ -96,7 +97,7 @@ def test_command_line_errors_exit_like_the_reference(tmp_path):
     for args, needle in (([], "Input file was not specified"), (["-i", "a"], "Output file was not specified"),
                          (["-i", "a", "-o", "b", "--checkpoint_interval", "5"], "Checkpoint file was not specified"),
                          (["-i", "a", "-o", "b", "--checkpoint_file", "c"], "Checkpoint interval or the number of time steps"),
-                         (["-i", "a", "-o", "b", "--Q_term"], "not available in this build"), (["-i", "a", "-o", "b", "--Q_term_c"], "--period or --frequency"),
+                         (["-i", "a", "-o", "b", "--post"], "not available in this build"), (["-i", "a", "-o", "b", "--Q_term_c"], "--period or --frequency"),
                          (["-i", "a", "-o", "b", "--p_c"], "--period or --frequency"), (["-i", "a", "-o", "b", "-s", "0"], "Invalid value"),
                          (["-i", "a", "-o", "b", "-c", "12"], "Invalid value"),
                          (["-i", str(tmp_path / "missing.h5"), "-o", "b"], "could not be opened")):  # fmt: skip

@@ -210,3 +210,33 @@ def test_q_term_c_matches_oracle(kw, synth, shape, sensor):
     err = rel_l2(got["KW_S_Q_TERM_C"], ref)
     print(f"Q_term_c {shape}: rel-L2 {err:.3e}, scale {np.abs(ref).max():.3e}")
     assert np.abs(ref).max() > 0 and err <= TOL
+
+
+@pytest.mark.parametrize("shape", [(32, 32, 32), (64, 32, 1)], ids=["3d", "2d"])
+def test_raw_series_intensity_and_q_term(kw, synth, shape):
+    """--I_avg / --Q_term building blocks (computeAverageIntensities cpp:1231-1534, computeQTerm :1783-2080): the half-step
+    temporal shift of the stored velocity series (any number of steps: 77 here) and the Q term, against the NumPy restatement."""
+    nt = 77
+    cfg, arrays = synth.make_case(*shape, nt=nt, nonlinear=True, absorbing=True, source="p_plane", n_sensor=150, shifts=True)
+    comps = ["X", "Y"] + (["Z"] if shape[2] > 1 else [])
+    streams = ["KW_S_P_RAW"] + [f"KW_S_U{a}_NS_RAW" for a in comps]
+    sim = kw.Simulation(cfg, arrays, streams=streams, raw_rows_capacity=nt)
+    assert sim.run(nt) == nt
+    sim.finish()
+    got = {s: sim.fetch(s) for s in streams}
+    p = got["KW_S_P_RAW"]
+    us = [got[f"KW_S_U{a}_NS_RAW"] for a in comps]
+    mine = kw.intensity_avg_block(p, us)
+    scale = max(np.abs(co.intensity_avg(p, u)).max() for u in us)
+    for a, m, u in zip(comps, mine, us):
+        ref = co.intensity_avg(p, u)
+        err = float(np.linalg.norm(m - ref) / max(np.linalg.norm(ref), 1e-300))
+        print(f"I{a.lower()}_avg {shape}: rel-L2 {err:.3e}, max-abs {np.abs(m - ref).max():.3e} (scale {scale:.3e})")
+        assert np.abs(m - ref).max() <= 2e-5 * scale
+    q = sim.q_term(mine)
+    sim.close()
+    idx = arrays["sensor_mask_index"].astype(np.int64) - 1
+    ref_q = co.q_term(cfg, mine, idx)
+    err = rel_l2(q, ref_q)
+    print(f"Q_term {shape}: rel-L2 {err:.3e}")
+    assert err <= TOL
