@@ -35,12 +35,16 @@ CASES = {
     # (cuboid masks with --Q_term_c / --I_avg_c: the reference's own binary aborts or writes NaN there, so that combination is
     #  checked against the oracle instead: tests/test_streams_gpu.py::test_q_term_c_matches_oracle[cuboid])
     "i_avg_q_term_raw": (dict(nonlinear=True, absorbing=True, source="p_plane", n_sensor=120, shifts=True), ["--I_avg", "--Q_term", "--block_size", "50"]),
+    "cuboid_compressed": (dict(nonlinear=True, absorbing=True, source="p_plane", sensor="cuboid", period=20, shifts=True),
+                          ["--p_c", "--u_c", "--u_non_staggered_c", "--period", "20", "--harmonics", "2", "-s", "3"]),
     "2d_p0": (dict(ny=32, nz=1, nonlinear=False, absorbing=False, source="p0", sensor="cuboid"), ["-p", "--p_min", "--u_max_all"]),
 }
 
 
-def run(binary, fin, fout, flags):
+def run(binary, fin, fout, flags, may_fail=False):
     r = subprocess.run([binary, "-i", fin, "-o", fout, "-t", "4", "--verbose", "0"] + flags, capture_output=True, text=True)
+    if may_fail and r.returncode != 0:
+        return None
     assert r.returncode == 0, f"{os.path.basename(binary)} failed:\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"
     return kwh5.read_file(fout)
 
@@ -58,8 +62,11 @@ def test_same_file_same_flags_same_output(synth, tmp_path, name):
     cfg, arrays = synth.make_case(32, ny, nz, nt=nt, **kwargs)
     fin = str(tmp_path / "in.h5")
     kwh5.write_input(fin, cfg, arrays)
-    ref = run(REF, fin, str(tmp_path / "ref.h5"), flags)
     got = run(OURS, fin, str(tmp_path / "out.h5"), flags)
+    ref = run(REF, fin, str(tmp_path / "ref.h5"), flags, may_fail=True)
+    if ref is None:  # the reference's own binary aborts on some flag / mask combinations: ours ran, nothing to compare with
+        assert all(np.isfinite(o["data"]).all() for o in got.values() if o["kind"] == "f32")
+        pytest.skip("the reference binary fails on this configuration")
     ref_ds = {p: o for p, o in ref.items() if o["kind"] != "group"}
     got_ds = {p: o for p, o in got.items() if o["kind"] != "group"}
     assert set(ref_ds) == set(got_ds), (sorted(set(ref_ds) ^ set(got_ds)))
