@@ -1671,9 +1671,22 @@ static int compute_q_term(kw_ctx* c, const float* const* intensity, float* q_out
   const Geometry& g = c->g;
   const kw_config& cf = c->cfg;
   Stream& q = c->streams[KW_S_P_RAW];  // only its "not whole-domain" flag matters to sample_one below
+  // two full-grid scratch arrays and the i*k vectors live only for this call
+  struct Scratch {
+    std::vector<void*> p;
+    ~Scratch() {
+      for (void* q : p) cudaFree(q);
+    }
+  } scratch;
+  auto salloc = [&](void** p, size_t bytes) -> int {
+    KW_CUDA(cudaMalloc(p, bytes));
+    scratch.p.push_back(*p);
+    return KW_OK;
+  };
   float *grid = nullptr, *acc = nullptr;
-  KW_TRY(dalloc(c, (void**)&grid, g.n * sizeof(float)));
-  KW_TRY(dalloc(c, (void**)&acc, g.n * sizeof(float)));
+  KW_TRY(salloc((void**)&grid, g.n * sizeof(float)));
+  KW_TRY(salloc((void**)&acc, g.n * sizeof(float)));
+  KW_CUDA(cudaMemsetAsync(acc, 0, g.n * sizeof(float), c->st));
   const int ncomp = g.nz == 1 ? 2 : 3;
   const int len[3] = {g.nxp, g.ny, g.nz}, n[3] = {g.nx, g.ny, g.nz};
   const float d[3] = {cf.dx, cf.dy, cf.dz};
@@ -1690,7 +1703,7 @@ static int compute_q_term(kw_ctx* c, const float* const* intensity, float* q_out
       ik[i] = make_float2(0.f, nyquist && f != 0 ? 0.f : (pi2 / d[f]) * ((float)shift / (float)n[f]));
     }
     float2* dik = nullptr;
-    KW_TRY(dalloc(c, (void**)&dik, ik.size() * sizeof(float2), false));
+    KW_TRY(salloc((void**)&dik, ik.size() * sizeof(float2)));
     KW_CUDA(cudaMemcpyAsync(dik, ik.data(), ik.size() * sizeof(float2), cudaMemcpyHostToDevice, c->st));
     KW_CUDA(cudaStreamSynchronize(c->st));
     const float* I = intensity[f];
@@ -1726,6 +1739,8 @@ static int compute_q_term(kw_ctx* c, const float* const* intensity, float* q_out
     k_negate<<<ew_grid(c->nsens), 256, 0, c->st>>>(q_out, c->nsens);
     c->launches++;
   }
+  KW_CUDA(cudaStreamSynchronize(c->st));  // the scratch arrays are released on return
+  if (c->cs) KW_CUDA(cudaStreamSynchronize(c->cs));
   return KW_OK;
 }
 static int compute_q_term_c(kw_ctx* c) {
@@ -2048,19 +2063,19 @@ int kw_q_term(kw_ctx* c, const float* const* intensity, int ncomp, float* q_out,
   if (ncomp != (c->g.nz == 1 ? 2 : 3)) return fail(KW_ERR_INVALID, "kw_q_term: one intensity per dimension");
   if (capacity < c->nsens) return fail(KW_ERR_INVALID, "kw_q_term: buffer too small");
   if (c->nsens == 0) return KW_OK;
+  float* dbuf = nullptr;  // [ncomp intensities | q]
+  KW_CUDA(cudaMalloc(&dbuf, (size_t)(ncomp + 1) * c->nsens * sizeof(float)));
   float* dI[3] = {};
-  float* dq = nullptr;
   for (int f = 0; f < ncomp; ++f) {
-    KW_TRY(dalloc(c, (void**)&dI[f], c->nsens * sizeof(float), false));
-    KW_CUDA(cudaMemcpyAsync(dI[f], intensity[f], c->nsens * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    dI[f] = dbuf + (size_t)f * c->nsens;
+    cudaMemcpyAsync(dI[f], intensity[f], c->nsens * sizeof(float), cudaMemcpyHostToDevice, c->st);
   }
-  KW_TRY(dalloc(c, (void**)&dq, c->nsens * sizeof(float)));
-  KW_CUDA(cudaStreamSynchronize(c->st));
-  KW_TRY(compute_q_term(c, dI, dq));
-  KW_CUDA(cudaMemcpyAsync(q_out, dq, c->nsens * sizeof(float), cudaMemcpyDeviceToHost, c->st));
-  KW_CUDA(cudaStreamSynchronize(c->st));
-  if (c->cs) KW_CUDA(cudaStreamSynchronize(c->cs));
-  return KW_OK;
+  float* dq = dbuf + (size_t)ncomp * c->nsens;
+  int rc = compute_q_term(c, dI, dq);
+  if (rc == KW_OK && cudaMemcpyAsync(q_out, dq, c->nsens * sizeof(float), cudaMemcpyDeviceToHost, c->st) != cudaSuccess) rc = fail(KW_ERR_CUDA, "kw_q_term: copy failed");
+  cudaStreamSynchronize(c->st);
+  cudaFree(dbuf);
+  return rc;
 }
 
 int kw_comm_mode(kw_ctx* c, int* mode) {
