@@ -167,6 +167,29 @@ def test_compression_matches_reference_run(synth):
     assert fixtures.rel_l2(ix, data["Ix_avg_c"].reshape(-1)) <= 1e-5
 
 
+def test_half_step_shift_kernel_equals_the_spectral_shift():
+    """kw_intensity_avg_block applies the half-step temporal shift of computeAverageIntensities (cpp:1257-1265, :1433-1470) as a
+    circular convolution; the kernel it builds must reproduce the R2C * exp(i pi shift / n) * C2R definition for odd and even n."""
+    rng = np.random.default_rng(3)
+    for n in (5, 8, 77, 120):
+        p, u = rng.standard_normal((n, 6)), rng.standard_normal((n, 6))
+        h = co.half_step_kernel(n)
+        idx = (np.arange(n)[:, None] - np.arange(n)[None, :]) % n
+        assert np.abs((p * (h[idx] @ u)).sum(0) / n - co.intensity_avg(p, u)).max() < 1e-12
+
+
+def test_q_term_of_a_plane_wave_intensity():
+    """computeQTerm restatement: for I_x = sin(2 pi m x / Nx) on the whole grid, Q = -dIx/dx analytically."""
+    nx = ny = nz = 16
+    cfg = dict(Nx=nx, Ny=ny, Nz=nz, dx=1e-3, dy=1e-3, dz=1e-3)
+    x = np.arange(nx)
+    ix = np.broadcast_to(np.sin(2 * np.pi * 3 * x / nx), (nz, ny, nx)).reshape(-1)
+    idx = np.arange(nx * ny * nz)
+    q = co.q_term(cfg, [ix, np.zeros_like(ix), np.zeros_like(ix)], idx)
+    want = -np.broadcast_to(2 * np.pi * 3 / (nx * 1e-3) * np.cos(2 * np.pi * 3 * x / nx), (nz, ny, nx)).reshape(-1)
+    assert np.abs(q - want).max() <= 1e-6 * np.abs(want).max()
+
+
 # ---- C ABI surface --------------------------------------------------------------------------------------------------
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "kwave_b200.h")).read()
