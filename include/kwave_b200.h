@@ -137,7 +137,11 @@ int kw_synchronize(kw_ctx* ctx);
 
 /* Streams: raw / compressed series return the rows buffered since the last fetch (row = one time step or one
  * compressed frame, Nsens (x harmonics x 2) floats, sample order = mask order / cuboids concatenated x-fastest);
- * aggregated streams return their accumulator (after kw_finish: post-processed, e.g. RMS). */
+ * aggregated streams return their accumulator (after kw_finish: post-processed, e.g. RMS).
+ * Available: every id of kw_stream except KW_S_I{X,Y,Z}_AVG and KW_S_Q_TERM, which the reference computes after the run from
+ * the STORED raw series (cpp:1231-1534): use kw_intensity_avg_block / kw_q_term below on the series the host has stored.
+ * KW_S_I?_AVG_C and KW_S_Q_TERM_C create the do-not-save streams they read (p_c, u?_non_staggered_c, I?_avg_c) themselves
+ * (OutputStreamContainer.cpp:273-323); such internal streams cannot be fetched. */
 int kw_stream_info(kw_ctx* ctx, int stream_id, uint64_t* row_floats, uint64_t* rows_buffered);
 int kw_stream_fetch(kw_ctx* ctx, int stream_id, float* host, uint64_t capacity_floats, uint64_t* rows_fetched);
 /* OutputStreamContainer::postProcessStreams (cpp:950-973): RMS scaling, I_avg_c division. */
