@@ -65,6 +65,84 @@ def _worker(rank, world, port, shape, q):
     dist.destroy_process_group()
 
 
+def _step_worker(rank, world, port, q):
+    """The oracle's whole time loop with every 3-D transform running through the slab scheme (local x/y transforms, ONE
+    all-to-all, local z transform, and back), sensors sampled by the rank that owns them and rows assembled by position."""
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    sl = importlib.import_module("k-wave-fluid-cuda_b200.slab")
+    sy = importlib.import_module("k-wave-fluid-cuda_b200.synth")
+    from oracle import kspace_oracle as ko
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+
+    def all_to_all(blocks):
+        send = [torch.from_numpy(np.ascontiguousarray(b).view(np.float64).copy()) for b in blocks]
+        recv = [torch.empty_like(s) for s in send]
+        ops = []
+        for peer in range(world):
+            if peer == rank:
+                recv[peer].copy_(send[peer])
+                continue
+            ops.append(dist.isend(send[peer], peer))
+            ops.append(dist.irecv(recv[peer], peer))
+        for o in ops:
+            o.wait()
+        return [r.numpy().view(np.complex128).reshape(blocks[0].shape) for r in recv]
+
+    def gather(part, axis):
+        parts = [None] * world
+        dist.all_gather_object(parts, part)
+        return np.concatenate(parts, axis=axis)
+
+    nx, ny, nz, nt = 16, 8, 16, 12
+    cfg, arrays = sy.make_case(nx, ny, nz, nt=nt, nonlinear=True, absorbing=True, source="p_many", source_mode=1, shuffle_sensor=True, n_sensor=40)
+    z0, nzl = sl.slab_extent(nz, rank, world)
+    y0, nyl = sl.slab_extent(ny, rank, world)
+
+    class SlabOracle(ko.KSpaceOracle):
+        def _fft(self, x):  # only this rank's z-slab goes in, only its ky range comes out of the exchange
+            spec = sl.slab_rfftn(np.asarray(x, np.float64)[z0 : z0 + nzl], world, all_to_all)
+            return gather(spec, 1).astype(self.cdt)
+
+        def _ifft(self, xk):
+            loc = sl.slab_irfftn(np.asarray(xk)[:, y0 : y0 + nyl, :], nx, world, all_to_all)
+            return gather(loc, 0).astype(self.dt)
+
+    o = SlabOracle(cfg, arrays, np.float64)
+    pos, loc = sl.index_partition(arrays["sensor_mask_index"], cfg, rank, world)
+    rows = []
+    for _ in range(nt):
+        o.step()
+        rows.append(o.p[z0 : z0 + nzl].reshape(-1)[loc.astype(np.int64)].copy())  # this rank samples ITS points only
+    parts = [None] * world
+    dist.all_gather_object(parts, (pos, np.stack(rows)))
+    full = sl.assemble_rows(arrays["sensor_mask_index"].size, parts)
+    ref = ko.run(cfg, arrays, nt=nt, dtype=np.float64, record=("p_raw",))["p"]
+    q.put((rank, float(np.abs(full - ref).max() / np.abs(ref).max())))
+    dist.destroy_process_group()
+
+
+def test_time_loop_through_slab_transforms_gloo():
+    import torch.multiprocessing as mp
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_step_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err in res:
+        assert err < 1e-10, (rank, err)
+
+
 @pytest.mark.parametrize("world,shape", [(2, (8, 12, 10)), (4, (16, 8, 16))])
 def test_slab_transform_and_row_assembly_gloo(world, shape):
     import torch.multiprocessing as mp
