@@ -225,3 +225,26 @@ def test_no_cpu_fallback(kw):
     with pytest.raises(kw.KwError) as e:
         kw.Simulation(cfg, arrays)
     assert e.value.code == -2
+
+
+def test_host_file_layer_round_trip(tmp_path):
+    """The C++ host's file layer (host/Hdf5Io.h over minih5) on the CPU: create / write rows / close / reopen read-write /
+    continue / read hyperslabs -- what checkpoint-restart and the raw-series post-processing rely on; the result is also read
+    with the Python reader of the same container."""
+    import subprocess
+    import sys
+
+    pkg = os.path.join(ROOT, "k-wave-fluid-cuda_b200")
+    exe, h5 = str(tmp_path / "hdf5io_roundtrip"), str(tmp_path / "f.h5")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-std=c++17", "-O1", "-I", os.path.join(pkg, "host"), "-I", os.path.join(pkg, "csrc", "minih5"),
+                    os.path.join(ROOT, "tests", "cpp", "hdf5io_roundtrip.cpp"), os.path.join(pkg, "csrc", "minih5", "minih5.cpp"), "-o", exe],
+                   check=True)  # fmt: skip
+    r = subprocess.run([exe, h5], capture_output=True, text=True)
+    assert r.returncode == 0 and "round trip ok" in r.stdout, r.stderr
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import kwh5
+
+    f = kwh5.read_file(h5)
+    assert f["/p"]["data"].shape == (1, 6, 4) and f["/p"]["data"][0, 5, 3] == 53.0
+    assert f["/p_max/1"]["data"].shape == (2, 3, 2) and f["/"]["attrs"]["file_type"] == "output"
