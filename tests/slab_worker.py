@@ -6,13 +6,13 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run_rank(rank, world, nccl_id, shape, kwargs, nt, streams, start_index, q):
+def run_rank(rank, world, nccl_id, shape, kwargs, nt, streams, start_index, q, compression=None):
     try:
         sys.path.insert(0, ROOT)
         kw = importlib.import_module("k-wave-fluid-cuda_b200")
         cfg, arrays = kw.synth.make_case(*shape, nt=nt, **kwargs)
         sim = kw.Simulation(cfg, arrays, streams=streams, start_index=start_index, raw_rows_capacity=nt, device=rank,
-                            rank=rank, nranks=world, nccl_id=nccl_id)
+                            rank=rank, nranks=world, nccl_id=nccl_id, compression=compression)
         done = sim.run(nt)
         sim.finish()
         total, pos = sim.sensor_layout()

@@ -25,13 +25,13 @@ def rel_l2(a, b):
     return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
 
 
-def run_sharded(kw, world, shape, kwargs, nt, streams, start_index=0):
+def run_sharded(kw, world, shape, kwargs, nt, streams, start_index=0, compression=None, per_point=1):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     nccl_id = kw.nccl_unique_id()
-    procs = [ctx.Process(target=slab_worker.run_rank, args=(r, world, nccl_id, shape, kwargs, nt, streams, start_index, q)) for r in range(world)]
+    procs = [ctx.Process(target=slab_worker.run_rank, args=(r, world, nccl_id, shape, kwargs, nt, streams, start_index, q, compression)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=600) for _ in procs)
@@ -45,6 +45,14 @@ def run_sharded(kw, world, shape, kwargs, nt, streams, start_index=0):
     for s in streams:
         if s.endswith("_ALL"):  # whole-domain aggregates: slabs concatenated along z
             out[s] = np.concatenate([res[r][s] for r in range(world)], axis=1)
+        elif s.endswith("_C") and "AVG" not in s and "Q_TERM" not in s:  # compressed frames: harmonics x (re, im) values per point
+            w = per_point
+            parts = [(res[r]["pos"], res[r][s].reshape(res[r][s].shape[0], -1, w)) for r in range(world)]
+            nrows = max(p[1].shape[0] for p in parts)
+            full = np.zeros((nrows, total, w), np.float32)
+            for pos, rows in parts:
+                full[:, pos.astype(np.int64)] = rows
+            out[s] = full.reshape(nrows, -1)
         else:
             out[s] = kw.slab.assemble_rows(total, [(res[r]["pos"], res[r][s]) for r in range(world)])
     out["p_final"] = np.concatenate([res[r]["p_final"] for r in range(world)], axis=0)
@@ -114,3 +122,26 @@ def test_nccl_fallback_path(kw, synth, monkeypatch):
     got = run_sharded(kw, 2, shape, kwargs, nt, ["KW_S_P_RAW"])
     assert got["comm_mode"] == ["nccl", "nccl"]
     assert rel_l2(got["KW_S_P_RAW"], ref["p"]) <= TOL
+
+
+def test_sharded_streams_match_single_gpu(kw, synth):
+    """Non-staggered velocity, compressed frames, compressed intensity and its Q term on two slabs: identical to one GPU."""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    shape = (32, 32, 32)
+    kwargs = dict(nonlinear=True, absorbing=True, source="p_plane", n_sensor=128, shuffle_sensor=True, period=20, shifts=True)
+    nt, harm = 90, 2
+    comp = dict(period=20.0, harmonics=harm)
+    streams = ["KW_S_P_C", "KW_S_UX_NS_RAW", "KW_S_UZ_NS_RAW", "KW_S_UX_NS_C", "KW_S_IX_AVG_C", "KW_S_IZ_AVG_C", "KW_S_Q_TERM_C"]
+    got = run_sharded(kw, 2, shape, kwargs, nt, streams, compression=comp, per_point=2 * harm)
+    cfg, arrays = synth.make_case(*shape, nt=nt, **kwargs)
+    one = kw.Simulation(cfg, arrays, streams=streams, raw_rows_capacity=nt, compression=comp)
+    one.run(nt)
+    one.finish()
+    single = {s: one.fetch(s) for s in streams}
+    one.close()
+    for s in streams:
+        assert got[s].shape == single[s].shape, (s, got[s].shape, single[s].shape)
+        err = rel_l2(got[s].reshape(-1), single[s].reshape(-1))
+        print(f"sharded {s}: rel-L2 vs single GPU {err:.3e}")
+        assert err <= TOL_SHARD, (s, err)
