@@ -248,3 +248,34 @@ def test_host_file_layer_round_trip(tmp_path):
     f = kwh5.read_file(h5)
     assert f["/p"]["data"].shape == (1, 6, 4) and f["/p"]["data"][0, 5, 3] == 53.0
     assert f["/p_max/1"]["data"].shape == (2, 3, 2) and f["/"]["attrs"]["file_type"] == "output"
+
+
+def test_configuration_errors_are_reported_before_any_device_work(kw):
+    """kw_ctx_create validates the configuration first (the reference's checks: Parameters.cpp:421-424 alpha_power, main.cpp:460
+    non-uniform grids) and reports KW_ERR_INVALID with a message -- on any machine, GPU or not."""
+    import ctypes as C
+
+    lib = kw.load_library()
+
+    def create(**over):
+        kc = kw.capi.KwConfig()
+        kc.abi_version, kc.struct_size = kw.capi.KW_ABI_VERSION, C.sizeof(kw.capi.KwConfig)
+        kc.nx = kc.ny = kc.nz = 32
+        kc.nt, kc.dt, kc.dx, kc.dy, kc.dz, kc.c_ref = 10, 1e-8, 1e-4, 1e-4, 1e-4, 1500.0
+        kc.device, kc.rank, kc.nranks = -1, 0, 1
+        for k, v in over.items():
+            setattr(kc, k, v)
+        ctx = C.c_void_p()
+        rc = lib.kw_ctx_create(C.byref(kc), C.byref(ctx))
+        msg = lib.kw_last_error().decode()
+        if rc == 0:
+            lib.kw_ctx_destroy(ctx)
+        return rc, msg
+
+    for over, needle in ((dict(abi_version=99), "ABI mismatch"), (dict(nonuniform_grid_flag=1), "nonuniform_grid_flag"),
+                         (dict(absorbing_flag=1, alpha_power=1.0), "alpha_power == 1"), (dict(nz=0), "Nz must be at least 1"),
+                         (dict(nranks=2), "ncclUniqueId"), (dict(nz=1, nranks=2, nccl_unique_id=1), "one GPU")):  # fmt: skip
+        rc, msg = create(**over)
+        assert rc == -1 and needle in msg, (over, rc, msg)
+    rc, msg = create()  # a valid configuration: fails only for lack of a device here, succeeds on a GPU box
+    assert rc in (0, -2), (rc, msg)
