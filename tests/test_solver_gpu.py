@@ -120,3 +120,4 @@ def test_matches_reference_fixture(kw, synth, name):
             assert err <= TOL, (name, k, err)
     if "p_final" in data:
         assert fixtures.rel_l2(got["p_final"], data["p_final"]) <= TOL
+
