@@ -155,6 +155,14 @@ int kw_set_source_row(kw_ctx* ctx, int array_id, uint64_t t_index, const float* 
  * buffers, cuFFT layout: real [nz][ny][nx], complex [nz][ny][nx/2+1] interleaved, both unnormalised. */
 int kw_fft_r2c_3d(uint64_t nx, uint64_t ny, uint64_t nz, const float* host_real, float* host_complex);
 int kw_fft_c2r_3d(uint64_t nx, uint64_t ny, uint64_t nz, const float* host_complex, float* host_real);
+/* The fused z pass on host buffers: the kernel that replaces the z stages of cuFFT together with cudaComputePressureGradient,
+ * cudaComputeVelocityGradient, cudaComputeAbsorbtionTerm, cudaComputeSourceGradient and cudaComputeVelocityShiftIn{X,Y,Z}
+ * (KSpaceSolver/SolverCudaKernels.cu:1139,1210,1812,740,2617-2689).  in, mul: [nz][ny][nx/2+1] (complex / real, mul may be
+ * NULL); e = FFT_z(in)*(mul*scal); axis -1: out0 = IFFT_z(e); axis 0|1|2: out0 = IFFT_z(e (x) vec_{x|y|z}[k along that axis]);
+ * axis 3: out0/1/2 = the three products with vec_x, vec_y, vec_z (one forward transform feeds three inverse ones).
+ * vec_x: nx/2+1, vec_y: ny, vec_z: nz complex values.  Unnormalised transforms.  Unit-test entry; no context needed. */
+int kw_fft_zmid(uint64_t nx, uint64_t ny, uint64_t nz, int axis, const float* in, const float* mul, float scal, const float* vec_x,
+                const float* vec_y, const float* vec_z, float* out0, float* out1, float* out2);
 
 /* Checkpoint / restart (KSpaceFirstOrderSolver::saveCheckpointData cpp:1176-1224, recovery in loadInputData :186-228).
  * The state of a run is t_index, the seven state arrays (kw_get_array / kw_set_array of KW_P, KW_RHO{X,Y,Z}, KW_U?_SG?, valid

@@ -14,6 +14,7 @@ from .capi import (  # noqa: F401
     fft_c2r_3d,
     intensity_avg_block,
     fft_r2c_3d,
+    fft_zmid,
     library_path,
     load_library,
     nccl_unique_id,

@@ -117,6 +117,7 @@ def load_library():
         "kw_set_source_row": [vp, i32, u64, vp, u64],
         "kw_fft_r2c_3d": [u64, u64, u64, vp, vp],
         "kw_fft_c2r_3d": [u64, u64, u64, vp, vp],
+        "kw_fft_zmid": [u64, u64, u64, i32, vp, vp, C.c_float, vp, vp, vp, vp, vp, vp],
         "kw_last_run_ms": [vp, C.POINTER(C.c_float)],
         "kw_launch_count": [vp, C.POINTER(u64)],
         "kw_profile": [vp, i32, i32],
@@ -168,6 +169,28 @@ def fft_c2r_3d(xk, nx):
     out = np.empty((nz, ny, nx), dtype=np.float32)
     _check(lib.kw_fft_c2r_3d(nx, ny, nz, xk.ctypes.data, out.ctypes.data))
     return out
+
+
+def fft_zmid(x, axis, mul=None, scal=1.0, vec_x=None, vec_y=None, vec_z=None):
+    """The fused z pass (k_zmid) on a host half spectrum of shape (nz, ny, nx/2+1); returns one array, or three for axis 3."""
+    lib = load_library()
+    x = np.ascontiguousarray(x, dtype=np.complex64)
+    nz, ny, nxr = x.shape
+    nx = 2 * (nxr - 1)
+    keep = [x]
+
+    def ptr(a, dt):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return a.ctypes.data
+
+    outs = [np.empty_like(x) for _ in range(3 if axis == 3 else 1)]
+    op = [o.ctypes.data for o in outs] + [None] * (3 - len(outs))
+    _check(lib.kw_fft_zmid(nx, ny, nz, axis, x.ctypes.data, ptr(mul, np.float32), float(scal), ptr(vec_x, np.complex64),
+                           ptr(vec_y, np.complex64), ptr(vec_z, np.complex64), op[0], op[1], op[2]))
+    return outs if axis == 3 else outs[0]
 
 
 def c40_encode(values, max_exp):

@@ -12,6 +12,7 @@
 #pragma once
 #include "fft_core.cuh"
 #include "fft_core2.cuh"
+#include "fft_paired.cuh"
 
 namespace kw {
 
@@ -428,6 +429,103 @@ template <int N, int AXIS> __global__ void __launch_bounds__(ZCfg<N>::THREADS, K
 #pragma unroll
         for (int e = 0; e < E; ++e) p[e * estride] = v[e];
       }
+    }
+  }
+}
+// The fused z pass for Nz = 512 / 1024 on the paired plan of fft_paired.cuh: 16 points per thread, 512 threads per tile
+// (W = 16 kx at N = 512, W = 8 at N = 1024), at most 128 registers -> 16 warps per SM instead of 8.  The operator is applied
+// in the order the forward butterflies leave their outputs (paired_k), the inverse transform brings the natural order
+// back for the stores; multiplier and next tile are staged with cp.async exactly as in k_zmid.
+template <int N> struct ZPairCfg {
+  using P = Plan3<N>;
+  static constexpr int W = P::W, WK = P::WK, THREADS = P::THREADS;
+  static constexpr size_t SMEM = (size_t)N * W * sizeof(float2) + (size_t)N * W * sizeof(float) + (size_t)N * sizeof(float2);
+};
+template <int N, int AXIS> __global__ void __launch_bounds__(Plan3<N>::THREADS, 1) k_zmid_paired(ZMidArgs a) {
+  using P = Plan3<N>;
+  constexpr int W = P::W, WK = P::WK, E = 16;
+  extern __shared__ float2 smem[];
+  const int lane = threadIdx.x, w = threadIdx.y;
+  ColExchange2<W, 0> ex{smem + lane, 1};
+  float* const mulbuf = reinterpret_cast<float*>(smem + (size_t)N * W) + w * W + lane;  // slot s at + s * (WK * W)
+  float2* const svec = reinterpret_cast<float2*>(reinterpret_cast<float*>(smem + (size_t)N * W) + (size_t)N * W);  // N entries
+  const float2* __restrict__ in = a.f.in;
+  const float* __restrict__ mul = a.f.mul;
+  const unsigned estride = (unsigned)WK * a.plane;
+  if (AXIS == 2 || AXIS == 3) {
+    const float2* zv = AXIS == 2 ? a.f.vec : a.f.vec_z;
+    for (int i = lane + W * w; i < N; i += P::THREADS) svec[i] = __ldg(zv + i);
+    __syncthreads();
+  }
+  const int k0 = paired_k0<N>(w);  // frequency of register slot s: k0 + paired_ks<N>(s)
+  auto tile_base = [&](int it, int& y, int& kx) -> unsigned {
+    y = it / a.ngroups, kx = (it % a.ngroups) * W + lane;
+    return (unsigned)y * a.nxp + kx;
+  };
+  auto prefetch = [&](int it) {
+    int y, kx;
+    const float2* p = in + tile_base(it, y, kx) + (unsigned)w * a.plane;
+#pragma unroll
+    for (int e = 0; e < E; ++e) cp_async8(ex.buf + (w + WK * e) * W, p + e * estride);
+    cp_async_commit();
+  };
+  int it = blockIdx.x;
+  if (it < a.ntiles) prefetch(it);
+  for (; it < a.ntiles; it += gridDim.x) {
+    int y, kx;
+    const unsigned tb = tile_base(it, y, kx);
+    const unsigned kb = tb + (unsigned)k0 * a.plane;  // operator / output-order base
+    if (mul) {
+#pragma unroll
+      for (int s = 0; s < E; ++s) cp_async4(mulbuf + s * (WK * W), mul + kb + (unsigned)paired_ks<N>(s) * a.plane);
+    }
+    cp_async_commit();
+    float2 v[E];
+    cp_async_wait<1>();  // the tile (older group) has landed; the multiplier may still be in flight
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = ex.get(w + WK * e);
+    ex.sync();
+    paired_fwd<N>(v, w, ex, ConstTab());
+    cp_async_wait<0>();
+    asm volatile("" ::: "memory");
+    const float scal = a.f.scal;
+    const int nxt = it + gridDim.x;
+    const unsigned ob = tb + (unsigned)w * a.plane;
+    if constexpr (AXIS == 3) {
+      float2 ev[E];
+#pragma unroll
+      for (int s = 0; s < E; ++s) ev[s] = cscale(v[s], mul ? mulbuf[s * (WK * W)] * scal : scal);
+      const float2 wx = __ldg(a.f.vec + kx), wy = __ldg(a.f.vec_y + y);
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+#pragma unroll
+        for (int s = 0; s < E; ++s) v[s] = cmul(ev[s], f == 0 ? wx : f == 1 ? wy : svec[k0 + paired_ks<N>(s)]);
+        if (f < 2) paired_inv<N>(v, w, ex, ConstTab());
+        else paired_inv<N>(v, w, ex, ConstTab(), [&] {
+          if (nxt < a.ntiles) prefetch(nxt);
+        });
+        float2* __restrict__ p = (f == 0 ? a.f.out : f == 1 ? a.f.out_y : a.f.out_z) + ob;
+#pragma unroll
+        for (int e = 0; e < E; ++e) p[e * estride] = v[e];
+      }
+    } else {
+      float2 w01 = make_float2(1.f, 0.f);
+      if (AXIS == 0) w01 = __ldg(a.f.vec + kx);
+      if (AXIS == 1) w01 = __ldg(a.f.vec + y);
+#pragma unroll
+      for (int s = 0; s < E; ++s) {
+        const float m = mul ? mulbuf[s * (WK * W)] * scal : scal;
+        float2 x = cscale(v[s], m);
+        if (AXIS == 0 || AXIS == 1) x = cmul(x, w01);
+        if (AXIS == 2) x = cmul(x, svec[k0 + paired_ks<N>(s)]);
+        v[s] = x;
+      }
+      paired_inv<N>(v, w, ex, ConstTab(), [&] {
+        if (nxt < a.ntiles) prefetch(nxt);
+      });
+      float2* __restrict__ p = a.f.out + ob;
+#pragma unroll
+      for (int e = 0; e < E; ++e) p[e * estride] = v[e];
     }
   }
 }

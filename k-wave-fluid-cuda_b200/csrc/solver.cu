@@ -2215,6 +2215,74 @@ int kw_bench_col(uint64_t nx, uint64_t ny, uint64_t nz, int axis, int fused, int
   return KW_OK;
 }
 
+// The fused z pass on host buffers (unit-test entry of k_zmid, the kernel that carries every k-space operator of the step):
+//   e      = FFT_z(in) * (mul * scal)                       in, mul: [nz][ny][nx/2+1] (cuFFT layout; mul real or NULL)
+//   axis -1: out0 = IFFT_z(e)          axis 0/1/2: out0 = IFFT_z(e (x) vec_{x|y|z}[coordinate])
+//   axis  3: out0/1/2 = IFFT_z(e (x) vec_x[kx]), IFFT_z(e (x) vec_y[ky]), IFFT_z(e (x) vec_z[kz])   (pressure gradient form)
+// vec_x has nx/2+1, vec_y ny, vec_z nz complex entries.  Transforms are unnormalised in both directions.
+int kw_fft_zmid(uint64_t nx, uint64_t ny, uint64_t nz, int axis, const float* in, const float* mul, float scal, const float* vec_x,
+                const float* vec_y, const float* vec_z, float* out0, float* out1, float* out2) {
+  if (!in || !out0 || axis < -1 || axis > 3) return fail(KW_ERR_INVALID, "kw_fft_zmid: bad argument");
+  if ((axis == 0 || axis == 3) && !vec_x) return fail(KW_ERR_INVALID, "kw_fft_zmid: vec_x missing");
+  if ((axis == 1 || axis == 3) && !vec_y) return fail(KW_ERR_INVALID, "kw_fft_zmid: vec_y missing");
+  if ((axis == 2 || axis == 3) && !vec_z) return fail(KW_ERR_INVALID, "kw_fft_zmid: vec_z missing");
+  if (axis == 3 && (!out1 || !out2)) return fail(KW_ERR_INVALID, "kw_fft_zmid: three outputs needed");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(KW_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  Geometry g;
+  KW_TRY(g.init(nx, ny, nz));
+  if (g.nz == 1) return fail(KW_ERR_INVALID, "kw_fft_zmid: Nz must be a transform length");
+  const size_t rows = (size_t)g.ny * g.nz, nnat = rows * g.nxr;
+  struct Scratch {
+    std::vector<void*> p;
+    ~Scratch() {
+      for (void* q : p) cudaFree(q);
+    }
+  } sc;
+  auto alloc = [&](void** p, size_t bytes) -> int {
+    KW_CUDA(cudaMalloc(p, bytes));
+    sc.p.push_back(*p);
+    return KW_OK;
+  };
+  float2 *dnat = nullptr, *din = nullptr, *dout[3] = {}, *dv[3] = {};
+  float *dmul_nat = nullptr, *dmul = nullptr;
+  KW_TRY(alloc((void**)&dnat, nnat * sizeof(float2)));
+  KW_TRY(alloc((void**)&din, g.nc * sizeof(float2)));
+  const int nout = axis == 3 ? 3 : 1;
+  // in place for the single-output forms, out of place for the gradient form: the way the time step launches them
+  if (axis == 3) for (int k = 0; k < nout; ++k) KW_TRY(alloc((void**)&dout[k], g.nc * sizeof(float2)));
+  else dout[0] = din;
+  KW_CUDA(cudaMemcpy(dnat, in, nnat * sizeof(float2), cudaMemcpyHostToDevice));
+  k_pad_complex<<<ew_grid(g.nc), 256>>>(din, dnat, g.nxr, g.nxp, rows, 1);
+  if (mul) {
+    KW_TRY(alloc((void**)&dmul_nat, nnat * sizeof(float)));
+    KW_TRY(alloc((void**)&dmul, g.nc * sizeof(float)));
+    KW_CUDA(cudaMemcpy(dmul_nat, mul, nnat * sizeof(float), cudaMemcpyHostToDevice));
+    k_pad_real<<<ew_grid(g.nc), 256>>>(dmul, dmul_nat, g.nxr, g.nxp, rows);
+  }
+  const float* hv[3] = {vec_x, vec_y, vec_z};
+  const size_t lv[3] = {(size_t)g.nxr, (size_t)g.ny, (size_t)g.nz}, lp[3] = {(size_t)g.nxp, (size_t)g.ny, (size_t)g.nz};
+  for (int k = 0; k < 3; ++k)
+    if (hv[k]) {
+      KW_TRY(alloc((void**)&dv[k], lp[k] * sizeof(float2)));
+      KW_CUDA(cudaMemset(dv[k], 0, lp[k] * sizeof(float2)));
+      KW_CUDA(cudaMemcpy(dv[k], hv[k], lv[k] * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+  ZMidArgs za{};
+  za.f = ZField{din, dout[0], dmul, scal, axis == 3 ? dv[0] : axis >= 0 ? dv[axis] : nullptr, dout[1], dout[2], dv[1], dv[2]};
+  za.axis = axis;
+  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->zmid_w, za.ntiles = g.ny * za.ngroups, za.plane = (unsigned)((size_t)g.ny * g.nxp);
+  g.oz->zmid(za, 0);
+  KW_CUDA(cudaGetLastError());
+  float* ho[3] = {out0, out1, out2};
+  for (int k = 0; k < nout; ++k) {
+    k_pad_complex<<<ew_grid(g.nc), 256>>>(dnat, dout[k], g.nxr, g.nxp, rows, 0);
+    KW_CUDA(cudaMemcpy(ho[k], dnat, nnat * sizeof(float2), cudaMemcpyDeviceToHost));
+  }
+  KW_CUDA(cudaDeviceSynchronize());
+  return KW_OK;
+}
+
 int kw_fft_r2c_3d(uint64_t nx, uint64_t ny, uint64_t nz, const float* host_real, float* host_complex) {
   return fft3d_host(nx, ny, nz, host_real, host_complex, true);
 }
