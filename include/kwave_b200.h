@@ -144,6 +144,10 @@ int kw_synchronize(kw_ctx* ctx);
  * (OutputStreamContainer.cpp:273-323); such internal streams cannot be fetched. */
 int kw_stream_info(kw_ctx* ctx, int stream_id, uint64_t* row_floats, uint64_t* rows_buffered);
 int kw_stream_fetch(kw_ctx* ctx, int stream_id, float* host, uint64_t capacity_floats, uint64_t* rows_fetched);
+/* Part of the running accumulator of an aggregate stream (rms / max / min [_all], I_avg_c) while the loop is in flight: `count`
+ * floats from `offset`, device -> host on the solver stream (the reference exposes these only at the end of the run;
+ * used for per-step monitoring and by the end-to-end benchmark). */
+int kw_stream_peek(kw_ctx* ctx, int stream_id, uint64_t offset, float* host, uint64_t count);
 /* OutputStreamContainer::postProcessStreams (cpp:950-973): RMS scaling, I_avg_c division. */
 int kw_finish(kw_ctx* ctx);
 

@@ -113,6 +113,7 @@ def load_library():
         "kw_synchronize": [vp],
         "kw_stream_info": [vp, i32, C.POINTER(u64), C.POINTER(u64)],
         "kw_stream_fetch": [vp, i32, vp, u64, C.POINTER(u64)],
+        "kw_stream_peek": [vp, i32, u64, vp, u64],
         "kw_finish": [vp],
         "kw_set_source_row": [vp, i32, u64, vp, u64],
         "kw_fft_r2c_3d": [u64, u64, u64, vp, vp],

@@ -1,5 +1,7 @@
 // One translation unit per transform length: nvcc ... -DKW_N=<N> fft_inst.cu -o fft_inst_<N>.o
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 #include "ops.h"
 
@@ -21,6 +23,24 @@ template <class K> static int blocks_per_sm(K kernel, int threads, size_t smem) 
   return b > 0 ? b : 1;
 }
 
+// Per-device launch state of one kernel: the dynamic shared-memory opt-in (cudaFuncSetAttribute is per device) and the
+// occupancy-derived CTAs per SM.  A process may hold contexts on several devices.
+struct PerDev {
+  bool once[64] = {};
+  int per_sm[64] = {};
+};
+template <class K> static int kernel_setup(PerDev& pd, K kernel, int threads, size_t smem) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!pd.once[dev]) {
+    if (smem > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pd.per_sm[dev] = blocks_per_sm(kernel, threads, smem);
+    pd.once[dev] = true;
+  }
+  return pd.per_sm[dev];
+}
+
 static int x_grid(int npairs, int per_sm) {
   constexpr int RP = kXThreads / (N / 8);
   const int groups = (npairs + RP - 1) / RP;
@@ -29,15 +49,14 @@ static int x_grid(int npairs, int per_sm) {
 }
 
 static void xfwd(const XFwdArgs& a, int nfields, cudaStream_t st) {
-  static const int per_sm = blocks_per_sm(k_xfwd<N>, kXThreads, 0);
+  static PerDev pd;
+  const int per_sm = kernel_setup(pd, k_xfwd<N>, kXThreads, 0);
   k_xfwd<N><<<dim3(x_grid(a.pair_end - a.pair_begin, per_sm), nfields), kXThreads, 0, st>>>(a);
 }
 template <int NF, class Epi> static void xinv(const XInvArgs<NF>& a, const Epi& e, int gy, cudaStream_t st) {
   constexpr size_t smem = (size_t)Epi::kStage * kXThreads * sizeof(float);  // staged epilogue operands
-  static const int per_sm = [] {
-    if (smem > 0) cudaFuncSetAttribute(k_xinv<N, NF, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    return blocks_per_sm(k_xinv<N, NF, Epi>, kXThreads, smem);
-  }();
+  static PerDev pd;
+  const int per_sm = kernel_setup(pd, k_xinv<N, NF, Epi>, kXThreads, smem);
   k_xinv<N, NF, Epi><<<dim3(x_grid(a.pair_end - a.pair_begin, per_sm), gy), kXThreads, smem, st>>>(a, e);
 }
 static void xinv_store(const XInvArgs<1>& a, const EpiStore& e, int nf, cudaStream_t st) { xinv<1>(a, e, nf, st); }
@@ -63,14 +82,9 @@ static void upload_twiddles() {  // forward table e^{-2 pi i m/N} in double prec
 
 template <int ID, class K> static int col_grid(K kernel, int ntiles, size_t smem) {
   using C = ColCfg<N>;
-  static bool once = false;
-  static int per_sm = 1;
+  static PerDev pd;
   upload_twiddles();
-  if (!once) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    per_sm = blocks_per_sm(kernel, C::THREADS, smem);
-    once = true;
-  }
+  const int per_sm = kernel_setup(pd, kernel, C::THREADS, smem);
   const int groups = (ntiles + C::TPC - 1) / C::TPC;
   const int cap = sm_count() * per_sm;
   return groups < cap ? groups : cap;
@@ -94,71 +108,53 @@ static void col(const ColArgs& a, int dir, int nfields, cudaStream_t st) {
     k_col<N, +1, true><<<dim3(g, nfields), block, C::SMEM, st>>>(a);
   }
 }
+// Variants of the fused z pass: KW_ZMID_VARIANT = 0 every thread copies its points with cp.async into the exchange buffer once the
+// last inverse butterfly has freed it; 1 = one thread requests the next tile through the TMA unit a whole tile ahead (N >= 256).
+// (A 16-points-per-thread "paired" plan -- radix-32 / 64 butterflies shared by 2 / 4 threads of a warp through shuffles, 16 warps
+//  per SM -- was built and measured in round 2: 3.2 / 1.5 TB/s at N = 512 / 1024 against 3.9 / 2.3 for this plan, 4.2 with TMA
+//  against 4.7; removed again, profiles/r02_d_zmid_variants.log keeps the numbers.)
+static int zmid_variant() {
+  static const int v = getenv("KW_ZMID_VARIANT") ? atoi(getenv("KW_ZMID_VARIANT")) : -1;
+  return v;
+}
+// ID distinguishes kernels of identical function type (the statics are per instantiation); W = kx values per tile
+template <int ID, bool DB, class K> static void zmid_go(K kernel, const ZMidArgs& a, int W, dim3 block, int tiles_per_cta, size_t smem, cudaStream_t st) {
+  static PerDev pd;
+  upload_twiddles();
+  const int per_sm = kernel_setup(pd, kernel, (int)(block.x * block.y * block.z), smem);
+  ZMaps maps{};
+  if (DB) {  // box = 256 rows (kz) of W neighbouring kx of one ky
+    const uint64_t ny = a.plane / a.nxp;
+    const uint32_t zb = N < 256 ? N : 256;
+    bool ok = make_tensor_map_3d(&maps.in, a.f.in, 2ull * a.nxp, ny, N, 8ull * a.nxp, 8ull * a.plane, 2u * W, 1, zb);
+    if (ok && a.f.mul) ok = make_tensor_map_3d(&maps.mul, a.f.mul, a.nxp, ny, N, 4ull * a.nxp, 4ull * a.plane, (uint32_t)W, 1, zb);
+    if (!ok) {
+      fprintf(stderr, "kwave_b200: cuTensorMapEncodeTiled failed for the fused z pass (N = %d)\n", N);
+      abort();
+    }
+  }
+  const int groups = (a.ntiles + tiles_per_cta - 1) / tiles_per_cta;
+  const int cap = sm_count() * per_sm;
+  kernel<<<groups < cap ? groups : cap, block, smem, st>>>(a, maps);
+}
+template <int NN, int AXIS, bool = (NN >= 256)> struct TmaZ {
+  static bool launch(const ZMidArgs&, cudaStream_t) { return false; }
+};
+template <int NN, int AXIS> struct TmaZ<NN, AXIS, true> {
+  static bool launch(const ZMidArgs& a, cudaStream_t st) {
+    using C = ZCfg<NN>;
+    zmid_go<10 + AXIS + 1, true>(k_zmid<NN, AXIS, true>, a, C::W, dim3(C::W, C::WK, C::TPC), C::TPC, C::SMEM_ZMID_DB, st);
+    return true;
+  }
+};
 template <int AXIS> static void zmid_axis(const ZMidArgs& a, cudaStream_t st) {
   using C = ZCfg<N>;
-  const int g = col_grid<10 + AXIS>(k_zmid<N, AXIS>, a.ntiles, C::SMEM_ZMID);
-  k_zmid<N, AXIS><<<g, dim3(C::W, C::WK, C::TPC), C::SMEM_ZMID, st>>>(a);
+  int variant = zmid_variant();
+  // default: TMA double-buffered tiles where they win (profiles/r02_d_zmid_variants.log: N = 256 +20 %, N = 512 +19 %, N = 1024 -5 %)
+  if (variant < 0) variant = (N == 256 || N == 512) ? 1 : 0;
+  if (variant == 1 && TmaZ<N, AXIS>::launch(a, st)) return;
+  zmid_go<AXIS + 1, false>(k_zmid<N, AXIS, false>, a, C::W, dim3(C::W, C::WK, C::TPC), C::TPC, C::SMEM_ZMID, st);
 }
-// ---- plane-fused x/y passes (fft_xy.cuh) ----------------------------------------------------------------------------
-// Fills the scheduling part of the arguments: items per plane, lag and ring depth from the grid that will run.
-template <int ID, class K> static int xy_setup(K kernel, PipeState& ps, PipeArgs* q, int planes, int i1, int i2, size_t slot_elems) {
-  using X = XYCfg<N>;
-  static bool once = false;
-  static int per_sm = 1;
-  upload_twiddles();
-  if (!once) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X::SMEM);
-    per_sm = blocks_per_sm(kernel, X::THREADS, X::SMEM);
-    once = true;
-  }
-  const int total = planes * (i1 + i2);
-  int grid = sm_count() * per_sm;
-  if (grid > total) grid = total;
-  const int per = i1 + i2;
-  int lag = (5 * grid + 2 * per - 1) / (2 * per) + 1;  // ~2.5 waves of CTAs between the two passes of a plane
-  int ring = lag + (grid + per - 1) / per + 2;
-  const int cap = (int)(ps.ring_elems / slot_elems);
-  if (ring > cap) ring = cap, lag = ring > 4 ? ring - 3 : ring - 1;
-  if (lag > planes) lag = planes;
-  if (ring <= lag) ring = lag + 1;  // only when planes is tiny; cap >= 2 is guaranteed by the allocation
-  q->ctr = ps.ctr[ps.cur], q->ctr_other = ps.ctr[ps.cur ^ 1], q->nctr = ps.nctr;
-  q->P = planes, q->I1 = i1, q->I2 = i2, q->L = lag, q->R = ring, q->err = ps.err;
-  ps.cur ^= 1;
-  return grid;
-}
-static bool xy_ok(const PipeState& ps, int planes, size_t slot_elems) {
-  return ps.ring && 2 * planes + 1 <= ps.nctr && ps.ring_elems / slot_elems >= 4;
-}
-static bool xy_fwd(XYFwdArgs& a, int nfields, PipeState& ps, cudaStream_t st) {
-  using X = XYCfg<N>;
-  using C = ColCfg<N>;
-  const size_t plane_c = (size_t)N * a.nxp;
-  const int planes = nfields * a.nz;
-  if (!xy_ok(ps, planes, plane_c)) return false;
-  const int i2 = (a.nxp / C::W + C::TPC - 1) / C::TPC;
-  a.ring = ps.ring;
-  const int grid = xy_setup<0>(k_xy_fwd<N>, ps, &a.pipe, planes, X::XI, i2, plane_c);
-  k_xy_fwd<N><<<grid, dim3(C::W, C::WK, C::TPC), X::SMEM, st>>>(a);
-  return true;
-}
-template <int ID, int NF, class Epi> static bool yx_inv(YXInvArgs<NF>& a, const Epi& e, PipeState& ps, cudaStream_t st) {
-  using X = XYCfg<N>;
-  using C = ColCfg<N>;
-  const size_t plane_c = (size_t)N * a.nxp;
-  const int planes = (NF == 1 ? a.nfields : 1) * a.nz;
-  if (!xy_ok(ps, planes, plane_c * NF)) return false;
-  const int i1 = NF * ((a.nxp / C::W + C::TPC - 1) / C::TPC);
-  a.ring = ps.ring;
-  const int grid = xy_setup<10 + ID>(k_yx_inv<N, NF, Epi>, ps, &a.pipe, planes, i1, X::XI, plane_c * NF);
-  k_yx_inv<N, NF, Epi><<<grid, dim3(C::W, C::WK, C::TPC), X::SMEM, st>>>(a, e);
-  return true;
-}
-static bool yx_store(YXInvArgs<1>& a, const EpiStore& e, PipeState& ps, cudaStream_t st) { return yx_inv<0, 1>(a, e, ps, st); }
-static bool yx_add(YXInvArgs<1>& a, const EpiAdd& e, PipeState& ps, cudaStream_t st) { return yx_inv<1, 1>(a, e, ps, st); }
-static bool yx_velocity(YXInvArgs<1>& a, const EpiVelocity& e, PipeState& ps, cudaStream_t st) { return yx_inv<2, 1>(a, e, ps, st); }
-static bool yx_density(YXInvArgs<3>& a, const EpiDensity& e, PipeState& ps, cudaStream_t st) { return yx_inv<3, 3>(a, e, ps, st); }
-static bool yx_psum(YXInvArgs<2>& a, const EpiPressureSum& e, PipeState& ps, cudaStream_t st) { return yx_inv<4, 2>(a, e, ps, st); }
-
 static void zmid(const ZMidArgs& a, cudaStream_t st) {
   switch (a.axis) {
     case 0: zmid_axis<0>(a, st); break;
@@ -174,8 +170,6 @@ static void zmid(const ZMidArgs& a, cudaStream_t st) {
 #define KW_OPS_NAME2(n) fft_ops_##n
 #define KW_OPS_NAME(n) KW_OPS_NAME2(n)
 extern const FftOps KW_OPS_NAME(KW_N) = {KW_N, ColCfg<KW_N>::W, ColCfg<KW_N>::WK, ZCfg<KW_N>::W, KW_CAT(inst_, KW_N)::xfwd, KW_CAT(inst_, KW_N)::xinv_store, KW_CAT(inst_, KW_N)::xinv_add, KW_CAT(inst_, KW_N)::xinv_velocity,
-                                            KW_CAT(inst_, KW_N)::xinv_density, KW_CAT(inst_, KW_N)::xinv_psum, KW_CAT(inst_, KW_N)::col, KW_CAT(inst_, KW_N)::zmid,
-                                            KW_CAT(inst_, KW_N)::xy_fwd, KW_CAT(inst_, KW_N)::yx_store, KW_CAT(inst_, KW_N)::yx_add, KW_CAT(inst_, KW_N)::yx_velocity,
-                                            KW_CAT(inst_, KW_N)::yx_density, KW_CAT(inst_, KW_N)::yx_psum};
+                                            KW_CAT(inst_, KW_N)::xinv_density, KW_CAT(inst_, KW_N)::xinv_psum, KW_CAT(inst_, KW_N)::col, KW_CAT(inst_, KW_N)::zmid};
 
 }  // namespace kw

@@ -12,7 +12,7 @@
 #pragma once
 #include "fft_core.cuh"
 #include "fft_core2.cuh"
-#include "fft_paired.cuh"
+#include "tma.cuh"
 
 namespace kw {
 
@@ -197,6 +197,8 @@ template <int N, int WV = 16> struct ColCfg {
   static constexpr size_t SMEM = (P::R2 > 1) ? (size_t)TPC * N * W * sizeof(float2) : 0;
   // + landing area of the real multiplier + the z-indexed 1-D operator
   static constexpr size_t SMEM_ZMID = SMEM + (size_t)TPC * N * W * sizeof(float) + (size_t)N * sizeof(float2);
+  // TMA variant: the next tile lands in its own buffer, the multiplier in alternating ones; + one mbarrier
+  static constexpr size_t SMEM_ZMID_DB = 2 * SMEM + 2 * (size_t)TPC * N * W * sizeof(float) + (size_t)N * sizeof(float2) + 16;
   // barrier flavour of a slot: whole CTA, named barrier (slot spans whole warps), or none (single-stage plans)
   static constexpr int BAR_THREADS = (P::R2 == 1) ? -1 : (TPC == 1 ? 0 : SLOT);
 };
@@ -327,15 +329,30 @@ struct ZMidArgs {
 #ifndef KW_ZMID_MULMODE
 #define KW_ZMID_MULMODE 0  // 0: multiplier lands in shared memory through cp.async; 1: plain loads at the point of use
 #endif
-template <int N, int AXIS> __global__ void __launch_bounds__(ZCfg<N>::THREADS, KW_ZMID_MINB) k_zmid(ZMidArgs a) {
+// DB (one tile slot per CTA, N >= 256): the next tile is requested as soon as the current one sits in registers -- a whole
+// tile of compute ahead -- by ONE thread through the TMA unit (box copies of 256 rows x 128 bytes, completion on an
+// mbarrier) into a landing buffer of its own, its multiplier into the other of two multiplier buffers.  Without DB every
+// thread copies its own points with cp.async once the last inverse butterfly has freed the exchange buffer.
+template <int N, int AXIS, bool DB = false> __global__ void __launch_bounds__(ZCfg<N>::THREADS, KW_ZMID_MINB) k_zmid(ZMidArgs a, const __grid_constant__ ZMaps maps) {
   using C = ZCfg<N>;
   using P = Plan2<N>;
+  static_assert(!DB || (P::R2 > 1 && C::TPC == 1), "the TMA variant needs a plan with an exchange and one tile slot per CTA");
   constexpr int W = C::W, WK = C::WK, E = P::E;
+  constexpr size_t TILES = (size_t)C::TPC * N * W;  // points of all tile slots of the CTA
   extern __shared__ float2 smem[];
   const int lane = threadIdx.x, w = threadIdx.y, tz = threadIdx.z;
   ColExchange2<W, C::BAR_THREADS> ex{smem + (size_t)tz * N * W + lane, 1 + tz};
-  float* const mulbuf = reinterpret_cast<float*>(smem + C::SMEM / sizeof(float2)) + (size_t)tz * N * W + w * W + lane;
-  float2* const svec = smem + (C::SMEM + (size_t)C::TPC * N * W * sizeof(float)) / sizeof(float2);  // N entries (AXIS == 2)
+  float2* const land = DB ? ex.buf + TILES : ex.buf;
+  float* const mulbase = reinterpret_cast<float*>(smem + (DB ? 2 : 1) * C::SMEM / sizeof(float2));
+  float* const mul0 = mulbase + (size_t)tz * N * W + w * W + lane;
+  float2* const svec = smem + ((DB ? 2 : 1) * (C::SMEM + TILES * sizeof(float))) / sizeof(float2);  // N entries (AXIS == 2)
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(svec + N);
+  const bool leader = DB && lane == 0 && w == 0 && tz == 0;
+  if (leader) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  if (DB) __syncthreads();
   const float2* __restrict__ in = a.f.in;
   const float* __restrict__ mul = a.f.mul;
   const int niter = (a.ntiles + C::TPC - 1) / C::TPC;
@@ -352,44 +369,64 @@ template <int N, int AXIS> __global__ void __launch_bounds__(ZCfg<N>::THREADS, K
     y = tl / a.ngroups, kx = (tl % a.ngroups) * W + lane;
     return (unsigned)y * a.nxp + kx + (unsigned)w * a.plane;  // point e of this worker: base + e*estride
   };
-  auto prefetch = [&](int it) {  // see k_col
+  auto prefetch = [&](int it, int par) {  // see k_col
     if constexpr (P::R2 > 1) {
       bool valid;
       int y, kx;
-      const float2* p = in + tile_base(it, valid, y, kx);
+      const unsigned b = tile_base(it, valid, y, kx);
+      if constexpr (DB) {
+        if (leader) {  // lane 0: kx is the first kx of the tile
+          constexpr int ZB = N < 256 ? N : 256;  // rows per box
+          mbar_expect_tx(bar, (uint32_t)(TILES * (mul ? 12 : 8)));
 #pragma unroll
-      for (int e = 0; e < E; ++e) cp_async8(ex.buf + (w + WK * e) * W, p + e * estride);
-      cp_async_commit();
+          for (int zb = 0; zb < N / ZB; ++zb) {
+            tma_load_3d(smem + TILES + (size_t)zb * ZB * W, &maps.in, 2 * kx, y, zb * ZB, bar);
+            if (mul) tma_load_3d(mulbase + par * TILES + (size_t)zb * ZB * W, &maps.mul, kx, y, zb * ZB, bar);
+          }
+        }
+      } else {
+        const float2* p = in + b;
+#pragma unroll
+        for (int e = 0; e < E; ++e) cp_async8(land + (w + WK * e) * W, p + e * estride);
+        cp_async_commit();
+      }
     }
   };
-  int it = blockIdx.x;
-  if (it < niter) prefetch(it);
-  for (; it < niter; it += gridDim.x) {
+  int it = blockIdx.x, par = 0;
+  if (it < niter) prefetch(it, 0);
+  for (; it < niter; it += gridDim.x, par ^= 1) {  // par = parity of the CTA's tile count = phase of the mbarrier
     bool valid;
     int y, kx;
     const unsigned base = tile_base(it, valid, y, kx);
+    const float* const mulbuf = mul0 + (DB ? par * TILES : 0);
+    const int nxt = it + gridDim.x;
     // the real multiplier of this tile lands in shared memory (cp.async, thread-private slots) while the forward
     // transform runs: no registers, no exposed latency.  Issued before the points are taken into registers.
-    if (mul && KW_ZMID_MULMODE == 0) {
+    if constexpr (!DB) {
+      if (mul && KW_ZMID_MULMODE == 0) {
 #pragma unroll
-      for (int e = 0; e < E; ++e) cp_async4(mulbuf + e * (WK * W), mul + base + e * estride);
+        for (int e = 0; e < E; ++e) cp_async4(mul0 + e * (WK * W), mul + base + e * estride);
+      }
+      cp_async_commit();
     }
-    cp_async_commit();
     float2 v[E];
     if constexpr (P::R2 > 1) {
-      cp_async_wait<1>();  // the tile (older group) has landed; the multiplier may still be in flight
+      if constexpr (DB) mbar_wait(bar, (uint32_t)par);
+      else cp_async_wait<1>();  // the tile (older group) has landed; the multiplier may still be in flight
 #pragma unroll
-      for (int e = 0; e < E; ++e) v[e] = ex.get(w + WK * e);
+      for (int e = 0; e < E; ++e) v[e] = land[(w + WK * e) * W];
       ex.sync();
+      if constexpr (DB) {
+        if (nxt < niter) prefetch(nxt, par ^ 1);
+      }
     } else {
 #pragma unroll
       for (int e = 0; e < E; ++e) v[e] = __ldg(in + base + e * estride);
     }
     fft2_worker<N, -1>(v, w, ex, ConstTab());
-    cp_async_wait<0>();
+    if constexpr (!DB) cp_async_wait<0>();
     asm volatile("" ::: "memory");  // keep the phases apart: interleaving them only lengthens live ranges
     const float scal = a.f.scal;
-    const int nxt = it + gridDim.x;
     if constexpr (AXIS == 3) {
       float2 ev[E];
 #pragma unroll
@@ -401,7 +438,7 @@ template <int N, int AXIS> __global__ void __launch_bounds__(ZCfg<N>::THREADS, K
         for (int e = 0; e < E; ++e) v[e] = cmul(ev[e], f == 0 ? wx : f == 1 ? wy : svec[w + WK * e]);
         if (f < 2) fft2_worker<N, +1>(v, w, ex, ConstTab());
         else fft2_worker<N, +1>(v, w, ex, ConstTab(), [&] {
-          if (nxt < niter) prefetch(nxt);
+          if (!DB && nxt < niter) prefetch(nxt, 0);
         });
         if (valid) {
           float2* __restrict__ p = (f == 0 ? a.f.out : f == 1 ? a.f.out_y : a.f.out_z) + base;
@@ -422,110 +459,13 @@ template <int N, int AXIS> __global__ void __launch_bounds__(ZCfg<N>::THREADS, K
         v[e] = x;
       }
       fft2_worker<N, +1>(v, w, ex, ConstTab(), [&] {
-        if (nxt < niter) prefetch(nxt);
+        if (!DB && nxt < niter) prefetch(nxt, 0);
       });
       if (valid) {
         float2* __restrict__ p = a.f.out + base;
 #pragma unroll
         for (int e = 0; e < E; ++e) p[e * estride] = v[e];
       }
-    }
-  }
-}
-// The fused z pass for Nz = 512 / 1024 on the paired plan of fft_paired.cuh: 16 points per thread, 512 threads per tile
-// (W = 16 kx at N = 512, W = 8 at N = 1024), at most 128 registers -> 16 warps per SM instead of 8.  The operator is applied
-// in the order the forward butterflies leave their outputs (paired_k), the inverse transform brings the natural order
-// back for the stores; multiplier and next tile are staged with cp.async exactly as in k_zmid.
-template <int N> struct ZPairCfg {
-  using P = Plan3<N>;
-  static constexpr int W = P::W, WK = P::WK, THREADS = P::THREADS;
-  static constexpr size_t SMEM = (size_t)N * W * sizeof(float2) + (size_t)N * W * sizeof(float) + (size_t)N * sizeof(float2);
-};
-template <int N, int AXIS> __global__ void __launch_bounds__(Plan3<N>::THREADS, 1) k_zmid_paired(ZMidArgs a) {
-  using P = Plan3<N>;
-  constexpr int W = P::W, WK = P::WK, E = 16;
-  extern __shared__ float2 smem[];
-  const int lane = threadIdx.x, w = threadIdx.y;
-  ColExchange2<W, 0> ex{smem + lane, 1};
-  float* const mulbuf = reinterpret_cast<float*>(smem + (size_t)N * W) + w * W + lane;  // slot s at + s * (WK * W)
-  float2* const svec = reinterpret_cast<float2*>(reinterpret_cast<float*>(smem + (size_t)N * W) + (size_t)N * W);  // N entries
-  const float2* __restrict__ in = a.f.in;
-  const float* __restrict__ mul = a.f.mul;
-  const unsigned estride = (unsigned)WK * a.plane;
-  if (AXIS == 2 || AXIS == 3) {
-    const float2* zv = AXIS == 2 ? a.f.vec : a.f.vec_z;
-    for (int i = lane + W * w; i < N; i += P::THREADS) svec[i] = __ldg(zv + i);
-    __syncthreads();
-  }
-  const int k0 = paired_k0<N>(w);  // frequency of register slot s: k0 + paired_ks<N>(s)
-  auto tile_base = [&](int it, int& y, int& kx) -> unsigned {
-    y = it / a.ngroups, kx = (it % a.ngroups) * W + lane;
-    return (unsigned)y * a.nxp + kx;
-  };
-  auto prefetch = [&](int it) {
-    int y, kx;
-    const float2* p = in + tile_base(it, y, kx) + (unsigned)w * a.plane;
-#pragma unroll
-    for (int e = 0; e < E; ++e) cp_async8(ex.buf + (w + WK * e) * W, p + e * estride);
-    cp_async_commit();
-  };
-  int it = blockIdx.x;
-  if (it < a.ntiles) prefetch(it);
-  for (; it < a.ntiles; it += gridDim.x) {
-    int y, kx;
-    const unsigned tb = tile_base(it, y, kx);
-    const unsigned kb = tb + (unsigned)k0 * a.plane;  // operator / output-order base
-    if (mul) {
-#pragma unroll
-      for (int s = 0; s < E; ++s) cp_async4(mulbuf + s * (WK * W), mul + kb + (unsigned)paired_ks<N>(s) * a.plane);
-    }
-    cp_async_commit();
-    float2 v[E];
-    cp_async_wait<1>();  // the tile (older group) has landed; the multiplier may still be in flight
-#pragma unroll
-    for (int e = 0; e < E; ++e) v[e] = ex.get(w + WK * e);
-    ex.sync();
-    paired_fwd<N>(v, w, ex, ConstTab());
-    cp_async_wait<0>();
-    asm volatile("" ::: "memory");
-    const float scal = a.f.scal;
-    const int nxt = it + gridDim.x;
-    const unsigned ob = tb + (unsigned)w * a.plane;
-    if constexpr (AXIS == 3) {
-      float2 ev[E];
-#pragma unroll
-      for (int s = 0; s < E; ++s) ev[s] = cscale(v[s], mul ? mulbuf[s * (WK * W)] * scal : scal);
-      const float2 wx = __ldg(a.f.vec + kx), wy = __ldg(a.f.vec_y + y);
-#pragma unroll
-      for (int f = 0; f < 3; ++f) {
-#pragma unroll
-        for (int s = 0; s < E; ++s) v[s] = cmul(ev[s], f == 0 ? wx : f == 1 ? wy : svec[k0 + paired_ks<N>(s)]);
-        if (f < 2) paired_inv<N>(v, w, ex, ConstTab());
-        else paired_inv<N>(v, w, ex, ConstTab(), [&] {
-          if (nxt < a.ntiles) prefetch(nxt);
-        });
-        float2* __restrict__ p = (f == 0 ? a.f.out : f == 1 ? a.f.out_y : a.f.out_z) + ob;
-#pragma unroll
-        for (int e = 0; e < E; ++e) p[e * estride] = v[e];
-      }
-    } else {
-      float2 w01 = make_float2(1.f, 0.f);
-      if (AXIS == 0) w01 = __ldg(a.f.vec + kx);
-      if (AXIS == 1) w01 = __ldg(a.f.vec + y);
-#pragma unroll
-      for (int s = 0; s < E; ++s) {
-        const float m = mul ? mulbuf[s * (WK * W)] * scal : scal;
-        float2 x = cscale(v[s], m);
-        if (AXIS == 0 || AXIS == 1) x = cmul(x, w01);
-        if (AXIS == 2) x = cmul(x, svec[k0 + paired_ks<N>(s)]);
-        v[s] = x;
-      }
-      paired_inv<N>(v, w, ex, ConstTab(), [&] {
-        if (nxt < a.ntiles) prefetch(nxt);
-      });
-      float2* __restrict__ p = a.f.out + ob;
-#pragma unroll
-      for (int e = 0; e < E; ++e) p[e * estride] = v[e];
     }
   }
 }

@@ -5,10 +5,11 @@
  * reported baseline (oracle/ref_build), and (b) the C++ host of this repository read and write k-Wave files through the
  * same calls.
  *
- * Storage back end: files are held in memory and serialised on H5Fclose in the "KWH5" container format described in
- * minih5.cpp (one record per object: path, attributes, shape, raw little-endian data).  It is NOT the HDF5 on-disk
- * format: tools/kwh5.py converts between NumPy dictionaries and this container.  Chunking and deflate settings are
- * accepted and recorded but do not change the bytes stored.
+ * Storage back end: REAL HDF5 files.  A file is parsed completely on H5Fopen and written completely on H5Fclose (objects live
+ * in memory in between), in the subset of the HDF5 1.8 file format that libhdf5 / MATLAB produce with default settings and that
+ * the reference itself writes: superblock 0, version-1 object headers, symbol-table groups, contiguous and chunked (version-1
+ * B-tree) datasets with the deflate filter, float32 / uint64 data, fixed-string / float / long long attributes (minih5.cpp).
+ * tools/h5lite.py is the independent Python implementation of the same subset used by the tests.
  */
 #ifndef MINIH5_HDF5_H
 #define MINIH5_HDF5_H

@@ -3,19 +3,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "fft_kernels.cuh"
-#include "fft_xy.cuh"
 #include "solver_kernels.cuh"
 
 namespace kw {
-
-// ring + counters of the plane-fused x/y kernels (fft_xy.cuh), owned by a context
-struct PipeState {
-  unsigned* ctr[2] = {nullptr, nullptr};  // two counter sets used alternately; a launch zeroes the other set
-  int cur = 0, nctr = 0;
-  float2* ring = nullptr;
-  size_t ring_elems = 0;
-  int* err = nullptr;  // device flag: a dependency wait timed out
-};
 
 struct FftOps {
   int n;
@@ -30,14 +20,6 @@ struct FftOps {
   void (*xinv_psum)(const XInvArgs<2>&, const EpiPressureSum&, cudaStream_t);
   void (*col)(const ColArgs&, int dir, int nfields, cudaStream_t);
   void (*zmid)(const ZMidArgs&, cudaStream_t);  // one field per launch
-  // plane-fused x/y passes for Nx == Ny == n; return false when the ring cannot hold the schedule (caller falls back to
-  // the separate passes)
-  bool (*xy_fwd)(XYFwdArgs&, int nfields, PipeState&, cudaStream_t);
-  bool (*yx_store)(YXInvArgs<1>&, const EpiStore&, PipeState&, cudaStream_t);
-  bool (*yx_add)(YXInvArgs<1>&, const EpiAdd&, PipeState&, cudaStream_t);
-  bool (*yx_velocity)(YXInvArgs<1>&, const EpiVelocity&, PipeState&, cudaStream_t);
-  bool (*yx_density)(YXInvArgs<3>&, const EpiDensity&, PipeState&, cudaStream_t);
-  bool (*yx_psum)(YXInvArgs<2>&, const EpiPressureSum&, PipeState&, cudaStream_t);
 };
 
 const FftOps* get_fft_ops(int n);  // nullptr when n is not a supported length

@@ -50,6 +50,25 @@ int sm_count() {
   return n;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry-point lookup: the library links no libcuda and still loads (and
+// exports its symbols) on a machine without a driver
+bool make_tensor_map_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                        uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+  using Fn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                          const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Fn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<Fn>(p);
+  }();
+  if (!fn) return false;
+  const cuuint64_t dims[3] = {d0, d1, d2}, strides[2] = {stride1_bytes, stride2_bytes};
+  const cuuint32_t box[3] = {b0, b1, b2}, estr[3] = {1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 const FftOps* get_fft_ops(int n) {
   switch (n) {
     case 16: return &fft_ops_16;
@@ -121,6 +140,7 @@ struct Geometry {
   int nzl = 0, nyl = 0, z0 = 0, y0 = 0;  // local extents / offsets
   int ny_log2 = 0, ysh = 0;              // log2(ny), log2(nyl)
   size_t n = 0, nc = 0;                  // LOCAL real voxels, LOCAL padded complex elements (nxp*ny*nzl == nxp*nyl*nz)
+  size_t nca = 0;                        // LOCAL complex elements without the padding, (nx/2+1)*ny*nzl: the algorithmic bytes of SURVEY 8(d)
   size_t ntot = 0;                       // global real voxels
   size_t blk = 0;                        // complex elements exchanged with one peer per field: nxp*nyl*nzl
   const FftOps *ox = nullptr, *oy = nullptr, *oz = nullptr;
@@ -148,6 +168,7 @@ struct Geometry {
     ntot = (size_t)nx * ny * nz;
     n = (size_t)nx * ny * nzl;
     nc = (size_t)nxp * ny * nzl;
+    nca = (size_t)nxr * ny * nzl;
     blk = (size_t)nxp * nyl * nzl;
     KW_TRY(twiddle_table(nx, &tx));
     KW_TRY(twiddle_table(ny, &ty));
@@ -224,7 +245,6 @@ struct kw_ctx {
   // non-staggered velocity (cpp:2714-2735): shift operators extended to the full ky / kz range
   float2* shift_full[3] = {};
   bool need_shifted = false;
-  PipeState pipe;  // ring + counters of the plane-fused x/y kernels (Nx == Ny only)
   std::vector<void*> owned;
 
   Fld fld(int id) const { return Fld{count[id] > 1 ? d[id] : nullptr, scalar[id]}; }
@@ -265,14 +285,6 @@ static cudaEvent_t mark(kw_ctx* c, cudaStream_t s) {
   cudaEvent_t e = c->ev_ring[c->ev_next++ % c->ev_ring.size()];
   cudaEventRecord(e, s);
   return e;
-}
-// the plane-fused kernels flag a dependency wait that timed out (a scheduling bug); stream must be idle
-static int pipe_check(kw_ctx* c) {
-  if (!c->pipe.err) return KW_OK;
-  int e = 0;
-  KW_CUDA(cudaMemcpy(&e, c->pipe.err, sizeof(int), cudaMemcpyDeviceToHost));
-  if (e) return fail(KW_ERR_CUDA, "plane-fused FFT pipeline: dependency wait timed out");
-  return KW_OK;
 }
 static void prof_resolve(kw_ctx* c) {  // stream must be idle
   const ProfPending* prev = nullptr;
@@ -730,8 +742,27 @@ int kw_preprocess(kw_ctx* c) {
   if (cf.transducer_source_flag && (!c->d[KW_TRANSDUCER_SOURCE_INPUT] || !c->di[KW_DELAY_MASK]))
     return fail(KW_ERR_INVALID, "transducer source arrays missing");
   if (cf.p0_source_flag && !c->d[KW_P0_SOURCE_INPUT]) return fail(KW_ERR_INVALID, "p0_source_input missing");
-  if (cf.p_source_flag && cf.p_source_many && c->count[KW_P_SOURCE_INPUT] < cf.p_source_flag * c->count_total[KW_P_SOURCE_INDEX])
-    return fail(KW_ERR_INVALID, "p_source_input shorter than p_source_flag * Nsrc");
+  {  // every signal must cover the steps it is read at: signal[t] (single), signal[t * Nsrc + j] (many), signal[delay[j] + t]
+     // (SolverCudaKernels.cu:463-471, :504-527, :570-629); the device kernels do not check bounds
+    const uint64_t nt = cf.nt;
+    auto need = [&](uint64_t flag, int many, int index_id) -> uint64_t {
+      const uint64_t steps = std::min<uint64_t>(flag, nt);
+      return many ? steps * c->count_total[index_id] : steps;
+    };
+    if (cf.p_source_flag && c->count[KW_P_SOURCE_INPUT] < need(cf.p_source_flag, cf.p_source_many, KW_P_SOURCE_INDEX))
+      return fail(KW_ERR_INVALID, "p_source_input shorter than min(p_source_flag, Nt) [* Nsrc]");
+    const uint64_t uflags[3] = {cf.ux_source_flag, cf.uy_source_flag, cf.uz_source_flag};
+    for (int k = 0; k < 3; ++k)
+      if (uflags[k] && c->count[KW_UX_SOURCE_INPUT + k] < need(uflags[k], cf.u_source_many, KW_U_SOURCE_INDEX))
+        return fail(KW_ERR_INVALID, "u" + std::string(1, "xyz"[k]) + "_source_input shorter than min(flag, Nt) [* Nsrc]");
+    if (cf.transducer_source_flag) {
+      if (c->count_total[KW_DELAY_MASK] != c->count_total[KW_U_SOURCE_INDEX]) return fail(KW_ERR_INVALID, "delay_mask and u_source_index differ in length");
+      uint64_t dmax = 0;
+      for (auto v : c->h_idx[KW_DELAY_MASK]) dmax = std::max(dmax, v);
+      if (!c->h_idx[KW_DELAY_MASK].empty() && c->count[KW_TRANSDUCER_SOURCE_INPUT] < dmax + std::min<uint64_t>(cf.transducer_source_flag, nt))
+        return fail(KW_ERR_INVALID, "transducer_source_input shorter than max(delay_mask) + min(transducer_source_flag, Nt)");
+    }
+  }
   // --- state and temporaries (state starts at zero, BaseFloatMatrix.cpp:144-145)
   for (int id : {KW_P, KW_RHOX, KW_RHOY, KW_RHOZ, KW_UX_SGX, KW_UY_SGY, KW_UZ_SGZ})
     if (!c->d[id]) {
@@ -749,21 +780,6 @@ int kw_preprocess(kw_ctx* c) {
     if (!env || atoi(env) != 0) {
       if (!c->peer.setup(c->nccl_id, sizeof(c->nccl_id), g.rank, g.nranks, c->arena) && getenv("KW_PEER_VERBOSE"))
         fprintf(stderr, "kwave_b200 rank %d: peer-memory exchange unavailable (%s); using NCCL send/recv\n", g.rank, c->peer.error.c_str());
-    }
-  }
-  {  // plane-fused x/y passes (fft_xy.cuh): an L2-resident ring of spectrum planes + two sets of progress counters
-    static const long long ring_mb = getenv("KW_RING_MB") ? atoll(getenv("KW_RING_MB")) : 0;  // opt-in: the first version is correct but slower than the separate passes (profiles/r01_e)
-    if (g.nx == g.ny && ring_mb > 0 && g.nranks == 1) {
-      const size_t plane_c = (size_t)g.ny * g.nxp;
-      size_t slots = ((size_t)ring_mb << 20) / (plane_c * sizeof(float2));
-      if (slots < 12) slots = 12;  // at least four slots of three planes
-      if (slots > (size_t)3 * g.nz + 3) slots = (size_t)3 * g.nz + 3;
-      c->pipe.ring_elems = slots * plane_c;
-      c->pipe.nctr = 2 * 3 * g.nz + 1;
-      KW_TRY(dalloc(c, (void**)&c->pipe.ring, c->pipe.ring_elems * sizeof(float2)));
-      KW_TRY(dalloc(c, (void**)&c->pipe.ctr[0], c->pipe.nctr * sizeof(unsigned)));
-      KW_TRY(dalloc(c, (void**)&c->pipe.ctr[1], c->pipe.nctr * sizeof(unsigned)));
-      KW_TRY(dalloc(c, (void**)&c->pipe.err, sizeof(int)));
     }
   }
   if (cf.absorbing_flag) {
@@ -971,33 +987,22 @@ static ColArgs ycol_args(const Geometry& g, float2* const* data, int nf) {
 // forward x and y passes of `nf` real fields into spectral buffers (x/y-local side)
 static void forward_xy(kw_ctx* c, const float* const* in, float2* const* out, int nf) {
   const Geometry& g = c->g;
-  if (c->pipe.ring) {  // one kernel, the x-transformed planes stay in L2
-    XYFwdArgs fa{};
-    for (int f = 0; f < nf; ++f) fa.in[f] = in[f], fa.out[f] = out[f];
-    fa.tab = g.tx, fa.nz = g.nz, fa.nxp = g.nxp;
-    bool ok = true;
-    launch(c, "xy_fwd", nf * (4.0 * g.n + 8.0 * g.nc), [&] { ok = g.ox->xy_fwd(fa, nf, c->pipe, c->st); });
-    if (ok) return;
-  }
   XFwdArgs xa{};
   for (int f = 0; f < nf; ++f) xa.in[f] = in[f], xa.out[f] = out[f];
   xa.tab = g.tx, xa.nxp = g.nxp, xa.map = g.row_map();
+  // (z-chunked launches that keep a chunk's half spectra in L2 between the x and the y pass were measured and lose: 16.8 / 13.5 /
+  //  12.1 ms per step at 24 / 48 / 96 MB chunks against 10.4 ms for whole-grid launches, profiles/r02_e_chunk_sweep.log)
   xa.pair_begin = 0, xa.pair_end = g.nzl * g.ny / 2;
   const ColArgs ca = ycol_args(g, out, nf);
-  launch(c, "xfwd", nf * (4.0 * g.n + 8.0 * g.nc), [&] { g.ox->xfwd(xa, nf, c->st); });
-  launch(c, "ycol_fwd", nf * 16.0 * g.nc, [&] { g.oy->col(ca, -1, nf, c->st); });
+  launch(c, "xfwd", nf * (4.0 * g.n + 8.0 * g.nca), [&] { g.ox->xfwd(xa, nf, c->st); });
+  launch(c, "ycol_fwd", nf * 16.0 * g.nca, [&] { g.oy->col(ca, -1, nf, c->st); });
 }
 // inverse y pass then the x inverse with its fused epilogue; xinv(pair_begin, pair_end) launches it
-template <class F, class FF>
-static void inverse_yx(kw_ctx* c, float2* const* data, int nf, const char* name, const char* fused_name, double xinv_bytes, F&& xinv, FF&& fused) {
+template <class F>
+static void inverse_yx(kw_ctx* c, float2* const* data, int nf, const char* name, double xinv_bytes, F&& xinv) {
   const Geometry& g = c->g;
-  if (c->pipe.ring) {
-    bool ok = true;
-    launch(c, fused_name, xinv_bytes, [&] { ok = fused(); });
-    if (ok) return;
-  }
   const ColArgs ca = ycol_args(g, data, nf);
-  launch(c, "ycol_inv", nf * 16.0 * g.nc, [&] { g.oy->col(ca, +1, nf, c->st); });
+  launch(c, "ycol_inv", nf * 16.0 * g.nca, [&] { g.oy->col(ca, +1, nf, c->st); });
   launch(c, name, xinv_bytes, [&] { xinv(0, g.nzl * g.ny / 2); });
 }
 
@@ -1125,7 +1130,7 @@ static void zmid_launch(kw_ctx* c, ZField f, int axis) {
   const Geometry& g = c->g;
   if (g.nz == 1) {  // 2-D: forward z, operator, inverse z collapse to the operator
     ZMulArgs ma{f, axis, g.nxp, (size_t)g.nxp * g.ny};
-    launch(c, axis == 3 ? "zmul_grad" : "zmul", (axis == 3 ? 32.0 : 16.0) * g.nc + (f.mul ? 4.0 * g.nc : 0.0),
+    launch(c, axis == 3 ? "zmul_grad" : "zmul", (axis == 3 ? 32.0 : 16.0) * g.nca + (f.mul ? 4.0 * g.nca : 0.0),
            [&] { k_zmul<<<ew_grid(ma.n), 256, 0, c->st>>>(ma); });
     return;
   }
@@ -1135,13 +1140,7 @@ static void zmid_launch(kw_ctx* c, ZField f, int axis) {
   if (axis == 3 && f.vec_y) f.vec_y += g.y0;
   za.f = f, za.axis = axis;
   za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->zmid_w, za.ntiles = g.nyl * za.ngroups, za.plane = (unsigned)((size_t)g.nyl * g.nxp);
-  launch(c, axis == 3 ? "zmid_grad" : "zmid", (axis == 3 ? 32.0 : 16.0) * g.nc + (f.mul ? 4.0 * g.nc : 0.0), [&] { g.oz->zmid(za, c->st); });
-}
-template <int NF> static YXInvArgs<NF> yx_args(kw_ctx* c, float2* const* in, int nfields = NF) {
-  YXInvArgs<NF> a{};
-  for (int f = 0; f < nfields; ++f) a.in[f] = in[f];
-  a.tab = c->g.tx, a.nz = c->g.nz, a.nxp = c->g.nxp, a.nfields = nfields;
-  return a;
+  launch(c, axis == 3 ? "zmid_grad" : "zmid", (axis == 3 ? 32.0 : 16.0) * g.nca + (f.mul ? 4.0 * g.nca : 0.0), [&] { g.oz->zmid(za, c->st); });
 }
 template <int NF> static XInvArgs<NF> xinv_args(kw_ctx* c, float2* const* in, int pb, int pe, int nfields = NF) {
   XInvArgs<NF> a{};
@@ -1183,9 +1182,8 @@ static int add_scaled_source(kw_ctx* c, const float* signal, int index_id, int m
   EpiAdd e{};
   for (int k = 0; k < ntargets; ++k) e.out[k] = targets[k];
   e.ntargets = ntargets;
-  inverse_yx(c, back, 1, "xinv_add_source", "yx_add_source", 8.0 * g.nc + 8.0 * g.n * ntargets,
-             [&](int pb, int pe) { g.ox->xinv_add(xinv_args<1>(c, back, pb, pe), e, c->st); },
-             [&] { auto a = yx_args<1>(c, back, 1); return g.ox->yx_add(a, e, c->pipe, c->st); });
+  inverse_yx(c, back, 1, "xinv_add_source", 8.0 * g.nca + 8.0 * g.n * ntargets,
+             [&](int pb, int pe) { g.ox->xinv_add(xinv_args<1>(c, back, pb, pe), e, c->st); });
   if (g.nranks > 1) KW_TRY(release_buffer(c, 3, c->st));
   return KW_OK;
 }
@@ -1261,9 +1259,8 @@ static int compute_shifted_velocity(kw_ctx* c) {
     if (g.nranks > 1) KW_TRY(release_buffer(c, 7, c->cs));
     EpiStore e{};
     e.out[0] = c->d[KW_UX_SHIFTED + f], e.scale = 1.0f;
-    inverse_yx(c, back, 1, "xinv_shifted_velocity", "yx_shifted_velocity", 8.0 * g.nc + 4.0 * g.n,
-               [&](int pb, int pe) { g.ox->xinv_store(xinv_args<1>(c, back, pb, pe), e, 1, c->st); },
-               [&] { auto a = yx_args<1>(c, back, 1); return g.ox->yx_store(a, e, c->pipe, c->st); });
+    inverse_yx(c, back, 1, "xinv_shifted_velocity", 8.0 * g.nca + 4.0 * g.n,
+               [&](int pb, int pe) { g.ox->xinv_store(xinv_args<1>(c, back, pb, pe), e, 1, c->st); });
     if (g.nranks > 1) KW_TRY(release_buffer(c, 3, c->st));
   }
   return KW_OK;
@@ -1377,9 +1374,8 @@ static int step(kw_ctx* c) {
   {
     const EpiVelocity e = velocity_epilogue(c, u, fd, 0);
     const double het = c->count[KW_RHO0_SGX] > 1 ? 4.0 : 0.0;
-    inverse_yx(c, sp, 3, "xinv_velocity", "yx_velocity", 3 * (8.0 * g.nc + (8.0 + het) * g.n),
-               [&](int pb, int pe) { g.ox->xinv_velocity(xinv_args<1>(c, sp, pb, pe, 3), e, 3, c->st); },
-               [&] { auto a = yx_args<1>(c, sp, 3); return g.ox->yx_velocity(a, e, c->pipe, c->st); });
+    inverse_yx(c, sp, 3, "xinv_velocity", 3 * (8.0 * g.nca + (8.0 + het) * g.n),
+               [&](int pb, int pe) { g.ox->xinv_velocity(xinv_args<1>(c, sp, pb, pe, 3), e, 3, c->st); });
   }
   // ---- addVelocitySource (cpp:2252-2303), transducer (cpp:894-897)
   const uint64_t uflag[3] = {cf.ux_source_flag, cf.uy_source_flag, cf.uz_source_flag};
@@ -1429,9 +1425,8 @@ static int step(kw_ctx* c) {
       if (cf.absorbing_flag) per += 4.0 + (e.defer_terms ? 0.0 : 4.0 + (cf.nonlinear_flag ? 4.0 : 0.0));  // A, B, NL
       else if (!e.defer_terms) per += 4.0 + (c->count[KW_C0] > 1 ? 4.0 : 0.0);                               // p, c2
       if (cf.nonlinear_flag && !e.defer_terms && c->count[KW_BONA] > 1) per += 4.0;
-      inverse_yx(c, sp, 3, "xinv_density", "yx_density", 24.0 * g.nc + per * g.n + fused_bytes,
-                 [&](int pb, int pe) { g.ox->xinv_density(xinv_args<3>(c, sp, pb, pe), e, c->st); },
-                 [&] { auto a = yx_args<3>(c, sp); return g.ox->yx_density(a, e, c->pipe, c->st); });
+      inverse_yx(c, sp, 3, "xinv_density", 24.0 * g.nca + per * g.n + fused_bytes,
+                 [&](int pb, int pe) { g.ox->xinv_density(xinv_args<3>(c, sp, pb, pe), e, c->st); });
     }
     // ---- addPressureSource (cpp:2310-2334)
     if (p_src) {
@@ -1471,9 +1466,8 @@ static int step(kw_ctx* c) {
     const double per = 8.0 + (c->count[KW_C0] > 1 ? 4.0 : 0.0) + (c->count[KW_ABSORB_TAU] > 1 ? 8.0 : 0.0);
     double fused_bytes = 0;
     e.sample = fused_p_sample(c, &e.fs, &fused_bytes);
-    inverse_yx(c, sp, 2, "xinv_pressure_sum", "yx_pressure_sum", 16.0 * g.nc + per * g.n + fused_bytes,
-               [&](int pb, int pe) { g.ox->xinv_psum(xinv_args<2>(c, sp, pb, pe), e, c->st); },
-               [&] { auto a = yx_args<2>(c, sp); return g.ox->yx_psum(a, e, c->pipe, c->st); });
+    inverse_yx(c, sp, 2, "xinv_pressure_sum", 16.0 * g.nca + per * g.n + fused_bytes,
+               [&](int pb, int pe) { g.ox->xinv_psum(xinv_args<2>(c, sp, pb, pe), e, c->st); });
   }
   // ---- addInitialPressureSource (cpp:2359-2396)
   if (t == 0 && cf.p0_source_flag == 1) {
@@ -1482,9 +1476,8 @@ static int step(kw_ctx* c) {
     });
     KW_TRY(pressure_gradient_spectra(c, sp));
     const EpiVelocity e = velocity_epilogue(c, u, fd, 1);
-    inverse_yx(c, sp, 3, "xinv_initial_velocity", "yx_initial_velocity", 3 * (8.0 * g.nc + 8.0 * g.n),
-               [&](int pb, int pe) { g.ox->xinv_velocity(xinv_args<1>(c, sp, pb, pe, 3), e, 3, c->st); },
-               [&] { auto a = yx_args<1>(c, sp, 3); return g.ox->yx_velocity(a, e, c->pipe, c->st); });
+    inverse_yx(c, sp, 3, "xinv_initial_velocity", 3 * (8.0 * g.nca + 8.0 * g.n),
+               [&](int pb, int pe) { g.ox->xinv_velocity(xinv_args<1>(c, sp, pb, pe, 3), e, 3, c->st); });
   }
   // ---- storeSensorData (cpp:1060-1093)
   if (t >= cf.sampling_start_index) KW_TRY(sample_streams(c));
@@ -1500,7 +1493,7 @@ static int step(kw_ctx* c) {
 static void ycol1(kw_ctx* c, float2* buf, int dir) {
   float2* b[1] = {buf};
   const ColArgs ca = ycol_args(c->g, b, 1);
-  launch(c, dir < 0 ? "ycol_fwd" : "ycol_inv", 16.0 * c->g.nc, [&] { c->g.oy->col(ca, dir, 1, c->st); });
+  launch(c, dir < 0 ? "ycol_fwd" : "ycol_inv", 16.0 * c->g.nca, [&] { c->g.oy->col(ca, dir, 1, c->st); });
 }
 static void forward1(kw_ctx* c, const float* in, float2* out) {
   const float* i[1] = {in};
@@ -1539,7 +1532,7 @@ static int step_sharded(kw_ctx* c) {
       ycol1(c, c->R[f], +1);
       XInvArgs<1> xa = xinv_args<1>(c, c->R, 0, npairs, 3);
       xa.field0 = f;
-      launch(c, init ? "xinv_initial_velocity" : "xinv_velocity", 8.0 * g.nc + (init ? 8.0 : 8.0 + het) * g.n,
+      launch(c, init ? "xinv_initial_velocity" : "xinv_velocity", 8.0 * g.nca + (init ? 8.0 : 8.0 + het) * g.n,
              [&] { g.ox->xinv_velocity(xa, e, 1, c->st); });
       KW_TRY(release_buffer(c, 4 + f, c->st));
       if (!forward_u) continue;
@@ -1599,7 +1592,7 @@ static int step_sharded(kw_ctx* c) {
     if (cf.absorbing_flag) per += 4.0 + (e.defer_terms ? 0.0 : 4.0 + (cf.nonlinear_flag ? 4.0 : 0.0));
     else if (!e.defer_terms) per += 4.0 + (c->count[KW_C0] > 1 ? 4.0 : 0.0);
     if (cf.nonlinear_flag && !e.defer_terms && c->count[KW_BONA] > 1) per += 4.0;
-    launch(c, "xinv_density", 24.0 * g.nc + per * g.n + fused_bytes, [&] { g.ox->xinv_density(xinv_args<3>(c, c->S, 0, npairs), e, c->st); });
+    launch(c, "xinv_density", 24.0 * g.nca + per * g.n + fused_bytes, [&] { g.ox->xinv_density(xinv_args<3>(c, c->S, 0, npairs), e, c->st); });
     for (int f = 0; f < 3; ++f) KW_TRY(release_buffer(c, f, c->st));
   }
   // ---- addPressureSource (cpp:2310-2334)
@@ -1647,7 +1640,7 @@ static int step_sharded(kw_ctx* c) {
     const double per = 8.0 + (c->count[KW_C0] > 1 ? 4.0 : 0.0) + (c->count[KW_ABSORB_TAU] > 1 ? 8.0 : 0.0);
     double fused_bytes = 0;
     e.sample = fused_p_sample(c, &e.fs, &fused_bytes);
-    launch(c, "xinv_pressure_sum", 16.0 * g.nc + per * g.n + fused_bytes, [&] { g.ox->xinv_psum(xinv_args<2>(c, c->S, 0, npairs), e, c->st); });
+    launch(c, "xinv_pressure_sum", 16.0 * g.nca + per * g.n + fused_bytes, [&] { g.ox->xinv_psum(xinv_args<2>(c, c->S, 0, npairs), e, c->st); });
     for (int f = 0; f < 2; ++f) KW_TRY(release_buffer(c, f, c->st));
   }
   // ---- addInitialPressureSource (cpp:2359-2396)
@@ -1727,9 +1720,8 @@ static int compute_q_term(kw_ctx* c, const float* const* intensity, float* q_out
     if (g.nranks > 1) KW_TRY(release_buffer(c, 7, c->cs));
     EpiAdd e{};
     e.out[0] = acc, e.ntargets = 1;
-    inverse_yx(c, back, 1, "xinv_q_term", "yx_q_term", 8.0 * g.nc + 8.0 * g.n,
-               [&](int pb, int pe) { g.ox->xinv_add(xinv_args<1>(c, back, pb, pe), e, c->st); },
-               [&] { auto a = yx_args<1>(c, back, 1); return g.ox->yx_add(a, e, c->pipe, c->st); });
+    inverse_yx(c, back, 1, "xinv_q_term", 8.0 * g.nca + 8.0 * g.n,
+               [&](int pb, int pe) { g.ox->xinv_add(xinv_args<1>(c, back, pb, pe), e, c->st); });
     if (g.nranks > 1) KW_TRY(release_buffer(c, 3, c->st));
   }
   if (c->nsens) {
@@ -1752,11 +1744,17 @@ static int compute_q_term_c(kw_ctx* c) {
 // each (series laid out [step][point], as in the output file): the velocity is shifted by half a time step -- the
 // reference's R2C / * exp(i pi shift / steps) / C2R along time is a circular convolution with the real kernel h built
 // below in double precision (any number of steps, no FFT length restriction) -- and I = sum_t p * u_shifted / steps.
-static __global__ void k_intensity_avg(const float* __restrict__ p, const float* __restrict__ u, const float* __restrict__ h, float* I, size_t n,
+// partial[c][i] = sum over the time chunk c of p * u_shifted: chunks are summed afterwards in a fixed order, so the result does
+// not depend on the order in which blocks run (a restart must reproduce the uninterrupted run bit for bit).
+// HS: the kernel h sits in shared memory (steps * 4 bytes fit), otherwise it is read through the read-only cache.
+template <bool HS>
+static __global__ void k_intensity_avg(const float* __restrict__ p, const float* __restrict__ u, const float* __restrict__ h, float* partial, size_t n,
                                        int steps, int tchunk) {
-  extern __shared__ float sh[];  // the kernel h
-  for (int m = threadIdx.x; m < steps; m += blockDim.x) sh[m] = h[m];
-  __syncthreads();
+  extern __shared__ float sh[];
+  if (HS) {
+    for (int m = threadIdx.x; m < steps; m += blockDim.x) sh[m] = h[m];
+    __syncthreads();
+  }
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int t0 = blockIdx.y * tchunk, t1 = min(steps, t0 + tchunk);
@@ -1765,12 +1763,20 @@ static __global__ void k_intensity_avg(const float* __restrict__ p, const float*
     float us = 0.f;
     int m = t;  // (t - s) mod steps, walked downwards
     for (int s = 0; s < steps; ++s) {
-      us = fmaf(__ldg(u + (size_t)s * n + i), sh[m], us);
+      us = fmaf(__ldg(u + (size_t)s * n + i), HS ? sh[m] : __ldg(h + m), us);
       m = m == 0 ? steps - 1 : m - 1;
     }
     acc = fmaf(__ldg(p + (size_t)t * n + i), us, acc);
   }
-  atomicAdd(I + i, acc);
+  partial[(size_t)blockIdx.y * n + i] = acc;
+}
+// I[i] = (sum_c partial[c][i]) / steps, chunks in ascending order
+static __global__ void k_intensity_reduce(const float* __restrict__ partial, float* I, size_t n, int nchunks, float steps) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < nchunks; ++c) acc += partial[(size_t)c * n + i];
+    I[i] = acc / steps;
+  }
 }
 
 }  // namespace kw
@@ -1792,18 +1798,19 @@ int kw_run(kw_ctx* c, uint64_t nsteps, uint64_t* steps_done, int sync) {
       rc = fail(KW_ERR_STREAM_FULL, "a raw stream buffer is full: fetch it with kw_stream_fetch");
       break;
     }
-    KW_TRY(c->g.nranks > 1 ? step_sharded(c) : step(c));
+    rc = c->g.nranks > 1 ? step_sharded(c) : step(c);
+    if (rc != KW_OK) break;  // steps_done and the end event are still recorded: the host's checkpoint bookkeeping relies on them
   }
   KW_CUDA(cudaEventRecord(c->ev1, c->st));
-  KW_CUDA(cudaGetLastError());
   if (steps_done) *steps_done = done;
+  if (rc != KW_OK && rc != KW_ERR_STREAM_FULL) return rc;
+  KW_CUDA(cudaGetLastError());
   if (sync) {
     KW_CUDA(cudaStreamSynchronize(c->st));
     if (c->cs) KW_CUDA(cudaStreamSynchronize(c->cs));
     if (c->ws) KW_CUDA(cudaStreamSynchronize(c->ws));
     KW_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
     prof_resolve(c);
-    KW_TRY(pipe_check(c));
   }
   return rc;
 }
@@ -1886,7 +1893,6 @@ int kw_synchronize(kw_ctx* c) {
   cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
   prof_resolve(c);
   KW_CUDA(cudaGetLastError());
-  KW_TRY(pipe_check(c));
   return KW_OK;
 }
 int kw_profile(kw_ctx* c, int enable, int reset) {
@@ -2022,7 +2028,7 @@ int kw_compression_bases(kw_ctx* c, int shifted, float* be, float* be1, uint64_t
 // ---- post-processing of stored raw series (--I_avg, --Q_term): cpp:1231-1534, :1783-2080 ----------------------------------
 int kw_intensity_avg_block(const float* p, const float* const* u, int ncomp, uint64_t n, uint64_t steps, float* const* intensity) {
   if (!p || !u || !intensity || ncomp < 1 || ncomp > 3 || n == 0 || steps == 0) return fail(KW_ERR_INVALID, "kw_intensity_avg_block: bad argument");
-  if (steps > 12000) return fail(KW_ERR_INVALID, "kw_intensity_avg_block: more than 12000 stored steps are not supported");
+  if (steps > 0x7fffffffull) return fail(KW_ERR_INVALID, "kw_intensity_avg_block: too many stored steps");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(KW_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
   std::vector<float> h(steps);
@@ -2035,26 +2041,42 @@ int kw_intensity_avg_block(const float* p, const float* const* u, int ncomp, uin
       h[m] = (float)(acc / (double)steps);
     }
   }
-  float *dp = nullptr, *du = nullptr, *dh = nullptr, *dI = nullptr;
+  struct Scratch {  // released on every return path
+    std::vector<void*> p;
+    ~Scratch() {
+      for (void* q : p) cudaFree(q);
+    }
+  } sc;
+  auto alloc = [&](float** q, size_t bytes) -> int {
+    KW_CUDA(cudaMalloc(q, bytes));
+    sc.p.push_back(*q);
+    return KW_OK;
+  };
+  // time chunks: enough of them to fill the device when the block has few points, never more than one per 32 steps
+  const int max_chunks = (int)((steps + 31) / 32);
+  int nchunks = (int)std::min<uint64_t>((uint64_t)max_chunks, std::max<uint64_t>(1, ((uint64_t)sm_count() * 8 * 128 + n - 1) / n));
+  const int tchunk = (int)((steps + nchunks - 1) / nchunks);
+  nchunks = (int)((steps + tchunk - 1) / tchunk);
+  float *dp = nullptr, *du = nullptr, *dh = nullptr, *dI = nullptr, *dpart = nullptr;
   const size_t bytes = n * steps * sizeof(float);
-  KW_CUDA(cudaMalloc(&dp, bytes));
-  KW_CUDA(cudaMalloc(&du, bytes));
-  KW_CUDA(cudaMalloc(&dh, steps * sizeof(float)));
-  KW_CUDA(cudaMalloc(&dI, n * sizeof(float)));
+  KW_TRY(alloc(&dp, bytes));
+  KW_TRY(alloc(&du, bytes));
+  KW_TRY(alloc(&dh, steps * sizeof(float)));
+  KW_TRY(alloc(&dI, n * sizeof(float)));
+  KW_TRY(alloc(&dpart, (size_t)nchunks * n * sizeof(float)));
   KW_CUDA(cudaMemcpy(dp, p, bytes, cudaMemcpyHostToDevice));
   KW_CUDA(cudaMemcpy(dh, h.data(), steps * sizeof(float), cudaMemcpyHostToDevice));
-  const int tchunk = 32;
-  const dim3 grid((unsigned)((n + 127) / 128), (unsigned)((steps + tchunk - 1) / tchunk));
-  KW_CUDA(cudaFuncSetAttribute(k_intensity_avg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(steps * sizeof(float))));
+  const dim3 grid((unsigned)((n + 127) / 128), (unsigned)nchunks);
+  const bool hs = steps * sizeof(float) <= 200 * 1024;  // the kernel h in shared memory when it fits
+  if (hs) KW_CUDA(cudaFuncSetAttribute(k_intensity_avg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(steps * sizeof(float))));
   for (int f = 0; f < ncomp; ++f) {
     KW_CUDA(cudaMemcpy(du, u[f], bytes, cudaMemcpyHostToDevice));
-    KW_CUDA(cudaMemset(dI, 0, n * sizeof(float)));
-    k_intensity_avg<<<grid, 128, steps * sizeof(float)>>>(dp, du, dh, dI, n, (int)steps, tchunk);
+    if (hs) k_intensity_avg<true><<<grid, 128, steps * sizeof(float)>>>(dp, du, dh, dpart, n, (int)steps, tchunk);
+    else k_intensity_avg<false><<<grid, 128>>>(dp, du, dh, dpart, n, (int)steps, tchunk);
     KW_CUDA(cudaGetLastError());
-    k_divide<<<ew_grid(n), 256>>>(dI, (float)steps, n);
+    k_intensity_reduce<<<ew_grid(n), 256>>>(dpart, dI, n, nchunks, (float)steps);
     KW_CUDA(cudaMemcpy(intensity[f], dI, n * sizeof(float), cudaMemcpyDeviceToHost));
   }
-  cudaFree(dp), cudaFree(du), cudaFree(dh), cudaFree(dI);
   return KW_OK;
 }
 int kw_q_term(kw_ctx* c, const float* const* intensity, int ncomp, float* q_out, uint64_t capacity) {
@@ -2110,6 +2132,16 @@ int kw_stream_fetch(kw_ctx* c, int sid, float* host, uint64_t cap, uint64_t* row
   }
   if (series) s.rows = 0;
   if (rows_fetched) *rows_fetched = rows;
+  return KW_OK;
+}
+
+int kw_stream_peek(kw_ctx* c, int sid, uint64_t offset, float* host, uint64_t count) {
+  if (!c || !host || sid < 0 || sid >= KW_STREAM_COUNT || !c->streams[sid].enabled) return fail(KW_ERR_INVALID, "stream not enabled");
+  Stream& s = c->streams[sid];
+  if (s.op == kOpNone || s.op == kOpC || !s.dbuf) return fail(KW_ERR_INVALID, "kw_stream_peek reads aggregate streams (use kw_stream_fetch for series)");
+  if (offset + count > s.row) return fail(KW_ERR_INVALID, "kw_stream_peek: range outside the accumulator");
+  KW_CUDA(cudaMemcpyAsync(host, s.dbuf + offset, count * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+  KW_CUDA(cudaStreamSynchronize(c->st));
   return KW_OK;
 }
 

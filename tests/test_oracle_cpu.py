@@ -238,7 +238,7 @@ def test_host_file_layer_round_trip(tmp_path):
     exe, h5 = str(tmp_path / "hdf5io_roundtrip"), str(tmp_path / "f.h5")
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     subprocess.run([cxx, "-std=c++17", "-O1", "-I", os.path.join(pkg, "host"), "-I", os.path.join(pkg, "csrc", "minih5"),
-                    os.path.join(ROOT, "tests", "cpp", "hdf5io_roundtrip.cpp"), os.path.join(pkg, "csrc", "minih5", "minih5.cpp"), "-o", exe],
+                    os.path.join(ROOT, "tests", "cpp", "hdf5io_roundtrip.cpp"), os.path.join(pkg, "csrc", "minih5", "minih5.cpp"), "-o", exe, "-lz"],
                    check=True)  # fmt: skip
     r = subprocess.run([exe, h5], capture_output=True, text=True)
     assert r.returncode == 0 and "round trip ok" in r.stdout, r.stderr

@@ -1,9 +1,14 @@
-"""Reader / writer of the KWH5 container used by minih5 (k-wave-fluid-cuda_b200/csrc/minih5/minih5.cpp) and helpers
+"""Reader / writer of the HDF5 files the host and the reference build exchange (through tools/h5lite.py, the Python counterpart of
+k-wave-fluid-cuda_b200/csrc/minih5/minih5.cpp; legacy KWH5 containers of round 1 are still read) and helpers
 that lay a synthetic case out with the k-Wave input-file schema (main.cpp:446-563 of the reference) and read an output
 file back.  Test / oracle tooling."""
 from __future__ import annotations
 
+import os
 import struct
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 import numpy as np
 
@@ -22,38 +27,14 @@ def _rstr(f):
 
 
 def write_file(path, objects):
-    """objects: ordered dict  abs_path -> dict(kind='group'|'f32'|'u64', attrs={name: str|int|float}, data=ndarray)"""
-    with open(path, "wb") as f:
-        f.write(MAGIC)
-        f.write(struct.pack("<Q", len(objects)))
-        for p, o in objects.items():
-            _wstr(f, p)
-            kind = {"group": 0, "f32": 1, "u64": 2}[o["kind"]]
-            f.write(struct.pack("<B", kind))
-            attrs = o.get("attrs", {})
-            f.write(struct.pack("<I", len(attrs)))
-            for k, v in attrs.items():
-                _wstr(f, k)
-                if isinstance(v, str):
-                    f.write(struct.pack("<B", 0))
-                    _wstr(f, v)
-                elif isinstance(v, (int, np.integer)):
-                    f.write(struct.pack("<Bq", 1, int(v)))
-                else:
-                    f.write(struct.pack("<Bf", 2, float(v)))
-            if kind:
-                a = np.ascontiguousarray(o["data"], dtype=np.float32 if kind == 1 else np.uint64)
-                f.write(struct.pack("<I", a.ndim))
-                f.write(struct.pack("<%dQ" % a.ndim, *a.shape))
-                chunk = o.get("chunk", ())
-                f.write(struct.pack("<I", len(chunk)))
-                if chunk:
-                    f.write(struct.pack("<%dQ" % len(chunk), *chunk))
-                f.write(struct.pack("<I", int(o.get("deflate", 0))))
-                f.write(a.tobytes())
+    """objects: ordered dict  abs_path -> dict(kind='group'|'f32'|'u64', attrs={name: str|int|float}, data=ndarray[, chunk=(), deflate=level])
+    Written as a real HDF5 file (tools/h5lite.py); datasets without `chunk` are contiguous, `deflate` adds the zlib filter."""
+    import h5lite
+
+    h5lite.write_hdf5(path, objects)
 
 
-def read_file(path):
+def _read_kwh5(path):
     out = {}
     with open(path, "rb") as f:
         assert f.read(8) == MAGIC, "not a KWH5 file"
@@ -81,20 +62,20 @@ def read_file(path):
     return out
 
 
+def read_file(path):
+    """Every object of an HDF5 file (or of a legacy KWH5 container of round 1): abs_path -> dict(kind, attrs, data, chunk, deflate)."""
+    import h5lite
+
+    if h5lite.is_hdf5(path):
+        return h5lite.read_hdf5(path)
+    return _read_kwh5(path)
+
+
 def read_root_attrs(path):
-    """Attributes of the root group only (first record), without touching the datasets."""
-    with open(path, "rb") as f:
-        assert f.read(8) == MAGIC, "not a KWH5 file"
-        f.read(8)
-        assert _rstr(f) == "/"
-        f.read(1)
-        (na,) = struct.unpack("<I", f.read(4))
-        attrs = {}
-        for _ in range(na):
-            k = _rstr(f)
-            (t,) = struct.unpack("<B", f.read(1))
-            attrs[k] = _rstr(f) if t == 0 else struct.unpack("<q", f.read(8))[0] if t == 1 else struct.unpack("<f", f.read(4))[0]
-        return attrs
+    """Attributes of the root group only, without touching the datasets."""
+    import h5lite
+
+    return h5lite.read_root_attrs(path)
 
 
 # ---- k-Wave input file ------------------------------------------------------------------------------------------------
