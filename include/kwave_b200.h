@@ -178,6 +178,13 @@ int kw_set_time_index(kw_ctx* ctx, uint64_t t_index);
 int kw_stream_state_size(kw_ctx* ctx, int stream_id, uint64_t* bytes);
 int kw_stream_state_get(kw_ctx* ctx, int stream_id, void* buffer, uint64_t bytes);
 int kw_stream_state_set(kw_ctx* ctx, int stream_id, const void* buffer, uint64_t bytes);
+/* The same state in the pieces the REFERENCE's checkpoint files hold (so that a run interrupted by one code can be resumed by the
+ * other): kw_set_time_index also sets the sampled / compressed step counters of every stream from t_index, as IndexOutputStream::reopen
+ * does (IndexOutputStream.cpp:203-213); buffer 0 = the accumulator of an aggregate stream, which the reference flushes into the OUTPUT
+ * file at a checkpoint and reloads from it (IndexOutputStream.cpp:536-557, :215-230); buffers 1 / 2 = the two compression accumulators
+ * of a *_c stream, the reference's Temp_<name>_1 / _2 datasets (BaseOutputStream.cpp:528-606).  host == NULL queries the size. */
+int kw_stream_buffer_get(kw_ctx* ctx, int stream_id, int which, float* host, uint64_t capacity_floats, uint64_t* floats);
+int kw_stream_buffer_set(kw_ctx* ctx, int stream_id, int which, const float* host, uint64_t floats);
 
 /* Post-processing of stored raw series (--I_avg, --Q_term; the reference re-reads them block-wise from the output file).
  * kw_intensity_avg_block = the block body of KSpaceFirstOrderSolver::computeAverageIntensities (cpp:1231-1534): p and the

@@ -208,8 +208,15 @@ template <int N> using ZCfg = ColCfg<N, (N >= 1024) ? 8 : 16>;  // tiles of the 
 template <int W, int NTHREADS> struct ColExchange2 {
   float2* buf;  // tile buffer + lane
   int bar;      // named barrier id of this slot
-  __device__ __forceinline__ void put(int i, float2 x) { buf[i * W] = x; }
-  __device__ __forceinline__ float2 get(int i) const { return buf[i * W]; }
+  // W = 16: a worker's 16 lanes cover all 32 banks, any row index is conflict free.  W = 8 (fused z pass of N = 1024, radix 32 x 32):
+  // a warp holds 4 workers of 64 bytes each; the stage-1 outputs of neighbouring workers lie 32 rows apart -- the same half of
+  // the banks, a 2-way conflict on every store (ncu: 36 % of the shared-memory wavefronts of k_zmid<1024> were conflicts,
+  // profiles/r02_j_zmid1024.summary.txt).  Swapping odd and even rows in every other group of 32 rows separates them and
+  // leaves the other access patterns (neighbouring workers = neighbouring rows) conflict free.
+  __device__ __forceinline__ static int row(int i) { return W == 8 ? (i ^ ((i >> 5) & 1)) : i; }
+  __device__ __forceinline__ float2* at(int i) const { return buf + row(i) * W; }
+  __device__ __forceinline__ void put(int i, float2 x) { buf[row(i) * W] = x; }
+  __device__ __forceinline__ float2 get(int i) const { return buf[row(i) * W]; }
   __device__ __forceinline__ void sync() {
     if (NTHREADS == 0) __syncthreads();
     else if (NTHREADS > 0) asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(NTHREADS > 0 ? NTHREADS : 32) : "memory");
@@ -387,7 +394,7 @@ template <int N, int AXIS, bool DB = false> __global__ void __launch_bounds__(ZC
       } else {
         const float2* p = in + b;
 #pragma unroll
-        for (int e = 0; e < E; ++e) cp_async8(land + (w + WK * e) * W, p + e * estride);
+        for (int e = 0; e < E; ++e) cp_async8(ex.at(w + WK * e), p + e * estride);
         cp_async_commit();
       }
     }
@@ -414,7 +421,7 @@ template <int N, int AXIS, bool DB = false> __global__ void __launch_bounds__(ZC
       if constexpr (DB) mbar_wait(bar, (uint32_t)par);
       else cp_async_wait<1>();  // the tile (older group) has landed; the multiplier may still be in flight
 #pragma unroll
-      for (int e = 0; e < E; ++e) v[e] = land[(w + WK * e) * W];
+      for (int e = 0; e < E; ++e) v[e] = DB ? land[(w + WK * e) * W] : ex.get(w + WK * e);  // TMA boxes land row by row
       ex.sync();
       if constexpr (DB) {
         if (nxt < niter) prefetch(nxt, par ^ 1);

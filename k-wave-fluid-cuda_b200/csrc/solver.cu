@@ -1827,6 +1827,49 @@ int kw_set_time_index(kw_ctx* c, uint64_t t) {
   if (!c->preprocessed) return fail(KW_ERR_STATE, "kw_set_time_index before kw_preprocess");
   if (t > c->cfg.nt) return fail(KW_ERR_INVALID, "time index beyond Nt");
   c->t = t;
+  // the step counters of the streams follow from the time index, as in IndexOutputStream::reopen (IndexOutputStream.cpp:203-213):
+  // sampled = t - start, compressed = floor(sampled / oSize); a blob restored afterwards (kw_stream_state_set) overrides them
+  const uint64_t sampled = t > c->cfg.sampling_start_index ? t - c->cfg.sampling_start_index : 0;
+  for (auto& s : c->streams) {
+    if (!s.enabled) continue;
+    s.rows = 0;
+    if (s.op == kOpC || s.op == kOpIAvgC) {
+      s.sampled = sampled;
+      s.compressed = c->c_osize > 0 ? sampled / (uint64_t)c->c_osize : 0;
+    }
+  }
+  return KW_OK;
+}
+// The buffers BaseOutputStream::checkpoint / reopen move through files (OutputStreams/BaseOutputStream.cpp:528-606, IndexOutputStream.cpp:177-247,
+// :536-557): which = 0 the accumulator of an aggregate stream (rms / max / min [_all], I_avg_c: flushed into / reloaded from the OUTPUT
+// file), which = 1 / 2 the two compression accumulators of a *_c stream (the reference's Temp_<name>_1 / _2 datasets of the checkpoint file).
+static int stream_buffer(kw_ctx* c, int sid, int which, void** ptr, size_t* floats) {
+  if (!c || sid < 0 || sid >= KW_STREAM_COUNT || !c->streams[sid].enabled) return fail(KW_ERR_INVALID, "stream not enabled");
+  if (!c->preprocessed) return fail(KW_ERR_STATE, "stream buffers exist after kw_preprocess");
+  Stream& s = c->streams[sid];
+  if (which == 0 && s.op != kOpNone && s.op != kOpC && s.dbuf) *ptr = s.dbuf, *floats = s.row;
+  else if ((which == 1 || which == 2) && s.op == kOpC) *ptr = which == 1 ? s.acc1 : s.acc2, *floats = s.acc_bytes / sizeof(float);
+  else return fail(KW_ERR_INVALID, "kw_stream_buffer: this stream has no such buffer");
+  return KW_OK;
+}
+int kw_stream_buffer_get(kw_ctx* c, int sid, int which, float* host, uint64_t capacity_floats, uint64_t* floats) {
+  void* p = nullptr;
+  size_t n = 0;
+  KW_TRY(stream_buffer(c, sid, which, &p, &n));
+  if (floats) *floats = n;
+  if (!host) return KW_OK;
+  if (capacity_floats < n) return fail(KW_ERR_INVALID, "kw_stream_buffer_get: buffer too small");
+  KW_CUDA(cudaStreamSynchronize(c->st));
+  KW_CUDA(cudaMemcpy(host, p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return KW_OK;
+}
+int kw_stream_buffer_set(kw_ctx* c, int sid, int which, const float* host, uint64_t floats) {
+  void* p = nullptr;
+  size_t n = 0;
+  KW_TRY(stream_buffer(c, sid, which, &p, &n));
+  if (!host || floats != n) return fail(KW_ERR_INVALID, "kw_stream_buffer_set: wrong size");
+  KW_CUDA(cudaStreamSynchronize(c->st));
+  KW_CUDA(cudaMemcpy(p, host, n * sizeof(float), cudaMemcpyHostToDevice));
   return KW_OK;
 }
 namespace {

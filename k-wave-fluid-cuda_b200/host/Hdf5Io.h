@@ -136,8 +136,9 @@ class Hdf5File {
     H5Dclose(d);
     if (e < 0) throw std::ios::failure("Error: cannot write dataset \"" + name + "\".");
   }
-  void writeScalar(hid_t loc, const std::string& name, float v) { writeWhole(loc, name, {1, 1, 1}, {}, &v, true, 0); }
-  void writeScalar(hid_t loc, const std::string& name, uint64_t v) { writeWhole(loc, name, {1, 1, 1}, {}, &v, false, 0); }
+  // Hdf5File::writeScalarValue (Hdf5File.cpp:695-748): an existing scalar (later leg of a checkpointed run) is overwritten
+  void writeScalar(hid_t loc, const std::string& name, float v) { writeScalarImpl(loc, name, &v, true); }
+  void writeScalar(hid_t loc, const std::string& name, uint64_t v) { writeScalarImpl(loc, name, &v, false); }
 
   void setStringAttribute(hid_t loc, const std::string& obj, const std::string& attr, const std::string& value) {
     H5LTset_attribute_string(loc, obj.c_str(), attr.c_str(), value.c_str());
@@ -155,6 +156,16 @@ class Hdf5File {
   }
 
  private:
+  void writeScalarImpl(hid_t loc, const std::string& name, const void* v, bool isFloat) {
+    if (!exists(loc, name)) {
+      writeWhole(loc, name, {1, 1, 1}, {}, v, isFloat, 0);
+      return;
+    }
+    const hid_t d = openDataset(loc, name);
+    const herr_t e = H5Dwrite(d, isFloat ? H5T_NATIVE_FLOAT : H5T_STD_U64LE, H5S_ALL, H5S_ALL, H5P_DEFAULT, v);
+    H5Dclose(d);
+    if (e < 0) throw std::ios::failure("Error: cannot write dataset \"" + name + "\".");
+  }
   hid_t mFile = -1;
   std::string mName;
 };

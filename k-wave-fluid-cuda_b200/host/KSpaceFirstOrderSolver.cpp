@@ -213,6 +213,9 @@ void KSpaceFirstOrderSolver::loadInputData() {
     mOutputFile.open(mCmd.outputFile, false);
     const std::string type = mOutputFile.getStringAttribute(mOutputFile.root(), "/", "file_type");
     if (type != "output") throw std::ios::failure("Error: \"" + mCmd.outputFile + "\" is not an output file of a checkpointed run.");
+  } else if (mCmd.post) {  // cpp:231-239: post-processing of an existing output file, opened read-write
+    if (!Hdf5File::canAccess(mCmd.outputFile)) throw std::ios::failure("Error: --post: the output file \"" + mCmd.outputFile + "\" does not exist.");
+    mOutputFile.open(mCmd.outputFile, false);
   } else {
     mOutputFile.create(mCmd.outputFile);  // cpp:230-235
   }
@@ -259,6 +262,7 @@ void KSpaceFirstOrderSolver::createStreams() {  // OutputStreamContainer::init (
 
 void KSpaceFirstOrderSolver::createOutputDatasets() {
   using K = OutputStream::Kind;
+  if (mCmd.post) return;  // --post works on the datasets an earlier run stored (postProcessOnly)
   const hid_t root = mOutputFile.root();
   const bool cuboids = mScalars.sensorMaskType == 1;
   const unsigned deflate = mCmd.compressionLevel;
@@ -266,7 +270,12 @@ void KSpaceFirstOrderSolver::createOutputDatasets() {
     uint64_t rowFloats = 0, rows = 0;
     check(kw_stream_info(mCtx, st.id, &rowFloats, &rows));
     st.rowFloats = rowFloats;
-    if (st.kind == K::kWholeDomain) continue;  // written at the end (WholeDomainOutputStream::create :78-99)
+    if (st.kind == K::kWholeDomain) {  // WholeDomainOutputStream::create (:78-99): (Nx, Ny, Nz), chunk (Nx, Ny, 1); reopen on recovery
+      const FileScalars& s = mScalars;
+      st.dataset = mRecover ? mOutputFile.openDataset(root, st.name)
+                            : mOutputFile.createDataset(root, st.name, {s.nz, s.ny, s.nx}, {1, s.ny, s.nx}, true, deflate);
+      continue;
+    }
     const bool series = st.kind == K::kSeries || st.kind == K::kCompressed;
     const uint64_t nRows = st.kind == K::kSeries ? mSamplingSteps : st.kind == K::kCompressed ? mCompressedSteps : 0;
     auto compressionAttributes = [&](hid_t loc, const std::string& name) {  // IndexOutputStream.cpp:147-157
@@ -349,6 +358,42 @@ void KSpaceFirstOrderSolver::flushSeries(bool final) {
   }
 }
 
+// the accumulator of one aggregate / whole-domain stream -> its dataset(s) in the output file
+void KSpaceFirstOrderSolver::writeStreamBuffer(OutputStream& st, const float* buf) {
+  using K = OutputStream::Kind;
+  const FileScalars& s = mScalars;
+  if (st.kind == K::kWholeDomain) {
+    mOutputFile.writeHyperslab(st.dataset, {0, 0, 0}, {s.nz, s.ny, s.nx}, buf);
+  } else if (st.dataset >= 0) {
+    mOutputFile.writeHyperslab(st.dataset, {0, 0, 0}, {1, 1, st.rowFloats}, buf);
+  } else {
+    uint64_t offset = 0;
+    for (size_t k = 0; k < st.cuboidDatasets.size(); ++k) {
+      const uint64_t* c = &mCorners[6 * k];
+      const hsize_t cx = c[3] - c[0] + 1, cy = c[4] - c[1] + 1, cz = c[5] - c[2] + 1;
+      mOutputFile.writeHyperslab(st.cuboidDatasets[k], {0, 0, 0}, {cz, cy, cx}, buf + offset);
+      offset += cx * cy * cz;
+    }
+  }
+}
+void KSpaceFirstOrderSolver::readStreamBuffer(OutputStream& st, float* buf) {
+  using K = OutputStream::Kind;
+  const FileScalars& s = mScalars;
+  if (st.kind == K::kWholeDomain) {
+    mOutputFile.readHyperslab(st.dataset, {0, 0, 0}, {s.nz, s.ny, s.nx}, buf);
+  } else if (st.dataset >= 0) {
+    mOutputFile.readHyperslab(st.dataset, {0, 0, 0}, {1, 1, st.rowFloats}, buf);
+  } else {
+    uint64_t offset = 0;
+    for (size_t k = 0; k < st.cuboidDatasets.size(); ++k) {
+      const uint64_t* c = &mCorners[6 * k];
+      const hsize_t cx = c[3] - c[0] + 1, cy = c[4] - c[1] + 1, cz = c[5] - c[2] + 1;
+      mOutputFile.readHyperslab(st.cuboidDatasets[k], {0, 0, 0}, {cz, cy, cx}, buf + offset);
+      offset += cx * cy * cz;
+    }
+  }
+}
+
 void KSpaceFirstOrderSolver::writeAggregates() {
   using K = OutputStream::Kind;
   const FileScalars& s = mScalars;
@@ -358,19 +403,7 @@ void KSpaceFirstOrderSolver::writeAggregates() {
     std::vector<float> buf(st.rowFloats);
     uint64_t got = 0;
     check(kw_stream_fetch(mCtx, st.id, buf.data(), buf.size(), &got));
-    if (st.kind == K::kWholeDomain) {
-      mOutputFile.writeWhole(root, st.name, {s.nz, s.ny, s.nx}, {1, s.ny, s.nx}, buf.data(), true, mCmd.compressionLevel);
-    } else if (st.dataset >= 0) {
-      mOutputFile.writeHyperslab(st.dataset, {0, 0, 0}, {1, 1, st.rowFloats}, buf.data());
-    } else {
-      uint64_t offset = 0;
-      for (size_t k = 0; k < st.cuboidDatasets.size(); ++k) {
-        const uint64_t* c = &mCorners[6 * k];
-        const hsize_t cx = c[3] - c[0] + 1, cy = c[4] - c[1] + 1, cz = c[5] - c[2] + 1;
-        mOutputFile.writeHyperslab(st.cuboidDatasets[k], {0, 0, 0}, {cz, cy, cx}, &buf[offset]);
-        offset += cx * cy * cz;
-      }
-    }
+    writeStreamBuffer(st, buf.data());
   }
   // p_final / u*_final (cpp:952-973; RealMatrix::writeData :88-121)
   std::vector<float> field;
@@ -455,13 +488,141 @@ void KSpaceFirstOrderSolver::computeAverageIntensities() {
   }
   const char* names[3] = {"Ix_avg", "Iy_avg", "Iz_avg"};
   if (mCmd.iAvg)
-    for (int k = 0; k < ncomp; ++k) writeSensorValues(names[k], intensity[k].data());
+    for (int k = 0; k < ncomp; ++k) replaceSensorValues(names[k], intensity[k].data());
   if (mCmd.qTerm) {
     std::vector<float> q(mSensorPoints, 0.f);
     const float* ip[3] = {intensity[0].data(), intensity[1].data(), ncomp == 3 ? intensity[2].data() : nullptr};
     check(kw_q_term(mCtx, ip, ncomp, q.data(), q.size()));
-    writeSensorValues("Q_term", q.data());
+    replaceSensorValues("Q_term", q.data());
   }
+}
+
+// replaces a dataset of per-sensor values (or the per-cuboid group) when an earlier run already stored it
+void KSpaceFirstOrderSolver::replaceSensorValues(const std::string& name, const float* data) {
+  const hid_t root = mOutputFile.root();
+  if (H5Lexists(root, name.c_str(), H5P_DEFAULT) <= 0) {
+    writeSensorValues(name, data);
+    return;
+  }
+  if (mScalars.sensorMaskType == 0) {
+    const hid_t d = mOutputFile.openDataset(root, name);
+    mOutputFile.writeHyperslab(d, {0, 0, 0}, {1, 1, mSensorPoints}, data);
+    mOutputFile.closeDataset(d);
+    return;
+  }
+  const hid_t group = mOutputFile.openGroup(root, name);
+  uint64_t offset = 0;
+  for (size_t k = 0; k < mCorners.size() / 6; ++k) {
+    const uint64_t* c = &mCorners[6 * k];
+    const hsize_t cx = c[3] - c[0] + 1, cy = c[4] - c[1] + 1, cz = c[5] - c[2] + 1;
+    const hid_t d = mOutputFile.openDataset(group, std::to_string(k + 1));
+    mOutputFile.writeHyperslab(d, {0, 0, 0}, {cz, cy, cx}, data + offset);
+    mOutputFile.closeDataset(d);
+    offset += cx * cy * cz;
+  }
+  mOutputFile.closeGroup(group);
+}
+
+// computeAverageIntensitiesC (KSpaceFirstOrderSolver.cpp:1543-1775): the time-averaged intensity from the STORED compression
+// coefficients p_c and u?_non_staggered_c -- for every sensor point the mean over the stored frames of
+// sum_h Re(P_h conj(U_h)) / 2, accumulated frame by frame and harmonic by harmonic as the reference does.
+void KSpaceFirstOrderSolver::computeAverageIntensitiesC(std::vector<std::vector<float>>& intensity) {
+  const int ncomp = mScalars.nz > 1 ? 3 : 2;
+  const uint64_t H = mCmd.harmonics;
+  const hid_t root = mOutputFile.root();
+  const char* unames[3] = {"ux_non_staggered_c", "uy_non_staggered_c", "uz_non_staggered_c"};
+  intensity.assign(ncomp, std::vector<float>(mSensorPoints, 0.f));
+  if (mCmd.c40bit) throw std::invalid_argument("Error: --post with --40-bit_complex is not available (the reference has no such path either, cpp:1580).");
+  auto accumulate = [&](const std::vector<float>& p, const std::vector<float>* u, uint64_t frames, uint64_t npts, uint64_t first) {
+    // frame layout: npts * H complex values (re, im), sensor-major then harmonic
+    for (uint64_t fr = 0; fr < frames; ++fr)
+      for (uint64_t x = 0; x < npts; ++x)
+        for (uint64_t ih = 0; ih < H; ++ih) {
+          const uint64_t q = 2 * (fr * npts * H + x * H + ih);
+          for (int k = 0; k < ncomp; ++k) intensity[k][first + x] += (p[q] * u[k][q] + p[q + 1] * u[k][q + 1]) / 2.0f;
+        }
+    for (uint64_t x = 0; x < npts; ++x)
+      for (int k = 0; k < ncomp; ++k) intensity[k][first + x] /= (float)frames;
+  };
+  std::vector<float> u[3];
+  if (mScalars.sensorMaskType == 0) {
+    for (const char* n : {"p_c", unames[0], unames[1]})
+      if (!mOutputFile.exists(root, n)) throw std::ios::failure(std::string("Error: --post: dataset \"") + n + "\" is missing in the output file (store --p_c --u_non_staggered_c).");
+    const std::vector<float> p = mOutputFile.readFloats(root, "p_c");
+    for (int k = 0; k < ncomp; ++k) u[k] = mOutputFile.readFloats(root, unames[k]);
+    const uint64_t frames = p.size() / (2 * H * mSensorPoints);
+    if (!frames || p.size() != frames * 2 * H * mSensorPoints) throw std::ios::failure("Error: --post: p_c does not match the sensor mask and --harmonics.");
+    for (int k = 0; k < ncomp; ++k)
+      if (u[k].size() != p.size()) throw std::ios::failure("Error: --post: the stored velocity coefficients do not match p_c.");
+    accumulate(p, u, frames, mSensorPoints, 0);
+  } else {
+    uint64_t offset = 0;
+    for (size_t c = 0; c < mCorners.size() / 6; ++c) {
+      const uint64_t* q = &mCorners[6 * c];
+      const uint64_t npts = (q[3] - q[0] + 1) * (q[4] - q[1] + 1) * (q[5] - q[2] + 1);
+      const std::string ds = std::to_string(c + 1);
+      const hid_t gp = mOutputFile.openGroup(root, "p_c");
+      const std::vector<float> p = mOutputFile.readFloats(gp, ds);
+      mOutputFile.closeGroup(gp);
+      for (int k = 0; k < ncomp; ++k) {
+        const hid_t gu = mOutputFile.openGroup(root, unames[k]);
+        u[k] = mOutputFile.readFloats(gu, ds);
+        mOutputFile.closeGroup(gu);
+        if (u[k].size() != p.size()) throw std::ios::failure("Error: --post: the stored velocity coefficients do not match p_c.");
+      }
+      const uint64_t frames = p.size() / (2 * H * npts);
+      if (!frames || p.size() != frames * 2 * H * npts) throw std::ios::failure("Error: --post: p_c does not match the sensor mask and --harmonics.");
+      accumulate(p, u, frames, npts, offset);
+      offset += npts;
+    }
+  }
+}
+
+// --post (KSpaceFirstOrderSolver.cpp:231-239, postProcessing :975-1030 without the time loop): the intensities and Q terms of an
+// existing output file, from its stored raw series (--I_avg, --Q_term) and / or its stored coefficients (--I_avg_c, --Q_term_c)
+void KSpaceFirstOrderSolver::postProcessOnly() {
+  using K = OutputStream::Kind;
+  const hid_t root = mOutputFile.root();
+  const int ncomp = mScalars.nz > 1 ? 3 : 2;
+  mPostProcessingTime.start();
+  if (mCmd.iAvg || mCmd.qTerm) {  // the raw series the earlier run stored
+    for (auto& st : mStreams) {
+      if (st.kind != K::kSeries) continue;
+      if (mScalars.sensorMaskType == 0) {
+        st.dataset = mOutputFile.openDataset(root, st.name);
+      } else {
+        st.group = mOutputFile.openGroup(root, st.name);
+        for (size_t k = 0; k < mCorners.size() / 6; ++k) st.cuboidDatasets.push_back(mOutputFile.openDataset(st.group, std::to_string(k + 1)));
+      }
+    }
+    // the number of stored steps comes from the file, not from -s / Nt of this command line
+    const OutputStream* sp = nullptr;
+    for (const auto& st : mStreams)
+      if (st.id == KW_S_P_RAW) sp = &st;
+    if (!sp) throw std::runtime_error("Error: --post: the raw pressure series is not part of this command line.");
+    const uint64_t stored = mScalars.sensorMaskType == 0 ? mOutputFile.elementCount(root, "p") / std::max<uint64_t>(mSensorPoints, 1)
+                                                          : mOutputFile.elementCount(sp->group, "1") /
+                                                                std::max<uint64_t>((mCorners[3] - mCorners[0] + 1) * (mCorners[4] - mCorners[1] + 1) * (mCorners[5] - mCorners[2] + 1), 1);
+    mSamplingSteps = stored;
+    computeAverageIntensities();
+  }
+  if (mCmd.iAvgC || mCmd.qTermC) {
+    std::vector<std::vector<float>> intensity;
+    computeAverageIntensitiesC(intensity);
+    const char* names[3] = {"Ix_avg_c", "Iy_avg_c", "Iz_avg_c"};
+    if (mCmd.iAvgC)
+      for (int k = 0; k < ncomp; ++k) replaceSensorValues(names[k], intensity[k].data());
+    if (mCmd.qTermC) {
+      std::vector<float> q(mSensorPoints, 0.f);
+      const float* ip[3] = {intensity[0].data(), intensity[1].data(), ncomp == 3 ? intensity[2].data() : nullptr};
+      check(kw_q_term(mCtx, ip, ncomp, q.data(), q.size()));
+      replaceSensorValues("Q_term_c", q.data());
+    }
+  }
+  mPostProcessingTime.stop();
+  mTotalTime.stop();
+  mOutputFile.close();
+  log(1, "Post-processing phase (--post): %s\n", formatSeconds(getPostProcessingTime()).c_str());
 }
 
 void KSpaceFirstOrderSolver::saveScalarsToOutputFile() {  // Parameters::saveScalarsToOutputFile (Parameters.cpp:559-650)
@@ -487,7 +648,7 @@ void KSpaceFirstOrderSolver::saveScalarsToOutputFile() {  // Parameters::saveSca
   if (s.pSourceFlag) o.writeScalar(root, "p_source_many", s.pSourceMany), o.writeScalar(root, "p_source_mode", s.pSourceMode);
   if (s.absorbingFlag) o.writeScalar(root, "alpha_power", s.alphaPower);
   o.writeScalar(root, "t_index", (uint64_t)timeIndex());
-  if (mCmd.copySensorMask) {  // cpp:1100-1116
+  if (mCmd.copySensorMask && !o.exists(root, s.sensorMaskType == 0 ? "sensor_mask_index" : "sensor_mask_corners")) {  // cpp:1100-1116
     o.writeScalar(root, "sensor_mask_type", s.sensorMaskType);
     if (s.sensorMaskType == 0) {
       const auto idx = mInputFile.readIndices(mInputFile.root(), "sensor_mask_index");
@@ -533,34 +694,69 @@ bool KSpaceFirstOrderSolver::isTimeToCheckpoint() const {  // Parameters::isTime
 namespace {
 const struct { const char* name; int id; } kCheckpointArrays[] = {  // the kCheckpoint records, Containers/MatrixContainer.cpp:101-115
     {"p", KW_P}, {"ux_sgx", KW_UX_SGX}, {"uy_sgy", KW_UY_SGY}, {"uz_sgz", KW_UZ_SGZ}, {"rhox", KW_RHOX}, {"rhoy", KW_RHOY}, {"rhoz", KW_RHOZ}};
-}
 
+// name of the reference's stream object behind a kw_stream id (OutputStreamContainer.cpp:70-325): the Temp_<name> datasets
+std::string streamObjectName(int sid) {
+  const char* axes[3] = {"x", "y", "z"};
+  if (sid == KW_S_P_C) return "p_c";
+  for (int k = 0; k < 3; ++k) {
+    if (sid == KW_S_UX_C + k) return std::string("u") + axes[k] + "_c";
+    if (sid == KW_S_UX_NS_C + k) return std::string("u") + axes[k] + "_non_staggered_c";
+    if (sid == KW_S_IX_AVG_C + k) return std::string("I") + axes[k] + "_avg_c";
+  }
+  return "";
+}
+}  // namespace
+
+// The reference's checkpoint (KSpaceFirstOrderSolver::saveCheckpointData cpp:1176-1224, OutputStreamContainer::checkpointStreams,
+// BaseOutputStream.cpp:528-606): the checkpoint file holds the seven state arrays, t_index, Nx, Ny, Nz, the header and the
+// compression accumulators Temp_<name>_1 / _2 (and Temp_<I?_avg_c>); the accumulators of the aggregate streams are flushed
+// into their datasets of the OUTPUT file.  Either code can resume a run the other one interrupted.
 void KSpaceFirstOrderSolver::saveCheckpointData() {
+  using K = OutputStream::Kind;
   const FileScalars& s = mScalars;
   Hdf5File ck;
   ck.create(mCmd.checkpointFile);  // overwrites the one of the previous leg
   const hid_t root = ck.root();
   std::vector<float> field(s.nx * s.ny * s.nz);
   for (const auto& a : kCheckpointArrays) {
+    if (s.nz == 1 && (a.id == KW_UZ_SGZ || a.id == KW_RHOZ)) continue;  // 2-D runs have no z components (MatrixContainer.cpp:101-115)
     check(kw_get_array(mCtx, a.id, field.data(), field.size()));
     ck.writeWhole(root, a.name, {s.nz, s.ny, s.nx}, {1, s.ny, s.nx}, field.data(), true, mCmd.compressionLevel);
   }
   ck.writeScalar(root, "t_index", (uint64_t)timeIndex());
   ck.writeScalar(root, "Nx", s.nx), ck.writeScalar(root, "Ny", s.ny), ck.writeScalar(root, "Nz", s.nz);
-  // stream state (OutputStreamContainer::checkpointStreams): aggregate buffers, compression accumulators, step counters,
-  // and how many rows of each series are already in the output file
-  for (int sid = 0; sid < KW_STREAM_COUNT; ++sid) {
-    uint64_t bytes = 0;
-    check(kw_stream_state_size(mCtx, sid, &bytes));
-    if (!bytes) continue;
-    std::vector<float> blob((bytes + 3) / 4, 0.f);
-    check(kw_stream_state_get(mCtx, sid, blob.data(), bytes));
-    const std::string name = "Temp_stream_" + std::to_string(sid);
-    ck.writeWhole(root, name, {1, 1, blob.size()}, {}, blob.data(), true, 0);
-    ck.setLongLongAttribute(root, name, "state_bytes", (long long)bytes);
+  if (timeIndex() > mCmd.samplingStartIndex) {  // cpp:1214-1220: nothing was sampled before
+    std::vector<float> buf;
+    for (auto& st : mStreams) {  // IndexOutputStream::checkpoint (:536-557): aggregates are flushed into the output file
+      if ((st.kind != K::kAggregate && st.kind != K::kWholeDomain) || st.id == KW_S_Q_TERM_C) continue;
+      uint64_t n = 0;
+      check(kw_stream_buffer_get(mCtx, st.id, 0, nullptr, 0, &n));
+      buf.resize(n);
+      check(kw_stream_buffer_get(mCtx, st.id, 0, buf.data(), buf.size(), &n));
+      writeStreamBuffer(st, buf.data());
+    }
+    for (int sid = 0; sid < KW_STREAM_COUNT; ++sid) {  // storeCheckpointCompressionCoefficients, do-not-save streams included
+      const std::string name = streamObjectName(sid);
+      uint64_t bytes = 0;
+      if (name.empty() || kw_stream_state_size(mCtx, sid, &bytes) != KW_OK || !bytes) continue;
+      const bool intensity = sid >= KW_S_IX_AVG_C && sid <= KW_S_IZ_AVG_C;
+      for (int which = intensity ? 0 : 1; which <= (intensity ? 0 : 2); ++which) {
+        uint64_t n = 0;
+        check(kw_stream_buffer_get(mCtx, sid, which, nullptr, 0, &n));
+        buf.resize(n);
+        check(kw_stream_buffer_get(mCtx, sid, which, buf.data(), buf.size(), &n));
+        const std::string ds = "Temp_" + name + (intensity ? "" : which == 1 ? "_1" : "_2");
+        ck.writeWhole(root, ds, {1, 1, n}, {1, 1, n}, buf.data(), true, mCmd.compressionLevel);
+      }
+    }
   }
-  for (const auto& st : mStreams) ck.writeScalar(root, "Temp_rows_" + std::to_string(st.id), (uint64_t)st.rowsWritten);
+  char date[64];
+  const time_t now = time(nullptr);
+  strftime(date, sizeof date, "%d-%b-%Y-%H-%M-%S", localtime(&now));
   ck.setStringAttribute(root, "/", "created_by", getCodeName());
+  ck.setStringAttribute(root, "/", "creation_date", date);
+  ck.setStringAttribute(root, "/", "file_description", "Checkpoint data created by the B200 time-step engine");
   ck.setStringAttribute(root, "/", "file_type", "checkpoint");
   ck.setStringAttribute(root, "/", "major_version", "1");
   ck.setStringAttribute(root, "/", "minor_version", "1");
@@ -568,6 +764,7 @@ void KSpaceFirstOrderSolver::saveCheckpointData() {
 }
 
 void KSpaceFirstOrderSolver::recoverFromCheckpoint() {
+  using K = OutputStream::Kind;
   const FileScalars& s = mScalars;
   Hdf5File ck;
   ck.open(mCmd.checkpointFile, true);
@@ -576,20 +773,46 @@ void KSpaceFirstOrderSolver::recoverFromCheckpoint() {
   if (ck.readIndexScalar(root, "Nx") != s.nx || ck.readIndexScalar(root, "Ny") != s.ny || ck.readIndexScalar(root, "Nz") != s.nz)
     throw std::ios::failure("Error: The checkpoint file was created for a different domain size (cpp:2846-2890).");
   for (const auto& a : kCheckpointArrays) {
+    if (s.nz == 1 && (a.id == KW_UZ_SGZ || a.id == KW_RHOZ)) continue;
     const auto v = ck.readFloats(root, a.name);
     check(kw_set_array(mCtx, a.id, v.data(), v.size()));
   }
-  check(kw_set_time_index(mCtx, ck.readIndexScalar(root, "t_index")));
-  for (int sid = 0; sid < KW_STREAM_COUNT; ++sid) {
-    uint64_t bytes = 0;
-    check(kw_stream_state_size(mCtx, sid, &bytes));
-    if (!bytes) continue;
-    const std::string name = "Temp_stream_" + std::to_string(sid);
-    if (!ck.exists(root, name)) throw std::ios::failure("Error: The checkpoint file was created with different output flags (" + name + " is missing).");
-    const auto blob = ck.readFloats(root, name);
-    check(kw_stream_state_set(mCtx, sid, blob.data(), blob.size() * sizeof(float)));
+  const uint64_t t = ck.readIndexScalar(root, "t_index");
+  check(kw_set_time_index(mCtx, t));  // also the sampled / compressed step counters of the streams (IndexOutputStream::reopen :203-213)
+  const uint64_t sampled = t > mCmd.samplingStartIndex ? t - mCmd.samplingStartIndex : 0;
+  uint64_t frameSteps = 0;
+  if (mCmd.anyCompressed()) {
+    const float period = mCmd.period > 0.f ? mCmd.period : 1.0f / (mCmd.frequency * s.dt);
+    frameSteps = (uint64_t)(period * (float)mCmd.mos);
   }
-  for (auto& st : mStreams) st.rowsWritten = ck.readIndexScalar(root, "Temp_rows_" + std::to_string(st.id));
+  for (auto& st : mStreams) {
+    if (st.kind == K::kSeries) st.rowsWritten = sampled;
+    else if (st.kind == K::kCompressed) st.rowsWritten = frameSteps ? sampled / frameSteps : 0;
+  }
+  if (sampled > 0) {
+    std::vector<float> buf;
+    for (auto& st : mStreams) {  // aggregated quantities are reloaded from the output file (IndexOutputStream::reopen :215-230)
+      if ((st.kind != K::kAggregate && st.kind != K::kWholeDomain) || st.id == KW_S_Q_TERM_C) continue;
+      if (st.id >= KW_S_IX_AVG_C && st.id <= KW_S_IZ_AVG_C) continue;  // restored from Temp_<name> below
+      uint64_t n = 0;
+      check(kw_stream_buffer_get(mCtx, st.id, 0, nullptr, 0, &n));
+      buf.resize(n);
+      readStreamBuffer(st, buf.data());
+      check(kw_stream_buffer_set(mCtx, st.id, 0, buf.data(), n));
+    }
+    for (int sid = 0; sid < KW_STREAM_COUNT; ++sid) {  // loadCheckpointCompressionCoefficients (BaseOutputStream.cpp:528-545)
+      const std::string name = streamObjectName(sid);
+      uint64_t bytes = 0;
+      if (name.empty() || kw_stream_state_size(mCtx, sid, &bytes) != KW_OK || !bytes) continue;
+      const bool intensity = sid >= KW_S_IX_AVG_C && sid <= KW_S_IZ_AVG_C;
+      for (int which = intensity ? 0 : 1; which <= (intensity ? 0 : 2); ++which) {
+        const std::string ds = "Temp_" + name + (intensity ? "" : which == 1 ? "_1" : "_2");
+        if (!ck.exists(root, ds)) throw std::ios::failure("Error: The checkpoint file was created with different output flags (" + ds + " is missing).");
+        const auto v = ck.readFloats(root, ds);
+        check(kw_stream_buffer_set(mCtx, sid, which, v.data(), v.size()));
+      }
+    }
+  }
   ck.close();
   log(1, "Recovered from the checkpoint at time step %llu\n", (unsigned long long)timeIndex());
 }
@@ -623,6 +846,10 @@ void KSpaceFirstOrderSolver::compute() {
   log(1, "Pre-processing phase: %s, device memory in use: %zu MB\n", formatSeconds(getPreProcessingTime()).c_str(), getDeviceMemoryUsage() >> 20);
 
   if (mRecover) recoverFromCheckpoint();
+  if (mCmd.post) {
+    postProcessOnly();
+    return;
+  }
 
   // computeMainLoop (cpp:864-943): the library runs until Nt, until a device-side row buffer is full, or until it is time
   // to checkpoint (cpp:885)
@@ -654,6 +881,7 @@ void KSpaceFirstOrderSolver::compute() {
   if (timeIndex() < nt) {  // interrupted to checkpoint (cpp:373-398): store the state, keep the output file for the next leg
     mPostProcessingTime.start();
     saveCheckpointData();
+    saveScalarsToOutputFile();  // writeOutputDataInfo runs on every leg (cpp:1099-1168): a resuming run checks Nx, Ny, Nz of the output file
     mPostProcessingTime.stop();
     mTotalTime.stop();
     writeOutputHeader();

@@ -83,6 +83,11 @@ class KSpaceFirstOrderSolver {
   void readScalars();
   void loadArray(const std::string& name, int arrayId, bool isIndex, bool required);
   void createStreams();
+  void postProcessOnly();             // --post (cpp:231-239, :975-1030)
+  void computeAverageIntensitiesC(std::vector<std::vector<float>>& intensity);  // cpp:1543-1775
+  void replaceSensorValues(const std::string& name, const float* data);
+  void writeStreamBuffer(OutputStream& st, const float* buf);  // accumulator of an aggregate stream -> output file
+  void readStreamBuffer(OutputStream& st, float* buf);
   void createOutputDatasets();
   bool isTimeToCheckpoint() const;   // Parameters::isTimeToCheckpoint (Parameters.cpp:683-692)
   void saveCheckpointData();         // cpp:1176-1224

@@ -17,7 +17,7 @@ std::string CommandLine::usage() {
          "  --I_avg_c  --Q_term_c  --period <steps> | --frequency <Hz>  --mos <n>  --harmonics <n>  --no_overlap  --40-bit_complex\n"
          "  --checkpoint_file <file> with --checkpoint_interval <seconds> and/or --checkpoint_timesteps <steps>\n"
          "  -h|--help  --version\n"
-         "Not available in this build: --post\n";
+         "";
 }
 
 static long toLong(const char* s, const char* what, long minValue) {
@@ -102,7 +102,7 @@ void CommandLine::parse(int argc, char** argv) {
       case 32: qTermC = true; break;
       case 29: iAvg = true; break;
       case 31: qTerm = true; break;
-      case 33: throw std::invalid_argument("Error: --post (post-processing of an existing output file only) is not available in this build.");
+      case 33: post = true; break;
       case 34: blockSize = (uint64_t)toLong(optarg, "--block_size", 1); break;
       case 35: noOverlap = true; break;
       case 36: c40bit = true; break;
@@ -121,6 +121,10 @@ void CommandLine::parse(int argc, char** argv) {
   // --I_avg / --Q_term are computed from the stored raw series of p and the non-staggered velocity, which are therefore
   // stored too (OutputStreamContainer.cpp:229-262)
   if (iAvg || qTerm) pRaw = uNonStaggeredRaw = true;
+  // --post: no simulation, only the post-processing of an existing output file (KSpaceFirstOrderSolver.cpp:231-239, :990-994)
+  if (post && !(iAvg || qTerm || iAvgC || qTermC))
+    throw std::invalid_argument("Error: --post needs at least one of --I_avg, --I_avg_c, --Q_term, --Q_term_c.");
+  if (post && isCheckpointEnabled()) throw std::invalid_argument("Error: --post cannot be combined with checkpointing.");
   // nothing selected: this fork of the reference stores nothing (CommandLineParameters.cpp:938-947 sets
   // mStorePressureRawFlag = false where upstream k-Wave defaults to --p_raw); the scalars and the header are still written
 }

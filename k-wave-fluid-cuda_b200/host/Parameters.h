@@ -1,7 +1,7 @@
 // Command-line flags and input-file scalars of the solver.  Flag names, meaning and validation follow the reference
 // (Parameters/CommandLineParameters.cpp:264-292, :888-964; Parameters/Parameters.cpp:111-163, :194-553): a run
 // scripted for kspaceFirstOrder-CUDA is accepted unchanged.  Flags whose feature lies outside the time-step hot path
-// (raw-series post-processing: --I_avg, --Q_term, --Q_term_c, --post) are recognised and rejected with an explicit message.
+// are still parsed.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -22,6 +22,7 @@ struct CommandLine {
   uint64_t samplingStartIndex = 0;  // -s, stored 0-based (CommandLineParameters.cpp:424)
   int verbose = 0;
   bool copySensorMask = false;
+  bool post = false;  // --post: only post-process an existing output file (I_avg / Q_term from stored series or coefficients)
   bool printVersion = false, printHelp = false;
   // outputs
   bool pRaw = false, pC = false, pRms = false, pMax = false, pMin = false, pMaxAll = false, pMinAll = false, pFinal = false;

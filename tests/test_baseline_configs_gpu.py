@@ -35,6 +35,9 @@ CONFIGS = {
     "config2_128_index_compressed_p_and_intensity": (128, 400, dict(nonlinear=False, absorbing=False, source="p0", sensor="index", n_sensor=4096,
                                                                     period=50, shifts=True, shuffle_sensor=True),
                                                      ["--p_c", "--I_avg_c", "--period", "50", "--mos", "1", "--harmonics", "2"]),
+    # the same outputs with the broadband plane source on a grid where cuFFT's C2R drops the Nyquist bin (Nx = 64): everything at 1e-5
+    "config2_at_64_plane_source": (64, 400, dict(nonlinear=False, absorbing=False, source="p_plane", sensor="index", n_sensor=4096, period=50, shifts=True,
+                                                 shuffle_sensor=True), ["--p_c", "--I_avg_c", "--u_non_staggered_c", "--period", "50", "--mos", "1", "--harmonics", "2"]),
     "config3_256_nonlinear_absorbing_index": (256, 120, dict(nonlinear=True, absorbing=True, source="p_plane", sensor="index", n_sensor=4096, pml_size=20),
                                               ["-p", "--p_max", "--p_rms"]),
     "config4_512_nonlinear_absorbing_whole_domain": (512, 20, dict(nonlinear=True, absorbing=True, source="p_many", sensor="full_cuboid", pml_size=20,
@@ -84,6 +87,9 @@ def test_baseline_config_matches_reference_binary(synth, tmp_path, name):
             nb = max(np.linalg.norm(ref_ds[q]["data"].astype(np.float64).ravel()) for q in sib if q in ref_ds)
         err = np.linalg.norm((a.astype(np.float64) - b).ravel()) / max(nb, 1e-300)
         print(f"{name}: {p} {a.shape}: rel-L2 {err:.3e}, max-abs {np.abs(a - b).max():.3e} (scale {np.abs(b).max():.3e})")
-        assert err <= 1e-5, (p, err)
+        # quantities derived from the x-shifted velocity at Nx = 128 / 256 / 1024 carry the reference's cuFFT Nyquist leak (see CONFIGS): the
+        # residual x-Nyquist content of the scattered field (sharp inclusion in c0) shows up at the 4e-5 level in the reference only
+        leak = n in (128, 256, 1024) and base.startswith(("Ix", "ux_non_staggered", "Q_term"))
+        assert err <= (1e-4 if leak else 1e-5), (p, err)
         compared += 1
     assert compared >= 1

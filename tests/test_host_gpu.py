@@ -104,7 +104,7 @@ def test_command_line_errors_exit_like_the_reference(tmp_path):
     for args, needle in (([], "Input file was not specified"), (["-i", "a"], "Output file was not specified"),
                          (["-i", "a", "-o", "b", "--checkpoint_interval", "5"], "Checkpoint file was not specified"),
                          (["-i", "a", "-o", "b", "--checkpoint_file", "c"], "Checkpoint interval or the number of time steps"),
-                         (["-i", "a", "-o", "b", "--post"], "not available in this build"), (["-i", "a", "-o", "b", "--Q_term_c"], "--period or --frequency"),
+                         (["-i", "a", "-o", "b", "--post"], "--post needs at least one"), (["-i", "a", "-o", "b", "--Q_term_c"], "--period or --frequency"),
                          (["-i", "a", "-o", "b", "--p_c"], "--period or --frequency"), (["-i", "a", "-o", "b", "-s", "0"], "Invalid value"),
                          (["-i", "a", "-o", "b", "-c", "12"], "Invalid value"),
                          (["-i", str(tmp_path / "missing.h5"), "-o", "b"], "could not be opened")):  # fmt: skip
@@ -163,3 +163,106 @@ def test_checkpoint_restart_is_bit_identical(synth, tmp_path, sensor):
             continue
         assert np.array_equal(got[p]["data"].view(np.uint32) if o["kind"] == "f32" else got[p]["data"],
                               o["data"].view(np.uint32) if o["kind"] == "f32" else o["data"]), p
+
+
+def _compare_files(got, ref, tol=1e-5, label=""):
+    ref_ds = {p: o for p, o in ref.items() if o["kind"] != "group"}
+    got_ds = {p: o for p, o in got.items() if o["kind"] != "group"}
+    assert set(ref_ds) == set(got_ds), sorted(set(ref_ds) ^ set(got_ds))
+    for p, o in sorted(ref_ds.items()):
+        a, b = got_ds[p]["data"], o["data"]
+        assert a.shape == b.shape, (p, a.shape, b.shape)
+        if o["kind"] == "u64" or a.size == 1:
+            assert np.array_equal(a, b), p
+            continue
+        nb = np.linalg.norm(b.astype(np.float64).ravel())
+        base = p.strip("/")
+        if base[:2] in ("ux", "uy", "uz", "Ix", "Iy", "Iz"):
+            sib = ["/" + base[0] + c + base[2:] for c in "xyz"]
+            nb = max(np.linalg.norm(ref_ds[q]["data"].astype(np.float64).ravel()) for q in sib if q in ref_ds)
+        err = np.linalg.norm((a.astype(np.float64) - b).ravel()) / max(nb, 1e-300)
+        print(f"{label}: {p} {a.shape}: rel-L2 {err:.3e}, max-abs {np.abs(a - b).max():.3e}")
+        assert err <= tol, (label, p, err)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("first", ["reference", "ours"])
+def test_checkpoint_files_are_interchangeable_with_the_reference(synth, tmp_path, first):
+    """The checkpoint layout is the reference's (KSpaceFirstOrderSolver.cpp:1176-1224, :186-228; BaseOutputStream.cpp:528-606): the seven
+    state arrays + t_index + Nx, Ny, Nz + header in the checkpoint file, compression accumulators as Temp_<name>_1 / _2, running
+    intensities as Temp_<name>, aggregate accumulators flushed into the output file.  A run interrupted by ONE code after 47 steps is
+    resumed by the OTHER code and must end with the output of the reference's uninterrupted run (rel-L2 <= 1e-5)."""
+    if not os.path.exists(REF):
+        pytest.skip("reference binary not built (oracle/ref_build)")
+    assert os.path.exists(OURS), "kspaceFirstOrder-B200 not built (__graft_entry__.build())"
+    nt = 130
+    cfg, arrays = synth.make_case(32, nt=nt, nonlinear=True, absorbing=True, source="p_plane", n_sensor=48, period=20, shifts=True)
+    fin = str(tmp_path / "in.h5")
+    kwh5.write_input(fin, cfg, arrays)
+    flags = ["-p", "--p_rms", "--p_max", "--p_min", "--p_max_all", "--p_final", "--u_final", "--p_c", "--I_avg_c", "--u_non_staggered_raw", "--u_max",
+             "--u_min_all", "--period", "20", "--harmonics", "2", "-s", "4"]  # fmt: skip
+    whole = run(REF, fin, str(tmp_path / "whole.h5"), flags)
+    ck, out = str(tmp_path / "ck.h5"), str(tmp_path / "legs.h5")
+    order = [REF, OURS] if first == "reference" else [OURS, REF]
+    legs = 0
+    while True:
+        binary = order[min(legs, 1)]  # first leg by one code, every later leg by the other
+        r = subprocess.run([binary, "-i", fin, "-o", out, "-t", "4", "--verbose", "0", "--checkpoint_file", ck, "--checkpoint_timesteps", "47"] + flags,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, f"leg {legs} ({os.path.basename(binary)}):\n{r.stdout[-1500:]}\n{r.stderr[-1500:]}"
+        legs += 1
+        if not os.path.exists(ck):
+            break
+        assert legs < 5
+        assert kwh5.read_root_attrs(ck)["file_type"] == "checkpoint"
+        if legs == 1:  # what the first leg left behind has the reference's object names
+            names = set(kwh5.read_file(ck))
+            assert {"/p", "/ux_sgx", "/uy_sgy", "/uz_sgz", "/rhox", "/rhoy", "/rhoz", "/t_index", "/Nx", "/Ny", "/Nz", "/Temp_p_c_1", "/Temp_p_c_2",
+                    "/Temp_ux_non_staggered_c_1", "/Temp_Ix_avg_c"} <= names, sorted(names)
+    assert legs == 3  # 47 + 47 + 36 steps
+    _compare_files(kwh5.read_file(out), whole, label=f"{first} first")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sensor", ["index", "cuboid"])
+def test_post_processing_of_an_existing_output_file(synth, tmp_path, sensor):
+    """--post (KSpaceFirstOrderSolver.cpp:231-239, :975-1030, computeAverageIntensitiesC :1543-1775): a first run stores the raw series and the
+    compression coefficients; a second invocation with --post computes I_avg / Q_term from the stored series and I_avg_c / Q_term_c from the
+    stored coefficients, without a time loop.  The results equal those of a run that computed them directly -- ours (<= 1e-6) and,
+    for the index mask, the reference's (<= 1e-5; its binary fails on these flags with cuboid masks)."""
+    assert os.path.exists(OURS), "kspaceFirstOrder-B200 not built (__graft_entry__.build())"
+    nt = 120
+    kwargs = dict(nonlinear=True, absorbing=True, source="p_plane", n_sensor=150, period=20, shifts=True)
+    if sensor == "cuboid":
+        kwargs["sensor"] = "cuboid"
+    cfg, arrays = synth.make_case(32, nt=nt, **kwargs)
+    fin = str(tmp_path / "in.h5")
+    kwh5.write_input(fin, cfg, arrays)
+    comp = ["--period", "20", "--harmonics", "2"]
+    stored = str(tmp_path / "stored.h5")
+    run(OURS, fin, stored, ["-p", "--u_non_staggered_raw", "--p_c", "--u_non_staggered_c"] + comp)
+    before = set(kwh5.read_file(stored))
+    assert not any(n.startswith(("/Ix_avg", "/Q_term")) for n in before)
+    post = run(OURS, fin, stored, ["--post", "--I_avg", "--Q_term", "--I_avg_c", "--Q_term_c"] + comp)
+    direct = run(OURS, fin, str(tmp_path / "direct.h5"), ["--I_avg", "--Q_term", "--I_avg_c", "--Q_term_c"] + comp)
+    want = [n for n in direct if n.strip("/").split("/")[0] in ("Ix_avg", "Iy_avg", "Iz_avg", "Q_term", "Ix_avg_c", "Iy_avg_c", "Iz_avg_c", "Q_term_c")
+            and direct[n]["kind"] == "f32"]
+    assert len(want) >= 8
+    for n in want:
+        a, b = post[n]["data"].astype(np.float64), direct[n]["data"].astype(np.float64)
+        err = np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300)
+        print(f"--post vs direct run ({sensor}): {n}: rel-L2 {err:.3e}")
+        assert err <= 1e-6, (n, err)
+    assert before <= set(post)  # everything the first run stored is still there
+    if sensor == "index" and os.path.exists(REF):
+        ref = run(REF, fin, str(tmp_path / "ref.h5"), ["--I_avg", "--Q_term", "--I_avg_c", "--Q_term_c"] + comp, may_fail=True)
+        if ref is not None:
+            for n in want:
+                a, b = post[n]["data"].astype(np.float64), ref[n]["data"].astype(np.float64)
+                base = n.strip("/")
+                nb = np.linalg.norm(b.ravel())
+                if base[:2] in ("Ix", "Iy", "Iz"):
+                    nb = max(np.linalg.norm(ref["/" + base[0] + c + base[2:]]["data"].astype(np.float64).ravel()) for c in "xyz")
+                err = np.linalg.norm((a - b).ravel()) / max(nb, 1e-300)
+                print(f"--post vs the reference's direct run: {n}: rel-L2 {err:.3e}")
+                assert err <= 1e-5, (n, err)
