@@ -108,54 +108,45 @@ template <int NF> struct XInvArgs {
   int field0;  // NF == 1: the launch covers fields field0 .. field0 + gridDim.y - 1 (per-field launches of pipelined runs)
 };
 
-// One row pair of NF fields: half spectra -> real rows, then the epilogue on the registers.
-// Epilogue contract:  epi.apply<N>(res, field, t, row0, y, z)  where res[f][m] = (row a, row b) values at x = t + m*T of
-// field f, row0 = flattened (z*Ny + y) index of row a (row b = row0 + 1, same z).
-template <int N, int NF, class Epi, class EX>
-__device__ __forceinline__ void xinv_rows(const XInvArgs<NF>& a, const Epi& epi, int field, size_t row0, bool valid, int t, const RegTw& twp, EX& ex,
-                                          float* stg = nullptr) {
+// The half-spectrum values one thread needs for one row pair of one field: 4 + 4 points of the two rows, and (thread 0 of the
+// transform) the two Nyquist bins.  They are loaded one transform AHEAD -- the next field of the voxel, or the first field of the
+// CTA's next row pair -- so that their HBM latency hides behind the butterflies of the current transform (ncu, round 1:
+// k_xinv<512,3,EpiDensity> stalled 2.9 cycles per issue on long_scoreboard with the loads at the head of each transform).
+struct SpecRegs {
+  float2 A[4], B[4], nA, nB;
+};
+template <int N> __device__ __forceinline__ SpecRegs load_spec(const float2* __restrict__ in, size_t off, int nxp, int t) {
   constexpr int T = N / 8;
-  float2 res[NF][8];
-  // real-space operands of the epilogue start their way into (thread-private slots of) shared memory now and land while
-  // the transforms run: their latency is hidden without holding registers for them
-  if constexpr (Epi::kStage > 0) {
-    if (valid) epi.template stage<N>(stg, t, row0);
-    cp_async_commit();
+  SpecRegs s;
+  const float2* ia = in + off;
+  const float2* ib = ia + nxp;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) s.A[m] = __ldg(ia + t + m * T), s.B[m] = __ldg(ib + t + m * T);
+  s.nA = s.nB = make_float2(0.f, 0.f);
+  if (t == 0) s.nA = __ldg(ia + N / 2), s.nB = __ldg(ib + N / 2);
+  return s;
+}
+// Hermitian merge of two rows + inverse transform: v[m] = (row a, row b) at x = t + m*T
+template <int N, class EX> __device__ __forceinline__ void xinv_transform(const SpecRegs& s, float2 (&v)[1][8], int t, const RegTw& twp, EX& ex) {
+  constexpr int T = N / 8;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int k = t + m * T;
+    float2 A = s.A[m], B = s.B[m];
+    if (m == 0 && t == 0) A.y = 0.f, B.y = 0.f;  // C2R ignores the imaginary part of DC
+    v[0][m] = make_float2(A.x - B.y, A.y + B.x);  // Z[k] = A + iB
+    if (!(m == 0 && t == 0)) ex.put(0, N - k, make_float2(A.x + B.y, B.x - A.y));  // Z[N-k] = conj(A) + i conj(B)
   }
+  if (t == 0) ex.put(0, N / 2, make_float2(s.nA.x, s.nB.x));  // imaginary parts of the Nyquist bin ignored
+  ex.sync();
 #pragma unroll
-  for (int f = 0; f < NF; ++f) {
-    const float2* __restrict__ in = (NF == 1) ? a.in[field] : a.in[f];
-    const float2* ia = in + a.map.off(row0, a.nxp);
-    const float2* ib = ia + a.nxp;
-    float2 v[1][8];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const int k = t + m * T;
-      float2 A = __ldg(ia + k), B = __ldg(ib + k);
-      if (m == 0 && t == 0) A.y = 0.f, B.y = 0.f;  // C2R ignores the imaginary part of DC
-      v[0][m] = make_float2(A.x - B.y, A.y + B.x);  // Z[k] = A + iB
-      if (!(m == 0 && t == 0)) ex.put(0, N - k, make_float2(A.x + B.y, B.x - A.y));  // Z[N-k] = conj(A) + i conj(B)
-    }
-    if (t == 0) {
-      const float2 A = __ldg(ia + N / 2), B = __ldg(ib + N / 2);
-      ex.put(0, N / 2, make_float2(A.x, B.x));  // imaginary parts of the Nyquist bin ignored
-    }
-    ex.sync();
-#pragma unroll
-    for (int m = 4; m < 8; ++m) v[0][m] = ex.get(0, t + m * T);
-    ex.sync();
-    fft_worker<N, +1, 1>(v, t, 0, twp, ex);
-#pragma unroll
-    for (int m = 0; m < 8; ++m) res[f][m] = v[0][m];
-  }
-  if constexpr (Epi::kStage > 0) cp_async_wait<0>();
-  if (valid) {
-    const int y = (int)(row0 % a.ny), z = (int)(row0 / a.ny);
-    if constexpr (Epi::kStage > 0) epi.template apply<N>(res, field, t, row0, y, z, stg);
-    else epi.template apply<N>(res, field, t, row0, y, z);
-  }
+  for (int m = 4; m < 8; ++m) v[0][m] = ex.get(0, t + m * T);
+  ex.sync();
+  fft_worker<N, +1, 1>(v, t, 0, twp, ex);
 }
 
+// Epilogue contract:  epi.apply<N>(res, field, t, row0, y, z)  where res[f][m] = (row a, row b) values at x = t + m*T of
+// field f, row0 = flattened (z*Ny + y) index of row a (row b = row0 + 1, same z).
 template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads, Epi::kMinBlocks) k_xinv(XInvArgs<NF> a, Epi epi) {
   using P = Plan<N>;
   constexpr int T = P::T;
@@ -168,11 +159,49 @@ template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads,
   load_twiddles<N>(twr, t, [tab](int m) { return __ldg(tab + m); });
   RegTw twp{twr};
   RowExchange<T> ex{sbuf, rp * N, 1 + rp};
+  float* const stg = stage_smem + threadIdx.x;
   const int npairs = a.pair_end - a.pair_begin;
-  for (int g = blockIdx.x; g * RP < npairs; g += gridDim.x) {
+  const int field = blockIdx.y + a.field0;  // NF == 1: the field of this CTA
+  auto row_of = [&](int g, bool& valid) -> size_t {
     const int pair = a.pair_begin + g * RP + rp;
-    const bool valid = pair < a.pair_end;
-    xinv_rows<N, NF>(a, epi, blockIdx.y + a.field0, 2 * (size_t)(valid ? pair : a.pair_begin), valid, t, twp, ex, stage_smem + threadIdx.x);
+    valid = pair < a.pair_end;
+    return 2 * (size_t)(valid ? pair : a.pair_begin);
+  };
+  int g = blockIdx.x;
+  if (g * RP >= npairs) return;
+  bool valid;
+  size_t row0 = row_of(g, valid);
+  SpecRegs cur = load_spec<N>(NF == 1 ? a.in[field] : a.in[0], a.map.off(row0, a.nxp), a.nxp, t);
+  for (; g * RP < npairs; g += gridDim.x) {
+    // real-space operands of the epilogue start their way into (thread-private slots of) shared memory now and land while
+    // the transforms run: their latency is hidden without holding registers for them
+    if constexpr (Epi::kStage > 0) {
+      if (valid) epi.template stage<N>(stg, t, row0);
+      cp_async_commit();
+    }
+    const int gn = g + gridDim.x;
+    const bool more = gn * RP < npairs;
+    bool valid_n = false;
+    const size_t row_n = more ? row_of(gn, valid_n) : row0;
+    float2 res[NF][8];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      SpecRegs nxt = cur;
+      if (f + 1 < NF) nxt = load_spec<N>(a.in[f + 1], a.map.off(row0, a.nxp), a.nxp, t);
+      else if (more) nxt = load_spec<N>(NF == 1 ? a.in[field] : a.in[0], a.map.off(row_n, a.nxp), a.nxp, t);
+      float2 v[1][8];
+      xinv_transform<N>(cur, v, t, twp, ex);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) res[f][m] = v[0][m];
+      cur = nxt;
+    }
+    if constexpr (Epi::kStage > 0) cp_async_wait<0>();
+    if (valid) {
+      const int y = (int)(row0 % a.ny), z = (int)(row0 / a.ny);
+      if constexpr (Epi::kStage > 0) epi.template apply<N>(res, field, t, row0, y, z, stg);
+      else epi.template apply<N>(res, field, t, row0, y, z);
+    }
+    row0 = row_n, valid = valid_n;
   }
 }
 

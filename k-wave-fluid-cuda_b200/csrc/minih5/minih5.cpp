@@ -30,6 +30,15 @@ struct Attr {
   float f = 0.f;
 };
 
+// a read-only mapping of an opened file; contiguous datasets of a matching element type are served straight from it
+struct Mapping {
+  void* p = nullptr;
+  size_t n = 0;
+  ~Mapping() {
+    if (p) munmap(p, n);
+  }
+};
+
 struct Node {
   bool is_group = true;
   int dtype = 1;  // 1 float32, 2 uint64
@@ -37,6 +46,18 @@ struct Node {
   unsigned deflate = 0;
   bool has_deflate = false;  // the deflate filter is part of the pipeline (the reference registers it even at level 0, Hdf5File.cpp:345)
   std::vector<uint8_t> data;
+  // zero-copy view of a contiguous dataset inside the file mapping (until the dataset is written to): a 1024^3 input is ~56 GB,
+  // and every rank of a slab-decomposed run opens it -- the pages are shared through the page cache instead of copied per process
+  const uint8_t* view = nullptr;
+  std::shared_ptr<Mapping> mapping;
+  const uint8_t* bytes() const { return view ? view : data.data(); }
+  size_t nbytes() const { return view ? elems() * esize() : data.size(); }
+  void materialize() {
+    if (!view) return;
+    data.assign(view, view + elems() * esize());
+    view = nullptr;
+    mapping.reset();
+  }
   std::map<std::string, Attr> attrs;
   std::map<std::string, std::unique_ptr<Node>> children;
   std::vector<std::string> order;  // creation order of children
@@ -374,7 +395,7 @@ uint64_t write_chunks(Writer& w, const Node& ds, bool filtered) {
       size_t src = 0, dst = 0;
       for (size_t d = 0; d + 1 < rank; ++d) src += (off[d] + r[d]) * dstride[d], dst += r[d] * cstride[d];
       src += off[rank - 1];
-      memcpy(block.data() + dst * es, ds.data.data() + src * es, ext[rank - 1] * es);
+      memcpy(block.data() + dst * es, ds.bytes() + src * es, ext[rank - 1] * es);
       for (size_t d = rank - 1; d-- > 0;) {
         if (++r[d] < ext[d]) break;
         r[d] = 0;
@@ -440,10 +461,10 @@ uint64_t write_dataset(Writer& w, const Node& ds) {
     lay.u32(ds.esize());
     add_msg(&msgs, 0x08, lay), ++n;
   } else {
-    const uint64_t addr = ds.data.empty() ? kUndef : w.alloc(ds.data.size());
-    w.put(addr, ds.data.data(), ds.data.size());
+    const uint64_t addr = ds.nbytes() == 0 ? kUndef : w.alloc(ds.nbytes());
+    w.put(addr, ds.bytes(), ds.nbytes());
     Buf lay;
-    lay.u8(3), lay.u8(1), lay.u64(addr), lay.u64(ds.data.size());
+    lay.u8(3), lay.u8(1), lay.u64(addr), lay.u64(ds.nbytes());
     add_msg(&msgs, 0x08, lay), ++n;
   }
   for (auto& kv : ds.attrs) add_attr(&msgs, kv.first, kv.second), ++n;
@@ -525,7 +546,9 @@ GroupAddr write_group(Writer& w, const Node& g) {
 }
 
 bool save_hdf5(const File& file) {
-  FILE* f = fopen(file.path.c_str(), "wb");
+  // written beside the target and renamed over it: datasets of this very file may still be served from its mapping
+  const std::string tmp = file.path + ".minih5-tmp";
+  FILE* f = fopen(tmp.c_str(), "wb");
   if (!f) return false;
   Writer w{f};
   w.alloc(96);
@@ -548,6 +571,8 @@ bool save_hdf5(const File& file) {
     }
   }
   ok = fclose(f) == 0 && ok;
+  if (ok) ok = rename(tmp.c_str(), file.path.c_str()) == 0;
+  else remove(tmp.c_str());
   return ok;
 }
 
@@ -555,6 +580,7 @@ bool save_hdf5(const File& file) {
 struct Reader {
   const uint8_t* b = nullptr;
   size_t n = 0;
+  std::shared_ptr<Mapping> mapping;
   std::string error;
   bool fail(const std::string& m) {
     if (error.empty()) error = m;
@@ -738,10 +764,17 @@ bool read_dataset(Reader& r, const std::vector<Msg>& msgs, Node* ds) {
   if (t.cls == 's') return r.fail("string datasets are not supported");
   ds->dtype = t.cls == 'f' ? 1 : 2;
   const size_t n = ds->elems();
-  ds->data.assign(n * ds->esize(), 0);
   const uint64_t lo = layout->off;
   if (r.b[lo] != 3) return r.fail("data layout message version " + std::to_string(r.b[lo]) + " is not supported");
   const unsigned cls = r.b[lo + 1];
+  const bool same_type = (t.cls == 'f' && t.size == 4) || (t.cls != 'f' && t.size == 8);
+  if (cls == 1 && same_type && r.u(lo + 2, 8) != kUndef && n * t.size >= (1u << 16)) {  // large contiguous data: served from the mapping
+    const uint64_t addr = r.u(lo + 2, 8);
+    if (!r.in(addr, n * t.size)) return r.fail("contiguous data outside the file");
+    ds->view = r.b + addr, ds->mapping = r.mapping;
+    return true;
+  }
+  ds->data.assign(n * ds->esize(), 0);
   if (cls == 1) {
     const uint64_t addr = r.u(lo + 2, 8);
     if (addr != kUndef) {
@@ -862,6 +895,8 @@ bool load_hdf5(File* file, std::string* why) {
   close(fd);
   if (map == MAP_FAILED) return false;
   Reader r;
+  r.mapping = std::make_shared<Mapping>();
+  r.mapping->p = map, r.mapping->n = (size_t)st.st_size;
   r.b = (const uint8_t*)map, r.n = (size_t)st.st_size;
   bool ok = memcmp(r.b, kSig, 8) == 0 || r.fail("not an HDF5 file");
   if (ok) {
@@ -874,9 +909,8 @@ bool load_hdf5(File* file, std::string* why) {
       else ok = read_object(r, r.u(p + 32 + 8, 8), &file->root, 0);
     }
   }
-  munmap(map, (size_t)st.st_size);
   if (!ok && why) *why = r.error;
-  return ok;
+  return ok;  // the mapping lives as long as a dataset views it
 }
 
 bool save(const File& file) { return save_hdf5(file); }
@@ -962,13 +996,16 @@ herr_t transfer(Node* ds, hid_t mem_type, hid_t mem_space, hid_t file_space, voi
   for_runs(msel.dims, msel.start, msel.count, [&](size_t o, size_t n) { mr.emplace_back(o, n); });
   size_t fi = 0, mi = 0, fo = 0, mo = 0;
   uint8_t* mem = static_cast<uint8_t*>(buf);
+  if (to_file) ds->materialize();  // a dataset served from the file mapping becomes an owned buffer on its first write
+  const uint8_t* fbase = ds->bytes();
+  const size_t fbytes = ds->nbytes();
   while (fi < fr.size() && mi < mr.size()) {
     const size_t n = std::min(fr[fi].second - fo, mr[mi].second - mo);
-    uint8_t* fp = ds->data.data() + (fr[fi].first + fo) * es;
+    const size_t foff = (fr[fi].first + fo) * es;
     uint8_t* mp = mem + (mr[mi].first + mo) * es;
-    if ((fr[fi].first + fo + n) * es > ds->data.size()) return -1;
-    if (to_file) memcpy(fp, mp, n * es);
-    else memcpy(mp, fp, n * es);
+    if (foff + n * es > fbytes) return -1;
+    if (to_file) memcpy(ds->data.data() + foff, mp, n * es);
+    else memcpy(mp, fbase + foff, n * es);
     fo += n, mo += n;
     if (fo == fr[fi].second) ++fi, fo = 0;
     if (mo == mr[mi].second) ++mi, mo = 0;
@@ -1045,7 +1082,7 @@ herr_t H5Fget_filesize(hid_t file, hsize_t* size) {
   // size the file would have on disk now
   struct Acc {
     static hsize_t of(const Node& n) {
-      hsize_t s = 64 + n.data.size();
+      hsize_t s = 64 + n.nbytes();
       for (auto& kv : n.children) s += of(*kv.second);
       return s;
     }

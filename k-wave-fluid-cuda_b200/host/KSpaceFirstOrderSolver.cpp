@@ -39,12 +39,12 @@ std::string formatSeconds(double s) {
 }
 }  // namespace
 
-KSpaceFirstOrderSolver::KSpaceFirstOrderSolver(const CommandLine& commandLine) : mCmd(commandLine) { mTotalTime.start(); }
+KSpaceFirstOrderSolver::KSpaceFirstOrderSolver(const CommandLine& commandLine, const Team* team) : mCmd(commandLine), mTeam(team) { mTotalTime.start(); }
 
 KSpaceFirstOrderSolver::~KSpaceFirstOrderSolver() { freeMemory(); }
 
 void KSpaceFirstOrderSolver::log(int level, const char* fmt, ...) const {
-  if (mCmd.verbose + 1 < level) return;  // 0 basic, 1 advanced, 2 full (Logger/Logger.h)
+  if (mCmd.verbose + 1 < level || !root()) return;  // 0 basic, 1 advanced, 2 full (Logger/Logger.h); rank 0 speaks for the team
   va_list ap;
   va_start(ap, fmt);
   vfprintf(stdout, fmt, ap);
@@ -135,6 +135,32 @@ void KSpaceFirstOrderSolver::allocateMemory() {
   cfg.device = mCmd.gpuDevice;
   cfg.raw_rows_capacity = 0;  // the library sizes the device-side row buffers (<= 256 MB per stream)
   cfg.rank = 0, cfg.nranks = 1;
+  char ncclId[128] = {};
+  if (multi()) {  // slab decomposition: one process per GPU, rank r on device (-g or 0) + r, planes [r Nz/P, (r+1) Nz/P)
+    const int P = mTeam->size;
+    if (s.nz % P || s.ny % P) throw std::invalid_argument("Error: --gpus " + std::to_string(P) + " must divide Ny and Nz.");
+    if (mCmd.iAvg || mCmd.qTerm || mCmd.post) throw std::invalid_argument("Error: --I_avg, --Q_term and --post run on one GPU (post-processing of stored series).");
+    if (mCmd.c40bit) throw std::invalid_argument("Error: --40-bit_complex runs on one GPU.");
+    cfg.rank = mTeam->rank, cfg.nranks = P;
+    cfg.device = (mCmd.gpuDevice < 0 ? 0 : mCmd.gpuDevice) + mTeam->rank;
+    if (root()) check(kw_nccl_unique_id(ncclId, sizeof ncclId));
+    mTeam->bcast(ncclId, sizeof ncclId);
+    cfg.nccl_unique_id = ncclId;
+    // every rank must hit a full row buffer at the same step (kw_run is collective): one capacity for all, from the complete row
+    uint64_t points = 1;  // sensor points of the whole mask, from the input file
+    const hid_t in = mInputFile.root();
+    if (s.sensorMaskType == 0 && mInputFile.exists(in, "sensor_mask_index")) points = mInputFile.elementCount(in, "sensor_mask_index");
+    if (s.sensorMaskType == 1 && mInputFile.exists(in, "sensor_mask_corners")) {
+      const auto c = mInputFile.readIndices(in, "sensor_mask_corners");
+      points = 0;
+      for (size_t k = 0; k + 5 < c.size(); k += 6) points += (c[k + 3] - c[k] + 1) * (c[k + 4] - c[k + 1] + 1) * (c[k + 5] - c[k + 2] + 1);
+    }
+    const uint64_t perRow = 4 * (points / P + 1) * (mCmd.anyCompressed() ? 2 * std::max<uint64_t>(mCmd.harmonics, 1) : 1);
+    cfg.raw_rows_capacity = std::max<uint64_t>(1, std::min<uint64_t>(mSamplingSteps, (64ull << 20) / perRow));
+    mNzLocal = s.nz / P, mZ0 = mTeam->rank * mNzLocal;
+  } else {
+    mNzLocal = s.nz, mZ0 = 0;
+  }
   check(kw_ctx_create(&cfg, &mCtx));
 }
 
@@ -163,6 +189,15 @@ void KSpaceFirstOrderSolver::loadArray(const std::string& name, int arrayId, boo
     check(kw_set_array(mCtx, arrayId, v.data(), v.size()));
     if (arrayId == KW_SENSOR_MASK_CORNERS) mCorners = v;
     if (arrayId == KW_SENSOR_MASK_INDEX) mSensorPoints = v.size();
+  } else if (multi() && mInputFile.elementCount(root, name) == mScalars.nx * mScalars.ny * mScalars.nz && mScalars.nx * mScalars.ny * mScalars.nz > 1) {
+    // a full-grid array: this rank loads its z-slab only (hyperslab read; minih5 serves it from the file mapping)
+    const FileScalars& s = mScalars;
+    std::vector<float> v(s.nx * s.ny * mNzLocal);
+    const hid_t d = mInputFile.openDataset(root, name);
+    mInputFile.readHyperslab(d, {mZ0, 0, 0}, {mNzLocal, s.ny, s.nx}, v.data());
+    mInputFile.closeDataset(d);
+    mHostBytes = std::max(mHostBytes, v.size() * sizeof(float));
+    check(kw_set_array(mCtx, arrayId, v.data(), v.size()));
   } else {
     const auto v = mInputFile.readFloats(root, name);
     mHostBytes = std::max(mHostBytes, v.size() * sizeof(float));
@@ -208,7 +243,8 @@ void KSpaceFirstOrderSolver::loadInputData() {
   }
   // cpp:185-240: a run with checkpointing enabled whose checkpoint file exists continues that run
   mRecover = mCmd.isCheckpointEnabled() && Hdf5File::canAccess(mCmd.checkpointFile);
-  if (mRecover) {
+  if (!root()) {  // rank 0 owns the output file
+  } else if (mRecover) {
     if (!Hdf5File::canAccess(mCmd.outputFile)) throw std::ios::failure("Error: The output file of the checkpointed run \"" + mCmd.outputFile + "\" is missing.");
     mOutputFile.open(mCmd.outputFile, false);
     const std::string type = mOutputFile.getStringAttribute(mOutputFile.root(), "/", "file_type");
@@ -224,6 +260,95 @@ void KSpaceFirstOrderSolver::loadInputData() {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// ---- slab-decomposed runs: host-side gathers towards rank 0 (the data plane between the GPUs lives in the engine library) ----------
+void KSpaceFirstOrderSolver::exchangeSensorLayout() {
+  uint64_t total = 0, local = 0;
+  check(kw_sensor_layout(mCtx, &total, &local, nullptr, 0));
+  mLocalPoints = local;
+  if (!multi()) return;
+  mPositions.assign(local, 0);
+  if (local) check(kw_sensor_layout(mCtx, &total, &local, mPositions.data(), mPositions.size()));
+  if (total) mSensorPoints = total;
+  if (root()) {
+    mRankPositions.assign(mTeam->size, {});
+    mRankPositions[0] = mPositions;
+    for (int r = 1; r < mTeam->size; ++r) mRankPositions[r] = mTeam->recvVec<uint64_t>(r);
+  } else {
+    mTeam->sendVec(0, mPositions);
+  }
+}
+// `rows` rows of `localFloats` floats (perPoint floats per local sensor point) -> rows of fullFloats floats in mask order on rank 0
+std::vector<float> KSpaceFirstOrderSolver::gatherPoints(const float* local, uint64_t rows, uint64_t localFloats, uint64_t perPoint, uint64_t fullFloats) {
+  if (!multi()) return std::vector<float>(local, local + rows * localFloats);
+  if (!root()) {
+    mTeam->send(0, &rows, sizeof rows);
+    if (rows && localFloats) mTeam->send(0, local, rows * localFloats * sizeof(float));
+    return {};
+  }
+  std::vector<float> full(rows * fullFloats, 0.f), part;
+  for (int r = 0; r < mTeam->size; ++r) {
+    const std::vector<uint64_t>& pos = mRankPositions[r];
+    const uint64_t lf = pos.size() * perPoint;
+    const float* src = local;
+    if (r > 0) {
+      uint64_t theirs = 0;
+      mTeam->recv(r, &theirs, sizeof theirs);
+      if (theirs != rows) throw std::runtime_error("Error: rank " + std::to_string(r) + " holds a different number of buffered rows.");
+      part.resize(rows * lf);
+      if (rows && lf) mTeam->recv(r, part.data(), rows * lf * sizeof(float));
+      src = part.data();
+    }
+    for (uint64_t row = 0; row < rows; ++row)
+      for (size_t j = 0; j < pos.size(); ++j) memcpy(&full[row * fullFloats + pos[j] * perPoint], src + row * lf + j * perPoint, perPoint * sizeof(float));
+  }
+  return full;
+}
+// this rank's z-slab of a grid -> the whole grid on rank 0 (slabs are consecutive plane ranges)
+std::vector<float> KSpaceFirstOrderSolver::gatherSlabs(const float* local) {
+  const FileScalars& s = mScalars;
+  const uint64_t slab = s.nx * s.ny * mNzLocal;
+  if (!multi()) return std::vector<float>(local, local + slab);
+  if (!root()) {
+    mTeam->send(0, local, slab * sizeof(float));
+    return {};
+  }
+  std::vector<float> full(s.nx * s.ny * s.nz);
+  memcpy(full.data(), local, slab * sizeof(float));
+  for (int r = 1; r < mTeam->size; ++r) mTeam->recv(r, full.data() + (uint64_t)r * slab, slab * sizeof(float));
+  return full;
+}
+// the entries of a complete per-sensor buffer that belong to this rank's points (read from a file every rank can open)
+void KSpaceFirstOrderSolver::scatterPointsFrom(const std::vector<float>& full, uint64_t perPoint, std::vector<float>* local) const {
+  if (!multi()) {
+    *local = full;
+    return;
+  }
+  local->resize(mPositions.size() * perPoint);
+  for (size_t j = 0; j < mPositions.size(); ++j) memcpy(&(*local)[j * perPoint], &full[mPositions[j] * perPoint], perPoint * sizeof(float));
+}
+
+// rank 0 holds a complete buffer (per-sensor values or a whole grid): every rank gets the part it owns
+std::vector<float> KSpaceFirstOrderSolver::distribute(const std::vector<float>& full, bool wholeDomain, uint64_t perPoint, uint64_t fullFloats) {
+  const FileScalars& s = mScalars;
+  if (wholeDomain) {
+    const uint64_t slab = s.nx * s.ny * mNzLocal;
+    std::vector<float> mine(slab);
+    if (root()) {
+      for (int r = 1; r < mTeam->size; ++r) mTeam->send(r, full.data() + (uint64_t)r * slab, slab * sizeof(float));
+      memcpy(mine.data(), full.data(), slab * sizeof(float));
+    } else {
+      mTeam->recv(0, mine.data(), slab * sizeof(float));
+    }
+    return mine;
+  }
+  std::vector<float> all(fullFloats);
+  if (root()) all = full;
+  mTeam->bcast(all.data(), all.size() * sizeof(float));
+  std::vector<float> mine;
+  scatterPointsFrom(all, perPoint, &mine);
+  return mine;
+}
+
 void KSpaceFirstOrderSolver::createStreams() {  // OutputStreamContainer::init (Containers/OutputStreamContainer.cpp:70-325)
   using K = OutputStream::Kind;
   auto add = [&](bool on, int id, const std::string& name, K kind, bool shifted = false) {
@@ -269,7 +394,12 @@ void KSpaceFirstOrderSolver::createOutputDatasets() {
   for (auto& st : mStreams) {
     uint64_t rowFloats = 0, rows = 0;
     check(kw_stream_info(mCtx, st.id, &rowFloats, &rows));
-    st.rowFloats = rowFloats;
+    st.localFloats = rowFloats;
+    st.perPoint = st.kind == K::kCompressed ? 2 * mCmd.harmonics : 1;
+    // the row in the file covers every sensor point (slab-decomposed runs: this rank holds mLocalPoints of them)
+    st.rowFloats = !multi() ? rowFloats : st.kind == K::kWholeDomain ? mScalars.nx * mScalars.ny * mScalars.nz : mSensorPoints * st.perPoint;
+    rowFloats = st.rowFloats;
+    if (!this->root()) continue;
     if (st.kind == K::kWholeDomain) {  // WholeDomainOutputStream::create (:78-99): (Nx, Ny, Nz), chunk (Nx, Ny, 1); reopen on recovery
       const FileScalars& s = mScalars;
       st.dataset = mRecover ? mOutputFile.openDataset(root, st.name)
@@ -335,9 +465,19 @@ void KSpaceFirstOrderSolver::flushSeries(bool final) {
     uint64_t rowFloats = 0, rows = 0;
     check(kw_stream_info(mCtx, st.id, &rowFloats, &rows));
     if (rows == 0) continue;
-    if (mRowBuffer.size() < rows * rowFloats) mRowBuffer.resize(rows * rowFloats);
+    if (mRowBuffer.size() < rows * rowFloats) mRowBuffer.resize(std::max<uint64_t>(rows * rowFloats, 1));
     uint64_t got = 0;
-    check(kw_stream_fetch(mCtx, st.id, mRowBuffer.data(), mRowBuffer.size(), &got));
+    if (rows && rowFloats) check(kw_stream_fetch(mCtx, st.id, mRowBuffer.data(), mRowBuffer.size(), &got));
+    else got = rows;
+    if (multi()) {  // rows of the local sensor points -> complete rows on rank 0
+      std::vector<float> full = gatherPoints(mRowBuffer.data(), got, st.localFloats, st.perPoint, st.rowFloats);
+      if (!root()) {
+        st.rowsWritten += got;
+        continue;
+      }
+      mRowBuffer.swap(full);
+      rowFloats = st.rowFloats;
+    }
     if (st.dataset >= 0) {
       mOutputFile.writeHyperslab(st.dataset, {0, st.rowsWritten, 0}, {1, got, rowFloats}, mRowBuffer.data());
     } else {
@@ -400,18 +540,20 @@ void KSpaceFirstOrderSolver::writeAggregates() {
   const hid_t root = mOutputFile.root();
   for (auto& st : mStreams) {
     if (st.kind != K::kAggregate && st.kind != K::kWholeDomain) continue;
-    std::vector<float> buf(st.rowFloats);
+    std::vector<float> buf(std::max<uint64_t>(st.localFloats, 1));
     uint64_t got = 0;
-    check(kw_stream_fetch(mCtx, st.id, buf.data(), buf.size(), &got));
-    writeStreamBuffer(st, buf.data());
+    if (st.localFloats) check(kw_stream_fetch(mCtx, st.id, buf.data(), buf.size(), &got));
+    if (multi()) buf = st.kind == K::kWholeDomain ? gatherSlabs(buf.data()) : gatherPoints(buf.data(), 1, st.localFloats, st.perPoint, st.rowFloats);
+    if (this->root()) writeStreamBuffer(st, buf.data());
   }
   // p_final / u*_final (cpp:952-973; RealMatrix::writeData :88-121)
   std::vector<float> field;
   auto final_field = [&](bool on, int id, const char* name) {
     if (!on) return;
-    field.resize(s.nx * s.ny * s.nz);
+    field.resize(s.nx * s.ny * mNzLocal);
     check(kw_get_array(mCtx, id, field.data(), field.size()));
-    mOutputFile.writeWhole(root, name, {s.nz, s.ny, s.nx}, {1, s.ny, s.nx}, field.data(), true, mCmd.compressionLevel);
+    if (multi()) field = gatherSlabs(field.data());
+    if (this->root()) mOutputFile.writeWhole(root, name, {s.nz, s.ny, s.nx}, {1, s.ny, s.nx}, field.data(), true, mCmd.compressionLevel);
   };
   final_field(mCmd.pFinal, KW_P, "p_final");
   final_field(mCmd.uFinal, KW_UX_SGX, "ux_final");
@@ -678,7 +820,7 @@ void KSpaceFirstOrderSolver::writeOutputHeader() {  // Hdf5FileHeader (Hdf5/Hdf5
   o.setStringAttribute(root, "/", "total_memory_in_use", std::to_string(getHostMemoryUsage() >> 20) + " MB");
   o.setStringAttribute(root, "/", "peak_core_memory_in_use", std::to_string(getDeviceMemoryUsage() >> 20) + " MB");
   o.setStringAttribute(root, "/", "total_execution_time", formatSeconds(getTotalTime()));
-  o.setStringAttribute(root, "/", "data_load_phase_execution_time", formatSeconds(getDataLoadTime()));
+  o.setStringAttribute(root, "/", "data_loading_phase_execution_time", formatSeconds(getDataLoadTime()));
   o.setStringAttribute(root, "/", "pre-processing_phase_execution_time", formatSeconds(getPreProcessingTime()));
   o.setStringAttribute(root, "/", "simulation_phase_execution_time", formatSeconds(getSimulationTime()));
   o.setStringAttribute(root, "/", "post-processing_phase_execution_time", formatSeconds(getPostProcessingTime()));
@@ -715,26 +857,32 @@ std::string streamObjectName(int sid) {
 void KSpaceFirstOrderSolver::saveCheckpointData() {
   using K = OutputStream::Kind;
   const FileScalars& s = mScalars;
-  Hdf5File ck;
-  ck.create(mCmd.checkpointFile);  // overwrites the one of the previous leg
-  const hid_t root = ck.root();
-  std::vector<float> field(s.nx * s.ny * s.nz);
+  Hdf5File ck;  // rank 0 owns the checkpoint file; the other ranks hand it their slabs and sensor points
+  const bool io = this->root();
+  if (io) ck.create(mCmd.checkpointFile);  // overwrites the one of the previous leg
+  const hid_t root = io ? ck.root() : -1;
+  std::vector<float> field(s.nx * s.ny * mNzLocal);
   for (const auto& a : kCheckpointArrays) {
     if (s.nz == 1 && (a.id == KW_UZ_SGZ || a.id == KW_RHOZ)) continue;  // 2-D runs have no z components (MatrixContainer.cpp:101-115)
+    field.resize(s.nx * s.ny * mNzLocal);
     check(kw_get_array(mCtx, a.id, field.data(), field.size()));
-    ck.writeWhole(root, a.name, {s.nz, s.ny, s.nx}, {1, s.ny, s.nx}, field.data(), true, mCmd.compressionLevel);
+    if (multi()) field = gatherSlabs(field.data());
+    if (io) ck.writeWhole(root, a.name, {s.nz, s.ny, s.nx}, {1, s.ny, s.nx}, field.data(), true, mCmd.compressionLevel);
   }
-  ck.writeScalar(root, "t_index", (uint64_t)timeIndex());
-  ck.writeScalar(root, "Nx", s.nx), ck.writeScalar(root, "Ny", s.ny), ck.writeScalar(root, "Nz", s.nz);
+  if (io) {
+    ck.writeScalar(root, "t_index", (uint64_t)timeIndex());
+    ck.writeScalar(root, "Nx", s.nx), ck.writeScalar(root, "Ny", s.ny), ck.writeScalar(root, "Nz", s.nz);
+  }
   if (timeIndex() > mCmd.samplingStartIndex) {  // cpp:1214-1220: nothing was sampled before
     std::vector<float> buf;
     for (auto& st : mStreams) {  // IndexOutputStream::checkpoint (:536-557): aggregates are flushed into the output file
       if ((st.kind != K::kAggregate && st.kind != K::kWholeDomain) || st.id == KW_S_Q_TERM_C) continue;
       uint64_t n = 0;
       check(kw_stream_buffer_get(mCtx, st.id, 0, nullptr, 0, &n));
-      buf.resize(n);
-      check(kw_stream_buffer_get(mCtx, st.id, 0, buf.data(), buf.size(), &n));
-      writeStreamBuffer(st, buf.data());
+      buf.resize(std::max<uint64_t>(n, 1));
+      if (n) check(kw_stream_buffer_get(mCtx, st.id, 0, buf.data(), buf.size(), &n));
+      if (multi()) buf = st.kind == K::kWholeDomain ? gatherSlabs(buf.data()) : gatherPoints(buf.data(), 1, n, st.perPoint, st.rowFloats);
+      if (io) writeStreamBuffer(st, buf.data());
     }
     for (int sid = 0; sid < KW_STREAM_COUNT; ++sid) {  // storeCheckpointCompressionCoefficients, do-not-save streams included
       const std::string name = streamObjectName(sid);
@@ -744,13 +892,19 @@ void KSpaceFirstOrderSolver::saveCheckpointData() {
       for (int which = intensity ? 0 : 1; which <= (intensity ? 0 : 2); ++which) {
         uint64_t n = 0;
         check(kw_stream_buffer_get(mCtx, sid, which, nullptr, 0, &n));
-        buf.resize(n);
-        check(kw_stream_buffer_get(mCtx, sid, which, buf.data(), buf.size(), &n));
+        buf.resize(std::max<uint64_t>(n, 1));
+        if (n) check(kw_stream_buffer_get(mCtx, sid, which, buf.data(), buf.size(), &n));
+        if (multi()) {  // accumulators are per sensor point (2 * harmonics floats each, one for the intensities)
+          const uint64_t per = intensity ? 1 : 2 * mCmd.harmonics;
+          buf = gatherPoints(buf.data(), 1, n, per, mSensorPoints * per);
+          n = mSensorPoints * per;
+        }
         const std::string ds = "Temp_" + name + (intensity ? "" : which == 1 ? "_1" : "_2");
-        ck.writeWhole(root, ds, {1, 1, n}, {1, 1, n}, buf.data(), true, mCmd.compressionLevel);
+        if (io) ck.writeWhole(root, ds, {1, 1, n}, {1, 1, n}, buf.data(), true, mCmd.compressionLevel);
       }
     }
   }
+  if (!io) return;
   char date[64];
   const time_t now = time(nullptr);
   strftime(date, sizeof date, "%d-%b-%Y-%H-%M-%S", localtime(&now));
@@ -772,9 +926,12 @@ void KSpaceFirstOrderSolver::recoverFromCheckpoint() {
   if (ck.getStringAttribute(root, "/", "file_type") != "checkpoint") throw std::ios::failure("Error: \"" + mCmd.checkpointFile + "\" is not a checkpoint file.");
   if (ck.readIndexScalar(root, "Nx") != s.nx || ck.readIndexScalar(root, "Ny") != s.ny || ck.readIndexScalar(root, "Nz") != s.nz)
     throw std::ios::failure("Error: The checkpoint file was created for a different domain size (cpp:2846-2890).");
-  for (const auto& a : kCheckpointArrays) {
+  for (const auto& a : kCheckpointArrays) {  // every rank reads its own slab
     if (s.nz == 1 && (a.id == KW_UZ_SGZ || a.id == KW_RHOZ)) continue;
-    const auto v = ck.readFloats(root, a.name);
+    std::vector<float> v(s.nx * s.ny * mNzLocal);
+    const hid_t d = ck.openDataset(root, a.name);
+    ck.readHyperslab(d, {mZ0, 0, 0}, {mNzLocal, s.ny, s.nx}, v.data());
+    ck.closeDataset(d);
     check(kw_set_array(mCtx, a.id, v.data(), v.size()));
   }
   const uint64_t t = ck.readIndexScalar(root, "t_index");
@@ -796,9 +953,18 @@ void KSpaceFirstOrderSolver::recoverFromCheckpoint() {
       if (st.id >= KW_S_IX_AVG_C && st.id <= KW_S_IZ_AVG_C) continue;  // restored from Temp_<name> below
       uint64_t n = 0;
       check(kw_stream_buffer_get(mCtx, st.id, 0, nullptr, 0, &n));
-      buf.resize(n);
-      readStreamBuffer(st, buf.data());
-      check(kw_stream_buffer_set(mCtx, st.id, 0, buf.data(), n));
+      if (!multi()) {
+        buf.resize(n);
+        readStreamBuffer(st, buf.data());
+      } else {  // rank 0 reads the complete buffer from the output file and hands every rank its part
+        std::vector<float> full;
+        if (this->root()) {
+          full.resize(st.rowFloats);
+          readStreamBuffer(st, full.data());
+        }
+        buf = distribute(full, st.kind == K::kWholeDomain, st.perPoint, st.rowFloats);
+      }
+      if (n) check(kw_stream_buffer_set(mCtx, st.id, 0, buf.data(), n));
     }
     for (int sid = 0; sid < KW_STREAM_COUNT; ++sid) {  // loadCheckpointCompressionCoefficients (BaseOutputStream.cpp:528-545)
       const std::string name = streamObjectName(sid);
@@ -808,8 +974,13 @@ void KSpaceFirstOrderSolver::recoverFromCheckpoint() {
       for (int which = intensity ? 0 : 1; which <= (intensity ? 0 : 2); ++which) {
         const std::string ds = "Temp_" + name + (intensity ? "" : which == 1 ? "_1" : "_2");
         if (!ck.exists(root, ds)) throw std::ios::failure("Error: The checkpoint file was created with different output flags (" + ds + " is missing).");
-        const auto v = ck.readFloats(root, ds);
-        check(kw_stream_buffer_set(mCtx, sid, which, v.data(), v.size()));
+        std::vector<float> v = ck.readFloats(root, ds);
+        if (multi()) {
+          std::vector<float> mine;
+          scatterPointsFrom(v, intensity ? 1 : 2 * mCmd.harmonics, &mine);
+          v.swap(mine);
+        }
+        if (!v.empty()) check(kw_stream_buffer_set(mCtx, sid, which, v.data(), v.size()));
       }
     }
   }
@@ -841,6 +1012,7 @@ void KSpaceFirstOrderSolver::compute() {
   mPreProcessingTime.start();
   createStreams();
   check(kw_preprocess(mCtx));
+  exchangeSensorLayout();
   createOutputDatasets();
   mPreProcessingTime.stop();
   log(1, "Pre-processing phase: %s, device memory in use: %zu MB\n", formatSeconds(getPreProcessingTime()).c_str(), getDeviceMemoryUsage() >> 20);
@@ -856,7 +1028,12 @@ void KSpaceFirstOrderSolver::compute() {
   mSimulationTime.start();
   const uint64_t nt = mScalars.nt;
   uint64_t nextReport = 0;
-  while (timeIndex() < nt && !isTimeToCheckpoint()) {
+  auto timeToCheckpoint = [&]() {  // the wall clock of rank 0 decides for the whole team (kw_run is collective)
+    int yes = isTimeToCheckpoint() ? 1 : 0;
+    if (multi()) mTeam->bcast(&yes, sizeof yes);
+    return yes != 0;
+  };
+  while (timeIndex() < nt && !timeToCheckpoint()) {
     uint64_t done = 0;
     uint64_t chunk = std::max<uint64_t>(1, nt * (uint64_t)mCmd.progressInterval / 100);
     chunk = std::min<uint64_t>(chunk, nt - timeIndex());
@@ -881,11 +1058,12 @@ void KSpaceFirstOrderSolver::compute() {
   if (timeIndex() < nt) {  // interrupted to checkpoint (cpp:373-398): store the state, keep the output file for the next leg
     mPostProcessingTime.start();
     saveCheckpointData();
-    saveScalarsToOutputFile();  // writeOutputDataInfo runs on every leg (cpp:1099-1168): a resuming run checks Nx, Ny, Nz of the output file
+    if (root()) saveScalarsToOutputFile();  // writeOutputDataInfo runs on every leg (cpp:1099-1168): a resuming run checks Nx, Ny, Nz of the output file
     mPostProcessingTime.stop();
     mTotalTime.stop();
-    writeOutputHeader();
+    if (root()) writeOutputHeader();
     mOutputFile.close();
+    if (multi()) mTeam->barrier();
     log(1, "Checkpoint created after %llu time steps; run the same command again to continue.\n", (unsigned long long)timeIndex());
     return;
   }
@@ -895,12 +1073,13 @@ void KSpaceFirstOrderSolver::compute() {
   check(kw_finish(mCtx));
   writeAggregates();
   if (mCmd.iAvg || mCmd.qTerm) computeAverageIntensities();
-  saveScalarsToOutputFile();
+  if (root()) saveScalarsToOutputFile();
   mPostProcessingTime.stop();
   mTotalTime.stop();
-  writeOutputHeader();
+  if (root()) writeOutputHeader();
   mOutputFile.close();
-  if (mCmd.isCheckpointEnabled()) std::remove(mCmd.checkpointFile.c_str());  // cpp:409-413
+  if (multi()) mTeam->barrier();  // nobody removes the checkpoint file while a rank may still read it
+  if (root() && mCmd.isCheckpointEnabled()) std::remove(mCmd.checkpointFile.c_str());  // cpp:409-413
   log(1, "Post-processing phase: %s, total: %s\n", formatSeconds(getPostProcessingTime()).c_str(), formatSeconds(getTotalTime()).c_str());
 }
 

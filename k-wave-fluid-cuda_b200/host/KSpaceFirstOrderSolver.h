@@ -19,6 +19,7 @@
 #include "../../include/kwave_b200.h"
 #include "Hdf5Io.h"
 #include "Parameters.h"
+#include "Team.h"
 
 namespace kwhost {
 
@@ -36,7 +37,8 @@ class TimeMeasure {  // Utils/TimeMeasure.h
 
 class KSpaceFirstOrderSolver {
  public:
-  explicit KSpaceFirstOrderSolver(const CommandLine& commandLine);
+  // `team`: the processes of a slab-decomposed run (--gpus N, host/Team.h); nullptr = one GPU
+  explicit KSpaceFirstOrderSolver(const CommandLine& commandLine, const Team* team = nullptr);
   KSpaceFirstOrderSolver(const KSpaceFirstOrderSolver&) = delete;
   virtual ~KSpaceFirstOrderSolver();
   KSpaceFirstOrderSolver& operator=(const KSpaceFirstOrderSolver&) = delete;
@@ -77,12 +79,22 @@ class KSpaceFirstOrderSolver {
     hid_t group = -1;
     std::vector<hid_t> cuboidDatasets;
     uint64_t rowsWritten = 0;
-    uint64_t rowFloats = 0;
+    uint64_t rowFloats = 0;       // floats of one row in the FILE (all sensor points)
+    uint64_t localFloats = 0;     // floats of one row held by this rank (== rowFloats on one GPU)
+    uint64_t perPoint = 1;        // floats per sensor point (2 * harmonics for compressed series)
   };
+  // slab-decomposed runs: what this rank holds of a per-sensor / whole-grid buffer -> the complete buffer on rank 0
+  std::vector<float> gatherPoints(const float* local, uint64_t rows, uint64_t localFloats, uint64_t perPoint, uint64_t fullFloats);
+  std::vector<float> gatherSlabs(const float* local);
+  std::vector<float> distribute(const std::vector<float>& full, bool wholeDomain, uint64_t perPoint, uint64_t fullFloats);
+  void scatterPointsFrom(const std::vector<float>& full, uint64_t perPoint, std::vector<float>* local) const;
+  bool root() const { return !mTeam || mTeam->root(); }
+  bool multi() const { return mTeam && mTeam->multi(); }
   void check(int status) const;  // C-ABI status -> the reference's exception types
   void readScalars();
   void loadArray(const std::string& name, int arrayId, bool isIndex, bool required);
   void createStreams();
+  void exchangeSensorLayout();
   void postProcessOnly();             // --post (cpp:231-239, :975-1030)
   void computeAverageIntensitiesC(std::vector<std::vector<float>>& intensity);  // cpp:1543-1775
   void replaceSensorValues(const std::string& name, const float* data);
@@ -101,6 +113,11 @@ class KSpaceFirstOrderSolver {
   void log(int level, const char* fmt, ...) const;
 
   CommandLine mCmd;
+  const Team* mTeam = nullptr;
+  uint64_t mZ0 = 0, mNzLocal = 0;                   // this rank's planes
+  std::vector<uint64_t> mPositions;                  // positions of this rank's sensor points in the complete row
+  std::vector<std::vector<uint64_t>> mRankPositions;  // rank 0: the same for every rank
+  uint64_t mLocalPoints = 0;
   FileScalars mScalars;
   Hdf5File mInputFile, mOutputFile;
   kw_ctx* mCtx = nullptr;

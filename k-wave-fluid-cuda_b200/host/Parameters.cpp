@@ -16,6 +16,8 @@ std::string CommandLine::usage() {
          "  --I_avg  --Q_term  --block_size <n>  (from the stored raw series)\n"
          "  --I_avg_c  --Q_term_c  --period <steps> | --frequency <Hz>  --mos <n>  --harmonics <n>  --no_overlap  --40-bit_complex\n"
          "  --checkpoint_file <file> with --checkpoint_interval <seconds> and/or --checkpoint_timesteps <steps>\n"
+         "  --post                      only post-process an existing output file (with --I_avg / --Q_term / --I_avg_c / --Q_term_c)\n"
+         "  --gpus <1|2|4|8>            slab-decompose the grid along z over that many GPUs (one process per GPU, devices -g .. -g + N - 1)\n"
          "  -h|--help  --version\n"
          "";
 }
@@ -56,6 +58,7 @@ void CommandLine::parse(int argc, char** argv) {
     {"u_non_staggered_c", no_argument, nullptr, 28}, {"I_avg", no_argument, nullptr, 29}, {"I_avg_c", no_argument, nullptr, 30},
     {"Q_term", no_argument, nullptr, 31}, {"Q_term_c", no_argument, nullptr, 32}, {"post", no_argument, nullptr, 33},
     {"block_size", required_argument, nullptr, 34}, {"no_overlap", no_argument, nullptr, 35}, {"40-bit_complex", no_argument, nullptr, 36},
+    {"gpus", required_argument, nullptr, 37},
     {nullptr, no_argument, nullptr, 0}};  // clang-format on
   optind = 1;
   int opt, idx = -1;
@@ -106,6 +109,7 @@ void CommandLine::parse(int argc, char** argv) {
       case 34: blockSize = (uint64_t)toLong(optarg, "--block_size", 1); break;
       case 35: noOverlap = true; break;
       case 36: c40bit = true; break;
+      case 37: gpus = (int)toLong(optarg, "--gpus (1, 2, 4, 8)", 1); if (gpus != 1 && gpus != 2 && gpus != 4 && gpus != 8) throw std::invalid_argument("Error: Invalid value of --gpus (1, 2, 4, 8)."); break;
       default: throw std::invalid_argument("Error: Unknown command line switch or missing argument.");
     }
   }

@@ -12,6 +12,7 @@ struct CommandLine {
   std::string inputFile, outputFile, checkpointFile;
   long numberOfThreads = 0;   // -t (host threads: file I/O and pre-processing only)
   int gpuDevice = -1;         // -g
+  int gpus = 1;               // --gpus: slab decomposition over N GPUs (no counterpart in the single-GPU reference)
   long progressInterval = 5;  // -r
   unsigned compressionLevel = 0;  // -c
   uint64_t checkpointInterval = 0;   // --checkpoint_interval <seconds>

@@ -5,6 +5,7 @@ extern "C" void omp_set_num_threads(int);  // libgomp (the engine library links 
 
 #include <cstdio>
 #include <cstdlib>
+#include <unistd.h>
 #include <exception>
 #include <new>
 #include <stdexcept>
@@ -35,12 +36,21 @@ int main(int argc, char** argv) {
     return EXIT_SUCCESS;
   }
   if (cmd.numberOfThreads > 0) omp_set_num_threads((int)cmd.numberOfThreads);
-  kwhost::KSpaceFirstOrderSolver solver(cmd);
+  // --gpus N: one process per GPU, forked BEFORE anything touches CUDA; rank 0 (this process) owns the files
+  kwhost::Team team;
+  if (cmd.gpus > 1 && !cmd.printVersion) {
+    try {
+      team.spawn(cmd.gpus);
+    } catch (const std::exception& e) {
+      errorAndTerminate(e.what());
+    }
+  }
+  kwhost::KSpaceFirstOrderSolver solver(cmd, &team);
   if (cmd.printVersion) {
     solver.printFullCodeNameAndLicense();
     return EXIT_SUCCESS;
   }
-  if (cmd.verbose > 0) solver.printFullCodeNameAndLicense();
+  if (cmd.verbose > 0 && team.root()) solver.printFullCodeNameAndLicense();
   try {
     solver.allocateMemory();
     solver.loadInputData();
@@ -56,6 +66,8 @@ int main(int argc, char** argv) {
   } catch (const std::exception& e) {
     errorAndTerminate(e.what());
   }
+  if (!team.root()) _exit(EXIT_SUCCESS);  // workers: done (no static destructors of the parent's state)
+  if (!team.join()) errorAndTerminate("Error: a worker process of the slab-decomposed run failed.");
   if (cmd.verbose >= 0)
     printf("Total execution time: %.2fs (load %.2fs, pre-processing %.2fs, simulation %.2fs, post-processing %.2fs)\n", solver.getTotalTime(),
            solver.getDataLoadTime(), solver.getPreProcessingTime(), solver.getSimulationTime(), solver.getPostProcessingTime());

@@ -1,0 +1,83 @@
+"""kspaceFirstOrder-B200 --gpus N (host/Team.h: one process per GPU, slab decomposition along z, rank 0 owns the files): the same input
+file run on 1 GPU and on 2 GPUs gives the same output file, bit for bit -- raw and compressed series assembled in mask order, aggregates,
+whole-domain maxima, final fields, intensities, Q term; also with cuboid masks and across checkpoint legs.  Needs >= 2 GPUs
+(gpurun --gpus 2); no counterpart in the single-GPU reference (main.cpp:840-966)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import kwh5  # noqa: E402
+
+OURS = os.path.join(ROOT, "k-wave-fluid-cuda_b200", "kspaceFirstOrder-B200")
+pytestmark = pytest.mark.gpu
+
+
+def _ngpus():
+    try:
+        import torch
+
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def run(fin, fout, flags, gpus):
+    r = subprocess.run([OURS, "-i", fin, "-o", fout, "-t", "4", "--verbose", "0", "--gpus", str(gpus)] + flags, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, f"--gpus {gpus} failed:\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"
+    return kwh5.read_file(fout)
+
+
+def same_bits(a, b):
+    assert set(a) == set(b), sorted(set(a) ^ set(b))
+    for p, o in a.items():
+        if o["kind"] == "group":
+            continue
+        x, y = o["data"], b[p]["data"]
+        assert x.shape == y.shape, p
+        assert np.array_equal(x.view(np.uint32) if o["kind"] == "f32" else x, y.view(np.uint32) if o["kind"] == "f32" else y), p
+
+
+CASES = {
+    "index": (dict(nonlinear=True, absorbing=True, source="p_plane", n_sensor=200, shuffle_sensor=True, period=20, shifts=True),
+              ["-p", "-u", "--p_rms", "--p_max", "--p_min", "--p_max_all", "--u_min_all", "--p_final", "--u_final", "--p_c", "--u_non_staggered_raw",
+               "--I_avg_c", "--Q_term_c", "--period", "20", "--harmonics", "2", "-s", "5"]),
+    "cuboid": (dict(nonlinear=False, absorbing=False, source="p0", sensor="cuboid"), ["-p", "--p_rms", "--p_max", "--u_max", "--p_max_all", "--copy_sensor_mask"]),
+}  # fmt: skip
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_two_gpus_write_the_file_one_gpu_writes(synth, tmp_path, name):
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    kwargs, flags = CASES[name]
+    cfg, arrays = synth.make_case(32, nt=90, **kwargs)
+    fin = str(tmp_path / "in.h5")
+    kwh5.write_input(fin, cfg, arrays)
+    one = run(fin, str(tmp_path / "one.h5"), flags, 1)
+    two = run(fin, str(tmp_path / "two.h5"), flags, 2)
+    same_bits(one, two)
+
+
+def test_two_gpu_run_resumes_from_its_checkpoint(synth, tmp_path):
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    kwargs, flags = CASES["index"]
+    cfg, arrays = synth.make_case(32, nt=90, **kwargs)
+    fin = str(tmp_path / "in.h5")
+    kwh5.write_input(fin, cfg, arrays)
+    whole = run(fin, str(tmp_path / "whole.h5"), flags, 2)
+    ck, out = str(tmp_path / "ck.h5"), str(tmp_path / "legs.h5")
+    legs = 0
+    while True:
+        run(fin, out, flags + ["--checkpoint_file", ck, "--checkpoint_timesteps", "40"], 2)
+        legs += 1
+        if not os.path.exists(ck):
+            break
+        assert legs < 5
+    assert legs == 3
+    same_bits(whole, kwh5.read_file(out))
