@@ -144,6 +144,14 @@ int kw_synchronize(kw_ctx* ctx);
  * (OutputStreamContainer.cpp:273-323); such internal streams cannot be fetched. */
 int kw_stream_info(kw_ctx* ctx, int stream_id, uint64_t* row_floats, uint64_t* rows_buffered);
 int kw_stream_fetch(kw_ctx* ctx, int stream_id, float* host, uint64_t capacity_floats, uint64_t* rows_fetched);
+/* Asynchronous output (OutputStreams/IndexOutputStream.cpp:583-591 writes every sampled step from a mapped host buffer; here rows are
+ * buffered on the device): with kw_stream_async(ctx, 1), called before kw_preprocess, every raw / compressed series owns TWO device row
+ * buffers and a pinned host buffer -- a full buffer is copied to the host on a separate stream while the time loop goes on sampling into
+ * the other, and kw_run only returns KW_ERR_STREAM_FULL when both are occupied.  kw_stream_pending tells how many rows of a stream are on
+ * their way to (or already in) pinned memory; kw_stream_info / kw_stream_fetch serve that older chunk first, then the rows still on the
+ * device. */
+int kw_stream_async(kw_ctx* ctx, int enable);
+int kw_stream_pending(kw_ctx* ctx, int stream_id, uint64_t* rows);
 /* Part of the running accumulator of an aggregate stream (rms / max / min [_all], I_avg_c) while the loop is in flight: `count`
  * floats from `offset`, device -> host on the solver stream (the reference exposes these only at the end of the run;
  * used for per-step monitoring and by the end-to-end benchmark). */

@@ -114,6 +114,10 @@ def load_library():
         "kw_stream_info": [vp, i32, C.POINTER(u64), C.POINTER(u64)],
         "kw_stream_fetch": [vp, i32, vp, u64, C.POINTER(u64)],
         "kw_stream_peek": [vp, i32, u64, vp, u64],
+        "kw_stream_async": [vp, i32],
+        "kw_stream_pending": [vp, i32, C.POINTER(u64)],
+        "kw_stream_buffer_get": [vp, i32, i32, vp, u64, C.POINTER(u64)],
+        "kw_stream_buffer_set": [vp, i32, i32, vp, u64],
         "kw_finish": [vp],
         "kw_set_source_row": [vp, i32, u64, vp, u64],
         "kw_fft_r2c_3d": [u64, u64, u64, vp, vp],
@@ -236,7 +240,7 @@ class Simulation:
     cut to this rank's z-slab here, see slab.slice_arrays) or slabs already; ``nccl_id`` is the shared ncclUniqueId."""
 
     def __init__(self, cfg, arrays, streams=(), start_index=0, raw_rows_capacity=0, device=-1, compression=None,
-                 rank=0, nranks=1, nccl_id=None):
+                 rank=0, nranks=1, nccl_id=None, async_output=False):
         self.lib = load_library()
         self.cfg = dict(cfg)
         kc = KwConfig()
@@ -273,6 +277,8 @@ class Simulation:
         self.streams = []
         for s in streams:
             self.enable(s)
+        if async_output:  # double-buffered series: full row buffers travel to pinned host memory while the loop goes on
+            _check(self.lib.kw_stream_async(self.ctx, 1))
         _check(self.lib.kw_preprocess(self.ctx))
 
     # -- arrays ----------------------------------------------------------------------------------------------------
@@ -311,6 +317,11 @@ class Simulation:
         got = C.c_uint64()
         _check(self.lib.kw_stream_fetch(self.ctx, sid, out.ctypes.data, out.size, C.byref(got)))
         return out[: got.value]
+
+    def pending(self, stream):
+        n = C.c_uint64()
+        _check(self.lib.kw_stream_pending(self.ctx, STREAM_IDS[stream], C.byref(n)))
+        return n.value
 
     # -- time loop -------------------------------------------------------------------------------------------------
     def run(self, nsteps, sync=True):

@@ -119,6 +119,12 @@ struct Stream {
   bool all = false;  // whole-domain aggregate
   float* dbuf = nullptr;
   size_t row = 0, cap_rows = 0, rows = 0;
+  // asynchronous output (kw_stream_async): series streams own two device buffers; a full one travels to pinned host memory on the
+  // output stream while sampling continues into the other (IndexOutputStream::flushBufferToFile :583-591 writes every step instead)
+  float* dalt = nullptr;       // the other device buffer
+  float* hbuf = nullptr;       // pinned host copy of the buffer in flight
+  size_t pending_rows = 0;     // rows of the buffer in flight / landed, not yet fetched
+  cudaEvent_t landed = nullptr;
   bool fused_this_step = false;  // accumulated by the kernel that produced the field
   // compressed streams (kOpC): two overlapped accumulators per (sensor, harmonic); frames are appended to dbuf
   bool nosave = false;          // created only because an I_avg_c stream needs it (OutputStreamContainer.cpp:273-323)
@@ -234,6 +240,8 @@ struct kw_ctx {
   cudaStream_t ws = nullptr;  // local copy of the own block (peer path): keeps the copy stream for the NVLink pushes
   std::vector<cudaEvent_t> ev_ring;
   size_t ev_next = 0;
+  bool async_out = false;     // kw_stream_async
+  cudaStream_t os = nullptr;  // output stream: device -> pinned host copies of full row buffers
   PeerLink peer;        // copy-engine pushes into peer memory (falls back to NCCL send/recv when unavailable)
   char* arena = nullptr;  // S[0..3], R[0..3] in one allocation (one IPC handle per rank)
   char nccl_id[128] = {};
@@ -490,6 +498,11 @@ int kw_ctx_destroy(kw_ctx* c) {
   if (c->ws) cudaStreamSynchronize(c->ws), cudaStreamDestroy(c->ws);
   if (c->peer.shm) c->peer.teardown();
   if (c->comm) nccl_api().CommDestroy(c->comm);
+  if (c->os) cudaStreamSynchronize(c->os), cudaStreamDestroy(c->os);
+  for (auto& s : c->streams) {
+    if (s.hbuf) cudaFreeHost(s.hbuf);
+    if (s.landed) cudaEventDestroy(s.landed);
+  }
   for (cudaEvent_t e : c->ev_ring) cudaEventDestroy(e);
   if (c->cs) cudaStreamDestroy(c->cs);
   for (void* p : c->owned) cudaFree(p);
@@ -588,6 +601,24 @@ int kw_stream_enable(kw_ctx* c, int sid) {
   s.op = kStreamTable[sid].op;
   s.src = kStreamTable[sid].src;
   s.all = kStreamTable[sid].all;
+  return KW_OK;
+}
+
+// second device buffer + pinned host buffer of a series stream (asynchronous output only)
+static int async_buffers(kw_ctx* c, Stream& s) {
+  if (!c->async_out || s.cap_rows == 0 || s.row == 0) return KW_OK;
+  const size_t bytes = s.cap_rows * s.row * sizeof(float);
+  KW_TRY(dalloc(c, (void**)&s.dalt, bytes));
+  KW_CUDA(cudaHostAlloc((void**)&s.hbuf, bytes, cudaHostAllocDefault));
+  KW_CUDA(cudaEventCreateWithFlags(&s.landed, cudaEventDisableTiming));
+  if (!c->os) KW_CUDA(cudaStreamCreateWithFlags(&c->os, cudaStreamNonBlocking));
+  return KW_OK;
+}
+
+int kw_stream_async(kw_ctx* c, int enable) {
+  if (!c) return fail(KW_ERR_INVALID, "null context");
+  if (c->preprocessed) return fail(KW_ERR_STATE, "kw_stream_async must precede kw_preprocess");
+  c->async_out = enable != 0;
   return KW_OK;
 }
 
@@ -937,6 +968,7 @@ int kw_preprocess(kw_ctx* c) {
       uint64_t cap = cf.raw_rows_capacity ? cf.raw_rows_capacity : std::max<uint64_t>(1, std::min<uint64_t>(nframes, (256ull << 20) / (s.row * sizeof(float) + 1)));
       s.cap_rows = s.nosave ? 0 : cap;
       if (!s.nosave) KW_TRY(dalloc(c, (void**)&s.dbuf, s.cap_rows * s.row * sizeof(float)));
+      if (!s.nosave) KW_TRY(async_buffers(c, s));
     } else if (s.op == kOpIAvgC || s.op == kOpQTermC) {
       s.cap_rows = 1;
       KW_TRY(dalloc(c, (void**)&s.dbuf, s.row * sizeof(float)));
@@ -945,6 +977,7 @@ int kw_preprocess(kw_ctx* c) {
       if (cap == 0) cap = std::max<uint64_t>(1, std::min<uint64_t>(nsamp ? nsamp : 1, (256ull << 20) / (s.row * sizeof(float) + 1)));
       s.cap_rows = cap;
       KW_TRY(dalloc(c, (void**)&s.dbuf, s.cap_rows * s.row * sizeof(float)));
+      KW_TRY(async_buffers(c, s));
     } else {
       s.cap_rows = 1;
       KW_TRY(dalloc(c, (void**)&s.dbuf, s.row * sizeof(float)));
@@ -1793,7 +1826,19 @@ int kw_run(kw_ctx* c, uint64_t nsteps, uint64_t* steps_done, int sync) {
   for (; done < nsteps && c->t < c->cfg.nt; ++done) {
     bool full = false;
     if (c->t >= c->cfg.sampling_start_index)
-      for (auto& s : c->streams) full |= s.enabled && !s.nosave && (s.op == kOpNone || s.op == kOpC) && s.rows >= s.cap_rows;
+      for (auto& s : c->streams) {
+        if (!(s.enabled && !s.nosave && (s.op == kOpNone || s.op == kOpC) && s.rows >= s.cap_rows)) continue;
+        if (s.dalt && s.pending_rows == 0) {  // asynchronous output: the full buffer leaves on the output stream, sampling goes on in the other
+          const cudaEvent_t filled = mark(c, c->st);
+          cudaStreamWaitEvent(c->os, filled, 0);
+          KW_CUDA(cudaMemcpyAsync(s.hbuf, s.dbuf, s.rows * s.row * sizeof(float), cudaMemcpyDeviceToHost, c->os));
+          KW_CUDA(cudaEventRecord(s.landed, c->os));
+          s.pending_rows = s.rows, s.rows = 0;
+          std::swap(s.dbuf, s.dalt);
+          continue;
+        }
+        full = true;
+      }
     if (full) {
       rc = fail(KW_ERR_STREAM_FULL, "a raw stream buffer is full: fetch it with kw_stream_fetch");
       break;
@@ -1895,7 +1940,7 @@ int kw_stream_state_get(kw_ctx* c, int sid, void* buf, uint64_t bytes) {
   KW_TRY(kw_stream_state_size(c, sid, &need));
   if (!buf || need == 0 || bytes < need) return fail(KW_ERR_INVALID, "kw_stream_state_get: stream not enabled or buffer too small");
   Stream& s = c->streams[sid];
-  if (s.rows) return fail(KW_ERR_STATE, "kw_stream_state_get: fetch the buffered rows first");
+  if (s.rows || s.pending_rows) return fail(KW_ERR_STATE, "kw_stream_state_get: fetch the buffered rows first");
   KW_CUDA(cudaStreamSynchronize(c->st));
   StreamStateHeader h{kStateMagic, (uint64_t)s.op, s.sampled, s.compressed, need - sizeof(StreamStateHeader), 0};
   memcpy(buf, &h, sizeof h);
@@ -2157,7 +2202,8 @@ int kw_comm_bytes(kw_ctx* c, double* bytes_sent) {
 int kw_stream_info(kw_ctx* c, int sid, uint64_t* row_floats, uint64_t* rows) {
   if (!c || sid < 0 || sid >= KW_STREAM_COUNT || !c->streams[sid].enabled) return fail(KW_ERR_INVALID, "stream not enabled");
   if (row_floats) *row_floats = c->streams[sid].row;
-  if (rows) *rows = (c->streams[sid].op == kOpNone || c->streams[sid].op == kOpC) ? c->streams[sid].rows : 1;
+  const Stream& si = c->streams[sid];
+  if (rows) *rows = (si.op == kOpNone || si.op == kOpC) ? (si.pending_rows ? si.pending_rows : si.rows) : 1;
   return KW_OK;
 }
 
@@ -2167,6 +2213,15 @@ int kw_stream_fetch(kw_ctx* c, int sid, float* host, uint64_t cap, uint64_t* row
   Stream& s = c->streams[sid];
   if (s.nosave) return fail(KW_ERR_INVALID, "stream exists only as an input of I_avg_c (not stored)");
   const bool series = s.op == kOpNone || s.op == kOpC;
+  if (series && s.pending_rows) {  // asynchronous output: the older chunk, already on its way to (or in) pinned host memory
+    const uint64_t n = s.pending_rows;
+    if (cap < n * s.row) return fail(KW_ERR_INVALID, "kw_stream_fetch: host buffer too small");
+    KW_CUDA(cudaEventSynchronize(s.landed));
+    memcpy(host, s.hbuf, n * s.row * sizeof(float));
+    s.pending_rows = 0;
+    if (rows_fetched) *rows_fetched = n;
+    return KW_OK;
+  }
   const uint64_t rows = series ? s.rows : 1;
   if (cap < rows * s.row) return fail(KW_ERR_INVALID, "kw_stream_fetch: host buffer too small");
   if (rows) {
@@ -2175,6 +2230,12 @@ int kw_stream_fetch(kw_ctx* c, int sid, float* host, uint64_t cap, uint64_t* row
   }
   if (series) s.rows = 0;
   if (rows_fetched) *rows_fetched = rows;
+  return KW_OK;
+}
+
+int kw_stream_pending(kw_ctx* c, int sid, uint64_t* rows) {
+  if (!c || !rows || sid < 0 || sid >= KW_STREAM_COUNT || !c->streams[sid].enabled) return fail(KW_ERR_INVALID, "stream not enabled");
+  *rows = c->streams[sid].pending_rows;
   return KW_OK;
 }
 

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <ctime>
 #include <functional>
+#include <limits>
 #include <new>
 #include <stdexcept>
 #include <thread>
@@ -457,23 +458,26 @@ void KSpaceFirstOrderSolver::createOutputDatasets() {
 }
 
 // rows buffered on the device -> output file (IndexOutputStream::flushBufferToFile :583-591, CuboidOutputStream :560-620)
-void KSpaceFirstOrderSolver::flushSeries(bool final) {
+// onlyLanded: only the chunks the library has already sent towards pinned host memory (asynchronous output, kw_stream_async): the
+// time loop is not held up for rows that still sit in a half-filled device buffer
+void KSpaceFirstOrderSolver::flushSeries(bool onlyLanded) {
   using K = OutputStream::Kind;
-  (void)final;
   for (auto& st : mStreams) {
     if (st.kind != K::kSeries && st.kind != K::kCompressed) continue;
-    uint64_t rowFloats = 0, rows = 0;
+   for (;;) {  // a landed chunk first, then (unless onlyLanded) the rows still on the device
+    uint64_t rowFloats = 0, rows = 0, pending = 0;
+    check(kw_stream_pending(mCtx, st.id, &pending));
+    if (onlyLanded && pending == 0) break;
     check(kw_stream_info(mCtx, st.id, &rowFloats, &rows));
-    if (rows == 0) continue;
+    if (rows == 0) break;
     if (mRowBuffer.size() < rows * rowFloats) mRowBuffer.resize(std::max<uint64_t>(rows * rowFloats, 1));
     uint64_t got = 0;
-    if (rows && rowFloats) check(kw_stream_fetch(mCtx, st.id, mRowBuffer.data(), mRowBuffer.size(), &got));
-    else got = rows;
+    check(kw_stream_fetch(mCtx, st.id, mRowBuffer.data(), mRowBuffer.size(), &got));  // (a rank without sensor points still counts rows)
     if (multi()) {  // rows of the local sensor points -> complete rows on rank 0
       std::vector<float> full = gatherPoints(mRowBuffer.data(), got, st.localFloats, st.perPoint, st.rowFloats);
       if (!root()) {
         st.rowsWritten += got;
-        continue;
+        continue;  // next chunk of this stream
       }
       mRowBuffer.swap(full);
       rowFloats = st.rowFloats;
@@ -495,6 +499,7 @@ void KSpaceFirstOrderSolver::flushSeries(bool final) {
       }
     }
     st.rowsWritten += got;
+   }
   }
 }
 
@@ -884,6 +889,21 @@ void KSpaceFirstOrderSolver::saveCheckpointData() {
       if (multi()) buf = st.kind == K::kWholeDomain ? gatherSlabs(buf.data()) : gatherPoints(buf.data(), 1, n, st.perPoint, st.rowFloats);
       if (io) writeStreamBuffer(st, buf.data());
     }
+    // IndexOutputStream::reopen / CuboidOutputStream::reopen read the attributes min, max, min_index, max_index of every raw / compressed
+    // dataset (IndexOutputStream.cpp:244, BaseOutputStream.cpp:492-506) -- the reference's index streams never store them (the calls are
+    // commented out, :505-509, :551-555), so it cannot resume its OWN index-mask runs; ours carry placeholders so that it can resume ours
+    if (io)
+      for (auto& st : mStreams) {
+        if (st.kind != K::kSeries && st.kind != K::kCompressed) continue;
+        auto mark = [&](hid_t loc, const std::string& name) {
+          mOutputFile.setFloatAttribute(loc, name, "min", std::numeric_limits<float>::max());
+          mOutputFile.setFloatAttribute(loc, name, "max", std::numeric_limits<float>::lowest());
+          mOutputFile.setLongLongAttribute(loc, name, "min_index", 0);
+          mOutputFile.setLongLongAttribute(loc, name, "max_index", 0);
+        };
+        if (st.dataset >= 0) mark(mOutputFile.root(), st.name);
+        for (size_t k = 0; k < st.cuboidDatasets.size(); ++k) mark(st.group, std::to_string(k + 1));
+      }
     for (int sid = 0; sid < KW_STREAM_COUNT; ++sid) {  // storeCheckpointCompressionCoefficients, do-not-save streams included
       const std::string name = streamObjectName(sid);
       uint64_t bytes = 0;
@@ -1011,6 +1031,7 @@ void KSpaceFirstOrderSolver::compute() {
   // preProcessing (cpp:784-857)
   mPreProcessingTime.start();
   createStreams();
+  check(kw_stream_async(mCtx, 1));  // double-buffered rows: full buffers travel to the host while the loop goes on (OutputStreams async path)
   check(kw_preprocess(mCtx));
   exchangeSensorLayout();
   createOutputDatasets();
@@ -1045,13 +1066,14 @@ void KSpaceFirstOrderSolver::compute() {
       continue;
     }
     check(status);
+    flushSeries(true);  // chunks that left the device while the loop ran: written without stalling it
     if (mCmd.verbose > 0 && timeIndex() >= nextReport) {
       log(2, "  %3llu%% done, step %llu of %llu\n", (unsigned long long)(100 * timeIndex() / nt), (unsigned long long)timeIndex(), (unsigned long long)nt);
       nextReport = timeIndex() + chunk;
     }
   }
   check(kw_synchronize(mCtx));
-  flushSeries(true);
+  flushSeries(false);
   mSimulationTime.stop();
   log(1, "Simulation phase: %s (%llu of %llu steps)\n", formatSeconds(getSimulationTime()).c_str(), (unsigned long long)timeIndex(), (unsigned long long)nt);
 
