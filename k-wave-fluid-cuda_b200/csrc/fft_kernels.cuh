@@ -127,7 +127,14 @@ template <int N> __device__ __forceinline__ SpecRegs load_spec(const float2* __r
   return s;
 }
 // Hermitian merge of two rows + inverse transform: v[m] = (row a, row b) at x = t + m*T
-template <int N, class EX> __device__ __forceinline__ void xinv_transform(const SpecRegs& s, float2 (&v)[1][8], int t, const RegTw& twp, EX& ex) {
+// loop-invariant twiddles of a row transform kept in shared memory (entry n of worker t at [n * T + t]): frees the 2 * NTW registers
+// RegTw holds, which is what lets k_xinv carry the prefetched spectrum of the next transform without spilling
+struct SmemTw {
+  const float2* tw;  // table + t
+  int stride;        // T
+  __device__ __forceinline__ float2 get(int n, int) const { return tw[n * stride]; }
+};
+template <int N, class TW, class EX> __device__ __forceinline__ void xinv_transform(const SpecRegs& s, float2 (&v)[1][8], int t, const TW& twp, EX& ex) {
   constexpr int T = N / 8;
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
@@ -152,12 +159,18 @@ template <int N, int NF, class Epi> __global__ void __launch_bounds__(kXThreads,
   constexpr int T = P::T;
   constexpr int RP = kXThreads / T;
   __shared__ float2 sbuf[RP * N];
+  __shared__ float2 stw[(P::NTW > 0 ? P::NTW : 1) * T];
   extern __shared__ float stage_smem[];  // Epi::kStage floats per thread (slot s of thread i at [s * kXThreads + i])
   const int t = threadIdx.x % T, rp = threadIdx.x / T;
-  float2 twr[P::NTW > 0 ? P::NTW : 1];
-  const float2* tab = a.tab;
-  load_twiddles<N>(twr, t, [tab](int m) { return __ldg(tab + m); });
-  RegTw twp{twr};
+  if (rp == 0) {
+    float2 twr[P::NTW > 0 ? P::NTW : 1];
+    const float2* tab = a.tab;
+    load_twiddles<N>(twr, t, [tab](int m) { return __ldg(tab + m); });
+#pragma unroll
+    for (int n = 0; n < P::NTW; ++n) stw[n * T + t] = twr[n];
+  }
+  __syncthreads();
+  SmemTw twp{stw + t, T};
   RowExchange<T> ex{sbuf, rp * N, 1 + rp};
   float* const stg = stage_smem + threadIdx.x;
   const int npairs = a.pair_end - a.pair_begin;

@@ -14,7 +14,7 @@ struct KwNcclUniqueId {
   char internal[128];
 };
 typedef struct ncclComm* KwNcclComm;
-enum { kNcclSuccess = 0, kNcclFloat = 7 };
+enum { kNcclSuccess = 0, kNcclInt32 = 2, kNcclFloat = 7, kNcclMin = 3 };
 
 struct NcclApi {
   int (*GetUniqueId)(KwNcclUniqueId*) = nullptr;
@@ -22,6 +22,7 @@ struct NcclApi {
   int (*CommDestroy)(KwNcclComm) = nullptr;
   int (*Send)(const void*, size_t, int, int, KwNcclComm, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, KwNcclComm, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, KwNcclComm, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -59,6 +60,7 @@ inline NcclApi& nccl_api() {
   KW_NCCL_SYM(CommDestroy, "ncclCommDestroy")
   KW_NCCL_SYM(Send, "ncclSend")
   KW_NCCL_SYM(Recv, "ncclRecv")
+  KW_NCCL_SYM(AllReduce, "ncclAllReduce")
   KW_NCCL_SYM(GroupStart, "ncclGroupStart")
   KW_NCCL_SYM(GroupEnd, "ncclGroupEnd")
   KW_NCCL_SYM(GetErrorString, "ncclGetErrorString")

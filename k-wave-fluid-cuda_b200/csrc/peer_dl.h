@@ -101,8 +101,39 @@ struct PeerLink {
 
   // `tag`: bytes shared by all ranks of this run and by nobody else (the ncclUniqueId); arena = this rank's cudaMalloc'ed
   // block holding the kPeerBufs exchange buffers.  Collective over the ranks; returns false (with `error`) when the peer
-  // path is unavailable -- the caller then keeps the NCCL exchange.  All ranks take the same decision.
-  bool setup(const void* tag, size_t tag_bytes, int rank_, int nranks_, void* arena) {
+  // path is unavailable -- the caller then keeps the NCCL exchange.  ALL RANKS TAKE THE SAME DECISION: `agree(ok)` is a collective
+  // of the caller (an all-reduce with min over the run's communicator) that returns true only when every rank passed true; it is
+  // called exactly twice by every rank, whatever happened locally -- a rank whose shm_open or registration failed no longer leaves
+  // the others waiting for a counter, and nobody ends up on the peer path while a neighbour fell back to NCCL.  `want` carries the
+  // per-process settings (KW_PEER) into the same agreement.
+  template <class Agree> bool setup(const void* tag, size_t tag_bytes, int rank_, int nranks_, void* arena, bool want, Agree&& agree) {
+    const bool ok1 = want && setup_local(tag, tag_bytes, rank_, nranks_, arena);
+    if (!want && error.empty()) error = "disabled by KW_PEER=0";
+    const bool all1 = agree(ok1);  // every rank has published its IPC handle (or nobody continues)
+    if (shm) shm_unlink(shm_name.c_str());  // every rank has it mapped (or gave up): the name can go, nothing leaks after a crash
+    bool ok2 = all1;
+    if (all1) {
+      peer_base[rank] = static_cast<char*>(arena);
+      for (int q = 0; q < nranks && ok2; ++q) {
+        if (q == rank) continue;
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, shm->handle[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          ok2 = false, error = "cudaIpcOpenMemHandle failed for rank " + std::to_string(q);
+        }
+        peer_base[q] = static_cast<char*>(p);
+      }
+    }
+    const bool all2 = agree(ok2);
+    if (!all2) {
+      if (error.empty()) error = "another rank could not set up the peer path";
+      if (shm) teardown();
+      return false;
+    }
+    active = true;
+    return true;
+  }
+  bool setup_local(const void* tag, size_t tag_bytes, int rank_, int nranks_, void* arena) {
     rank = rank_, nranks = nranks_;
     if (nranks > kPeerMaxRanks) return fail_local("more ranks than kPeerMaxRanks");
     uint64_t hsh = 1469598103934665603ull;
@@ -133,31 +164,7 @@ struct PeerLink {
       cudaGetLastError();
       ok = false, error = "cudaIpcGetMemHandle failed";
     }
-    if (!ok) shm->failed.fetch_add(1);
-    shm->attached.fetch_add(1, std::memory_order_release);
-    if (!wait_count(shm->attached, (uint32_t)nranks, 120.0)) return fail_local("timeout waiting for the other ranks (attach)");
-    if (shm->failed.load() == 0) {
-      peer_base[rank] = static_cast<char*>(arena);
-      for (int q = 0; q < nranks && ok; ++q) {
-        if (q == rank) continue;
-        void* p = nullptr;
-        if (cudaIpcOpenMemHandle(&p, shm->handle[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-          cudaGetLastError();
-          ok = false, error = "cudaIpcOpenMemHandle failed for rank " + std::to_string(q);
-          shm->failed.fetch_add(1);
-        }
-        peer_base[q] = static_cast<char*>(p);
-      }
-    }
-    shm->opened.fetch_add(1, std::memory_order_release);
-    if (!wait_count(shm->opened, (uint32_t)nranks, 120.0)) return fail_local("timeout waiting for the other ranks (open)");
-    if (shm->failed.load() != 0) {
-      if (error.empty()) error = "another rank could not set up the peer path";
-      return false;
-    }
-    shm_unlink(name);  // every rank has it mapped: the name can go
-    active = true;
-    return true;
+    return ok;
   }
   bool fail_local(const char* why) {
     error = why;

@@ -808,10 +808,23 @@ int kw_preprocess(kw_ctx* c) {
     for (int k = 0; k < 4; ++k) c->S[k] = reinterpret_cast<float2*>(c->arena + k * per), c->R[k] = reinterpret_cast<float2*>(c->arena + (4 + k) * per);
     KW_CUDA(cudaStreamSynchronize(c->st));
     const char* env = getenv("KW_PEER");
-    if (!env || atoi(env) != 0) {
-      if (!c->peer.setup(c->nccl_id, sizeof(c->nccl_id), g.rank, g.nranks, c->arena) && getenv("KW_PEER_VERBOSE"))
-        fprintf(stderr, "kwave_b200 rank %d: peer-memory exchange unavailable (%s); using NCCL send/recv\n", g.rank, c->peer.error.c_str());
-    }
+    const bool want = !env || atoi(env) != 0;
+    int* dflag = nullptr;
+    KW_CUDA(cudaMalloc(&dflag, sizeof(int)));
+    int agree_err = 0;
+    auto agree = [&](bool ok) -> bool {  // min over the ranks of `ok`: the run's NCCL communicator is the one thing all ranks share for sure
+      int v = ok ? 1 : 0;
+      if (cudaMemcpyAsync(dflag, &v, sizeof v, cudaMemcpyHostToDevice, c->cs) != cudaSuccess) agree_err = 1;
+      if (nccl_api().AllReduce(dflag, dflag, 1, kNcclInt32, kNcclMin, c->comm, c->cs) != kNcclSuccess) agree_err = 1;
+      if (cudaMemcpyAsync(&v, dflag, sizeof v, cudaMemcpyDeviceToHost, c->cs) != cudaSuccess) agree_err = 1;
+      if (cudaStreamSynchronize(c->cs) != cudaSuccess) agree_err = 1;
+      return !agree_err && v == 1;
+    };
+    const bool peer_ok = c->peer.setup(c->nccl_id, sizeof(c->nccl_id), g.rank, g.nranks, c->arena, want, agree);
+    cudaFree(dflag);
+    if (agree_err) return fail(KW_ERR_COMM, "NCCL all-reduce failed while agreeing on the exchange path");
+    if (!peer_ok && getenv("KW_PEER_VERBOSE"))
+      fprintf(stderr, "kwave_b200 rank %d: peer-memory exchange unavailable (%s); using NCCL send/recv\n", g.rank, c->peer.error.c_str());
   }
   if (cf.absorbing_flag) {
     KW_TRY(dalloc(c, (void**)&c->tA, g.n * sizeof(float)));

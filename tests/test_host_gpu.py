@@ -190,8 +190,12 @@ def _compare_files(got, ref, tol=1e-5, label=""):
 def test_checkpoint_files_are_interchangeable_with_the_reference(synth, tmp_path, first):
     """The checkpoint layout is the reference's (KSpaceFirstOrderSolver.cpp:1176-1224, :186-228; BaseOutputStream.cpp:528-606): the seven
     state arrays + t_index + Nx, Ny, Nz + header in the checkpoint file, compression accumulators as Temp_<name>_1 / _2, running
-    intensities as Temp_<name>, aggregate accumulators flushed into the output file.  A run interrupted by ONE code after 47 steps is
-    resumed by the OTHER code and must end with the output of the reference's uninterrupted run (rel-L2 <= 1e-5)."""
+    intensities as Temp_<name>, aggregate accumulators flushed into the output file.  A run interrupted by ONE code is resumed by the
+    OTHER code and must end with the output of the reference's uninterrupted run (rel-L2 <= 1e-5).
+    Two defects of the reference shape the test: its index streams read min / max attributes on reopen that it never stores
+    (IndexOutputStream.cpp:244 vs :551-555) -- our checkpoints carry placeholders, so it can resume OURS but not its own; and after a
+    reopen its I_avg_c stream flushes at row t_index - start of a one-row dataset (IndexOutputStream.cpp:203-207, :583-591), so the
+    reference can never finish a resumed run that has --I_avg_c -- the direction in which IT resumes runs without that flag."""
     if not os.path.exists(REF):
         pytest.skip("reference binary not built (oracle/ref_build)")
     assert os.path.exists(OURS), "kspaceFirstOrder-B200 not built (__graft_entry__.build())"
@@ -201,13 +205,16 @@ def test_checkpoint_files_are_interchangeable_with_the_reference(synth, tmp_path
     kwh5.write_input(fin, cfg, arrays)
     flags = ["-p", "--p_rms", "--p_max", "--p_min", "--p_max_all", "--p_final", "--u_final", "--p_c", "--I_avg_c", "--u_non_staggered_raw", "--u_max",
              "--u_min_all", "--period", "20", "--harmonics", "2", "-s", "4"]  # fmt: skip
+    if first == "ours":
+        flags.remove("--I_avg_c")
     whole = run(REF, fin, str(tmp_path / "whole.h5"), flags)
     ck, out = str(tmp_path / "ck.h5"), str(tmp_path / "legs.h5")
     order = [REF, OURS] if first == "reference" else [OURS, REF]
+    every = "47" if first == "reference" else "70"  # reference first: legs of 47 + 47 + 36 steps; ours first: 70 + 60
     legs = 0
     while True:
         binary = order[min(legs, 1)]  # first leg by one code, every later leg by the other
-        r = subprocess.run([binary, "-i", fin, "-o", out, "-t", "4", "--verbose", "0", "--checkpoint_file", ck, "--checkpoint_timesteps", "47"] + flags,
+        r = subprocess.run([binary, "-i", fin, "-o", out, "-t", "4", "--verbose", "0", "--checkpoint_file", ck, "--checkpoint_timesteps", every] + flags,
                            capture_output=True, text=True)
         assert r.returncode == 0, f"leg {legs} ({os.path.basename(binary)}):\n{r.stdout[-1500:]}\n{r.stderr[-1500:]}"
         legs += 1
@@ -217,9 +224,11 @@ def test_checkpoint_files_are_interchangeable_with_the_reference(synth, tmp_path
         assert kwh5.read_root_attrs(ck)["file_type"] == "checkpoint"
         if legs == 1:  # what the first leg left behind has the reference's object names
             names = set(kwh5.read_file(ck))
-            assert {"/p", "/ux_sgx", "/uy_sgy", "/uz_sgz", "/rhox", "/rhoy", "/rhoz", "/t_index", "/Nx", "/Ny", "/Nz", "/Temp_p_c_1", "/Temp_p_c_2",
-                    "/Temp_ux_non_staggered_c_1", "/Temp_Ix_avg_c"} <= names, sorted(names)
-    assert legs == 3  # 47 + 47 + 36 steps
+            want = {"/p", "/ux_sgx", "/uy_sgy", "/uz_sgz", "/rhox", "/rhoy", "/rhoz", "/t_index", "/Nx", "/Ny", "/Nz", "/Temp_p_c_1", "/Temp_p_c_2"}
+            if "--I_avg_c" in flags:
+                want |= {"/Temp_ux_non_staggered_c_1", "/Temp_Ix_avg_c"}
+            assert want <= names, sorted(names)
+    assert legs == (3 if first == "reference" else 2)
     _compare_files(kwh5.read_file(out), whole, label=f"{first} first")
 
 

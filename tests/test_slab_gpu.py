@@ -145,3 +145,27 @@ def test_sharded_streams_match_single_gpu(kw, synth):
         err = rel_l2(got[s].reshape(-1), single[s].reshape(-1))
         print(f"sharded {s}: rel-L2 vs single GPU {err:.3e}")
         assert err <= TOL_SHARD, (s, err)
+
+
+def test_shard_invariance_at_256(kw, synth):
+    """p_max_all of a 256^3 nonlinear absorbing run on all GPUs of the box (P = 2, 4 or 8) against the same run on
+    one GPU, rel-L2 <= 1e-6 -- the single-GPU 256^3 path itself is compared with the reference's binary in
+    tests/test_baseline_configs_gpu.py (config 3)."""
+    world = max(w for w in (1, 2, 4, 8) if w <= _ngpus()) if _ngpus() else 0
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    shape = (256, 256, 256)
+    kwargs = dict(nonlinear=True, absorbing=True, source="p_plane", sensor="full_cuboid", pml_size=20, medium="waves")
+    nt = 12
+    streams = ["KW_S_P_MAX_ALL", "KW_S_P_RMS"]
+    got = run_sharded(kw, world, shape, kwargs, nt, streams)
+    cfg, arrays = synth.make_case(*shape, nt=nt, **kwargs)
+    one = kw.Simulation(cfg, arrays, streams=streams)
+    one.run(nt)
+    one.finish()
+    for s in streams:
+        a, b = got[s].reshape(-1), one.fetch(s).reshape(-1)
+        err = rel_l2(a, b)
+        print(f"256^3 P={world}: {s}: rel-L2 vs single GPU {err:.3e}, identical bits: {bool(np.array_equal(a.view(np.uint32), b.view(np.uint32)))}")
+        assert err <= 1e-6, (s, err)
+    one.close()
