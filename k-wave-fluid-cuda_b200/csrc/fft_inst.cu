@@ -108,6 +108,9 @@ static void col(const ColArgs& a, int dir, int nfields, cudaStream_t st) {
     k_col<N, +1, true><<<dim3(g, nfields), block, C::SMEM, st>>>(a);
   }
 }
+#ifndef KW_ZMID_1024_DEFAULT
+#define KW_ZMID_1024_DEFAULT 2
+#endif
 // Variants of the fused z pass: KW_ZMID_VARIANT = 0 every thread copies its points with cp.async into the exchange buffer once the
 // last inverse butterfly has freed it; 1 = one thread requests the next tile through the TMA unit a whole tile ahead (N >= 256).
 // (A 16-points-per-thread "paired" plan -- radix-32 / 64 butterflies shared by 2 / 4 threads of a warp through shuffles, 16 warps
@@ -138,22 +141,31 @@ template <int ID, bool DB, class K> static void zmid_go(K kernel, const ZMidArgs
   kernel<<<groups < cap ? groups : cap, block, smem, st>>>(a, maps);
 }
 template <int NN, int AXIS, bool = (NN >= 256)> struct TmaZ {
-  static bool launch(const ZMidArgs&, cudaStream_t) { return false; }
+  static bool launch(const ZMidArgs&, int, cudaStream_t) { return false; }
 };
 template <int NN, int AXIS> struct TmaZ<NN, AXIS, true> {
-  static bool launch(const ZMidArgs& a, cudaStream_t st) {
-    using C = ZCfg<NN>;
-    zmid_go<10 + AXIS + 1, true>(k_zmid<NN, AXIS, true>, a, C::W, dim3(C::W, C::WK, C::TPC), C::TPC, C::SMEM_ZMID_DB, st);
+  template <int MODE> static void go(ZMidArgs a, cudaStream_t st) {
+    using C = ZCfgM<NN, MODE>;
+    const int ny = a.ntiles / a.ngroups;  // the caller sized the tiles for FftOps::zmid_w
+    a.ngroups = a.nxp / C::W, a.ntiles = ny * a.ngroups;
+    const size_t smem = MODE == 1 ? C::SMEM_ZMID_DB : C::SMEM_ZMID + 16;
+    zmid_go<10 * MODE + AXIS + 1, true>(k_zmid<NN, AXIS, MODE>, a, C::W, dim3(C::W, C::WK, C::TPC), C::TPC, smem, st);
+  }
+  static bool launch(const ZMidArgs& a, int variant, cudaStream_t st) {
+    if (variant == 1) go<1>(a, st);
+    else if (variant == 2) go<2>(a, st);
+    else return false;
     return true;
   }
 };
 template <int AXIS> static void zmid_axis(const ZMidArgs& a, cudaStream_t st) {
   using C = ZCfg<N>;
   int variant = zmid_variant();
-  // default: TMA double-buffered tiles where they win (profiles/r02_d_zmid_variants.log: N = 256 +20 %, N = 512 +19 %, N = 1024 -5 %)
-  if (variant < 0) variant = (N == 256 || N == 512) ? 1 : 0;
-  if (variant == 1 && TmaZ<N, AXIS>::launch(a, st)) return;
-  zmid_go<AXIS + 1, false>(k_zmid<N, AXIS, false>, a, C::W, dim3(C::W, C::WK, C::TPC), C::TPC, C::SMEM_ZMID, st);
+  // default: TMA double-buffered tiles where they win (profiles/r02_d_zmid_variants.log: N = 256 +20 %, N = 512 +19 %, N = 1024 -5 %);
+  // N = 1024: 16-wide single-buffered TMA tiles (see ZCfgM)
+  if (variant < 0) variant = (N == 256 || N == 512) ? 1 : (N == 1024 ? KW_ZMID_1024_DEFAULT : 0);
+  if (TmaZ<N, AXIS>::launch(a, variant, st)) return;
+  zmid_go<AXIS + 1, false>(k_zmid<N, AXIS, 0>, a, C::W, dim3(C::W, C::WK, C::TPC), C::TPC, C::SMEM_ZMID, st);
 }
 static void zmid(const ZMidArgs& a, cudaStream_t st) {
   switch (a.axis) {

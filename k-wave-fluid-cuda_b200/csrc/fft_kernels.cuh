@@ -244,7 +244,12 @@ template <int N, int WV = 16> struct ColCfg {
   // barrier flavour of a slot: whole CTA, named barrier (slot spans whole warps), or none (single-stage plans)
   static constexpr int BAR_THREADS = (P::R2 == 1) ? -1 : (TPC == 1 ? 0 : SLOT);
 };
-template <int N> using ZCfg = ColCfg<N, (N >= 1024) ? 8 : 16>;  // tiles of the fused z pass
+template <int N> using ZCfg = ColCfg<N, (N >= 1024) ? 8 : 16>;  // tiles of the fused z pass (cp.async / double-buffered TMA forms)
+// MODE of k_zmid: 0 = cp.async into the exchange buffer (late), 1 = TMA, double-buffered (a tile ahead), 2 = TMA into the exchange
+// buffer (late, single-buffered).  MODE 2 exists for N = 1024: with no per-thread copy addresses to keep, 32 points per thread fit
+// into 128 registers with < 130 bytes of spills (cp.async form: 530), so the tile can be 16 kx wide with 512 threads = 16 warps per SM
+// instead of 8-wide with 8 warps; 128 KB exchange + 64 KB multiplier leave no room for a second tile buffer.
+template <int N, int MODE> using ZCfgM = ColCfg<N, (N >= 1024 && MODE != 2) ? 8 : 16>;
 
 
 template <int W, int NTHREADS> struct ColExchange2 {
@@ -373,35 +378,38 @@ struct ZMidArgs {
 #ifndef KW_ZMID_MINB
 // E = 32 points per thread need ~150 registers to stay spill free (ncu/ptxas: 128 registers spill 300+ bytes and run
 // 25-55% slower than one CTA per SM at 254 registers)
-#define KW_ZMID_MINB ((Plan2<N>::E >= 32 || AXIS == 3) ? 1 : ZCfg<N>::MINB)
+#define KW_ZMID_MINB ((Plan2<N>::E >= 32 || AXIS == 3) ? 1 : ZCfgM<N, MODE>::MINB)
 #endif
 #ifndef KW_ZMID_MULMODE
 #define KW_ZMID_MULMODE 0  // 0: multiplier lands in shared memory through cp.async; 1: plain loads at the point of use
 #endif
-// DB (one tile slot per CTA, N >= 256): the next tile is requested as soon as the current one sits in registers -- a whole
+// MODE 1 (one tile slot per CTA, N >= 256): the next tile is requested as soon as the current one sits in registers -- a whole
 // tile of compute ahead -- by ONE thread through the TMA unit (box copies of 256 rows x 128 bytes, completion on an
-// mbarrier) into a landing buffer of its own, its multiplier into the other of two multiplier buffers.  Without DB every
-// thread copies its own points with cp.async once the last inverse butterfly has freed the exchange buffer.
-template <int N, int AXIS, bool DB = false> __global__ void __launch_bounds__(ZCfg<N>::THREADS, KW_ZMID_MINB) k_zmid(ZMidArgs a, const __grid_constant__ ZMaps maps) {
-  using C = ZCfg<N>;
+// mbarrier) into a landing buffer of its own, its multiplier into the other of two multiplier buffers.  MODE 0: every
+// thread copies its own points with cp.async once the last inverse butterfly has freed the exchange buffer.  MODE 2: see ZCfgM.
+template <int N, int AXIS, int MODE = 0> __global__ void __launch_bounds__(ZCfgM<N, MODE>::THREADS, KW_ZMID_MINB) k_zmid(ZMidArgs a, const __grid_constant__ ZMaps maps) {
+  using C = ZCfgM<N, MODE>;
   using P = Plan2<N>;
-  static_assert(!DB || (P::R2 > 1 && C::TPC == 1), "the TMA variant needs a plan with an exchange and one tile slot per CTA");
+  constexpr bool DB = MODE == 1, TS = MODE == 2, TMA = DB || TS;
+  static_assert(!TMA || (P::R2 > 1 && C::TPC == 1), "the TMA variants need a plan with an exchange and one tile slot per CTA");
+  static_assert(!TS || C::W == 16, "single-buffered TMA tiles land in the exchange buffer, whose rows are only linear for W = 16");
   constexpr int W = C::W, WK = C::WK, E = P::E;
   constexpr size_t TILES = (size_t)C::TPC * N * W;  // points of all tile slots of the CTA
   extern __shared__ float2 smem[];
   const int lane = threadIdx.x, w = threadIdx.y, tz = threadIdx.z;
   ColExchange2<W, C::BAR_THREADS> ex{smem + (size_t)tz * N * W + lane, 1 + tz};
   float2* const land = DB ? ex.buf + TILES : ex.buf;
+  float2* const land0 = DB ? smem + TILES : smem;  // where the TMA boxes go
   float* const mulbase = reinterpret_cast<float*>(smem + (DB ? 2 : 1) * C::SMEM / sizeof(float2));
   float* const mul0 = mulbase + (size_t)tz * N * W + w * W + lane;
   float2* const svec = smem + ((DB ? 2 : 1) * (C::SMEM + TILES * sizeof(float))) / sizeof(float2);  // N entries (AXIS == 2)
   uint64_t* const bar = reinterpret_cast<uint64_t*>(svec + N);
-  const bool leader = DB && lane == 0 && w == 0 && tz == 0;
+  const bool leader = TMA && lane == 0 && w == 0 && tz == 0;
   if (leader) {
     mbar_init(bar, 1);
     mbar_fence_init();
   }
-  if (DB) __syncthreads();
+  if (TMA) __syncthreads();
   const float2* __restrict__ in = a.f.in;
   const float* __restrict__ mul = a.f.mul;
   const int niter = (a.ntiles + C::TPC - 1) / C::TPC;
@@ -423,14 +431,14 @@ template <int N, int AXIS, bool DB = false> __global__ void __launch_bounds__(ZC
       bool valid;
       int y, kx;
       const unsigned b = tile_base(it, valid, y, kx);
-      if constexpr (DB) {
+      if constexpr (TMA) {
         if (leader) {  // lane 0: kx is the first kx of the tile
           constexpr int ZB = N < 256 ? N : 256;  // rows per box
           mbar_expect_tx(bar, (uint32_t)(TILES * (mul ? 12 : 8)));
 #pragma unroll
           for (int zb = 0; zb < N / ZB; ++zb) {
-            tma_load_3d(smem + TILES + (size_t)zb * ZB * W, &maps.in, 2 * kx, y, zb * ZB, bar);
-            if (mul) tma_load_3d(mulbase + par * TILES + (size_t)zb * ZB * W, &maps.mul, kx, y, zb * ZB, bar);
+            tma_load_3d(land0 + (size_t)zb * ZB * W, &maps.in, 2 * kx, y, zb * ZB, bar);
+            if (mul) tma_load_3d(mulbase + (DB ? par * TILES : 0) + (size_t)zb * ZB * W, &maps.mul, kx, y, zb * ZB, bar);
           }
         }
       } else {
@@ -451,7 +459,7 @@ template <int N, int AXIS, bool DB = false> __global__ void __launch_bounds__(ZC
     const int nxt = it + gridDim.x;
     // the real multiplier of this tile lands in shared memory (cp.async, thread-private slots) while the forward
     // transform runs: no registers, no exposed latency.  Issued before the points are taken into registers.
-    if constexpr (!DB) {
+    if constexpr (!TMA) {
       if (mul && KW_ZMID_MULMODE == 0) {
 #pragma unroll
         for (int e = 0; e < E; ++e) cp_async4(mul0 + e * (WK * W), mul + base + e * estride);
@@ -460,7 +468,7 @@ template <int N, int AXIS, bool DB = false> __global__ void __launch_bounds__(ZC
     }
     float2 v[E];
     if constexpr (P::R2 > 1) {
-      if constexpr (DB) mbar_wait(bar, (uint32_t)par);
+      if constexpr (TMA) mbar_wait(bar, (uint32_t)par);
       else cp_async_wait<1>();  // the tile (older group) has landed; the multiplier may still be in flight
 #pragma unroll
       for (int e = 0; e < E; ++e) v[e] = DB ? land[(w + WK * e) * W] : ex.get(w + WK * e);  // TMA boxes land row by row
@@ -473,7 +481,7 @@ template <int N, int AXIS, bool DB = false> __global__ void __launch_bounds__(ZC
       for (int e = 0; e < E; ++e) v[e] = __ldg(in + base + e * estride);
     }
     fft2_worker<N, -1>(v, w, ex, ConstTab());
-    if constexpr (!DB) cp_async_wait<0>();
+    if constexpr (!TMA) cp_async_wait<0>();
     asm volatile("" ::: "memory");  // keep the phases apart: interleaving them only lengthens live ranges
     const float scal = a.f.scal;
     if constexpr (AXIS == 3) {

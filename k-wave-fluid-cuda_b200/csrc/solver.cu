@@ -606,8 +606,9 @@ int kw_stream_enable(kw_ctx* c, int sid) {
 
 // second device buffer + pinned host buffer of a series stream (asynchronous output only)
 static int async_buffers(kw_ctx* c, Stream& s) {
-  if (!c->async_out || s.cap_rows == 0 || s.row == 0) return KW_OK;
-  const size_t bytes = s.cap_rows * s.row * sizeof(float);
+  if (!c->async_out || s.cap_rows == 0) return KW_OK;
+  // (a rank of a slab-decomposed run that holds no sensor point still switches buffers in step with the others: kw_run is collective)
+  const size_t bytes = std::max<size_t>(s.cap_rows * s.row * sizeof(float), 4);
   KW_TRY(dalloc(c, (void**)&s.dalt, bytes));
   KW_CUDA(cudaHostAlloc((void**)&s.hbuf, bytes, cudaHostAllocDefault));
   KW_CUDA(cudaEventCreateWithFlags(&s.landed, cudaEventDisableTiming));
@@ -1844,7 +1845,7 @@ int kw_run(kw_ctx* c, uint64_t nsteps, uint64_t* steps_done, int sync) {
         if (s.dalt && s.pending_rows == 0) {  // asynchronous output: the full buffer leaves on the output stream, sampling goes on in the other
           const cudaEvent_t filled = mark(c, c->st);
           cudaStreamWaitEvent(c->os, filled, 0);
-          KW_CUDA(cudaMemcpyAsync(s.hbuf, s.dbuf, s.rows * s.row * sizeof(float), cudaMemcpyDeviceToHost, c->os));
+          if (s.row) KW_CUDA(cudaMemcpyAsync(s.hbuf, s.dbuf, s.rows * s.row * sizeof(float), cudaMemcpyDeviceToHost, c->os));
           KW_CUDA(cudaEventRecord(s.landed, c->os));
           s.pending_rows = s.rows, s.rows = 0;
           std::swap(s.dbuf, s.dalt);
@@ -1902,7 +1903,7 @@ int kw_set_time_index(kw_ctx* c, uint64_t t) {
 // :536-557): which = 0 the accumulator of an aggregate stream (rms / max / min [_all], I_avg_c: flushed into / reloaded from the OUTPUT
 // file), which = 1 / 2 the two compression accumulators of a *_c stream (the reference's Temp_<name>_1 / _2 datasets of the checkpoint file).
 static int stream_buffer(kw_ctx* c, int sid, int which, void** ptr, size_t* floats) {
-  if (!c || sid < 0 || sid >= KW_STREAM_COUNT || !c->streams[sid].enabled) return fail(KW_ERR_INVALID, "stream not enabled");
+  if (!c || sid < 0 || sid >= KW_STREAM_COUNT || !c->streams[sid].enabled) return fail(KW_ERR_INVALID, std::string("stream_buffer: stream ") + std::to_string(sid) + " is not enabled (or a null argument)");
   if (!c->preprocessed) return fail(KW_ERR_STATE, "stream buffers exist after kw_preprocess");
   Stream& s = c->streams[sid];
   if (which == 0 && s.op != kOpNone && s.op != kOpC && s.dbuf) *ptr = s.dbuf, *floats = s.row;
@@ -2213,7 +2214,7 @@ int kw_comm_bytes(kw_ctx* c, double* bytes_sent) {
 }
 
 int kw_stream_info(kw_ctx* c, int sid, uint64_t* row_floats, uint64_t* rows) {
-  if (!c || sid < 0 || sid >= KW_STREAM_COUNT || !c->streams[sid].enabled) return fail(KW_ERR_INVALID, "stream not enabled");
+  if (!c || sid < 0 || sid >= KW_STREAM_COUNT || !c->streams[sid].enabled) return fail(KW_ERR_INVALID, std::string("kw_stream_info: stream ") + std::to_string(sid) + " is not enabled (or a null argument)");
   if (row_floats) *row_floats = c->streams[sid].row;
   const Stream& si = c->streams[sid];
   if (rows) *rows = (si.op == kOpNone || si.op == kOpC) ? (si.pending_rows ? si.pending_rows : si.rows) : 1;
@@ -2222,7 +2223,7 @@ int kw_stream_info(kw_ctx* c, int sid, uint64_t* row_floats, uint64_t* rows) {
 
 int kw_stream_fetch(kw_ctx* c, int sid, float* host, uint64_t cap, uint64_t* rows_fetched) {
   if (rows_fetched) *rows_fetched = 0;
-  if (!c || !host || sid < 0 || sid >= KW_STREAM_COUNT || !c->streams[sid].enabled) return fail(KW_ERR_INVALID, "stream not enabled");
+  if (!c || !host || sid < 0 || sid >= KW_STREAM_COUNT || !c->streams[sid].enabled) return fail(KW_ERR_INVALID, std::string("kw_stream_fetch: stream ") + std::to_string(sid) + " is not enabled (or a null argument)");
   Stream& s = c->streams[sid];
   if (s.nosave) return fail(KW_ERR_INVALID, "stream exists only as an input of I_avg_c (not stored)");
   const bool series = s.op == kOpNone || s.op == kOpC;
@@ -2247,13 +2248,13 @@ int kw_stream_fetch(kw_ctx* c, int sid, float* host, uint64_t cap, uint64_t* row
 }
 
 int kw_stream_pending(kw_ctx* c, int sid, uint64_t* rows) {
-  if (!c || !rows || sid < 0 || sid >= KW_STREAM_COUNT || !c->streams[sid].enabled) return fail(KW_ERR_INVALID, "stream not enabled");
+  if (!c || !rows || sid < 0 || sid >= KW_STREAM_COUNT || !c->streams[sid].enabled) return fail(KW_ERR_INVALID, std::string("kw_stream_pending: stream ") + std::to_string(sid) + " is not enabled (or a null argument)");
   *rows = c->streams[sid].pending_rows;
   return KW_OK;
 }
 
 int kw_stream_peek(kw_ctx* c, int sid, uint64_t offset, float* host, uint64_t count) {
-  if (!c || !host || sid < 0 || sid >= KW_STREAM_COUNT || !c->streams[sid].enabled) return fail(KW_ERR_INVALID, "stream not enabled");
+  if (!c || !host || sid < 0 || sid >= KW_STREAM_COUNT || !c->streams[sid].enabled) return fail(KW_ERR_INVALID, std::string("kw_stream_peek: stream ") + std::to_string(sid) + " is not enabled (or a null argument)");
   Stream& s = c->streams[sid];
   if (s.op == kOpNone || s.op == kOpC || !s.dbuf) return fail(KW_ERR_INVALID, "kw_stream_peek reads aggregate streams (use kw_stream_fetch for series)");
   if (offset + count > s.row) return fail(KW_ERR_INVALID, "kw_stream_peek: range outside the accumulator");

@@ -470,7 +470,7 @@ void KSpaceFirstOrderSolver::flushSeries(bool onlyLanded) {
     if (onlyLanded && pending == 0) break;
     check(kw_stream_info(mCtx, st.id, &rowFloats, &rows));
     if (rows == 0) break;
-    if (mRowBuffer.size() < rows * rowFloats) mRowBuffer.resize(std::max<uint64_t>(rows * rowFloats, 1));
+    if (mRowBuffer.size() < std::max<uint64_t>(rows * rowFloats, 1)) mRowBuffer.resize(std::max<uint64_t>(rows * rowFloats, 1));
     uint64_t got = 0;
     check(kw_stream_fetch(mCtx, st.id, mRowBuffer.data(), mRowBuffer.size(), &got));  // (a rank without sensor points still counts rows)
     if (multi()) {  // rows of the local sensor points -> complete rows on rank 0
