@@ -378,7 +378,7 @@ struct ZMidArgs {
 #ifndef KW_ZMID_MINB
 // E = 32 points per thread need ~150 registers to stay spill free (ncu/ptxas: 128 registers spill 300+ bytes and run
 // 25-55% slower than one CTA per SM at 254 registers)
-#define KW_ZMID_MINB ((Plan2<N>::E >= 32 || AXIS == 3) ? 1 : ZCfgM<N, MODE>::MINB)
+#define KW_ZMID_MINB ((MODE == 2) ? ZCfgM<N, MODE>::MINB : (Plan2<N>::E >= 32 || AXIS == 3) ? 1 : ZCfgM<N, MODE>::MINB)
 #endif
 #ifndef KW_ZMID_MULMODE
 #define KW_ZMID_MULMODE 0  // 0: multiplier lands in shared memory through cp.async; 1: plain loads at the point of use
