@@ -24,10 +24,11 @@ constexpr int kXThreads = 256;
 // the x/y-local spectra in the y-blocked "exchange" layout [q][z_local][y_local][NXP] (q = rank that owns y after the
 // transpose, y = q*nyl + y_local), so that the block sent to rank q by the all-to-all is one contiguous range.
 struct RowMap {
-  int ny_log2;   // log2(Ny)
+  int ny_log2;   // log2(Ny); < 0: Ny is not a power of two (single GPU only, fft_generic.cu): plain [z][y][NXP]
   int ysh;       // log2(nyl), nyl = Ny / nranks  (== ny_log2 on one GPU)
   size_t blk;    // elements of one block: nzl * nyl * NXP
   __device__ __forceinline__ size_t off(size_t row, int nxp) const {
+    if (ny_log2 < 0) return row * (size_t)nxp;
     const size_t z = row >> ny_log2;
     const unsigned y = (unsigned)row & ((1u << ny_log2) - 1u);
     return (size_t)(y >> ysh) * blk + ((z << ysh) + (y & ((1u << ysh) - 1u))) * (size_t)nxp;
@@ -41,6 +42,7 @@ struct XFwdArgs {
   int pair_begin, pair_end;  // range of row pairs (row = z*Ny + y) this launch transforms
   int nxp;
   RowMap map;
+  int n;  // Nx (read by the run-time-length kernels of fft_generic.cu; the tuned kernels have it as a template argument)
 };
 
 // One row pair (rows row0, row0+1) of one field: real -> half spectrum.  T = N/8 threads cooperate through `ex`.
@@ -106,6 +108,7 @@ template <int NF> struct XInvArgs {
   int pair_begin, pair_end, nxp, ny;
   RowMap map;
   int field0;  // NF == 1: the launch covers fields field0 .. field0 + gridDim.y - 1 (per-field launches of pipelined runs)
+  int n;       // Nx (fft_generic.cu)
 };
 
 // The half-spectrum values one thread needs for one row pair of one field: 4 + 4 points of the two rows, and (thread 0 of the
@@ -288,6 +291,7 @@ struct ColArgs {
   // (e >> blk_es) * blk + (e & ((1 << blk_es) - 1)) * WK * stride;  requires nyl >= WK.  Unused by k_col<.., false>.
   int blk_es;
   size_t blk;
+  int n;  // length of the transform axis (fft_generic.cu)
 };
 
 #ifdef KW_N
@@ -372,6 +376,7 @@ struct ZMidArgs {
   int axis;
   int nxp, ngroups, ntiles;  // ntiles = Ny * ngroups
   unsigned plane;            // Ny * NXP
+  int n;                     // Nz (fft_generic.cu)
 };
 
 #ifdef KW_N

@@ -22,7 +22,9 @@ struct FftOps {
   void (*zmid)(const ZMidArgs&, cudaStream_t);  // one field per launch
 };
 
-const FftOps* get_fft_ops(int n);  // nullptr when n is not a supported length
+const FftOps* get_fft_ops(int n);  // tuned table (powers of two in [16, 1024]), else the run-time-length kernels; nullptr: unsupported
+const FftOps* get_generic_fft_ops(int n);  // fft_generic.cu: N = 8 m <= 2048 with prime factors 2, 3, 5, 7
+bool generic_length_supported(int n);
 int sm_count();
 
 #define KW_DECLARE_OPS(N) extern const FftOps fft_ops_##N;

@@ -78,7 +78,7 @@ const FftOps* get_fft_ops(int n) {
     case 256: return &fft_ops_256;
     case 512: return &fft_ops_512;
     case 1024: return &fft_ops_1024;
-    default: return nullptr;
+    default: return get_generic_fft_ops(n);  // other lengths 8 m with factors 2, 3, 5, 7: run-time-length kernels (fft_generic.cu)
   }
 }
 
@@ -158,7 +158,8 @@ struct Geometry {
     // z extent of one (the z components stay exactly zero, so the sums of the reference's 2-D kernels are reproduced)
     ox = get_fft_ops(nx), oy = get_fft_ops(ny), oz = nz == 1 ? nullptr : get_fft_ops(nz);
     if (!ox || !oy || (!oz && nz != 1))
-      return fail(KW_ERR_INVALID, "grid sizes must be powers of two in [16,1024] (hand-written FFT plan table); got " +
+      return fail(KW_ERR_INVALID, "grid sizes must be multiples of 8 in [16,2048] with prime factors 2, 3, 5, 7 (powers of two up to 1024 run the tuned "
+                                  "kernels, other lengths the run-time-length ones); got " +
                                       std::to_string(nx_) + "x" + std::to_string(ny_) + "x" + std::to_string(nz_));
     rank = rank_, nranks = nranks_ < 1 ? 1 : nranks_;
     if (rank < 0 || rank >= nranks || (nranks & (nranks - 1)) || nz % nranks || ny % nranks)
@@ -167,8 +168,12 @@ struct Geometry {
     if (nranks > 1 && (nyl < oy->col_wk || (nyl & 1)))
       return fail(KW_ERR_INVALID, "slab decomposition: Ny / nranks = " + std::to_string(nyl) + " is below the y-pass worker count " +
                                       std::to_string(oy->col_wk) + " of this Ny (use fewer ranks)");
+    const bool pow2_yz = !(ny & (ny - 1)) && !(nz & (nz - 1));
+    if (nranks > 1 && !pow2_yz)
+      return fail(KW_ERR_INVALID, "slab decomposition needs Ny and Nz to be powers of two (the y-blocked exchange layout); run this grid on one GPU");
     for (ny_log2 = 0; (1 << ny_log2) < ny; ++ny_log2) {}
     for (ysh = 0; (1 << ysh) < nyl; ++ysh) {}
+    if (ny & (ny - 1)) ny_log2 = -1, ysh = 0;  // RowMap: plain [z][y][NXP]
     nxr = nx / 2 + 1;
     nxp = (nxr + 15) / 16 * 16;
     ntot = (size_t)nx * ny * nz;
@@ -1022,7 +1027,7 @@ static ColArgs ycol_args(const Geometry& g, float2* const* data, int nf) {
   ColArgs ca{};
   for (int f = 0; f < nf; ++f) ca.data[f] = data[f];
   ca.stride = g.nxp, ca.outer_stride = (size_t)g.nyl * g.nxp, ca.ngroups = g.nxp / g.oy->col_w;
-  ca.tile_begin = 0, ca.tile_end = g.nzl * ca.ngroups;
+  ca.tile_begin = 0, ca.tile_end = g.nzl * ca.ngroups, ca.n = g.ny;
   if (g.nranks > 1) {
     int wk_log2 = 0;
     while ((1 << wk_log2) < g.oy->col_wk) ++wk_log2;
@@ -1036,7 +1041,7 @@ static void forward_xy(kw_ctx* c, const float* const* in, float2* const* out, in
   const Geometry& g = c->g;
   XFwdArgs xa{};
   for (int f = 0; f < nf; ++f) xa.in[f] = in[f], xa.out[f] = out[f];
-  xa.tab = g.tx, xa.nxp = g.nxp, xa.map = g.row_map();
+  xa.tab = g.tx, xa.nxp = g.nxp, xa.map = g.row_map(), xa.n = g.nx;
   // (z-chunked launches that keep a chunk's half spectra in L2 between the x and the y pass were measured and lose: 16.8 / 13.5 /
   //  12.1 ms per step at 24 / 48 / 96 MB chunks against 10.4 ms for whole-grid launches, profiles/r02_e_chunk_sweep.log)
   xa.pair_begin = 0, xa.pair_end = g.nzl * g.ny / 2;
@@ -1186,13 +1191,13 @@ static void zmid_launch(kw_ctx* c, ZField f, int axis) {
   if (axis == 1 && f.vec) f.vec += g.y0;
   if (axis == 3 && f.vec_y) f.vec_y += g.y0;
   za.f = f, za.axis = axis;
-  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->zmid_w, za.ntiles = g.nyl * za.ngroups, za.plane = (unsigned)((size_t)g.nyl * g.nxp);
+  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->zmid_w, za.ntiles = g.nyl * za.ngroups, za.plane = (unsigned)((size_t)g.nyl * g.nxp), za.n = g.nz;
   launch(c, axis == 3 ? "zmid_grad" : "zmid", (axis == 3 ? 32.0 : 16.0) * g.nca + (f.mul ? 4.0 * g.nca : 0.0), [&] { g.oz->zmid(za, c->st); });
 }
 template <int NF> static XInvArgs<NF> xinv_args(kw_ctx* c, float2* const* in, int pb, int pe, int nfields = NF) {
   XInvArgs<NF> a{};
   for (int f = 0; f < nfields; ++f) a.in[f] = in[f];
-  a.tab = c->g.tx, a.pair_begin = pb, a.pair_end = pe, a.nxp = c->g.nxp, a.ny = c->g.ny, a.map = c->g.row_map();
+  a.tab = c->g.tx, a.pair_begin = pb, a.pair_end = pe, a.nxp = c->g.nxp, a.ny = c->g.ny, a.map = c->g.row_map(), a.n = c->g.nx;
   return a;
 }
 
@@ -2300,12 +2305,12 @@ static int fft3d_host(uint64_t nx, uint64_t ny, uint64_t nz, const float* in, fl
   KW_CUDA(cudaMemset(dspec, 0, g.nc * sizeof(float2)));
   ColArgs cy{}, cz{};
   cy.data[0] = cz.data[0] = dspec;
-  cy.stride = g.nxp, cy.outer_stride = (size_t)g.ny * g.nxp, cy.ngroups = g.nxp / g.oy->col_w, cy.tile_begin = 0, cy.tile_end = g.nz * cy.ngroups;
-  if (g.nz > 1) cz.stride = (size_t)g.ny * g.nxp, cz.outer_stride = g.nxp, cz.ngroups = g.nxp / g.oz->col_w, cz.tile_begin = 0, cz.tile_end = g.ny * cz.ngroups;
+  cy.stride = g.nxp, cy.outer_stride = (size_t)g.ny * g.nxp, cy.ngroups = g.nxp / g.oy->col_w, cy.tile_begin = 0, cy.tile_end = g.nz * cy.ngroups, cy.n = g.ny;
+  if (g.nz > 1) cz.stride = (size_t)g.ny * g.nxp, cz.outer_stride = g.nxp, cz.ngroups = g.nxp / g.oz->col_w, cz.tile_begin = 0, cz.tile_end = g.ny * cz.ngroups, cz.n = g.nz;
   if (forward) {
     KW_CUDA(cudaMemcpy(dreal, in, g.n * sizeof(float), cudaMemcpyHostToDevice));
     XFwdArgs xa{};
-    xa.in[0] = dreal, xa.out[0] = dspec, xa.tab = g.tx, xa.pair_begin = 0, xa.pair_end = (int)(rows / 2), xa.nxp = g.nxp, xa.map = g.row_map();
+    xa.in[0] = dreal, xa.out[0] = dspec, xa.tab = g.tx, xa.pair_begin = 0, xa.pair_end = (int)(rows / 2), xa.nxp = g.nxp, xa.map = g.row_map(), xa.n = g.nx;
     g.ox->xfwd(xa, 1, 0);
     g.oy->col(cy, -1, 1, 0);
     if (g.nz > 1) g.oz->col(cz, -1, 1, 0);
@@ -2318,7 +2323,7 @@ static int fft3d_host(uint64_t nx, uint64_t ny, uint64_t nz, const float* in, fl
     if (g.nz > 1) g.oz->col(cz, +1, 1, 0);
     g.oy->col(cy, +1, 1, 0);
     XInvArgs<1> xa{};
-    xa.in[0] = dspec, xa.tab = g.tx, xa.pair_begin = 0, xa.pair_end = (int)(rows / 2), xa.nxp = g.nxp, xa.ny = g.ny, xa.map = g.row_map();
+    xa.in[0] = dspec, xa.tab = g.tx, xa.pair_begin = 0, xa.pair_end = (int)(rows / 2), xa.nxp = g.nxp, xa.ny = g.ny, xa.map = g.row_map(), xa.n = g.nx;
     EpiStore e{};
     e.out[0] = dreal, e.scale = 1.0f;
     g.ox->xinv_store(xa, e, 1, 0);
@@ -2344,11 +2349,11 @@ int kw_bench_col(uint64_t nx, uint64_t ny, uint64_t nz, int axis, int fused, int
   ColArgs ca{};
   ca.data[0] = d;
   const FftOps* op = axis == 1 ? g.oy : g.oz;
-  if (axis == 1) ca.stride = g.nxp, ca.outer_stride = (size_t)g.ny * g.nxp, ca.ngroups = g.nxp / op->col_w, ca.tile_end = g.nz * ca.ngroups;
-  else ca.stride = (size_t)g.ny * g.nxp, ca.outer_stride = g.nxp, ca.ngroups = g.nxp / op->col_w, ca.tile_end = g.ny * ca.ngroups;
+  if (axis == 1) ca.stride = g.nxp, ca.outer_stride = (size_t)g.ny * g.nxp, ca.ngroups = g.nxp / op->col_w, ca.tile_end = g.nz * ca.ngroups, ca.n = g.ny;
+  else ca.stride = (size_t)g.ny * g.nxp, ca.outer_stride = g.nxp, ca.ngroups = g.nxp / op->col_w, ca.tile_end = g.ny * ca.ngroups, ca.n = g.nz;
   ZMidArgs za{};
   za.f = ZField{d, d, mul, 1.0f, nullptr}, za.axis = -1;
-  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->zmid_w, za.ntiles = g.ny * za.ngroups, za.plane = (unsigned)((size_t)g.ny * g.nxp);
+  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->zmid_w, za.ntiles = g.ny * za.ngroups, za.plane = (unsigned)((size_t)g.ny * g.nxp), za.n = g.nz;
   for (int i = 0; i < iters + 2; ++i) {
     if (i == 2) cudaEventRecord(e0);
     if (fused) g.oz->zmid(za, 0);
@@ -2421,7 +2426,7 @@ int kw_fft_zmid(uint64_t nx, uint64_t ny, uint64_t nz, int axis, const float* in
   ZMidArgs za{};
   za.f = ZField{din, dout[0], dmul, scal, axis == 3 ? dv[0] : axis >= 0 ? dv[axis] : nullptr, dout[1], dout[2], dv[1], dv[2]};
   za.axis = axis;
-  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->zmid_w, za.ntiles = g.ny * za.ngroups, za.plane = (unsigned)((size_t)g.ny * g.nxp);
+  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->zmid_w, za.ntiles = g.ny * za.ngroups, za.plane = (unsigned)((size_t)g.ny * g.nxp), za.n = g.nz;
   g.oz->zmid(za, 0);
   KW_CUDA(cudaGetLastError());
   float* ho[3] = {out0, out1, out2};

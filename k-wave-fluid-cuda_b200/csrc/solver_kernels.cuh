@@ -54,8 +54,8 @@ struct EpiStore {
   static constexpr int kMinBlocks = 3;  // CTAs per SM the register budget is sized for  // plain C2R:  out = scale * ifft
   float* out[3];
   float scale;
-  template <int N> __device__ __forceinline__ void apply(float2 (&res)[1][8], int field, int t, size_t row0, int, int) const {
-    constexpr int T = N / 8;
+  template <int NT> __device__ __forceinline__ void apply(float2 (&res)[1][8], int field, int t, size_t row0, int, int, const float* = nullptr, int n_rt = 0) const {
+    const int N = NT ? NT : n_rt, T = N / 8;  // NT == 0: length at run time (fft_generic.cu)
     float* o = out[field] + row0 * N;
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
@@ -70,8 +70,8 @@ struct EpiAdd {
   static constexpr int kMinBlocks = 3;  // CTAs per SM the register budget is sized for  // additive (k-space corrected) source: target_j += ifft   (SolverCudaKernels.cu:765-807)
   float* out[3];
   int ntargets;
-  template <int N> __device__ __forceinline__ void apply(float2 (&res)[1][8], int, int t, size_t row0, int, int) const {
-    constexpr int T = N / 8;
+  template <int NT> __device__ __forceinline__ void apply(float2 (&res)[1][8], int, int t, size_t row0, int, int, const float* = nullptr, int n_rt = 0) const {
+    const int N = NT ? NT : n_rt, T = N / 8;  // NT == 0: length at run time (fft_generic.cu)
     for (int j = 0; j < ntargets; ++j) {
       float* o = out[j] + row0 * N;
 #pragma unroll
@@ -93,8 +93,8 @@ struct EpiVelocity {
   const float* pml_sg[3];
   float fd;
   int init;
-  template <int N> __device__ __forceinline__ void apply(float2 (&res)[1][8], int field, int t, size_t row0, int y, int z) const {
-    constexpr int T = N / 8;
+  template <int NT> __device__ __forceinline__ void apply(float2 (&res)[1][8], int field, int t, size_t row0, int y, int z, const float* = nullptr, int n_rt = 0) const {
+    const int N = NT ? NT : n_rt, T = N / 8;  // NT == 0: length at run time (fft_generic.cu)
     const int f = field;
     float* ua = u[f] + row0 * N;
     const Fld d = dtrho[f];
@@ -160,8 +160,8 @@ struct EpiDensity {
   float* p;
   FusedSample fs;  // sampling of p when this epilogue produces the final pressure of the step (lossless)
   int sample;
-  template <int N> __device__ __forceinline__ void apply(float2 (&res)[3][8], int, int t, size_t row0, int y, int z, const float* stg = nullptr) const {
-    constexpr int T = N / 8;
+  template <int NT> __device__ __forceinline__ void apply(float2 (&res)[3][8], int, int t, size_t row0, int y, int z, const float* stg = nullptr, int n_rt = 0) const {
+    const int N = NT ? NT : n_rt, T = N / 8;  // NT == 0: length at run time (fft_generic.cu)
     // restrict-qualified locals: the arrays never alias, which lets the loads of all voxels be issued ahead of the stores
     float* __restrict__ rxp = rho[0];
     float* __restrict__ ryp = rho[1];
@@ -250,8 +250,8 @@ struct EpiPressureSum {
   float fd;
   FusedSample fs;
   int sample;
-  template <int N> __device__ __forceinline__ void apply(float2 (&res)[2][8], int, int t, size_t row0, int y, int z, const float* stg = nullptr) const {
-    constexpr int T = N / 8;
+  template <int NT> __device__ __forceinline__ void apply(float2 (&res)[2][8], int, int t, size_t row0, int y, int z, const float* stg = nullptr, int n_rt = 0) const {
+    const int N = NT ? NT : n_rt, T = N / 8;  // NT == 0: length at run time (fft_generic.cu)
     float* __restrict__ pp = p;
     float pv[16];
 #pragma unroll

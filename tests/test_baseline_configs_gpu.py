@@ -42,6 +42,12 @@ CONFIGS = {
                                               ["-p", "--p_max", "--p_rms"]),
     "config4_512_nonlinear_absorbing_whole_domain": (512, 20, dict(nonlinear=True, absorbing=True, source="p_many", sensor="full_cuboid", pml_size=20,
                                                                    medium="waves"), ["--p_max_all", "--p_rms"]),
+    # not in BASELINE.json: a grid no axis of which is a power of two (run-time-length kernels, csrc/fft_generic.cu) -- cuFFT plans any size
+    # (CufftComplexMatrix.cpp:87-91), so the same file must run in both binaries
+    "nonpow2_96x120x80_nonlinear_absorbing": ((96, 120, 80), 100, dict(nonlinear=True, absorbing=True, source="p_plane", sensor="index", n_sensor=4096,
+                                                                        pml_size=10), ["-p", "--p_max", "--p_rms", "--u_max", "--p_final", "--u_final"]),
+    "nonpow2_mixed_256x96x160_linear_p0_cuboids": ((256, 96, 160), 60, dict(nonlinear=False, absorbing=False, source="p0", sensor="cuboid", pml_size=10),
+                                                   ["-p", "--p_min", "--p_max_all"]),
 }  # fmt: skip
 
 
@@ -59,7 +65,8 @@ def test_baseline_config_matches_reference_binary(synth, tmp_path, name):
     assert os.path.exists(OURS), "kspaceFirstOrder-B200 not built (__graft_entry__.build())"
     n, nt, kwargs, flags = CONFIGS[name]
     t0 = time.time()
-    cfg, arrays = synth.make_case(n, nt=nt, **kwargs)
+    cfg, arrays = synth.make_case(*n, nt=nt, **kwargs) if isinstance(n, tuple) else synth.make_case(n, nt=nt, **kwargs)
+    n = n[0] if isinstance(n, tuple) else n  # Nx decides the cuFFT C2R behaviour below
     fin = str(tmp_path / "in.h5")
     kwh5.write_input(fin, cfg, arrays)
     del arrays
