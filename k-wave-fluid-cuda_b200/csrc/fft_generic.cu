@@ -40,8 +40,9 @@ static bool make_plan(int n, GenPlan* pl) {
   take(4), take(2), take(3), take(5), take(7);
   return m == 1;
 }
-// kx values per column tile: as wide as three tile buffers (fused gradient pass) allow
-static int tile_w(int n) { return n <= 512 ? 16 : n <= 1024 ? 8 : 4; }
+// kx values per column tile: two tile buffers of at most 64 KB, so that three CTAs (24 warps) share an SM -- with one 123 KB CTA per SM
+// the first version of these kernels issued on 26 % of the cycles and waited on memory for the rest (ncu, N = 480, 16-wide tiles)
+static int tile_w(int n) { return n <= 256 ? 16 : n <= 512 ? 8 : 4; }
 
 // ---- device side ----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 gmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
@@ -81,9 +82,9 @@ __device__ __forceinline__ void odd_butterfly(const float2* __restrict__ x, floa
 // One radix-r butterfly of a Stockham pass over a transform of n points stored with element stride es.
 // s = product of the radices of the earlier passes; butterfly t in [0, n / r): p = t / s, q = t % s;
 //   inputs  x[t + (n / r) k],  k < r          outputs  y[q + s (r p + j)] = (sum_k x_k w_r^{jk}) W_n^{p j s},  j < r
-__device__ __forceinline__ void butterfly(const float2* __restrict__ x, float2* __restrict__ y, int es, int n, int s, int r, int t,
+__device__ __forceinline__ void butterfly(const float2* __restrict__ x, float2* __restrict__ y, int es, int n, int s, float inv_s, int r, int t,
                                           const float2* __restrict__ tab, int dir) {
-  const int p = t / s, q = t - p * s;
+  const int p = __float2int_rz(((float)t + 0.5f) * inv_s), q = t - p * s;  // t / s, exact for t < 2^20
   const int nr = n / r;
   const int ob = q + s * r * p;
   if (r == 4) {
@@ -112,19 +113,23 @@ __device__ __forceinline__ void butterfly(const float2* __restrict__ x, float2* 
 
 // `batch` transforms at once.  Transform b, point i at buf[b * bs + i * es].  Returns the buffer that holds the result
 // (natural order).  Every thread of the CTA must call it; ends with a barrier.
-__device__ __forceinline__ float2* fft_batch(float2* a, float2* b, int batch, int bs, int es, const GenPlan& pl, const float2* tab, int dir) {
+// W > 0: column tile, batch = es = W (compile time), bs = 1; W == 0: rows, es = 1, bs = n.
+template <int W>
+__device__ __forceinline__ float2* fft_batch(float2* a, float2* b, int batch, const GenPlan& pl, const float2* tab, int dir) {
   int s = 1;
   for (int f = 0; f < pl.nf; ++f) {
     const int r = pl.r[f], nb = pl.n / r;
-    if (es == 1) {  // rows: consecutive threads take consecutive butterflies of one transform
+    const float inv_s = 1.0f / (float)s;
+    if constexpr (W == 0) {  // rows: consecutive threads take consecutive butterflies of one transform
+      const float inv_nb = 1.0f / (float)nb;
       for (int idx = threadIdx.x; idx < batch * nb; idx += blockDim.x) {
-        const int bi = idx / nb, t = idx - bi * nb;
-        butterfly(a + (size_t)bi * bs, b + (size_t)bi * bs, 1, pl.n, s, r, t, tab, dir);
+        const int bi = __float2int_rz(((float)idx + 0.5f) * inv_nb), t = idx - bi * nb;
+        butterfly(a + (size_t)bi * pl.n, b + (size_t)bi * pl.n, 1, pl.n, s, inv_s, r, t, tab, dir);
       }
     } else {  // column tiles: consecutive threads take the same butterfly of consecutive kx
-      for (int idx = threadIdx.x; idx < batch * nb; idx += blockDim.x) {
-        const int t = idx / batch, bi = idx - t * batch;
-        butterfly(a + (size_t)bi * bs, b + (size_t)bi * bs, es, pl.n, s, r, t, tab, dir);
+      for (int idx = threadIdx.x; idx < W * nb; idx += blockDim.x) {
+        const int t = idx / W, bi = idx % W;
+        butterfly(a + bi, b + bi, W, pl.n, s, inv_s, r, t, tab, dir);
       }
     }
     __syncthreads();
@@ -134,6 +139,9 @@ __device__ __forceinline__ float2* fft_batch(float2* a, float2* b, int batch, in
   }
   return a;
 }
+
+// idx / d for idx < 2^20 through a float reciprocal (a 32-bit integer division costs ~20 instructions)
+__device__ __forceinline__ int fdiv(int idx, float inv_d) { return __float2int_rz(((float)idx + 0.5f) * inv_d); }
 
 __device__ __forceinline__ size_t row_off(const RowMap& map, size_t row, int nxp) { return map.off(row, nxp); }
 
@@ -149,11 +157,12 @@ static __global__ void __launch_bounds__(kThreads) g_xfwd(XFwdArgs a, GenPlan pl
   float2* __restrict__ out = a.out[blockIdx.y];
   const int npairs = a.pair_end - a.pair_begin;
   const int nxr = n / 2 + 1;
+  const float inv_n = 1.0f / (float)n, inv_nxp = 1.0f / (float)a.nxp;
   __syncthreads();
   for (int g = blockIdx.x; g * rp < npairs; g += gridDim.x) {
     const int pair0 = a.pair_begin + g * rp;
     for (int idx = threadIdx.x; idx < rp * n; idx += blockDim.x) {
-      const int b = idx / n, x = idx - b * n;
+      const int b = fdiv(idx, inv_n), x = idx - b * n;
       const int pair = pair0 + b;
       float2 v = make_float2(0.f, 0.f);
       if (pair < a.pair_end) {
@@ -163,9 +172,9 @@ static __global__ void __launch_bounds__(kThreads) g_xfwd(XFwdArgs a, GenPlan pl
       A[idx] = v;
     }
     __syncthreads();
-    const float2* Z = fft_batch(A, B, rp, n, 1, pl, tab, -1);
+    const float2* Z = fft_batch<0>(A, B, rp, pl, tab, -1);
     for (int idx = threadIdx.x; idx < rp * a.nxp; idx += blockDim.x) {
-      const int b = idx / a.nxp, k = idx - b * a.nxp;
+      const int b = fdiv(idx, inv_nxp), k = idx - b * a.nxp;
       const int pair = pair0 + b;
       if (pair >= a.pair_end) continue;
       const size_t off = row_off(a.map, 2 * (size_t)pair, a.nxp);
@@ -195,6 +204,7 @@ template <int NF, class Epi> static __global__ void __launch_bounds__(kThreads) 
   const int field = blockIdx.y + a.field0;
   const int b_own = threadIdx.x / T, t_own = threadIdx.x - b_own * T;
   const int half = n / 2;
+  const float inv_h1 = 1.0f / (float)(half + 1);
   __syncthreads();
   for (int g = blockIdx.x; g * rp < npairs; g += gridDim.x) {
     const int pair0 = a.pair_begin + g * rp;
@@ -203,7 +213,7 @@ template <int NF, class Epi> static __global__ void __launch_bounds__(kThreads) 
     for (int f = 0; f < NF; ++f) {
       const float2* __restrict__ in = NF == 1 ? a.in[field] : a.in[f];
       for (int idx = threadIdx.x; idx < rp * (half + 1); idx += blockDim.x) {
-        const int b = idx / (half + 1), k = idx - b * (half + 1);
+        const int b = fdiv(idx, inv_h1), k = idx - b * (half + 1);
         const int pair = pair0 + b;
         float2 va = make_float2(0.f, 0.f), vb = va;
         if (pair < a.pair_end) {
@@ -221,7 +231,7 @@ template <int NF, class Epi> static __global__ void __launch_bounds__(kThreads) 
         }
       }
       __syncthreads();
-      const float2* R = fft_batch(A, B, rp, n, 1, pl, tab, +1);
+      const float2* R = fft_batch<0>(A, B, rp, pl, tab, +1);
       if (b_own < rp) {
 #pragma unroll
         for (int m = 0; m < 8; ++m) res[f][m] = R[(size_t)b_own * n + t_own + m * T];
@@ -238,7 +248,7 @@ template <int NF, class Epi> static __global__ void __launch_bounds__(kThreads) 
 }
 
 // in-place complex transform along y or z of [..][..][NXP] (k_col)
-static __global__ void __launch_bounds__(kThreads) g_col(ColArgs a, GenPlan pl, int W, int dir) {
+template <int W> static __global__ void __launch_bounds__(kThreads) g_col(ColArgs a, GenPlan pl, int dir) {
   extern __shared__ float2 gsm[];
   const int n = pl.n;
   float2* tab = gsm;
@@ -254,7 +264,7 @@ static __global__ void __launch_bounds__(kThreads) g_col(ColArgs a, GenPlan pl, 
       A[idx] = base[(size_t)i * a.stride + c];
     }
     __syncthreads();
-    const float2* R = fft_batch(A, B, W, 1, W, pl, tab, dir);
+    const float2* R = fft_batch<W>(A, B, W, pl, tab, dir);
     for (int idx = threadIdx.x; idx < n * W; idx += blockDim.x) {
       const int i = idx / W, c = idx - i * W;
       base[(size_t)i * a.stride + c] = R[idx];
@@ -264,7 +274,7 @@ static __global__ void __launch_bounds__(kThreads) g_col(ColArgs a, GenPlan pl, 
 }
 
 // forward z -> k-space operator -> inverse z (k_zmid; same operator semantics, axis as a run-time argument)
-static __global__ void __launch_bounds__(kThreads) g_zmid(ZMidArgs a, GenPlan pl, int W) {
+template <int W> static __global__ void __launch_bounds__(kThreads) g_zmid(ZMidArgs a, GenPlan pl) {
   extern __shared__ float2 gsm[];
   const int n = pl.n, axis = a.axis;
   float2* tab = gsm;
@@ -284,7 +294,7 @@ static __global__ void __launch_bounds__(kThreads) g_zmid(ZMidArgs a, GenPlan pl
       A[idx] = __ldg(in + base + (size_t)i * a.plane + c);
     }
     __syncthreads();
-    float2* S = fft_batch(A, B, W, 1, W, pl, tab, -1);
+    float2* S = fft_batch<W>(A, B, W, pl, tab, -1);
     float2* O = S == A ? B : A;  // the other buffer
     if (axis == 3) {
       for (int idx = threadIdx.x; idx < n * W; idx += blockDim.x) {
@@ -301,7 +311,7 @@ static __global__ void __launch_bounds__(kThreads) g_zmid(ZMidArgs a, GenPlan pl
           S[idx] = gmul(E[idx], w);
         }
         __syncthreads();
-        const float2* R = fft_batch(S, O, W, 1, W, pl, tab, +1);
+        const float2* R = fft_batch<W>(S, O, W, pl, tab, +1);
         float2* __restrict__ out = f == 0 ? a.f.out : f == 1 ? a.f.out_y : a.f.out_z;
         for (int idx = threadIdx.x; idx < n * W; idx += blockDim.x) {
           const int i = idx / W, c = idx - i * W;
@@ -321,7 +331,7 @@ static __global__ void __launch_bounds__(kThreads) g_zmid(ZMidArgs a, GenPlan pl
         S[idx] = v;
       }
       __syncthreads();
-      const float2* R = fft_batch(S, O, W, 1, W, pl, tab, +1);
+      const float2* R = fft_batch<W>(S, O, W, pl, tab, +1);
       for (int idx = threadIdx.x; idx < n * W; idx += blockDim.x) {
         const int i = idx / W, c = idx - i * W;
         a.f.out[base + (size_t)i * a.plane + c] = R[idx];
@@ -338,6 +348,10 @@ template <class K> static void opt_in(K kernel, size_t smem) {
 static int grid_for(int work, int per_sm) {
   const int cap = sm_count() * per_sm;
   return work < cap ? (work > 0 ? work : 1) : cap;
+}
+static int ctas_per_sm(size_t smem) {
+  const int k = (int)((size_t)220 * 1024 / (smem + 1024));
+  return k < 1 ? 1 : k > 4 ? 4 : k;
 }
 static GenPlan plan_of(int n) {
   GenPlan pl{};
@@ -376,15 +390,23 @@ static void col(const ColArgs& a, int dir, int nfields, cudaStream_t st) {
   const GenPlan pl = plan_of(a.n);
   const int W = tile_w(a.n);
   const size_t smem = ((size_t)a.n + 2 * (size_t)a.n * W) * sizeof(float2);
-  opt_in(g_col, smem);
-  g_col<<<dim3(grid_for(a.tile_end - a.tile_begin, smem > 100 * 1024 ? 1 : 2), nfields), kThreads, smem, st>>>(a, pl, W, dir);
+  const dim3 grid(grid_for(a.tile_end - a.tile_begin, ctas_per_sm(smem)), nfields);
+  auto go = [&](auto kernel) {
+    opt_in(kernel, smem);
+    kernel<<<grid, kThreads, smem, st>>>(a, pl, dir);
+  };
+  W == 16 ? go(g_col<16>) : W == 8 ? go(g_col<8>) : go(g_col<4>);
 }
 static void zmid(const ZMidArgs& a, cudaStream_t st) {
   const GenPlan pl = plan_of(a.n);
   const int W = tile_w(a.n);
   const size_t smem = ((size_t)a.n + (a.axis == 3 ? 3 : 2) * (size_t)a.n * W) * sizeof(float2);
-  opt_in(g_zmid, smem);
-  g_zmid<<<grid_for(a.ntiles, smem > 100 * 1024 ? 1 : 2), kThreads, smem, st>>>(a, pl, W);
+  const int grid = grid_for(a.ntiles, ctas_per_sm(smem));
+  auto go = [&](auto kernel) {
+    opt_in(kernel, smem);
+    kernel<<<grid, kThreads, smem, st>>>(a, pl);
+  };
+  W == 16 ? go(g_zmid<16>) : W == 8 ? go(g_zmid<8>) : go(g_zmid<4>);
 }
 
 }  // namespace generic
