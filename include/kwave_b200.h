@@ -164,7 +164,9 @@ int kw_finish(kw_ctx* ctx);
 int kw_set_source_row(kw_ctx* ctx, int array_id, uint64_t t_index, const float* host_row, uint64_t count);
 
 /* CufftComplexMatrix::computeR2CFftND / computeC2RFftND (MatrixClasses/CufftComplexMatrix.cpp:508-534) on host
- * buffers, cuFFT layout: real [nz][ny][nx], complex [nz][ny][nx/2+1] interleaved, both unnormalised. */
+ * buffers, cuFFT layout: real [nz][ny][nx], complex [nz][ny][nx/2+1] interleaved, both unnormalised.
+ * Grid sizes (here and in kw_ctx_create): each of nx, ny, nz (nz may be 1) a power of two in [16, 1024] (tuned kernels) or any
+ * other multiple of 8 up to 2048 whose prime factors are 2, 3, 5, 7 (run-time-length kernels); anything else: KW_ERR_INVALID. */
 int kw_fft_r2c_3d(uint64_t nx, uint64_t ny, uint64_t nz, const float* host_real, float* host_complex);
 int kw_fft_c2r_3d(uint64_t nx, uint64_t ny, uint64_t nz, const float* host_complex, float* host_real);
 /* The fused z pass on host buffers: the kernel that replaces the z stages of cuFFT together with cudaComputePressureGradient,
