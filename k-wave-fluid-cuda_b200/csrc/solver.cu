@@ -461,7 +461,26 @@ int kw_ctx_create(const kw_config* cfg, kw_ctx** out) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) return fail(KW_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
-  if (cfg->device >= 0) KW_CUDA(cudaSetDevice(cfg->device));
+  // CudaParameters::selectDevice (Parameters/CudaParameters.cpp:81-167): a given index must exist and be usable; without one the
+  // first device that accepts a context and runs this library's sm_100a code is taken (a device in exclusive-process mode that
+  // another process holds fails the probe and is skipped).  Unlike the reference the library never resets a device: the process
+  // may hold other contexts (PyTorch in the benchmark).
+  auto usable = [](int d) {
+    int v = 0;
+    const bool ok = cudaSetDevice(d) == cudaSuccess && cudaFree(nullptr) == cudaSuccess && kw_cuda_code_version(&v) == KW_OK && v >= 100;
+    cudaGetLastError();
+    return ok;
+  };
+  if (cfg->device >= 0) {
+    if (cfg->device >= ndev)
+      return fail(KW_ERR_INVALID, "Wrong CUDA device id " + std::to_string(cfg->device) + ". Allowed devices <0, " + std::to_string(ndev - 1) + ">.");
+    if (!usable(cfg->device)) return fail(KW_ERR_CUDA, "CUDA device id " + std::to_string(cfg->device) + " is busy or unavailable.");
+  } else {
+    int found = -1;
+    for (int d = 0; d < ndev && found < 0; ++d)
+      if (usable(d)) found = d;
+    if (found < 0) return fail(KW_ERR_CUDA, "All CUDA-capable devices are busy or unavailable.");
+  }
   kw_ctx* c = new kw_ctx();
   c->cfg = *cfg;
   int r = c->g.init(cfg->nx, cfg->ny, cfg->nz, cfg->rank, cfg->nranks);

@@ -115,6 +115,21 @@ def test_command_line_errors_exit_like_the_reference(tmp_path):
     assert r.returncode == 0 and "--p_max_all" in r.stdout
 
 
+@pytest.mark.gpu
+def test_device_selection_follows_the_reference(synth, tmp_path):
+    """-g N must name an existing device (CudaParameters::selectDevice, Parameters/CudaParameters.cpp:81-167: "Wrong CUDA device id");
+    without -g the first usable device is taken."""
+    cfg, arrays = synth.make_case(16, nt=4, source="p0")
+    fin = str(tmp_path / "in.h5")
+    kwh5.write_input(fin, cfg, arrays)
+    r = subprocess.run([OURS, "-i", fin, "-o", str(tmp_path / "o.h5"), "-g", "97"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Wrong CUDA device id 97. Allowed devices <0," in r.stderr, r.stderr
+    r = subprocess.run([OURS, "-i", fin, "-o", str(tmp_path / "o.h5"), "-g", "0"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([OURS, "-i", fin, "-o", str(tmp_path / "o2.h5")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_no_gpu_means_error_exit_not_cpu_fallback(synth, tmp_path):
     import torch
 
