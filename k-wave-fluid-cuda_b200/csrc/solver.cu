@@ -2210,17 +2210,17 @@ int kw_q_term(kw_ctx* c, const float* const* intensity, int ncomp, float* q_out,
   if (!c->preprocessed) return fail(KW_ERR_STATE, "kw_q_term before kw_preprocess");
   if (ncomp != (c->g.nz == 1 ? 2 : 3)) return fail(KW_ERR_INVALID, "kw_q_term: one intensity per dimension");
   if (capacity < c->nsens) return fail(KW_ERR_INVALID, "kw_q_term: buffer too small");
-  if (c->nsens == 0) return KW_OK;
+  if (c->nsens == 0 && c->g.nranks == 1) return KW_OK;  // (slab-decomposed: collective -- a rank without sensor points still transforms its slab)
   float* dbuf = nullptr;  // [ncomp intensities | q]
-  KW_CUDA(cudaMalloc(&dbuf, (size_t)(ncomp + 1) * c->nsens * sizeof(float)));
+  KW_CUDA(cudaMalloc(&dbuf, std::max<size_t>((size_t)(ncomp + 1) * c->nsens, 1) * sizeof(float)));
   float* dI[3] = {};
   for (int f = 0; f < ncomp; ++f) {
     dI[f] = dbuf + (size_t)f * c->nsens;
-    cudaMemcpyAsync(dI[f], intensity[f], c->nsens * sizeof(float), cudaMemcpyHostToDevice, c->st);
+    if (c->nsens) cudaMemcpyAsync(dI[f], intensity[f], c->nsens * sizeof(float), cudaMemcpyHostToDevice, c->st);
   }
   float* dq = dbuf + (size_t)ncomp * c->nsens;
   int rc = compute_q_term(c, dI, dq);
-  if (rc == KW_OK && cudaMemcpyAsync(q_out, dq, c->nsens * sizeof(float), cudaMemcpyDeviceToHost, c->st) != cudaSuccess) rc = fail(KW_ERR_CUDA, "kw_q_term: copy failed");
+  if (rc == KW_OK && c->nsens && cudaMemcpyAsync(q_out, dq, c->nsens * sizeof(float), cudaMemcpyDeviceToHost, c->st) != cudaSuccess) rc = fail(KW_ERR_CUDA, "kw_q_term: copy failed");
   cudaStreamSynchronize(c->st);
   cudaFree(dbuf);
   return rc;

@@ -140,7 +140,6 @@ void KSpaceFirstOrderSolver::allocateMemory() {
   if (multi()) {  // slab decomposition: one process per GPU, rank r on device (-g or 0) + r, planes [r Nz/P, (r+1) Nz/P)
     const int P = mTeam->size;
     if (s.nz % P || s.ny % P) throw std::invalid_argument("Error: --gpus " + std::to_string(P) + " must divide Ny and Nz.");
-    if (mCmd.iAvg || mCmd.qTerm || mCmd.post) throw std::invalid_argument("Error: --I_avg, --Q_term and --post run on one GPU (post-processing of stored series).");
     if (mCmd.c40bit) throw std::invalid_argument("Error: --40-bit_complex runs on one GPU.");
     cfg.rank = mTeam->rank, cfg.nranks = P;
     cfg.device = (mCmd.gpuDevice < 0 ? 0 : mCmd.gpuDevice) + mTeam->rank;
@@ -598,7 +597,9 @@ void KSpaceFirstOrderSolver::computeAverageIntensities() {
       if (st.id == KW_S_UX_NS_RAW + k) su[k] = &st;
   }
   if (!sp || !su[0] || !su[1] || (ncomp == 3 && !su[2])) throw std::runtime_error("Error: the raw series needed by --I_avg / --Q_term were not stored.");
-  std::vector<std::vector<float>> intensity(ncomp, std::vector<float>(mSensorPoints, 0.f));
+  // slab-decomposed runs: the stored series live in rank 0's output file, so rank 0 alone forms the intensities
+  // (kw_intensity_avg_block needs no context); the Q term is a 3-D transform and runs on every rank (writeQTerm)
+  std::vector<std::vector<float>> intensity(ncomp, std::vector<float>(root() ? mSensorPoints : 0, 0.f));
   // block size: --block_size points, else what keeps the five host / device buffers of a block near 1 GB (cpp:1281-1300)
   uint64_t maxPoints = mCmd.blockSize ? mCmd.blockSize : std::max<uint64_t>(1, (48ull << 20) / steps);
   std::vector<float> bp, bu[3];
@@ -614,7 +615,8 @@ void KSpaceFirstOrderSolver::computeAverageIntensities() {
     }
     check(kw_intensity_avg_block(bp.data(), up, ncomp, n, steps, ip));
   };
-  if (mScalars.sensorMaskType == 0) {
+  if (!root()) {
+  } else if (mScalars.sensorMaskType == 0) {
     for (uint64_t i = 0; i < mSensorPoints; i += maxPoints) {
       const uint64_t n = std::min<uint64_t>(maxPoints, mSensorPoints - i);
       process(i, n, [&](const OutputStream& st, float* dst) { mOutputFile.readHyperslab(st.dataset, {0, 0, i}, {1, steps, n}, dst); });
@@ -634,14 +636,33 @@ void KSpaceFirstOrderSolver::computeAverageIntensities() {
     }
   }
   const char* names[3] = {"Ix_avg", "Iy_avg", "Iz_avg"};
-  if (mCmd.iAvg)
+  if (mCmd.iAvg && root())
     for (int k = 0; k < ncomp; ++k) replaceSensorValues(names[k], intensity[k].data());
-  if (mCmd.qTerm) {
+  if (mCmd.qTerm) writeQTerm(intensity, "Q_term");
+}
+
+// Q = -div I of per-sensor intensities held by rank 0 (complete rows in mask order) -> dataset `name`.  kw_q_term is collective on a
+// slab-decomposed context: every rank gets the values of its own sensor points, the results return to rank 0 in mask order.
+void KSpaceFirstOrderSolver::writeQTerm(const std::vector<std::vector<float>>& intensity, const char* name) {
+  const int ncomp = mScalars.nz > 1 ? 3 : 2;
+  if (!multi()) {
     std::vector<float> q(mSensorPoints, 0.f);
     const float* ip[3] = {intensity[0].data(), intensity[1].data(), ncomp == 3 ? intensity[2].data() : nullptr};
     check(kw_q_term(mCtx, ip, ncomp, q.data(), q.size()));
-    replaceSensorValues("Q_term", q.data());
+    replaceSensorValues(name, q.data());
+    return;
   }
+  std::vector<float> local[3];
+  const float* ip[3] = {};
+  for (int k = 0; k < ncomp; ++k) {
+    local[k] = distribute(intensity[k], false, 1, mSensorPoints);
+    local[k].resize(std::max<uint64_t>(mLocalPoints, 1));
+    ip[k] = local[k].data();
+  }
+  std::vector<float> ql(std::max<uint64_t>(mLocalPoints, 1), 0.f);
+  check(kw_q_term(mCtx, ip, ncomp, ql.data(), ql.size()));
+  const std::vector<float> q = gatherPoints(ql.data(), 1, mLocalPoints, 1, mSensorPoints);
+  if (root()) replaceSensorValues(name, q.data());
 }
 
 // replaces a dataset of per-sensor values (or the per-cuboid group) when an earlier run already stored it
@@ -732,9 +753,9 @@ void KSpaceFirstOrderSolver::postProcessOnly() {
   const hid_t root = mOutputFile.root();
   const int ncomp = mScalars.nz > 1 ? 3 : 2;
   mPostProcessingTime.start();
-  if (mCmd.iAvg || mCmd.qTerm) {  // the raw series the earlier run stored
+  if (mCmd.iAvg || mCmd.qTerm) {  // the raw series the earlier run stored (rank 0 owns the file)
     for (auto& st : mStreams) {
-      if (st.kind != K::kSeries) continue;
+      if (st.kind != K::kSeries || !this->root()) continue;
       if (mScalars.sensorMaskType == 0) {
         st.dataset = mOutputFile.openDataset(root, st.name);
       } else {
@@ -747,28 +768,27 @@ void KSpaceFirstOrderSolver::postProcessOnly() {
     for (const auto& st : mStreams)
       if (st.id == KW_S_P_RAW) sp = &st;
     if (!sp) throw std::runtime_error("Error: --post: the raw pressure series is not part of this command line.");
-    const uint64_t stored = mScalars.sensorMaskType == 0 ? mOutputFile.elementCount(root, "p") / std::max<uint64_t>(mSensorPoints, 1)
-                                                          : mOutputFile.elementCount(sp->group, "1") /
-                                                                std::max<uint64_t>((mCorners[3] - mCorners[0] + 1) * (mCorners[4] - mCorners[1] + 1) * (mCorners[5] - mCorners[2] + 1), 1);
+    uint64_t stored = 0;
+    if (this->root())
+      stored = mScalars.sensorMaskType == 0 ? mOutputFile.elementCount(root, "p") / std::max<uint64_t>(mSensorPoints, 1)
+                                            : mOutputFile.elementCount(sp->group, "1") /
+                                                  std::max<uint64_t>((mCorners[3] - mCorners[0] + 1) * (mCorners[4] - mCorners[1] + 1) * (mCorners[5] - mCorners[2] + 1), 1);
+    if (multi()) mTeam->bcast(&stored, sizeof stored);
     mSamplingSteps = stored;
     computeAverageIntensities();
   }
   if (mCmd.iAvgC || mCmd.qTermC) {
-    std::vector<std::vector<float>> intensity;
-    computeAverageIntensitiesC(intensity);
+    std::vector<std::vector<float>> intensity(ncomp);
+    if (this->root()) computeAverageIntensitiesC(intensity);
     const char* names[3] = {"Ix_avg_c", "Iy_avg_c", "Iz_avg_c"};
-    if (mCmd.iAvgC)
+    if (mCmd.iAvgC && this->root())
       for (int k = 0; k < ncomp; ++k) replaceSensorValues(names[k], intensity[k].data());
-    if (mCmd.qTermC) {
-      std::vector<float> q(mSensorPoints, 0.f);
-      const float* ip[3] = {intensity[0].data(), intensity[1].data(), ncomp == 3 ? intensity[2].data() : nullptr};
-      check(kw_q_term(mCtx, ip, ncomp, q.data(), q.size()));
-      replaceSensorValues("Q_term_c", q.data());
-    }
+    if (mCmd.qTermC) writeQTerm(intensity, "Q_term_c");
   }
   mPostProcessingTime.stop();
   mTotalTime.stop();
-  mOutputFile.close();
+  if (this->root()) mOutputFile.close();
+  if (multi()) mTeam->barrier();
   log(1, "Post-processing phase (--post): %s\n", formatSeconds(getPostProcessingTime()).c_str());
 }
 

@@ -98,6 +98,7 @@ class KSpaceFirstOrderSolver {
   void postProcessOnly();             // --post (cpp:231-239, :975-1030)
   void computeAverageIntensitiesC(std::vector<std::vector<float>>& intensity);  // cpp:1543-1775
   void replaceSensorValues(const std::string& name, const float* data);
+  void writeQTerm(const std::vector<std::vector<float>>& intensity, const char* name);  // computeQTerm (cpp:1783-2080), collective on slabs
   void writeStreamBuffer(OutputStream& st, const float* buf);  // accumulator of an aggregate stream -> output file
   void readStreamBuffer(OutputStream& st, float* buf);
   void createOutputDatasets();

@@ -81,3 +81,35 @@ def test_two_gpu_run_resumes_from_its_checkpoint(synth, tmp_path):
         assert legs < 5
     assert legs == 3
     same_bits(whole, kwh5.read_file(out))
+
+
+@pytest.mark.parametrize("sensor", ["index", "cuboid"])
+def test_intensities_q_term_and_post_on_two_gpus(synth, tmp_path, sensor):
+    """--I_avg / --Q_term (post-processing of the stored raw series, KSpaceFirstOrderSolver.cpp:1231-1534, computeQTerm :1783-2080) and --post
+    (:231-239) on a slab-decomposed run: rank 0 forms the intensities from its file, the Q term's 3-D transforms run on every rank.
+    --gpus 2 writes the datasets --gpus 1 writes, bit for bit; --post --gpus 2 on a stored file equals --post --gpus 1."""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    kwargs = dict(nonlinear=True, absorbing=True, source="p_plane", n_sensor=150, period=20, shifts=True, shuffle_sensor=(sensor == "index"))
+    if sensor == "cuboid":
+        kwargs["sensor"] = "cuboid"
+    cfg, arrays = synth.make_case(32, nt=80, **kwargs)
+    fin = str(tmp_path / "in.h5")
+    kwh5.write_input(fin, cfg, arrays)
+    comp = ["--period", "20", "--harmonics", "2"]
+    flags = ["--I_avg", "--Q_term", "--I_avg_c", "--Q_term_c", "-p"] + comp
+    one = run(fin, str(tmp_path / "one.h5"), flags, 1)
+    two = run(fin, str(tmp_path / "two.h5"), flags, 2)
+    assert any(n.startswith("/Q_term") for n in one) and any(n.startswith("/Ix_avg") for n in one)
+    same_bits(one, two)
+    # --post: the same stored file post-processed by one and by two GPUs
+    import shutil
+
+    stored = str(tmp_path / "stored.h5")
+    run(fin, stored, ["-p", "--u_non_staggered_raw", "--p_c", "--u_non_staggered_c"] + comp, 2)
+    shutil.copy(stored, str(tmp_path / "stored1.h5"))
+    post = ["--post", "--I_avg", "--Q_term", "--I_avg_c", "--Q_term_c"] + comp
+    p1 = run(fin, str(tmp_path / "stored1.h5"), post, 1)
+    p2 = run(fin, stored, post, 2)
+    assert any(n.startswith("/Q_term_c") for n in p2)
+    same_bits(p1, p2)
