@@ -167,6 +167,10 @@ int kw_set_source_row(kw_ctx* ctx, int array_id, uint64_t t_index, const float* 
  * buffers, cuFFT layout: real [nz][ny][nx], complex [nz][ny][nx/2+1] interleaved, both unnormalised.
  * Grid sizes (here and in kw_ctx_create): each of nx, ny, nz (nz may be 1) a power of two in [16, 1024] (tuned kernels) or any
  * other multiple of 8 up to 2048 whose prime factors are 2, 3, 5, 7 (run-time-length kernels); anything else: KW_ERR_INVALID. */
+/* Which kernel family transforms an axis of length n: 2 = tuned (powers of two in [16, 1024]), 1 = run-time-length kernels (other
+ * multiples of 8 up to 2048 with prime factors 2, 3, 5, 7), 0 = not supported.  Host-side only (no device work): lets a front end
+ * reject a grid before it loads gigabytes of input.  The reference accepts whatever cuFFT plans (CufftComplexMatrix.cpp:87-91). */
+int kw_length_supported(uint64_t n);
 int kw_fft_r2c_3d(uint64_t nx, uint64_t ny, uint64_t nz, const float* host_real, float* host_complex);
 int kw_fft_c2r_3d(uint64_t nx, uint64_t ny, uint64_t nz, const float* host_complex, float* host_real);
 /* The fused z pass on host buffers: the kernel that replaces the z stages of cuFFT together with cudaComputePressureGradient,

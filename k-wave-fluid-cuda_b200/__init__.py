@@ -15,6 +15,7 @@ from .capi import (  # noqa: F401
     intensity_avg_block,
     fft_r2c_3d,
     fft_zmid,
+    length_supported,
     library_path,
     load_library,
     nccl_unique_id,

@@ -120,6 +120,7 @@ def load_library():
         "kw_stream_buffer_set": [vp, i32, i32, vp, u64],
         "kw_finish": [vp],
         "kw_set_source_row": [vp, i32, u64, vp, u64],
+        "kw_length_supported": [u64],
         "kw_fft_r2c_3d": [u64, u64, u64, vp, vp],
         "kw_fft_c2r_3d": [u64, u64, u64, vp, vp],
         "kw_fft_zmid": [u64, u64, u64, i32, vp, vp, C.c_float, vp, vp, vp, vp, vp, vp],
@@ -154,6 +155,11 @@ def load_library():
 def _check(rc):
     if rc != 0:
         raise KwError(rc, load_library().kw_last_error().decode())
+
+
+def length_supported(n):
+    """2: tuned kernels, 1: run-time-length kernels, 0: unsupported transform length (kw_length_supported)."""
+    return int(load_library().kw_length_supported(int(n)))
 
 
 def fft_r2c_3d(x):

@@ -2457,6 +2457,14 @@ int kw_fft_zmid(uint64_t nx, uint64_t ny, uint64_t nz, int axis, const float* in
   return KW_OK;
 }
 
+int kw_length_supported(uint64_t n) {
+  if (n > 2048) return 0;
+  switch ((int)n) {
+    case 16: case 32: case 64: case 128: case 256: case 512: case 1024: return 2;
+    default: return generic_length_supported((int)n) ? 1 : 0;
+  }
+}
+
 int kw_fft_r2c_3d(uint64_t nx, uint64_t ny, uint64_t nz, const float* host_real, float* host_complex) {
   return fft3d_host(nx, ny, nz, host_real, host_complex, true);
 }

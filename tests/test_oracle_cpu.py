@@ -206,6 +206,18 @@ def test_library_exports_every_declared_symbol(kw):
     assert kw.load_library().kw_abi_version() == 1
 
 
+def test_supported_transform_lengths(kw):
+    """host-side rule of the two kernel families (csrc/fft_inst.cu, csrc/fft_generic.cu); no device needed"""
+    lib = kw.load_library()
+    tuned = [16, 32, 64, 128, 256, 512, 1024]
+    for n in tuned:
+        assert lib.kw_length_supported(n) == 2, n
+    for n in (24, 40, 48, 56, 72, 80, 96, 112, 120, 160, 192, 240, 320, 384, 480, 640, 768, 960, 1000, 1080, 1296, 1536, 2048):
+        assert lib.kw_length_supported(n) == 1, n
+    for n in (0, 8, 12, 20, 36, 88, 100, 104, 136, 150, 2056, 4096):  # too short, not 8 m, a prime factor above 7, too long
+        assert lib.kw_length_supported(n) == 0, n
+
+
 def test_enum_ids_follow_the_reference_order(kw):
     assert kw.STREAM_IDS["KW_S_P_RAW"] == 0 and kw.STREAM_IDS["KW_S_P_MAX_ALL"] == 5
     assert kw.STREAM_IDS["KW_S_UX_RAW"] == 7 and kw.STREAM_IDS["KW_S_Q_TERM_C"] == kw.STREAM_IDS["KW_STREAM_COUNT"] - 1
