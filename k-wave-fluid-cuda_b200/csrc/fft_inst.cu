@@ -129,8 +129,10 @@ template <int ID, bool DB, class K> static void zmid_go(K kernel, const ZMidArgs
   if (DB) {  // box = 256 rows (kz) of W neighbouring kx of one ky
     const uint64_t ny = a.plane / a.nxp;
     const uint32_t zb = N < 256 ? N : 256;
-    bool ok = make_tensor_map_3d(&maps.in, a.f.in, 2ull * a.nxp, ny, N, 8ull * a.nxp, 8ull * a.plane, 2u * W, 1, zb);
-    if (ok && a.f.mul) ok = make_tensor_map_3d(&maps.mul, a.f.mul, a.nxp, ny, N, 4ull * a.nxp, 4ull * a.plane, (uint32_t)W, 1, zb);
+    // the tensors end at the last valid kx: the padding columns of a box are filled with zeros without being read (ZMidArgs::nvalid)
+    const uint64_t nv = a.nvalid ? (uint64_t)a.nvalid : (uint64_t)a.nxp;
+    bool ok = make_tensor_map_3d(&maps.in, a.f.in, 2ull * nv, ny, N, 8ull * a.nxp, 8ull * a.plane, 2u * W, 1, zb);
+    if (ok && a.f.mul) ok = make_tensor_map_3d(&maps.mul, a.f.mul, nv, ny, N, 4ull * a.nxp, 4ull * a.plane, (uint32_t)W, 1, zb);
     if (!ok) {
       fprintf(stderr, "kwave_b200: cuTensorMapEncodeTiled failed for the fused z pass (N = %d)\n", N);
       abort();

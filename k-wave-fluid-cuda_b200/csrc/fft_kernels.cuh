@@ -292,6 +292,9 @@ struct ColArgs {
   int blk_es;
   size_t blk;
   int n;  // length of the transform axis (fft_generic.cu)
+  // kx >= nvalid are padding columns (NXP - (Nx/2+1) <= 15 of them): they are transformed like the others (their lanes carry whatever shared
+  // memory holds) but neither loaded nor stored -- 5.5 % of the traffic of a column pass at Nx = 512.  0 = every column is moved.
+  int nvalid;
 };
 
 #ifdef KW_N
@@ -310,29 +313,34 @@ template <int N, int DIR, bool BLOCKED> __global__ void __launch_bounds__(ColCfg
     if constexpr (BLOCKED) return (size_t)(e >> a.blk_es) * a.blk + (size_t)(e & ((1 << a.blk_es) - 1)) * estride;
     else return e * estride;
   };
-  auto tile_ptr = [&](int it, bool& valid) -> float2* {
+  const int nvalid = a.nvalid ? a.nvalid : a.ngroups * W;
+  auto tile_ptr = [&](int it, bool& valid, bool& moved) -> float2* {
     const int tile = a.tile_begin + it * C::TPC + tz;
     valid = tile < a.tile_end;
     const int tl = valid ? tile : a.tile_begin;
-    return data + (size_t)(tl / a.ngroups) * a.outer_stride + (size_t)(tl % a.ngroups) * W + lane + (size_t)w * a.stride;
+    const int kx = (tl % a.ngroups) * W + lane;
+    moved = kx < nvalid;  // padding columns are neither loaded nor stored
+    return data + (size_t)(tl / a.ngroups) * a.outer_stride + kx + (size_t)w * a.stride;
   };
   // The points of the next tile are copied asynchronously (LDGSTS) into the exchange buffer as soon as the current
   // transform has read its last exchange back, each thread fetching exactly the points it will own: the global-load
   // latency hides behind the second butterfly and the stores.  Single-stage plans (N <= 32) load straight to registers.
   auto prefetch = [&](int it) {
     if constexpr (P::R2 > 1) {
-      bool valid;
-      const float2* p = tile_ptr(it, valid);
+      bool valid, moved;
+      const float2* p = tile_ptr(it, valid, moved);
+      if (moved) {
 #pragma unroll
-      for (int e = 0; e < E; ++e) cp_async8(ex.buf + (w + WK * e) * W, p + poff(e));
+        for (int e = 0; e < E; ++e) cp_async8(ex.buf + (w + WK * e) * W, p + poff(e));
+      }
       cp_async_commit();
     }
   };
   int it = blockIdx.x;
   if (it < niter) prefetch(it);
   for (; it < niter; it += gridDim.x) {
-    bool valid;
-    float2* p = tile_ptr(it, valid);
+    bool valid, moved;
+    float2* p = tile_ptr(it, valid, moved);
     float2 v[E];
     if constexpr (P::R2 > 1) {
       cp_async_wait<0>();
@@ -341,13 +349,13 @@ template <int N, int DIR, bool BLOCKED> __global__ void __launch_bounds__(ColCfg
       ex.sync();  // landing slots of other workers must be consumed before stage-1 outputs overwrite them
     } else {
 #pragma unroll
-      for (int e = 0; e < E; ++e) v[e] = p[poff(e)];
+      for (int e = 0; e < E; ++e) v[e] = moved ? p[poff(e)] : make_float2(0.f, 0.f);
     }
     const int nxt = it + gridDim.x;
     fft2_worker<N, DIR>(v, w, ex, ConstTab(), [&] {
       if (nxt < niter) prefetch(nxt);
     });
-    if (valid) {
+    if (valid && moved) {
 #pragma unroll
       for (int e = 0; e < E; ++e) p[poff(e)] = v[e];
     }
@@ -377,6 +385,7 @@ struct ZMidArgs {
   int nxp, ngroups, ntiles;  // ntiles = Ny * ngroups
   unsigned plane;            // Ny * NXP
   int n;                     // Nz (fft_generic.cu)
+  int nvalid;                // as in ColArgs: Nx/2 + 1, or 0
 };
 
 #ifdef KW_N
@@ -424,6 +433,7 @@ template <int N, int AXIS, int MODE = 0> __global__ void __launch_bounds__(ZCfgM
     for (int i = threadIdx.x + W * (threadIdx.y + WK * threadIdx.z); i < N; i += C::THREADS) svec[i] = __ldg(zv + i);
     __syncthreads();
   }
+  const int nvalid = a.nvalid ? a.nvalid : a.nxp;  // kx >= nvalid: padding columns, neither loaded nor stored
   auto tile_base = [&](int it, bool& valid, int& y, int& kx) -> unsigned {
     const int tile = it * C::TPC + tz;
     valid = tile < a.ntiles;
@@ -448,8 +458,10 @@ template <int N, int AXIS, int MODE = 0> __global__ void __launch_bounds__(ZCfgM
         }
       } else {
         const float2* p = in + b;
+        if (kx < nvalid) {
 #pragma unroll
-        for (int e = 0; e < E; ++e) cp_async8(ex.at(w + WK * e), p + e * estride);
+          for (int e = 0; e < E; ++e) cp_async8(ex.at(w + WK * e), p + e * estride);
+        }
         cp_async_commit();
       }
     }
@@ -464,8 +476,9 @@ template <int N, int AXIS, int MODE = 0> __global__ void __launch_bounds__(ZCfgM
     const int nxt = it + gridDim.x;
     // the real multiplier of this tile lands in shared memory (cp.async, thread-private slots) while the forward
     // transform runs: no registers, no exposed latency.  Issued before the points are taken into registers.
+    const bool moved = kx < nvalid;
     if constexpr (!TMA) {
-      if (mul && KW_ZMID_MULMODE == 0) {
+      if (mul && KW_ZMID_MULMODE == 0 && moved) {
 #pragma unroll
         for (int e = 0; e < E; ++e) cp_async4(mul0 + e * (WK * W), mul + base + e * estride);
       }
@@ -483,7 +496,7 @@ template <int N, int AXIS, int MODE = 0> __global__ void __launch_bounds__(ZCfgM
       }
     } else {
 #pragma unroll
-      for (int e = 0; e < E; ++e) v[e] = __ldg(in + base + e * estride);
+      for (int e = 0; e < E; ++e) v[e] = moved ? __ldg(in + base + e * estride) : make_float2(0.f, 0.f);
     }
     fft2_worker<N, -1>(v, w, ex, ConstTab());
     if constexpr (!TMA) cp_async_wait<0>();
@@ -502,7 +515,7 @@ template <int N, int AXIS, int MODE = 0> __global__ void __launch_bounds__(ZCfgM
         else fft2_worker<N, +1>(v, w, ex, ConstTab(), [&] {
           if (!DB && nxt < niter) prefetch(nxt, 0);
         });
-        if (valid) {
+        if (valid && moved) {
           float2* __restrict__ p = (f == 0 ? a.f.out : f == 1 ? a.f.out_y : a.f.out_z) + base;
 #pragma unroll
           for (int e = 0; e < E; ++e) p[e * estride] = v[e];
@@ -514,7 +527,7 @@ template <int N, int AXIS, int MODE = 0> __global__ void __launch_bounds__(ZCfgM
       if (AXIS == 1) w01 = __ldg(a.f.vec + y);
 #pragma unroll
       for (int e = 0; e < E; ++e) {
-        const float m = mul ? (KW_ZMID_MULMODE == 0 ? mulbuf[e * (WK * W)] : __ldg(mul + base + e * estride)) * scal : scal;
+        const float m = mul ? (KW_ZMID_MULMODE == 0 ? mulbuf[e * (WK * W)] : (moved ? __ldg(mul + base + e * estride) : 0.f)) * scal : scal;
         float2 x = cscale(v[e], m);
         if (AXIS == 0 || AXIS == 1) x = cmul(x, w01);
         if (AXIS == 2) x = cmul(x, svec[w + WK * e]);
@@ -523,7 +536,7 @@ template <int N, int AXIS, int MODE = 0> __global__ void __launch_bounds__(ZCfgM
       fft2_worker<N, +1>(v, w, ex, ConstTab(), [&] {
         if (!DB && nxt < niter) prefetch(nxt, 0);
       });
-      if (valid) {
+      if (valid && moved) {
         float2* __restrict__ p = a.f.out + base;
 #pragma unroll
         for (int e = 0; e < E; ++e) p[e * estride] = v[e];

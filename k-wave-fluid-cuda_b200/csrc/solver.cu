@@ -1046,7 +1046,7 @@ static ColArgs ycol_args(const Geometry& g, float2* const* data, int nf) {
   ColArgs ca{};
   for (int f = 0; f < nf; ++f) ca.data[f] = data[f];
   ca.stride = g.nxp, ca.outer_stride = (size_t)g.nyl * g.nxp, ca.ngroups = g.nxp / g.oy->col_w;
-  ca.tile_begin = 0, ca.tile_end = g.nzl * ca.ngroups, ca.n = g.ny;
+  ca.tile_begin = 0, ca.tile_end = g.nzl * ca.ngroups, ca.n = g.ny, ca.nvalid = g.nxr;
   if (g.nranks > 1) {
     int wk_log2 = 0;
     while ((1 << wk_log2) < g.oy->col_wk) ++wk_log2;
@@ -1210,7 +1210,7 @@ static void zmid_launch(kw_ctx* c, ZField f, int axis) {
   if (axis == 1 && f.vec) f.vec += g.y0;
   if (axis == 3 && f.vec_y) f.vec_y += g.y0;
   za.f = f, za.axis = axis;
-  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->zmid_w, za.ntiles = g.nyl * za.ngroups, za.plane = (unsigned)((size_t)g.nyl * g.nxp), za.n = g.nz;
+  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->zmid_w, za.ntiles = g.nyl * za.ngroups, za.plane = (unsigned)((size_t)g.nyl * g.nxp), za.n = g.nz, za.nvalid = g.nxr;
   launch(c, axis == 3 ? "zmid_grad" : "zmid", (axis == 3 ? 32.0 : 16.0) * g.nca + (f.mul ? 4.0 * g.nca : 0.0), [&] { g.oz->zmid(za, c->st); });
 }
 template <int NF> static XInvArgs<NF> xinv_args(kw_ctx* c, float2* const* in, int pb, int pe, int nfields = NF) {
@@ -2324,8 +2324,8 @@ static int fft3d_host(uint64_t nx, uint64_t ny, uint64_t nz, const float* in, fl
   KW_CUDA(cudaMemset(dspec, 0, g.nc * sizeof(float2)));
   ColArgs cy{}, cz{};
   cy.data[0] = cz.data[0] = dspec;
-  cy.stride = g.nxp, cy.outer_stride = (size_t)g.ny * g.nxp, cy.ngroups = g.nxp / g.oy->col_w, cy.tile_begin = 0, cy.tile_end = g.nz * cy.ngroups, cy.n = g.ny;
-  if (g.nz > 1) cz.stride = (size_t)g.ny * g.nxp, cz.outer_stride = g.nxp, cz.ngroups = g.nxp / g.oz->col_w, cz.tile_begin = 0, cz.tile_end = g.ny * cz.ngroups, cz.n = g.nz;
+  cy.stride = g.nxp, cy.outer_stride = (size_t)g.ny * g.nxp, cy.ngroups = g.nxp / g.oy->col_w, cy.tile_begin = 0, cy.tile_end = g.nz * cy.ngroups, cy.n = g.ny, cy.nvalid = g.nxr;
+  if (g.nz > 1) cz.stride = (size_t)g.ny * g.nxp, cz.outer_stride = g.nxp, cz.ngroups = g.nxp / g.oz->col_w, cz.tile_begin = 0, cz.tile_end = g.ny * cz.ngroups, cz.n = g.nz, cz.nvalid = g.nxr;
   if (forward) {
     KW_CUDA(cudaMemcpy(dreal, in, g.n * sizeof(float), cudaMemcpyHostToDevice));
     XFwdArgs xa{};
@@ -2368,11 +2368,11 @@ int kw_bench_col(uint64_t nx, uint64_t ny, uint64_t nz, int axis, int fused, int
   ColArgs ca{};
   ca.data[0] = d;
   const FftOps* op = axis == 1 ? g.oy : g.oz;
-  if (axis == 1) ca.stride = g.nxp, ca.outer_stride = (size_t)g.ny * g.nxp, ca.ngroups = g.nxp / op->col_w, ca.tile_end = g.nz * ca.ngroups, ca.n = g.ny;
-  else ca.stride = (size_t)g.ny * g.nxp, ca.outer_stride = g.nxp, ca.ngroups = g.nxp / op->col_w, ca.tile_end = g.ny * ca.ngroups, ca.n = g.nz;
+  if (axis == 1) ca.stride = g.nxp, ca.outer_stride = (size_t)g.ny * g.nxp, ca.ngroups = g.nxp / op->col_w, ca.tile_end = g.nz * ca.ngroups, ca.n = g.ny, ca.nvalid = g.nxr;
+  else ca.stride = (size_t)g.ny * g.nxp, ca.outer_stride = g.nxp, ca.ngroups = g.nxp / op->col_w, ca.tile_end = g.ny * ca.ngroups, ca.n = g.nz, ca.nvalid = g.nxr;
   ZMidArgs za{};
   za.f = ZField{d, d, mul, 1.0f, nullptr}, za.axis = -1;
-  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->zmid_w, za.ntiles = g.ny * za.ngroups, za.plane = (unsigned)((size_t)g.ny * g.nxp), za.n = g.nz;
+  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->zmid_w, za.ntiles = g.ny * za.ngroups, za.plane = (unsigned)((size_t)g.ny * g.nxp), za.n = g.nz, za.nvalid = g.nxr;
   for (int i = 0; i < iters + 2; ++i) {
     if (i == 2) cudaEventRecord(e0);
     if (fused) g.oz->zmid(za, 0);
@@ -2445,7 +2445,7 @@ int kw_fft_zmid(uint64_t nx, uint64_t ny, uint64_t nz, int axis, const float* in
   ZMidArgs za{};
   za.f = ZField{din, dout[0], dmul, scal, axis == 3 ? dv[0] : axis >= 0 ? dv[axis] : nullptr, dout[1], dout[2], dv[1], dv[2]};
   za.axis = axis;
-  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->zmid_w, za.ntiles = g.ny * za.ngroups, za.plane = (unsigned)((size_t)g.ny * g.nxp), za.n = g.nz;
+  za.nxp = g.nxp, za.ngroups = g.nxp / g.oz->zmid_w, za.ntiles = g.ny * za.ngroups, za.plane = (unsigned)((size_t)g.ny * g.nxp), za.n = g.nz, za.nvalid = g.nxr;
   g.oz->zmid(za, 0);
   KW_CUDA(cudaGetLastError());
   float* ho[3] = {out0, out1, out2};
