@@ -153,7 +153,7 @@ __device__ __forceinline__ void butterfly(const float2* __restrict__ x, float2* 
 // ---- the same passes with the length known at compile time ---------------------------------------------------------------------
 // A handful of common lengths (kCommon below) get their own instantiation of every kernel: radices, strides, trip counts and the
 // divisions of the index arithmetic become constants and the butterfly loop of a thread unrolls, so that the shared-memory loads of
-// its butterflies are in flight together.  Same radix order as make_plan, so both forms round identically.
+// its butterflies are in flight together.  Same radix order as make_plan (the two forms agree to rounding; both are tested against the DFT).
 template <int M> struct NextRadix {  // M = product of the radices still to do
   static constexpr int value = (M % 8 == 0) ? 8 : (M % 4 == 0) ? 4 : (M % 2 == 0) ? (M % 3 == 0 ? 6 : 2) : (M % 3 == 0) ? 3 : (M % 5 == 0) ? 5 : 7;
 };
@@ -397,7 +397,8 @@ template <int CN, int W> static __global__ void __launch_bounds__(kThreads) g_co
   auto fetch = [&](int tile, float2* dst) {
     if (tile < a.tile_end) {
       const float2* base = tile_base(tile);
-      for (int idx = threadIdx.x; idx < n * W; idx += blockDim.x) {
+#pragma unroll 4
+      for (int idx = threadIdx.x; idx < n * W; idx += kThreads) {
         const int i = idx / W, c = idx - i * W;
         cp_async8(dst + idx, base + (size_t)i * a.stride + c);
       }
@@ -412,7 +413,8 @@ template <int CN, int W> static __global__ void __launch_bounds__(kThreads) g_co
     __syncthreads();
     const float2* R = dir < 0 ? fft_batch<W, -1, CN, kThreads, W>(cur, oth, W, pl, tab) : fft_batch<W, +1, CN, kThreads, W>(cur, oth, W, pl, tab);
     float2* base = tile_base(tile);
-    for (int idx = threadIdx.x; idx < n * W; idx += blockDim.x) {
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < n * W; idx += kThreads) {
       const int i = idx / W, c = idx - i * W;
       base[(size_t)i * a.stride + c] = R[idx];
     }
@@ -440,7 +442,8 @@ template <int CN, int W> static __global__ void __launch_bounds__(kThreads) g_zm
   auto fetch = [&](int tile, float2* dst) {
     if (tile < a.ntiles) {
       const size_t base = (size_t)(tile / a.ngroups) * a.nxp + (size_t)(tile % a.ngroups) * W;
-      for (int idx = threadIdx.x; idx < n * W; idx += blockDim.x) {
+#pragma unroll 4
+      for (int idx = threadIdx.x; idx < n * W; idx += kThreads) {
         const int i = idx / W, c = idx - i * W;
         cp_async8(dst + idx, in + base + (size_t)i * a.plane + c);
       }
@@ -458,7 +461,7 @@ template <int CN, int W> static __global__ void __launch_bounds__(kThreads) g_zm
     float2* S = fft_batch<W, -1, CN, kThreads, W>(cur, oth, W, pl, tab);
     float2* O = S == cur ? oth : cur;
 #pragma unroll 4  // several multiplier loads in flight per thread
-    for (int idx = threadIdx.x; idx < n * W; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < n * W; idx += kThreads) {
       const int i = idx / W, c = idx - i * W;
       const float m = mul ? __ldg(mul + base + (size_t)i * a.plane + c) * scal : scal;
       float2 v = S[idx];
@@ -470,7 +473,8 @@ template <int CN, int W> static __global__ void __launch_bounds__(kThreads) g_zm
     }
     __syncthreads();
     const float2* R = fft_batch<W, +1, CN, kThreads, W>(S, O, W, pl, tab);
-    for (int idx = threadIdx.x; idx < n * W; idx += blockDim.x) {
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < n * W; idx += kThreads) {
       const int i = idx / W, c = idx - i * W;
       a.f.out[base + (size_t)i * a.plane + c] = R[idx];
     }
@@ -497,7 +501,8 @@ template <int CN, int W> static __global__ void __launch_bounds__(kThreads) g_zm
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const int y = tile / a.ngroups, kx0 = (tile % a.ngroups) * W;
     const size_t base = (size_t)y * a.nxp + kx0;
-    for (int idx = threadIdx.x; idx < n * W; idx += blockDim.x) {
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < n * W; idx += kThreads) {
       const int i = idx / W, c = idx - i * W;
       A[idx] = __ldg(in + base + (size_t)i * a.plane + c);
     }
@@ -505,7 +510,8 @@ template <int CN, int W> static __global__ void __launch_bounds__(kThreads) g_zm
     float2* S = fft_batch<W, -1, CN, kThreads, W>(A, B, W, pl, tab);
     float2* O = S == A ? B : A;  // the other buffer
     if (axis == 3) {
-      for (int idx = threadIdx.x; idx < n * W; idx += blockDim.x) {
+#pragma unroll 4
+      for (int idx = threadIdx.x; idx < n * W; idx += kThreads) {
         const int i = idx / W, c = idx - i * W;
         const float m = mul ? __ldg(mul + base + (size_t)i * a.plane + c) * scal : scal;
         const float2 v = S[idx];
@@ -513,7 +519,8 @@ template <int CN, int W> static __global__ void __launch_bounds__(kThreads) g_zm
       }
       __syncthreads();
       for (int f = 0; f < 3; ++f) {
-        for (int idx = threadIdx.x; idx < n * W; idx += blockDim.x) {
+#pragma unroll 4
+        for (int idx = threadIdx.x; idx < n * W; idx += kThreads) {
           const int i = idx / W, c = idx - i * W;
           const float2 w = f == 0 ? __ldg(a.f.vec + kx0 + c) : f == 1 ? __ldg(a.f.vec_y + y) : __ldg(a.f.vec_z + i);
           S[idx] = gmul(E[idx], w);
@@ -521,14 +528,16 @@ template <int CN, int W> static __global__ void __launch_bounds__(kThreads) g_zm
         __syncthreads();
         const float2* R = fft_batch<W, +1, CN, kThreads, W>(S, O, W, pl, tab);
         float2* __restrict__ out = f == 0 ? a.f.out : f == 1 ? a.f.out_y : a.f.out_z;
-        for (int idx = threadIdx.x; idx < n * W; idx += blockDim.x) {
+#pragma unroll 4
+        for (int idx = threadIdx.x; idx < n * W; idx += kThreads) {
           const int i = idx / W, c = idx - i * W;
           out[base + (size_t)i * a.plane + c] = R[idx];
         }
         __syncthreads();
       }
     } else {
-      for (int idx = threadIdx.x; idx < n * W; idx += blockDim.x) {
+#pragma unroll 4
+      for (int idx = threadIdx.x; idx < n * W; idx += kThreads) {
         const int i = idx / W, c = idx - i * W;
         const float m = mul ? __ldg(mul + base + (size_t)i * a.plane + c) * scal : scal;
         float2 v = S[idx];
@@ -540,7 +549,8 @@ template <int CN, int W> static __global__ void __launch_bounds__(kThreads) g_zm
       }
       __syncthreads();
       const float2* R = fft_batch<W, +1, CN, kThreads, W>(S, O, W, pl, tab);
-      for (int idx = threadIdx.x; idx < n * W; idx += blockDim.x) {
+#pragma unroll 4
+      for (int idx = threadIdx.x; idx < n * W; idx += kThreads) {
         const int i = idx / W, c = idx - i * W;
         a.f.out[base + (size_t)i * a.plane + c] = R[idx];
       }
