@@ -394,13 +394,19 @@ template <int CN, int W> static __global__ void __launch_bounds__(kThreads) g_co
   fill_table(tab, n);
   float2* __restrict__ data = a.data[blockIdx.y];
   auto tile_base = [&](int tile) { return data + (size_t)(tile / a.ngroups) * a.outer_stride + (size_t)(tile % a.ngroups) * W; };
+  // slab-decomposed runs: the y axis is split into blocks of nyl points, one per rank that owns them after the exchange (RowMap)
+  auto point = [&](int i) -> size_t {
+    if (a.nyl == 0) return (size_t)i * a.stride;
+    const int q = i / a.nyl;
+    return (size_t)q * a.blk + (size_t)(i - q * a.nyl) * a.stride;
+  };
   auto fetch = [&](int tile, float2* dst) {
     if (tile < a.tile_end) {
       const float2* base = tile_base(tile);
 #pragma unroll 4
       for (int idx = threadIdx.x; idx < n * W; idx += kThreads) {
         const int i = idx / W, c = idx - i * W;
-        cp_async8(dst + idx, base + (size_t)i * a.stride + c);
+        cp_async8(dst + idx, base + point(i) + c);
       }
     }
     cp_async_commit();  // (an empty group when there is no further tile: the wait below counts groups)
@@ -416,7 +422,7 @@ template <int CN, int W> static __global__ void __launch_bounds__(kThreads) g_co
 #pragma unroll 4
     for (int idx = threadIdx.x; idx < n * W; idx += kThreads) {
       const int i = idx / W, c = idx - i * W;
-      base[(size_t)i * a.stride + c] = R[idx];
+      base[point(i) + c] = R[idx];
     }
     __syncthreads();
     float2* t = cur;

@@ -24,11 +24,17 @@ constexpr int kXThreads = 256;
 // the x/y-local spectra in the y-blocked "exchange" layout [q][z_local][y_local][NXP] (q = rank that owns y after the
 // transpose, y = q*nyl + y_local), so that the block sent to rank q by the all-to-all is one contiguous range.
 struct RowMap {
-  int ny_log2;   // log2(Ny); < 0: Ny is not a power of two (single GPU only, fft_generic.cu): plain [z][y][NXP]
+  int ny_log2;   // log2(Ny); < 0: Ny is not a power of two (the same layouts, addressed with divisions)
   int ysh;       // log2(nyl), nyl = Ny / nranks  (== ny_log2 on one GPU)
   size_t blk;    // elements of one block: nzl * nyl * NXP
+  int ny, nyl;   // Ny and Ny / nranks (used when Ny is not a power of two)
   __device__ __forceinline__ size_t off(size_t row, int nxp) const {
-    if (ny_log2 < 0) return row * (size_t)nxp;
+    if (ny_log2 < 0) {
+      if (nyl == ny) return row * (size_t)nxp;
+      const size_t z = row / (unsigned)ny;
+      const unsigned y = (unsigned)(row - z * (unsigned)ny), q = y / (unsigned)nyl;
+      return (size_t)q * blk + (z * (unsigned)nyl + (y - q * (unsigned)nyl)) * (size_t)nxp;
+    }
     const size_t z = row >> ny_log2;
     const unsigned y = (unsigned)row & ((1u << ny_log2) - 1u);
     return (size_t)(y >> ysh) * blk + ((z << ysh) + (y & ((1u << ysh) - 1u))) * (size_t)nxp;
@@ -295,6 +301,7 @@ struct ColArgs {
   // kx >= nvalid are padding columns (NXP - (Nx/2+1) <= 15 of them): they are transformed like the others (their lanes carry whatever shared
   // memory holds) but neither loaded nor stored -- 5.5 % of the traffic of a column pass at Nx = 512.  0 = every column is moved.
   int nvalid;
+  int nyl;  // fft_generic.cu, y-blocked layout with a length that is not a power of two: point i lives at (i / nyl) * blk + (i % nyl) * stride; 0 = plain
 };
 
 #ifdef KW_N

@@ -151,7 +151,7 @@ struct Geometry {
   size_t blk = 0;                        // complex elements exchanged with one peer per field: nxp*nyl*nzl
   const FftOps *ox = nullptr, *oy = nullptr, *oz = nullptr;
   const float2 *tx = nullptr, *ty = nullptr, *tz = nullptr;
-  RowMap row_map() const { return RowMap{ny_log2, ysh, blk}; }
+  RowMap row_map() const { return RowMap{ny_log2, ysh, blk, ny, nyl}; }
   int init(uint64_t nx_, uint64_t ny_, uint64_t nz_, int rank_ = 0, int nranks_ = 1) {
     nx = (int)nx_, ny = (int)ny_, nz = (int)nz_;
     // Nz == 1 (2-D simulations, Parameters.h:88-94): the z transforms are identities; everything else is the 3-D path with a
@@ -168,9 +168,6 @@ struct Geometry {
     if (nranks > 1 && (nyl < oy->col_wk || (nyl & 1)))
       return fail(KW_ERR_INVALID, "slab decomposition: Ny / nranks = " + std::to_string(nyl) + " is below the y-pass worker count " +
                                       std::to_string(oy->col_wk) + " of this Ny (use fewer ranks)");
-    const bool pow2_yz = !(ny & (ny - 1)) && !(nz & (nz - 1));
-    if (nranks > 1 && !pow2_yz)
-      return fail(KW_ERR_INVALID, "slab decomposition needs Ny and Nz to be powers of two (the y-blocked exchange layout); run this grid on one GPU");
     for (ny_log2 = 0; (1 << ny_log2) < ny; ++ny_log2) {}
     for (ysh = 0; (1 << ysh) < nyl; ++ysh) {}
     if (ny & (ny - 1)) ny_log2 = -1, ysh = 0;  // RowMap: plain [z][y][NXP]
@@ -1050,7 +1047,7 @@ static ColArgs ycol_args(const Geometry& g, float2* const* data, int nf) {
   if (g.nranks > 1) {
     int wk_log2 = 0;
     while ((1 << wk_log2) < g.oy->col_wk) ++wk_log2;
-    ca.blk_es = g.ysh - wk_log2, ca.blk = g.blk;
+    ca.blk_es = g.ysh - wk_log2, ca.blk = g.blk, ca.nyl = g.nyl;
   }
   return ca;
 }

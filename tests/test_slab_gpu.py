@@ -68,6 +68,9 @@ CASES = {
     "additive_p_source_many": ((32, 32, 32), dict(nonlinear=True, absorbing=True, source="p_many", source_mode=2)),
     "transducer": ((32, 32, 32), dict(nonlinear=False, absorbing=True, source="transducer")),
     "non_cubic": ((64, 32, 16), dict(nonlinear=True, absorbing=True, source="p_plane", shuffle_sensor=True)),
+    # Nx and Ny not powers of two: run-time-length kernels (csrc/fft_generic.cuh) on the y-blocked exchange layout addressed with divisions
+    "non_power_of_two_xy": ((48, 48, 32), dict(nonlinear=True, absorbing=True, source="p_plane", shuffle_sensor=True)),
+    "non_power_of_two_xyz": ((40, 96, 48), dict(nonlinear=False, absorbing=False, source="p0", sensor="cuboid")),
 }
 
 
