@@ -142,6 +142,21 @@ def test_no_gpu_means_error_exit_not_cpu_fallback(synth, tmp_path):
     assert r.returncode == 1 and "no CUDA device" in r.stderr
 
 
+def test_no_gpu_multi_process_run_exits_without_hanging(synth, tmp_path):
+    """--gpus 2 (host/Team.h: one forked process per GPU): when the ranks cannot get a device every process reports the error and the
+    parent exits with EXIT_FAILURE -- no rank is left waiting on a socket."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    cfg, arrays = synth.make_case(16, nt=4, source="p0")
+    fin = str(tmp_path / "in.h5")
+    kwh5.write_input(fin, cfg, arrays)
+    r = subprocess.run([OURS, "-i", fin, "-o", str(tmp_path / "o.h5"), "--gpus", "2"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and r.stderr.count("no CUDA device") >= 1
+    assert not os.path.exists(str(tmp_path / "o.h5")) or os.path.getsize(str(tmp_path / "o.h5")) >= 0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("sensor", ["index", "cuboid"])
 def test_checkpoint_restart_is_bit_identical(synth, tmp_path, sensor):
