@@ -154,7 +154,9 @@ def test_no_gpu_multi_process_run_exits_without_hanging(synth, tmp_path):
     kwh5.write_input(fin, cfg, arrays)
     r = subprocess.run([OURS, "-i", fin, "-o", str(tmp_path / "o.h5"), "--gpus", "2"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and r.stderr.count("no CUDA device") >= 1
-    assert not os.path.exists(str(tmp_path / "o.h5")) or os.path.getsize(str(tmp_path / "o.h5")) >= 0
+    # rank counts other than 1, 2, 4, 8 are rejected on the command line, before any process is forked
+    r = subprocess.run([OURS, "-i", fin, "-o", str(tmp_path / "o.h5"), "--gpus", "3"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "Invalid value of --gpus" in r.stderr, r.stderr
 
 
 @pytest.mark.gpu
